@@ -1,0 +1,199 @@
+"""Pins oracle/hgnn_oracle.py (the CPU restatement) against fixtures recorded
+from the unmodified reference (oracle/make_golden.py). CPU only."""
+import pytest
+import torch
+
+from oracle import hgnn_oracle as O
+
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+def _grads(loss, sd):
+    names = [k for k, v in sd.items() if v.requires_grad]
+    gs = torch.autograd.grad(loss, [sd[k] for k in names], allow_unused=True)
+    return dict(zip(names, gs))
+
+
+def _cmp_param_grads(got, want, prefix=""):
+    for k, w in want.items():
+        g = got.get(prefix + k)
+        if w is None:
+            assert g is None or float(g.abs().max()) == 0.0, k
+        else:
+            torch.testing.assert_close(g, w, rtol=1e-4, atol=2e-5, msg=lambda m: f"{k}: {m}")
+
+
+def test_make_mlp_layout_and_values(golden):
+    for (n, ln, oa), rec in golden("make_mlp.pt").items():
+        lay = O.mlp_layout(n, "GELU", oa, ln)
+        keys = []
+        for lin, lnidx, _ in lay:
+            keys += [f"{lin}.weight", f"{lin}.bias"]
+            if lnidx is not None:
+                keys += [f"{lnidx}.weight", f"{lnidx}.bias"]
+        assert keys == rec["keys"]
+        sd = {"m." + k: v for k, v in rec["state"].items()}
+        y = O.mlp_apply(sd, "m", rec["x"], n, "GELU", oa, ln)
+        torch.testing.assert_close(y, rec["y"], **TOL)
+
+
+@pytest.mark.parametrize("tag", ["ln_gelu", "noln_relu", "silu"])
+def test_interaction_cell(golden, tag):
+    r = golden("cell_interaction.pt")[tag]
+    sd = O.leaf_state({"c." + k: v for k, v in r["state"].items()})
+    nodes = r["nodes"].clone().requires_grad_(True)
+    edges = r["edges"].clone().requires_grad_(True)
+    n2, e2 = O.interaction_cell(sd, "c", r["hparams"], nodes, edges, r["graph"])
+    torch.testing.assert_close(n2, r["out_nodes"], **TOL)
+    torch.testing.assert_close(e2, r["out_edges"], **TOL)
+    loss = (n2 * r["w_nodes"]).sum() + (e2 * r["w_edges"]).sum()
+    gn, ge = torch.autograd.grad(loss, [nodes, edges], retain_graph=True)
+    torch.testing.assert_close(gn, r["grad_nodes"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ge, r["grad_edges"], rtol=1e-4, atol=1e-5)
+    _cmp_param_grads(_grads(loss, sd), r["grad_params"], "c.")
+
+
+def test_hierarchical_cell(golden):
+    r = golden("cell_hierarchical.pt")
+    sd = O.leaf_state({"c." + k: v for k, v in r["state"].items()})
+    names = ["nodes", "edges", "supernodes", "superedges", "bipartite_weights", "super_weights"]
+    t = {k: r[k].clone().requires_grad_(True) for k in names}
+    outs = O.hierarchical_cell(sd, "c", r["hparams"], t["nodes"], t["edges"], t["supernodes"], t["superedges"],
+                               r["graph"], r["bipartite_graph"], t["bipartite_weights"], r["super_graph"],
+                               t["super_weights"])
+    for o, w in zip(outs, r["outs"]):
+        torch.testing.assert_close(o, w, **TOL)
+    loss = sum((o * w).sum() for o, w in zip(outs, r["ws"]))
+    gs = torch.autograd.grad(loss, [t[k] for k in names], retain_graph=True)
+    for k, g in zip(names, gs):
+        torch.testing.assert_close(g, r["grads"][k], rtol=1e-4, atol=1e-5, msg=lambda m: f"{k}: {m}")
+    _cmp_param_grads(_grads(loss, sd), r["grad_params"], "c.")
+
+
+@pytest.mark.parametrize("tag", ["bip_train", "bip_eval", "sup_train", "sup_eval"])
+def test_dynamic_graph(golden, tag):
+    r = golden("dynamic_graph.pt")[tag]
+    sd = {"g." + k: v.clone() for k, v in r["state_before"].items()}
+    src = r["src"].clone().requires_grad_(True)
+    dst = src if r["sym"] else r["dst"].clone().requires_grad_(True)
+    k = r["k"]
+    assert O.knn_margin(src.detach(), dst.detach(), k, float(sd["g.knn_radius"])) > 1e-5
+    graph, w, logits, bufs = O.dynamic_graph(sd, "g", src, dst, weighting=r["weighting"], sym=r["sym"], norm=True,
+                                             k=k, training=r["training"])
+    po, pr = O.canonical_edge_order(graph), O.canonical_edge_order(r["graph"])
+    assert torch.equal(graph[:, po], r["graph"][:, pr])
+    torch.testing.assert_close(w[po], r["weights"][pr], **TOL)
+    torch.testing.assert_close(logits[po], r["logits"][pr], rtol=2e-5, atol=1e-5)
+    inv = torch.empty_like(po)
+    inv[po] = torch.arange(len(po))
+    wt = r["wt"][pr][inv]  # golden cotangent re-expressed in our edge order
+    loss = (w * wt).sum()
+    if r["sym"]:
+        (gs,) = torch.autograd.grad(loss, [src])
+        torch.testing.assert_close(gs, r["grad_src"], rtol=1e-4, atol=1e-5)
+    else:
+        gs, gd = torch.autograd.grad(loss, [src, dst])
+        torch.testing.assert_close(gs, r["grad_src"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(gd, r["grad_dst"], rtol=1e-4, atol=1e-5)
+    for key, want in r["state_after"].items():
+        got = bufs.get("g." + key, sd["g." + key])
+        torch.testing.assert_close(got.reshape(want.shape).to(want.dtype), want, rtol=1e-5, atol=1e-6,
+                                   msg=lambda m: f"{key}: {m}")
+
+
+@pytest.mark.parametrize("tag", ["default", "shared_noln"])
+def test_ec_model(golden, tag):
+    r = golden("ec_model.pt")[tag]
+    sd = O.leaf_state(r["state"])
+    x = r["x"].clone().requires_grad_(True)
+    scores = O.ec_forward(sd, r["hparams"], x, r["graph"])
+    torch.testing.assert_close(scores, r["scores"], **TOL)
+    loss = torch.nn.functional.binary_cross_entropy(scores, r["y"].float())
+    torch.testing.assert_close(loss, r["loss"], **TOL)
+    (gx,) = torch.autograd.grad(loss, [x], retain_graph=True)
+    torch.testing.assert_close(gx, r["grad_x"], rtol=1e-4, atol=1e-6)
+    got = _grads(loss, sd)
+    if r["hparams"]["share_weight"]:
+        # one shared cell: the oracle holds an independent leaf per alias, so the
+        # reference's single gradient equals the sum over aliases
+        n = r["hparams"]["n_interaction_graph_iters"]
+        for k in [k for k in got if ".ignn_cells.0." in k]:
+            got[k] = sum(got[k.replace(".ignn_cells.0.", f".ignn_cells.{i}.")] for i in range(n))
+    _cmp_param_grads(got, r["grad_params"])
+
+
+def test_ec_fp64_close_to_fp32(golden):
+    r = golden("ec_model.pt")["default"]
+    sd = O.cast_state(r["state"], torch.float64)
+    s64 = O.ec_forward(sd, r["hparams"], r["x"].double(), r["graph"])
+    assert float((s64.float() - r["scores"]).abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_bc_model(golden, mode):
+    G = golden("bc_model.pt")
+    r = G[mode]
+    state = dict(G["train"]["state_before"])
+    if mode == "eval":
+        state.update(G["train"]["state_after"])
+    sd = O.leaf_state(state)
+    x = G["x"].clone().requires_grad_(True)
+    bg, scores, emb, aux = O.bc_forward(sd, G["hparams"], x, G["graph"], clusters=r["clusters"],
+                                        training=(mode == "train"), return_aux=True)
+    po, pr = O.canonical_edge_order(bg), O.canonical_edge_order(r["bipartite_graph"])
+    assert torch.equal(bg[:, po], r["bipartite_graph"][:, pr])
+    torch.testing.assert_close(emb, r["embeddings"], **TOL)
+    torch.testing.assert_close(scores[po], r["scores"][pr], rtol=1e-4, atol=1e-5)
+    inv = torch.empty_like(po)
+    inv[po] = torch.arange(len(po))
+    loss = (scores * r["ws"][pr][inv]).sum() + (emb * r["we"]).sum()
+    (gx,) = torch.autograd.grad(loss, [x], retain_graph=True)
+    torch.testing.assert_close(gx, r["grad_x"], rtol=2e-3, atol=1e-4)
+    got = _grads(loss, sd)
+    for k, w in r["grad_params"].items():
+        g = got.get(k)
+        if w is None:
+            assert g is None or float(g.abs().max()) == 0.0, k
+        else:
+            torch.testing.assert_close(g, w, rtol=2e-3, atol=1e-4, msg=lambda m: f"{k}: {m}")
+    for key, want in r["state_after"].items():
+        if key == "hgnn_block.score_cut":
+            continue  # produced by the (injected) clustering stage
+        gotb = aux["buffers"].get(key, state[key])
+        torch.testing.assert_close(gotb.reshape(want.shape).to(want.dtype), want, rtol=1e-4, atol=1e-5,
+                                   msg=lambda m: f"{key}: {m}")
+
+
+def test_bc_dead_parameters_have_no_grad(golden):
+    """the last HGNN cell's edge / superedge networks never reach the output."""
+    G = golden("bc_model.pt")
+    last = G["hparams"]["n_hierarchical_graph_iters"] - 1
+    dead = [k for k, v in G["train"]["grad_params"].items() if v is None]
+    assert dead and all(f"hgnn_cells.{last}.edge_network" in k or f"hgnn_cells.{last}.superedge_network" in k for k in dead)
+
+
+def test_clustering_restatement_matches_reference_clusters(golden):
+    G = golden("bc_model.pt")
+    state = G["train"]["state_before"]
+    x = G["x"]
+    directed = torch.cat([G["graph"], G["graph"].flip(0)], 1)
+    emb, _, _ = O.ignn_block(state, "ignn_block", G["hparams"], x, directed, G["hparams"]["n_interaction_graph_iters"], True)
+    clusters, cut = O.gmm_clustering(G["hparams"], emb, directed, state["hgnn_block.score_cut"], training=True)
+    assert torch.equal(clusters, G["train"]["clusters"])
+    torch.testing.assert_close(cut.float(), G["train"]["state_after"]["hgnn_block.score_cut"], rtol=1e-4, atol=1e-5)
+
+
+def test_scatter_and_knn_primitives_tiny():
+    src = torch.tensor([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]])
+    idx = torch.tensor([2, 0, 2])
+    assert O.scatter_add(src, idx, 4).tolist() == [[3.0, 4.0], [0.0, 0.0], [6.0, 8.0], [0.0, 0.0]]
+    assert O.scatter_mean(src, idx, 3).tolist() == [[3.0, 4.0], [0.0, 0.0], [3.0, 4.0]]
+    q = torch.tensor([[0.0, 0.0], [10.0, 0.0]])
+    r = torch.tensor([[1.0, 0.0], [0.0, 0.5], [0.0, -0.5], [3.0, 0.0]])
+    out = O.knn_radius(q, r, 3, 2.0)
+    assert out.tolist() == [[1, 2, 0], [-1, -1, -1]]  # tie (0.5 vs 0.5) -> smaller index first
+    g = torch.tensor([[0, 1, 2, 2], [1, 0, 2, 0]])
+    assert O.symmetrize(g).tolist() == [[0, 0, 1, 2, 2], [1, 2, 0, 0, 2]]
+    lab = O.connected_component_labels(torch.tensor([[0, 3], [1, 4]]), 6)
+    assert lab.tolist() == [0, 0, -1, 3, 3, -1]
+    assert O.cluster_labels_from_components(torch.tensor([0, 0, -1, 3, 3, 3]), 3).tolist() == [-1, -1, -1, 0, 0, 0]
