@@ -1,0 +1,95 @@
+"""Task base of the bipartite classifier (reference:
+BipartiteClassification/bipartite_classification_base.py).
+
+Hook names, optimiser, and the two-term loss (pT-weighted hinge embedding loss
++ assignment BCE against a minimum-weight particle<->supernode matching, sine
+loss schedule) follow the reference. The matching itself stays scipy on the
+host exactly as in the reference (loss-side CPU stage, next
+in line, not on the message-passing path).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ..EdgeClassifier.edge_classifier_base import balanced_edge_weights, pt_weighting
+from ..lightning_compat import LightningModule
+
+
+class BipartiteClassificationBase(LightningModule):
+    def __init__(self, hparams):
+        super().__init__()
+        self.save_hyperparameters(hparams)
+
+    def configure_optimizers(self):
+        opt = torch.optim.AdamW(self.parameters(), lr=self.hparams["lr"], betas=(0.9, 0.999), eps=1e-08, amsgrad=True)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=self.hparams["patience"], gamma=self.hparams["factor"])
+        return [opt], [{"scheduler": sched, "interval": "epoch", "frequency": 1}]
+
+    # ---- embedding (hinge) term: bipartite_classification_base.py:141-150,196-204 ----
+    def embedding_loss(self, batch, embeddings):
+        graph = batch.edge_index
+        y = batch.pid[graph[0]] == batch.pid[graph[1]]
+        weights = balanced_edge_weights(batch.pt, graph, y, self.hparams)
+        hinge = torch.where(y, 1, -1)
+        dist = ((embeddings[graph[0]] - embeddings[graph[1]]).square().sum(-1) + 1e-12).sqrt()
+        loss = F.hinge_embedding_loss(dist / self.hparams["train_r"], hinge, margin=1, reduction="none").square()
+        return torch.dot(loss, weights)
+
+    # ---- assignment term: bipartite_classification_base.py:152-191 ----
+    def assignment_loss(self, batch, bipartite_graph, bipartite_scores):
+        from scipy.sparse import csr_matrix
+        from scipy.sparse.csgraph import min_weight_full_bipartite_matching
+        dev = bipartite_scores.device
+        original_pid, pid = torch.unique(batch.pid, return_inverse=True)
+        n_p = int(pid.max()) + 1
+        n_s = int(bipartite_graph[1].max()) + 1
+        pt = torch.full((n_p,), float("inf"), device=dev).scatter_reduce(0, pid, batch.pt.float(), "amin")
+        with torch.no_grad():
+            # virtual supernodes (one per particle, epsilon score) guarantee a full matching exists
+            rows = torch.cat([pid[bipartite_graph[0]], torch.arange(n_p, device=dev)])
+            cols = torch.cat([bipartite_graph[1], torch.arange(n_s, n_s + n_p, device=dev)])
+            vals = torch.cat([bipartite_scores.detach(), torch.full((n_p,), 1e-12, device=dev)])
+            table = csr_matrix((vals.cpu().numpy(), (rows.cpu().numpy(), cols.cpu().numpy())), shape=(n_p, n_s + n_p))
+            rm, cm = min_weight_full_bipartite_matching(table, maximize=True)
+            rm, cm = torch.as_tensor(rm, device=dev).long(), torch.as_tensor(cm, device=dev).long()
+            real = (original_pid[rm] != 0) & (cm < n_s)
+            rm, cm = rm[real], cm[real]
+            assigned = torch.full((n_p,), -1, dtype=torch.long, device=dev)
+            assigned[rm] = cm
+            truth = assigned[pid[bipartite_graph[0]]] == bipartite_graph[1]
+            sn_pt = torch.zeros(n_s, device=dev)
+            sn_pt[cm] = pt[rm]
+            w = torch.maximum(pt_weighting(batch.pt[bipartite_graph[0]], self.hparams),
+                              pt_weighting(sn_pt[bipartite_graph[1]], self.hparams))
+            ratio = torch.as_tensor(float(self.hparams["log_weight_ratio"]), device=dev)
+            ts, fs = (w * truth).sum().clamp(min=1e-30), (w * ~truth).sum().clamp(min=1e-30)
+            w = torch.where(truth, w / ts * torch.sigmoid(ratio), w / fs * torch.sigmoid(-ratio)).float()
+        return torch.dot(F.binary_cross_entropy(bipartite_scores, truth.float(), reduction="none"), w)
+
+    def loss_schedule(self):
+        if self.hparams.get("loss_schedule") is not None:
+            return self.hparams["loss_schedule"]
+        ep, emb_ep = self.trainer.current_epoch, self.hparams["emb_epoch"]
+        return 1 - math.sin(ep / 2 / emb_ep * math.pi) if ep < emb_ep else 0
+
+    def training_step(self, batch, batch_idx=0):
+        bipartite_graph, bipartite_scores, embeddings = self(batch.x, batch.edge_index)
+        emb_loss = self.embedding_loss(batch, embeddings)
+        asgmt_loss = self.assignment_loss(batch, bipartite_graph, bipartite_scores)
+        s = self.loss_schedule()
+        loss = s * emb_loss + (1 - s) * asgmt_loss
+        self.log_dict({"training_loss": loss, "embedding_loss": emb_loss, "assignment_loss": asgmt_loss})
+        return loss
+
+    def optimizer_step(self, epoch=None, batch_idx=None, optimizer=None, optimizer_idx=None, optimizer_closure=None,
+                       on_tpu=False, using_native_amp=False, using_lbfgs=False):
+        warm = self.hparams.get("warmup")
+        if warm and self.trainer.global_step < warm:
+            scale = min(1.0, float(self.trainer.global_step + 1) / warm)
+            for group in optimizer.param_groups:
+                group["lr"] = scale * self.hparams["lr"]
+        optimizer.step(closure=optimizer_closure)
+        optimizer.zero_grad()

@@ -1,0 +1,470 @@
+// Graph-side kernels of the HGNN hot path: segment plan (CSR) build, segmented
+// weighted row reductions, row gathers, gathered row dots, radius-kNN,
+// kNN->edge-list compaction, symmetrize, radius tracker.
+// All HBM-bound integer/float streaming work: coalesced float4 rows, one
+// deterministic sequential sum per segment (no float atomics).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+using namespace hgnn;
+
+// ---------------------------------------------------------------------------
+// CSR build
+// ---------------------------------------------------------------------------
+namespace {
+
+__global__ void k_narrow_iota(const int64_t* __restrict__ keys, int64_t n, int64_t limit, int32_t* __restrict__ k32,
+                              int32_t* __restrict__ iota, int32_t* __restrict__ bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t k = keys[i];
+  if (k < 0 || k >= limit) {
+    if (bad) atomicAdd(bad, 1);
+    k = k < 0 ? 0 : limit - 1;
+  }
+  k32[i] = (int32_t)k;
+  if (iota) iota[i] = (int32_t)i;
+}
+
+__global__ void k_rowptr(const int32_t* __restrict__ sorted, int64_t n, int64_t n_seg, int32_t* __restrict__ rowptr) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n_seg) return;
+  // lower_bound(sorted, s)
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted[mid] < (int32_t)s) lo = mid + 1; else hi = mid;
+  }
+  rowptr[s] = (int32_t)lo;
+}
+
+__global__ void k_gather_i32(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n,
+                             int32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+inline int bits_for(int64_t n) {
+  int b = 1;
+  while (b < 63 && ((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
+size_t csr_cub_bytes(int64_t n) {
+  size_t t = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)n, 0, 32);
+  return t;
+}
+
+}  // namespace
+
+extern "C" size_t hgnn_csr_build_workspace_bytes(int64_t n_items) {
+  if (n_items <= 0) return 256;
+  size_t n = (size_t)n_items;
+  return 4 * align_up(n * 4, 256) + align_up(csr_cub_bytes(n_items), 256) + 1024;
+}
+
+extern "C" int hgnn_csr_build(const int64_t* keys, int64_t n_items, int64_t n_segments, int32_t* perm, int32_t* rowptr,
+                              int32_t* keys32, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  HGNN_REQUIRE(n_items >= 0 && n_segments >= 0 && n_items < INT32_MAX && n_segments < INT32_MAX, "csr_build: sizes out of range");
+  HGNN_REQUIRE(rowptr != nullptr, "csr_build: rowptr is NULL");
+  if (n_items == 0) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(rowptr, 0, (size_t)(n_segments + 1) * 4, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(keys && perm, "csr_build: NULL keys/perm");
+  Workspace w(ws, ws_bytes);
+  int32_t* k_in = w.take<int32_t>(n_items);
+  int32_t* k_out = w.take<int32_t>(n_items);
+  int32_t* v_in = w.take<int32_t>(n_items);
+  size_t cub_bytes = csr_cub_bytes(n_items);
+  char* cub_ws = w.take<char>(cub_bytes);
+  if (!w.ok()) return fail(HGNN_ERR_WORKSPACE, "csr_build: workspace too small (%zu given)", ws_bytes);
+  int T = 256;
+  k_narrow_iota<<<(unsigned)((n_items + T - 1) / T), T, 0, st>>>(keys, n_items, n_segments, k_in, v_in, nullptr);
+  HGNN_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, k_in, k_out, v_in, perm, (int)n_items, 0,
+                                                bits_for(n_segments), st));
+  k_rowptr<<<(unsigned)((n_segments + 1 + T - 1) / T), T, 0, st>>>(k_out, n_items, n_segments, rowptr);
+  if (keys32) HGNN_CUDA_TRY(cudaMemcpyAsync(keys32, k_in, (size_t)n_items * 4, cudaMemcpyDeviceToDevice, st));
+  return check_launch("csr_build");
+}
+
+extern "C" int hgnn_index_to_i32(const int64_t* in, int64_t n, int64_t limit, int32_t* out, int32_t* bad, void* stream) {
+  if (n <= 0) return HGNN_OK;
+  HGNN_REQUIRE(in && out, "index_to_i32: NULL pointer");
+  k_narrow_iota<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, n, limit, out, nullptr, bad);
+  return check_launch("index_to_i32");
+}
+
+// ---------------------------------------------------------------------------
+// segmented reduce / gather / dot
+// ---------------------------------------------------------------------------
+namespace {
+
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> { using type = float4; };
+template <>
+struct VecT<1> { using type = float; };
+
+__device__ __forceinline__ void fma_acc(float4& a, float w, const float4& v) {
+  a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+}
+__device__ __forceinline__ void fma_acc(float& a, float w, const float& v) { a = fmaf(w, v, a); }
+__device__ __forceinline__ void scale_v(float4& a, float s) { a.x *= s; a.y *= s; a.z *= s; a.w *= s; }
+__device__ __forceinline__ void scale_v(float& a, float s) { a *= s; }
+template <typename V> __device__ __forceinline__ V zero_v();
+template <> __device__ __forceinline__ float4 zero_v<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ float zero_v<float>() { return 0.f; }
+
+// one thread = one (segment, column-chunk); consecutive threads = consecutive chunks
+template <int VEC>
+__global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict__ src, int chunks, const int32_t* __restrict__ gather,
+                                 const float* __restrict__ weight, const int32_t* __restrict__ perm,
+                                 const int32_t* __restrict__ rowptr, int64_t n_seg, int mean, float* __restrict__ out) {
+  using V = typename VecT<VEC>::type;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t s = t / chunks;
+  int c = (int)(t - s * chunks);
+  if (s >= n_seg) return;
+  const V* __restrict__ rows = reinterpret_cast<const V*>(src);
+  int beg = rowptr[s], end = rowptr[s + 1];
+  V acc = zero_v<V>();
+  int j = beg;
+  for (; j + 4 <= end; j += 4) {
+    int i0 = perm ? perm[j] : j, i1 = perm ? perm[j + 1] : j + 1, i2 = perm ? perm[j + 2] : j + 2, i3 = perm ? perm[j + 3] : j + 3;
+    int64_t r0 = gather ? gather[i0] : i0, r1 = gather ? gather[i1] : i1, r2 = gather ? gather[i2] : i2, r3 = gather ? gather[i3] : i3;
+    float w0 = weight ? weight[i0] : 1.f, w1 = weight ? weight[i1] : 1.f, w2 = weight ? weight[i2] : 1.f, w3 = weight ? weight[i3] : 1.f;
+    V v0 = rows[r0 * chunks + c], v1 = rows[r1 * chunks + c], v2 = rows[r2 * chunks + c], v3 = rows[r3 * chunks + c];
+    fma_acc(acc, w0, v0); fma_acc(acc, w1, v1); fma_acc(acc, w2, v2); fma_acc(acc, w3, v3);
+  }
+  for (; j < end; ++j) {
+    int i0 = perm ? perm[j] : j;
+    int64_t r0 = gather ? gather[i0] : i0;
+    float w0 = weight ? weight[i0] : 1.f;
+    fma_acc(acc, w0, rows[r0 * chunks + c]);
+  }
+  if (mean) scale_v(acc, 1.0f / (float)max(end - beg, 1));
+  reinterpret_cast<V*>(out)[s * chunks + c] = acc;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ src, int chunks, const int32_t* __restrict__ idx,
+                              const float* __restrict__ weight, int64_t n, float* __restrict__ out) {
+  using V = typename VecT<VEC>::type;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = t / chunks;
+  int c = (int)(t - i * chunks);
+  if (i >= n) return;
+  int64_t r = idx ? idx[i] : i;
+  V v = reinterpret_cast<const V*>(src)[r * chunks + c];
+  if (weight) scale_v(v, weight[i]);
+  reinterpret_cast<V*>(out)[i * chunks + c] = v;
+}
+
+// LANES threads cooperate on one item (LANES = 1, 8 or 32)
+template <int LANES>
+__global__ void __launch_bounds__(256) k_edge_dot(const float* __restrict__ a, const int32_t* __restrict__ ai, const float* __restrict__ b,
+                           const int32_t* __restrict__ bi, int width, int64_t n, float* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = t / LANES;
+  int l = (int)(t % LANES);
+  float acc = 0.f;
+  if (i < n) {
+    const float* ra = a + (int64_t)(ai ? ai[i] : i) * width;
+    const float* rb = b + (int64_t)(bi ? bi[i] : i) * width;
+    if ((width & 3) == 0) {
+      for (int d = l * 4; d < width; d += LANES * 4) {
+        float4 x = *reinterpret_cast<const float4*>(ra + d), y = *reinterpret_cast<const float4*>(rb + d);
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+      }
+    } else {
+      for (int d = l; d < width; d += LANES) acc = fmaf(ra[d], rb[d], acc);
+    }
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (i < n && l == 0) out[i] = acc;
+}
+
+}  // namespace
+
+extern "C" int hgnn_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight,
+                                   const int32_t* perm, const int32_t* rowptr, int64_t n_segments, int mean, float* out,
+                                   void* stream) {
+  if (n_segments <= 0 || width <= 0) return HGNN_OK;
+  HGNN_REQUIRE(src && rowptr && out, "segment_reduce: NULL pointer");
+  HGNN_REQUIRE(width <= 65536, "segment_reduce: width too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = (width % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
+  int chunks = vec ? (int)(width / 4) : (int)width;
+  int64_t threads = n_segments * chunks;
+  unsigned grid = (unsigned)((threads + 255) / 256);
+  if (vec) k_segment_reduce<4><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out);
+  else k_segment_reduce<1><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out);
+  return check_launch("segment_reduce");
+}
+
+extern "C" int hgnn_gather_rows(const float* src, int64_t width, const int32_t* idx, const float* weight, int64_t n_items,
+                                float* out, void* stream) {
+  if (n_items <= 0 || width <= 0) return HGNN_OK;
+  HGNN_REQUIRE(src && out, "gather_rows: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = (width % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
+  int chunks = vec ? (int)(width / 4) : (int)width;
+  int64_t threads = n_items * chunks;
+  unsigned grid = (unsigned)((threads + 255) / 256);
+  if (vec) k_gather_rows<4><<<grid, 256, 0, st>>>(src, chunks, idx, weight, n_items, out);
+  else k_gather_rows<1><<<grid, 256, 0, st>>>(src, chunks, idx, weight, n_items, out);
+  return check_launch("gather_rows");
+}
+
+extern "C" int hgnn_edge_dot(const float* a, const int32_t* ai, const float* b, const int32_t* bi, int64_t width,
+                             int64_t n_items, float* out, void* stream) {
+  if (n_items <= 0) return HGNN_OK;
+  HGNN_REQUIRE(a && b && out && width > 0, "edge_dot: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((width & 3) == 0 && (((uintptr_t)a | (uintptr_t)b) % 16 != 0))
+    return fail(HGNN_ERR_BAD_ARG, "edge_dot: rows must be 16-byte aligned when width %% 4 == 0");
+  if (width <= 16) k_edge_dot<1><<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(a, ai, b, bi, (int)width, n_items, out);
+  else if (width <= 64) k_edge_dot<8><<<(unsigned)((n_items * 8 + 255) / 256), 256, 0, st>>>(a, ai, b, bi, (int)width, n_items, out);
+  else k_edge_dot<32><<<(unsigned)((n_items * 32 + 255) / 256), 256, 0, st>>>(a, ai, b, bi, (int)width, n_items, out);
+  return check_launch("edge_dot");
+}
+
+// ---------------------------------------------------------------------------
+// radius kNN (brute force, shared-memory tiled)
+// ---------------------------------------------------------------------------
+namespace {
+
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_TILE = 128;
+constexpr int KNN_KMAX = 32;
+
+template <int DIM>  // DIM > 0: compile-time dimension with the query in registers; 0: runtime dim (<= 32)
+__global__ void __launch_bounds__(KNN_THREADS) k_knn_radius(const float* __restrict__ query, int64_t nq, const float* __restrict__ ref,
+                                                           int64_t nr, int dim_rt, int k, float r2, int64_t* __restrict__ idx) {
+  extern __shared__ float smem[];
+  const int dim = DIM > 0 ? DIM : dim_rt;
+  float* s_ref = smem;                           // [KNN_TILE][dim]
+  float* s_q = smem + KNN_TILE * dim;            // [KNN_THREADS][dim+1] (runtime-dim path only)
+  int64_t q = (int64_t)blockIdx.x * KNN_THREADS + threadIdx.x;
+  bool live = q < nq;
+  float qreg[DIM > 0 ? DIM : 1];
+  if (DIM > 0) {
+#pragma unroll
+    for (int d = 0; d < (DIM > 0 ? DIM : 1); ++d) qreg[d] = live ? query[q * dim + d] : 0.f;
+  } else {
+    for (int d = 0; d < dim; ++d) s_q[threadIdx.x * (dim + 1) + d] = live ? query[q * dim + d] : 0.f;
+  }
+  float bd[KNN_KMAX];
+  int bi[KNN_KMAX];
+#pragma unroll
+  for (int j = 0; j < KNN_KMAX; ++j) { bd[j] = INFINITY; bi[j] = -1; }
+  float kth = INFINITY;  // current k-th best distance
+
+  for (int64_t base = 0; base < nr; base += KNN_TILE) {
+    int cnt = (int)min((int64_t)KNN_TILE, nr - base);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * dim; t += KNN_THREADS) s_ref[t] = ref[base * dim + t];
+    __syncthreads();
+    if (!live) continue;
+    for (int j = 0; j < cnt; ++j) {
+      float d2 = 0.f;
+      if (DIM > 0) {
+#pragma unroll
+        for (int d = 0; d < (DIM > 0 ? DIM : 1); ++d) { float df = qreg[d] - s_ref[j * dim + d]; d2 = fmaf(df, df, d2); }
+      } else {
+        for (int d = 0; d < dim; ++d) { float df = s_q[threadIdx.x * (dim + 1) + d] - s_ref[j * dim + d]; d2 = fmaf(df, df, d2); }
+      }
+      if (d2 < r2 && d2 < kth) {
+        float cd = d2;
+        int ci = (int)(base + j);
+#pragma unroll
+        for (int m = 0; m < KNN_KMAX; ++m) {
+          if (m < k) {
+            // strict '<': an equal distance never displaces an earlier (smaller) index
+            if (cd < bd[m]) { float td = bd[m]; int ti = bi[m]; bd[m] = cd; bi[m] = ci; cd = td; ci = ti; }
+          }
+        }
+        // refresh the k-th best (bd[k-1]) without dynamic register indexing
+#pragma unroll
+        for (int m = 0; m < KNN_KMAX; ++m) if (m == k - 1) kth = bd[m];
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int m = 0; m < KNN_KMAX; ++m) if (m < k) idx[q * k + m] = (int64_t)bi[m];
+  }
+}
+
+__global__ void k_knn_count(const int64_t* __restrict__ idx, int64_t nq, int k, int32_t* __restrict__ cnt) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  int c = 0;
+  for (int m = 0; m < k; ++m) c += idx[q * k + m] >= 0;
+  cnt[q] = c;
+}
+
+__global__ void k_knn_fill(const int64_t* __restrict__ idx, int64_t nq, int k, const int32_t* __restrict__ cnt,
+                           const int32_t* __restrict__ off, int64_t ld, int64_t* __restrict__ graph, int64_t* __restrict__ total) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  int o = off[q];
+  for (int m = 0; m < k; ++m) {
+    int64_t v = idx[q * k + m];
+    if (v >= 0) { graph[o] = q; graph[ld + o] = v; ++o; }
+  }
+  if (q == nq - 1) *total = (int64_t)off[q] + cnt[q];
+}
+
+}  // namespace
+
+extern "C" int hgnn_knn_radius(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                               float radius, int64_t* idx, void* stream) {
+  if (n_query <= 0 || k <= 0) return HGNN_OK;
+  HGNN_REQUIRE(query && idx, "knn_radius: NULL pointer");
+  HGNN_REQUIRE(dim >= 1 && dim <= 32, "knn_radius: dim must be in [1,32], got %lld", (long long)dim);
+  HGNN_REQUIRE(k <= KNN_KMAX, "knn_radius: k must be <= %d, got %lld", KNN_KMAX, (long long)k);
+  HGNN_REQUIRE(n_ref >= 0 && n_ref < INT32_MAX, "knn_radius: n_ref out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned grid = (unsigned)((n_query + KNN_THREADS - 1) / KNN_THREADS);
+  float r2 = radius * radius;
+  size_t smem = (size_t)(KNN_TILE * dim + KNN_THREADS * (dim + 1)) * sizeof(float);
+  if (dim == 8) k_knn_radius<8><<<grid, KNN_THREADS, smem, st>>>(query, n_query, ref, n_ref, 8, (int)k, r2, idx);
+  else k_knn_radius<0><<<grid, KNN_THREADS, smem, st>>>(query, n_query, ref, n_ref, (int)dim, (int)k, r2, idx);
+  return check_launch("knn_radius");
+}
+
+extern "C" size_t hgnn_knn_edges_workspace_bytes(int64_t n_query) {
+  if (n_query <= 0) return 256;
+  size_t t = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, t, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_query);
+  return 2 * align_up((size_t)n_query * 4, 256) + align_up(t, 256) + 1024;
+}
+
+extern "C" int hgnn_knn_edges(const int64_t* idx, int64_t n_query, int64_t k, int64_t* graph, int64_t* count, void* ws,
+                              size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  HGNN_REQUIRE(count != nullptr, "knn_edges: count is NULL");
+  if (n_query <= 0 || k <= 0) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(count, 0, 8, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(idx && graph, "knn_edges: NULL pointer");
+  HGNN_REQUIRE(n_query * k < INT32_MAX, "knn_edges: too many candidate edges");
+  Workspace w(ws, ws_bytes);
+  int32_t* cnt = w.take<int32_t>(n_query);
+  int32_t* off = w.take<int32_t>(n_query);
+  size_t t = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, t, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_query);
+  char* cub_ws = w.take<char>(t);
+  if (!w.ok()) return fail(HGNN_ERR_WORKSPACE, "knn_edges: workspace too small");
+  unsigned grid = (unsigned)((n_query + 255) / 256);
+  k_knn_count<<<grid, 256, 0, st>>>(idx, n_query, (int)k, cnt);
+  HGNN_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_ws, t, cnt, off, (int)n_query, st));
+  k_knn_fill<<<grid, 256, 0, st>>>(idx, n_query, (int)k, cnt, off, n_query * k, graph, count);
+  return check_launch("knn_edges");
+}
+
+// ---------------------------------------------------------------------------
+// symmetrize: pack -> radix sort -> unique -> unpack
+// ---------------------------------------------------------------------------
+namespace {
+
+__global__ void k_pack_both(const int64_t* __restrict__ g, int64_t ld, int64_t n, int64_t nv, uint64_t* __restrict__ keys) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t s = (uint64_t)g[i], d = (uint64_t)g[ld + i];
+  keys[i] = s * (uint64_t)nv + d;
+  keys[n + i] = d * (uint64_t)nv + s;
+}
+
+__global__ void k_unpack(const uint64_t* __restrict__ keys, const int64_t* __restrict__ count, int64_t ld, int64_t nv,
+                         int64_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *count) return;
+  uint64_t k = keys[i];
+  out[i] = (int64_t)(k / (uint64_t)nv);
+  out[ld + i] = (int64_t)(k % (uint64_t)nv);
+}
+
+struct SymSizes { size_t sort, uniq; };
+SymSizes sym_cub_bytes(int64_t n2) {
+  SymSizes s{0, 0};
+  cub::DeviceRadixSort::SortKeys(nullptr, s.sort, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n2, 0, 64);
+  cub::DeviceSelect::Unique(nullptr, s.uniq, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t*)nullptr, (int)n2);
+  return s;
+}
+
+}  // namespace
+
+extern "C" size_t hgnn_symmetrize_workspace_bytes(int64_t n_edges) {
+  if (n_edges <= 0) return 256;
+  int64_t n2 = 2 * n_edges;
+  SymSizes s = sym_cub_bytes(n2);
+  return 3 * align_up((size_t)n2 * 8, 256) + align_up(s.sort > s.uniq ? s.sort : s.uniq, 256) + 1024;
+}
+
+extern "C" int hgnn_symmetrize(const int64_t* graph_in, int64_t ld_in, int64_t n_edges, int64_t n_vertices, int64_t* graph_out,
+                               int64_t* count, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  HGNN_REQUIRE(count != nullptr, "symmetrize: count is NULL");
+  if (n_edges <= 0) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(count, 0, 8, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(graph_in && graph_out && n_vertices > 0, "symmetrize: bad argument");
+  HGNN_REQUIRE(2 * n_edges < INT32_MAX && n_vertices < ((int64_t)1 << 31), "symmetrize: sizes out of range");
+  int64_t n2 = 2 * n_edges;
+  Workspace w(ws, ws_bytes);
+  uint64_t* k0 = w.take<uint64_t>(n2);
+  uint64_t* k1 = w.take<uint64_t>(n2);
+  uint64_t* k2 = w.take<uint64_t>(n2);
+  SymSizes s = sym_cub_bytes(n2);
+  size_t tb = s.sort > s.uniq ? s.sort : s.uniq;
+  char* cub_ws = w.take<char>(tb);
+  if (!w.ok()) return fail(HGNN_ERR_WORKSPACE, "symmetrize: workspace too small");
+  k_pack_both<<<(unsigned)((n_edges + 255) / 256), 256, 0, st>>>(graph_in, ld_in, n_edges, n_vertices, k0);
+  int bits = 2 * bits_for(n_vertices);
+  if (bits > 64) bits = 64;
+  size_t t1 = s.sort;
+  HGNN_CUDA_TRY(cub::DeviceRadixSort::SortKeys(cub_ws, t1, k0, k1, (int)n2, 0, bits, st));
+  size_t t2 = s.uniq;
+  HGNN_CUDA_TRY(cub::DeviceSelect::Unique(cub_ws, t2, k1, k2, count, (int)n2, st));
+  k_unpack<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(k2, count, n2, n_vertices, graph_out);
+  return check_launch("symmetrize");
+}
+
+// ---------------------------------------------------------------------------
+// radius tracker: max Euclidean edge length
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void k_edge_max_dist(const float* __restrict__ a, const int64_t* __restrict__ ai, const float* __restrict__ b,
+                                const int64_t* __restrict__ bi, int width, int64_t n, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float d2 = 0.f;
+  if (i < n) {
+    const float* ra = a + (ai ? ai[i] : i) * width;
+    const float* rb = b + (bi ? bi[i] : i) * width;
+    for (int d = 0; d < width; ++d) { float df = ra[d] - rb[d]; d2 = fmaf(df, df, d2); }
+  }
+  float v = sqrtf(d2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(v));  // v >= 0: int order == float order
+}
+}  // namespace
+
+extern "C" int hgnn_edge_max_dist(const float* a, const int64_t* ai, const float* b, const int64_t* bi, int64_t width,
+                                  int64_t n_items, float* out, void* stream) {
+  if (n_items <= 0) return HGNN_OK;
+  HGNN_REQUIRE(a && b && out && width > 0, "edge_max_dist: bad argument");
+  k_edge_max_dist<<<(unsigned)((n_items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, ai, b, bi, (int)width, n_items, out);
+  return check_launch("edge_max_dist");
+}

@@ -1,0 +1,494 @@
+"""PyTorch-facing operators over the C ABI (include/hgnn_b200.h).
+
+Every function here launches hand-written sm_100a kernels from
+libhgnn_b200.so on ``torch.cuda.current_stream()``; torch only owns the device
+memory and the autograd graph. There is no CPU / eager fallback: CPU tensors
+raise.
+
+Reference call sites replaced (under /root/reference/Modules):
+  scatter_add / scatter_mean     gnn_utils.py:50,124-125,142-143; BC/Models/HGNN_GMM.py:251,269
+  gathered-concat MLP + skip     gnn_utils.py:45-64,119-153 (edge/node/supernode/superedge updates)
+  find_neighbors (frnn)          utils.py:228-239
+  symmetrize (cugraph)           gnn_utils.py:198-199
+  einsum('ij,ij->i') edge dots   gnn_utils.py:208; BC/Models/HGNN_GMM.py:188
+  connected components + GMM     BC/Models/HGNN_GMM.py:184-234
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import MAX_LAYERS, MAX_SEGS, ACT_CODES, MlpDesc, check
+
+Tensor = torch.Tensor
+
+# kernel-launch counter (bench.py reports it as gpu_launches)
+LAUNCHES = {"count": 0}
+
+
+def _count(n=1):
+    LAUNCHES["count"] += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.HgnnError("hierarchicalgnn_b200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+def _f32(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        raise _lib.HgnnError(f"expected float32 features, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------
+# segment plans (destination-sorted CSR), cached per index tensor
+# ---------------------------------------------------------------------------
+class SegmentPlan:
+    """CSR over an int64 key vector: items ordered by (key, item id)."""
+
+    def __init__(self, keys: Tensor, n_segments: int):
+        _need_cuda(keys)
+        if keys.dtype != torch.int64 or keys.dim() != 1:
+            raise _lib.HgnnError("SegmentPlan needs a 1-D int64 key tensor")
+        keys = keys.contiguous()
+        n = keys.numel()
+        self.n_items = n
+        self.n_segments = int(n_segments)
+        dev = keys.device
+        self.perm = torch.empty(n, dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(self.n_segments + 1, dtype=torch.int32, device=dev)
+        self.keys32 = torch.empty(n, dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        ws = _workspace(L.hgnn_csr_build_workspace_bytes(n), dev)
+        check(L.hgnn_csr_build(_ptr(keys), n, self.n_segments, _ptr(self.perm), _ptr(self.rowptr), _ptr(self.keys32),
+                               _ptr(ws), ws.numel(), _stream()), "csr_build")
+        _count(4)
+        self._counts_inv = None
+
+    def inv_counts(self) -> Tensor:
+        if self._counts_inv is None:
+            cnt = (self.rowptr[1:] - self.rowptr[:-1]).clamp(min=1).to(torch.float32)
+            self._counts_inv = 1.0 / cnt
+        return self._counts_inv
+
+
+_PLAN_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_PLAN_CACHE_MAX = 32
+
+
+def plan_for(keys: Tensor, n_segments: int) -> SegmentPlan:
+    """Cached SegmentPlan for an index tensor. The cache entry keeps the key
+    tensor alive, so its storage address cannot be recycled while cached, and is
+    invalidated by in-place modification (version counter)."""
+    k = (keys.data_ptr(), keys.numel(), int(n_segments), keys._version, keys.stride(0) if keys.numel() else 1)
+    hit = _PLAN_CACHE.get(k)
+    if hit is not None:
+        _PLAN_CACHE.move_to_end(k)
+        return hit[1]
+    plan = SegmentPlan(keys, n_segments)
+    _PLAN_CACHE[k] = (keys, plan)
+    while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
+
+
+# ---------------------------------------------------------------------------
+# raw launches
+# ---------------------------------------------------------------------------
+def segment_reduce_raw(src: Tensor, plan: SegmentPlan, gather32: Optional[Tensor] = None,
+                       weight: Optional[Tensor] = None, mean: bool = False) -> Tensor:
+    src = _f32(src)
+    width = src.shape[1]
+    if plan.n_items == 0:
+        return torch.zeros((plan.n_segments, width), dtype=torch.float32, device=src.device)
+    out = torch.empty((plan.n_segments, width), dtype=torch.float32, device=src.device)
+    if plan.n_segments and width:
+        check(_lib.lib().hgnn_segment_reduce(_ptr(src), width, _ptr(gather32), _ptr(weight), _ptr(plan.perm),
+                                             _ptr(plan.rowptr), plan.n_segments, int(mean), _ptr(out), _stream()),
+              "segment_reduce")
+        _count()
+    return out
+
+
+def gather_rows_raw(src: Tensor, idx32: Optional[Tensor], weight: Optional[Tensor], n_items: int) -> Tensor:
+    src = _f32(src)
+    width = src.shape[1]
+    out = torch.empty((n_items, width), dtype=torch.float32, device=src.device)
+    if n_items and width:
+        check(_lib.lib().hgnn_gather_rows(_ptr(src), width, _ptr(idx32), _ptr(weight), n_items, _ptr(out), _stream()),
+              "gather_rows")
+        _count()
+    return out
+
+
+def edge_dot_raw(a: Tensor, ai32: Optional[Tensor], b: Tensor, bi32: Optional[Tensor], n_items: int) -> Tensor:
+    a, b = _f32(a), _f32(b)
+    out = torch.empty(n_items, dtype=torch.float32, device=a.device)
+    if n_items:
+        check(_lib.lib().hgnn_edge_dot(_ptr(a), _ptr(ai32), _ptr(b), _ptr(bi32), a.shape[1], n_items, _ptr(out), _stream()),
+              "edge_dot")
+        _count()
+    return out
+
+
+# ---------------------------------------------------------------------------
+# autograd: weighted gather -> segmented sum
+# ---------------------------------------------------------------------------
+class _GatherScatter(torch.autograd.Function):
+    """out[s] = sum_{i: seg[i]=s} w[i] * src[gather[i]]  (gather / w optional)."""
+
+    @staticmethod
+    def forward(ctx, src, weight, gather_plan, seg_plan, mean):
+        _need_cuda(src, weight)
+        src = _f32(src)
+        w = None if weight is None else _f32(weight).reshape(-1)
+        g32 = None if gather_plan is None else gather_plan.keys32
+        out = segment_reduce_raw(src, seg_plan, g32, w, mean)
+        ctx.save_for_backward(src, w)
+        ctx.plans = (gather_plan, seg_plan)
+        ctx.mean = mean
+        ctx.wshape = None if weight is None else weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        src, w = ctx.saved_tensors
+        gather_plan, seg_plan = ctx.plans
+        gout = _f32(gout)
+        d_src = d_w = None
+        w_eff = w
+        if ctx.mean:
+            inv = seg_plan.inv_counts()[seg_plan.keys32.long()]
+            w_eff = inv if w is None else w * inv
+        if ctx.needs_input_grad[0]:
+            if gather_plan is None:
+                d_src = gather_rows_raw(gout, seg_plan.keys32, w_eff, seg_plan.n_items)
+            else:
+                d_src = segment_reduce_raw(gout, gather_plan, seg_plan.keys32, w_eff, False)
+        if w is not None and ctx.needs_input_grad[1]:
+            g32 = None if gather_plan is None else gather_plan.keys32
+            d_w = edge_dot_raw(src, g32, gout, seg_plan.keys32, seg_plan.n_items)
+            if ctx.mean:
+                d_w = d_w * seg_plan.inv_counts()[seg_plan.keys32.long()]
+            d_w = d_w.reshape(ctx.wshape)
+        return d_src, d_w, None, None, None
+
+
+def scatter_add(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int] = None,
+                plan: Optional[SegmentPlan] = None) -> Tensor:
+    """Drop-in for torch_scatter.scatter_add(src, index, dim=0, dim_size=n) on 2-D rows."""
+    if dim != 0 or src.dim() != 2:
+        raise _lib.HgnnError("scatter_add: only dim=0 on [items, width] rows is supported")
+    if plan is None:
+        if dim_size is None:
+            dim_size = int(index.max()) + 1 if index.numel() else 0
+        plan = plan_for(index, int(dim_size))
+    return _GatherScatter.apply(src, None, None, plan, False)
+
+
+def scatter_mean(src: Tensor, index: Tensor, dim: int = 0, dim_size: Optional[int] = None,
+                 plan: Optional[SegmentPlan] = None) -> Tensor:
+    if dim != 0 or src.dim() != 2:
+        raise _lib.HgnnError("scatter_mean: only dim=0 on [items, width] rows is supported")
+    if plan is None:
+        if dim_size is None:
+            dim_size = int(index.max()) + 1 if index.numel() else 0
+        plan = plan_for(index, int(dim_size))
+    return _GatherScatter.apply(src, None, None, plan, True)
+
+
+def gather_scatter(src: Tensor, weight: Optional[Tensor], gather_plan: SegmentPlan, seg_plan: SegmentPlan) -> Tensor:
+    """scatter_add(weight * src[gather], seg) without materialising the product
+    (gnn_utils.py:124,142; BC/Models/HGNN_GMM.py:269). ``gather_plan`` is the plan
+    over the gather index (n_segments = src rows), ``seg_plan`` over the segment index."""
+    return _GatherScatter.apply(src, weight, gather_plan, seg_plan, False)
+
+
+# ---------------------------------------------------------------------------
+# autograd: gathered row dot
+# ---------------------------------------------------------------------------
+class _EdgeDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, plan_a, plan_b):
+        _need_cuda(a, b)
+        a, b = _f32(a), _f32(b)
+        out = edge_dot_raw(a, plan_a.keys32, b, plan_b.keys32, plan_a.n_items)
+        ctx.save_for_backward(a, b)
+        ctx.plans = (plan_a, plan_b)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        plan_a, plan_b = ctx.plans
+        gout = _f32(gout)
+        d_a = d_b = None
+        if ctx.needs_input_grad[0]:
+            d_a = segment_reduce_raw(b, plan_a, plan_b.keys32, gout, False)
+        if ctx.needs_input_grad[1]:
+            d_b = segment_reduce_raw(a, plan_b, plan_a.keys32, gout, False)
+        return d_a, d_b, None, None
+
+
+def edge_dot(a: Tensor, b: Tensor, plan_a: SegmentPlan, plan_b: SegmentPlan) -> Tensor:
+    """out[i] = <a[ia[i]], b[ib[i]]> where plan_a / plan_b are the plans over ia / ib."""
+    return _EdgeDot.apply(a, b, plan_a, plan_b)
+
+
+# ---------------------------------------------------------------------------
+# fused gathered-concat MLP
+# ---------------------------------------------------------------------------
+class MlpMeta:
+    """Static description of one fused MLP call."""
+
+    def __init__(self, seg_plans: Sequence[Optional[SegmentPlan]], acts: Sequence[Optional[str]],
+                 has_ln: Sequence[bool], skip_seg: int = -1, eps: float = 1e-5):
+        self.seg_plans = list(seg_plans)
+        self.acts = [ACT_CODES[a] for a in acts]
+        self.has_ln = list(has_ln)
+        self.skip_seg = int(skip_seg)
+        self.eps = float(eps)
+        if len(self.seg_plans) > MAX_SEGS or len(self.acts) > MAX_LAYERS:
+            raise _lib.HgnnError("fused MLP supports at most %d segments and %d layers" % (MAX_SEGS, MAX_LAYERS))
+
+
+def _build_desc(meta: MlpMeta, segs: List[Tensor], params: List[Tensor]):
+    d = MlpDesc()
+    d.n_seg = len(segs)
+    d.n_layers = len(meta.acts)
+    d.skip_seg = meta.skip_seg
+    d.ln_eps = meta.eps
+    rows = None
+    for s, t in enumerate(segs):
+        d.seg_ptr[s] = t.data_ptr()
+        d.seg_width[s] = t.shape[1]
+        plan = meta.seg_plans[s]
+        if plan is not None:
+            d.seg_idx[s] = plan.keys32.data_ptr()
+            n = plan.n_items
+        else:
+            d.seg_idx[s] = None
+            n = t.shape[0]
+        if rows is None:
+            rows = n
+        elif rows != n:
+            raise _lib.HgnnError(f"fused MLP: segment {s} yields {n} rows, expected {rows}")
+    i = 0
+    layer_params = []
+    for l in range(d.n_layers):
+        W, b = params[i], params[i + 1]
+        i += 2
+        g = bt = None
+        if meta.has_ln[l]:
+            g, bt = params[i], params[i + 1]
+            i += 2
+        d.W[l], d.b[l] = W.data_ptr(), b.data_ptr()
+        d.gamma[l] = None if g is None else g.data_ptr()
+        d.beta[l] = None if bt is None else bt.data_ptr()
+        d.out_width[l] = W.shape[0]
+        d.act[l] = meta.acts[l]
+        layer_params.append((W, b, g, bt))
+    d.out_idx = None
+    return d, rows, layer_params
+
+
+class _FusedMLP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meta: MlpMeta, n_seg: int, *tensors):
+        _need_cuda(*tensors)
+        segs = [_f32(t) for t in tensors[:n_seg]]
+        params = [_f32(t) for t in tensors[n_seg:]]
+        d, rows, layers = _build_desc(meta, segs, params)
+        out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=segs[0].device)
+        if rows:
+            check(_lib.lib().hgnn_mlp_forward(C.byref(d), rows, _ptr(out), _stream()), "mlp_forward")
+            _count()
+        ctx.meta, ctx.n_seg = meta, n_seg
+        ctx.save_for_backward(*segs, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        meta, n_seg = ctx.meta, ctx.n_seg
+        saved = ctx.saved_tensors
+        segs, params = list(saved[:n_seg]), list(saved[n_seg:])
+        d, rows, layers = _build_desc(meta, segs, params)
+        dev = segs[0].device
+        gout = _f32(gout)
+        L = _lib.lib()
+        need = ctx.needs_input_grad[2:]
+        dseg_rows: List[Optional[Tensor]] = []
+        dseg_arr = (C.c_void_p * MAX_SEGS)()
+        for s in range(n_seg):
+            if need[s]:
+                t = torch.empty((rows, segs[s].shape[1]), dtype=torch.float32, device=dev)
+                dseg_rows.append(t)
+                dseg_arr[s] = t.data_ptr()
+            else:
+                dseg_rows.append(None)
+                dseg_arr[s] = None
+        dvec, dW = [], []
+        dvec_arr = (C.c_void_p * MAX_LAYERS)()
+        dW_arr = (C.c_void_p * MAX_LAYERS)()
+        for l, (W, b, g, bt) in enumerate(layers):
+            v = torch.empty((3, W.shape[0]), dtype=torch.float32, device=dev)
+            w = torch.empty_like(W)
+            dvec.append(v)
+            dW.append(w)
+            dvec_arr[l] = v.data_ptr()
+            dW_arr[l] = w.data_ptr()
+        if rows:
+            nbytes = L.hgnn_mlp_backward_workspace_bytes(C.byref(d), rows)
+            ws = _workspace(nbytes, dev)
+            check(L.hgnn_mlp_backward_data(C.byref(d), rows, _ptr(gout), C.byref(dseg_arr), C.byref(dvec_arr), _ptr(ws),
+                                           ws.numel(), _stream()), "mlp_backward_data")
+            check(L.hgnn_mlp_backward_weights(C.byref(d), rows, C.byref(dW_arr), _ptr(ws), ws.numel(), _stream()),
+                  "mlp_backward_weights")
+            _count(1 + len(layers) + 2 * len(layers))
+        else:
+            for v in dvec:
+                v.zero_()
+            for w in dW:
+                w.zero_()
+        grads: List[Optional[Tensor]] = [None, None]
+        for s in range(n_seg):
+            g = dseg_rows[s]
+            if g is not None and meta.seg_plans[s] is not None:
+                plan = meta.seg_plans[s]
+                if plan.n_segments != segs[s].shape[0]:
+                    raise _lib.HgnnError("fused MLP: gather plan does not cover the gathered tensor")
+                g = segment_reduce_raw(g, plan)
+            grads.append(g)
+        for l, (W, b, gm, bt) in enumerate(layers):
+            grads += [dW[l], dvec[l][0]]
+            if gm is not None:
+                grads += [dvec[l][1], dvec[l][2]]
+        return tuple(grads)
+
+
+def fused_mlp(meta: MlpMeta, segs: Sequence[Tensor], params: Sequence[Tensor]) -> Tensor:
+    """Row-wise MLP on the concatenation of (optionally gathered) segments, with
+    LayerNorm/activation per layer and an optional skip connection — one kernel
+    forward, recompute-in-backward."""
+    return _FusedMLP.apply(meta, len(segs), *segs, *params)
+
+
+# ---------------------------------------------------------------------------
+# graph construction
+# ---------------------------------------------------------------------------
+def knn_radius(query: Tensor, ref: Tensor, k: int, radius: float) -> Tensor:
+    """[n_query, k] int64 neighbour ids, ascending distance, d < radius, -1 padded
+    (frnn.frnn_grid_points as used by find_neighbors, utils.py:228-239)."""
+    _need_cuda(query, ref)
+    q, r = _f32(query.detach()), _f32(ref.detach())
+    idx = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+    if q.shape[0] and k:
+        check(_lib.lib().hgnn_knn_radius(_ptr(q), q.shape[0], _ptr(r), r.shape[0], q.shape[1], k, float(radius), _ptr(idx),
+                                         _stream()), "knn_radius")
+        _count()
+    return idx
+
+
+def knn_edges(idx: Tensor) -> Tensor:
+    """Compacts a -1 padded [n_query, k] neighbour table into graph[2, E'] in
+    query-major, rank-minor order (gnn_utils.py:195-202). One host sync (E')."""
+    _need_cuda(idx)
+    nq, k = idx.shape
+    dev = idx.device
+    graph = torch.empty((2, max(nq * k, 1)), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.hgnn_knn_edges_workspace_bytes(nq), dev)
+    check(L.hgnn_knn_edges(_ptr(idx), nq, k, _ptr(graph), _ptr(count), _ptr(ws), ws.numel(), _stream()), "knn_edges")
+    _count(3)
+    n = int(count.item())
+    return graph[:, :n]
+
+
+def symmetrize(graph: Tensor, n_vertices: int) -> Tensor:
+    """Union with the transpose, de-duplicated, lexicographic column order
+    (cugraph symmetrize, gnn_utils.py:198-199). One host sync (edge count)."""
+    _need_cuda(graph)
+    E = graph.shape[1]
+    dev = graph.device
+    if E == 0:
+        return graph.new_zeros((2, 0))
+    g = graph.contiguous()
+    out = torch.empty((2, 2 * E), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    ws = _workspace(L.hgnn_symmetrize_workspace_bytes(E), dev)
+    check(L.hgnn_symmetrize(_ptr(g), g.stride(0), E, int(n_vertices), _ptr(out), _ptr(count), _ptr(ws), ws.numel(),
+                            _stream()), "symmetrize")
+    _count(4)
+    n = int(count.item())
+    return out[:, :n]
+
+
+def edge_max_dist(a: Tensor, b: Tensor, graph: Tensor) -> Tensor:
+    """max_e ||a[graph[0,e]] - b[graph[1,e]]||_2 as a 0-d device tensor (gnn_utils.py:204)."""
+    _need_cuda(a, b, graph)
+    a, b = _f32(a.detach()), _f32(b.detach())
+    out = torch.zeros(1, dtype=torch.float32, device=a.device)
+    E = graph.shape[1]
+    if E:
+        g0, g1 = graph[0].contiguous(), graph[1].contiguous()
+        check(_lib.lib().hgnn_edge_max_dist(_ptr(a), _ptr(g0), _ptr(b), _ptr(g1), a.shape[1], E, _ptr(out), _stream()),
+              "edge_max_dist")
+        _count()
+    return out[0]
+
+
+def connected_components(graph: Tensor, n_vertices: int, keep: Optional[Tensor] = None) -> Tensor:
+    """labels[v] = min vertex id of v's component over kept edges; -1 if v touches
+    no kept edge (cugraph connected_components as consumed at BC/Models/HGNN_GMM.py:215-232)."""
+    _need_cuda(graph, keep)
+    dev = graph.device
+    g = graph.contiguous()
+    labels = torch.empty(n_vertices, dtype=torch.int32, device=dev)
+    k8 = None
+    if keep is not None:
+        k8 = keep.to(torch.uint8).contiguous()
+    L = _lib.lib()
+    ws = _workspace(L.hgnn_connected_components_workspace_bytes(n_vertices), dev)
+    check(L.hgnn_connected_components(_ptr(g), g.stride(0) if g.shape[1] else 0, g.shape[1], _ptr(k8), n_vertices,
+                                      _ptr(labels), _ptr(ws), ws.numel(), _stream()), "connected_components")
+    _count(3)
+    return labels
+
+
+def gmm1d_fit(x: Tensor, max_iter: int = 100, tol: float = 1e-3) -> Tensor:
+    """Two-component 1-D Gaussian mixture by EM on device; returns a device tensor
+    (pi0, mu0, var0, pi1, mu1, var1). Replaces sklearn GaussianMixture.fit
+    (BC/Models/HGNN_GMM.py:192)."""
+    _need_cuda(x)
+    x = _f32(x.detach().reshape(-1))
+    params = torch.empty(6, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws = _workspace(L.hgnn_gmm1d_workspace_bytes(), x.device)
+    check(L.hgnn_gmm1d_fit(_ptr(x), x.numel(), int(max_iter), float(tol), _ptr(params), _ptr(ws), ws.numel(), _stream()),
+          "gmm1d_fit")
+    _count(2 * (max_iter + 1))
+    return params

@@ -1,0 +1,101 @@
+"""Host-side mirror of the hot-path pieces of the reference's Modules/utils.py:
+``make_mlp`` (utils.py:169-196) and ``find_neighbors`` (utils.py:228-239).
+
+``make_mlp`` returns an ``nn.Sequential`` subclass whose children are the very
+same ``nn.Linear`` / ``nn.LayerNorm`` / activation modules at the very same
+indices, so ``state_dict()`` keys and order are identical to the reference and
+reference checkpoints load with ``strict=True``. Execution, however, never
+walks the children: the whole stack runs as one fused CUDA kernel
+(``ops.fused_mlp``), with the concatenation / gathers of its input folded in.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+_SUPPORTED_ACTS = ("GELU", "Tanh", "ReLU", "SiLU", "Sigmoid")
+
+
+class FusedMLP(nn.Sequential):
+    """nn.Sequential-compatible container executed as a single fused kernel."""
+
+    def _layers(self):
+        """[(linear, layernorm|None, act_name|None)] parsed from the children."""
+        cached = getattr(self, "_layer_cache", None)
+        if cached is not None:
+            return cached
+        out, cur = [], None
+        for m in self:
+            if isinstance(m, nn.Linear):
+                if cur is not None:
+                    out.append(tuple(cur))
+                cur = [m, None, None]
+            elif isinstance(m, nn.LayerNorm):
+                cur[1] = m
+            else:
+                name = type(m).__name__
+                if name not in _SUPPORTED_ACTS:
+                    raise NotImplementedError(f"activation {name} has no CUDA implementation in hgnn_b200")
+                cur[2] = name
+        out.append(tuple(cur))
+        object.__setattr__(self, "_layer_cache", out)
+        return out
+
+    def _params(self):
+        ps, acts, lns = [], [], []
+        eps = 1e-5
+        for lin, ln, act in self._layers():
+            ps += [lin.weight, lin.bias]
+            if ln is not None:
+                ps += [ln.weight, ln.bias]
+                eps = ln.eps
+            acts.append(act)
+            lns.append(ln is not None)
+        return ps, acts, lns, eps
+
+    def fused(self, segs: Sequence[torch.Tensor], plans: Sequence[Optional[ops.SegmentPlan]] = None, skip: int = -1):
+        """MLP(concat_s segs[s][plans[s].keys]) (+ segs[skip] rows). ``plans[s]`` is the
+        SegmentPlan over the gather index of segment s (None = rows used as they are)."""
+        if plans is None:
+            plans = [None] * len(segs)
+        ps, acts, lns, eps = self._params()
+        meta = ops.MlpMeta(plans, acts, lns, skip, eps)
+        return ops.fused_mlp(meta, list(segs), ps)
+
+    def forward(self, x):
+        lead = x.shape[:-1]
+        y = self.fused([x.reshape(-1, x.shape[-1])])
+        return y.reshape(*lead, y.shape[-1])
+
+
+def make_mlp(input_size, hidden_size, output_size, hidden_layers, hidden_activation="GELU",
+             output_activation="GELU", layer_norm=False):
+    """Same signature, same Sequential index layout as the reference factory:
+    ``[Linear, (LayerNorm), act] x (hidden_layers-1)``, then ``Linear`` and, only
+    when ``output_activation`` is given, ``(LayerNorm), act``."""
+    hidden_cls = getattr(nn, hidden_activation)
+    out_cls = getattr(nn, output_activation) if output_activation is not None else None
+    widths = [input_size] + [hidden_size] * (hidden_layers - 1) + [output_size]
+    mods = []
+    n = len(widths) - 1
+    for i in range(n):
+        mods.append(nn.Linear(widths[i], widths[i + 1]))
+        final = i == n - 1
+        act_cls = out_cls if final else hidden_cls
+        if act_cls is None:
+            continue
+        if layer_norm:
+            mods.append(nn.LayerNorm(widths[i + 1]))
+        mods.append(act_cls())
+    return FusedMLP(*mods)
+
+
+def find_neighbors(embedding1, embedding2, r_max=1.0, k_max=10):
+    """[P1, k_max] int64 neighbour table, -1 padded (brute-force tiled CUDA kernel
+    in place of frnn.frnn_grid_points)."""
+    r = float(r_max.reshape(-1)[0]) if torch.is_tensor(r_max) else float(r_max)
+    return ops.knn_radius(embedding1, embedding2, int(k_max), r)

@@ -1,0 +1,226 @@
+/*
+ * hgnn_b200.h — C ABI of libhgnn_b200.so: hand-written sm_100a kernels for the
+ * HierarchicalGNN message-passing hot path.
+ *
+ * Conventions ("Third-party op boundary being replaced"):
+ *   - plain C: raw device pointers + explicit int64 sizes; no torch types;
+ *   - every call launches on the caller's `stream` (a cudaStream_t passed as
+ *     void*), never allocates device memory, never synchronises unless stated,
+ *     and keeps no global mutable state; scratch comes from the caller through
+ *     `ws`/`ws_bytes`, sized by the matching *_workspace_bytes() query;
+ *   - returns 0 (HGNN_OK) or a negative hgnn_status; hgnn_last_error() gives a
+ *     thread-local message for the last non-zero status on this host thread;
+ *   - feature rows are fp32, row-major, contiguous; graphs cross the boundary
+ *     as int64 (as the reference passes them) and are int32 internally.
+ *
+ * Each entry point cites the reference interface (file:line under
+ * /root/reference/Modules) that it replaces.
+ */
+#ifndef HGNN_B200_H
+#define HGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGNN_ABI_VERSION 1
+
+typedef enum {
+  HGNN_OK = 0,
+  HGNN_ERR_BAD_ARG = -1,
+  HGNN_ERR_UNSUPPORTED = -2,
+  HGNN_ERR_WORKSPACE = -3,
+  HGNN_ERR_CUDA = -4
+} hgnn_status;
+
+/* activation codes: the torch.nn names accepted by make_mlp (utils.py:178-181) */
+typedef enum {
+  HGNN_ACT_NONE = 0,
+  HGNN_ACT_GELU = 1, /* exact erf form, nn.GELU() default */
+  HGNN_ACT_TANH = 2,
+  HGNN_ACT_RELU = 3,
+  HGNN_ACT_SILU = 4,
+  HGNN_ACT_SIGMOID = 5
+} hgnn_act;
+
+int hgnn_abi_version(void);
+const char* hgnn_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Destination-sorted CSR ("segment plan") — built once per graph and reused by
+ * every cell, forward and backward. Replaces the per-call float-atomic
+ * scatter inside torch_scatter.scatter_add (gnn_utils.py:50,124,125,142,143).
+ *   keys[n_items]  int64 segment id of each item (e.g. graph[1]), 0 <= key < n_segments
+ *   perm[n_items]  int32 out: item ids ordered by (key, item id)  (stable)
+ *   rowptr[n_segments+1] int32 out: segment s owns perm[rowptr[s] .. rowptr[s+1])
+ *   keys32[n_items] int32 out (optional, may be NULL): keys narrowed to int32
+ * ------------------------------------------------------------------------ */
+size_t hgnn_csr_build_workspace_bytes(int64_t n_items);
+int hgnn_csr_build(const int64_t* keys, int64_t n_items, int64_t n_segments, int32_t* perm, int32_t* rowptr,
+                   int32_t* keys32, void* ws, size_t ws_bytes, void* stream);
+
+/* Narrow an int64 index array to int32 (range-checked on device: out-of-range
+ * entries are clamped and counted into *bad if bad != NULL). */
+int hgnn_index_to_i32(const int64_t* in, int64_t n, int64_t limit, int32_t* out, int32_t* bad, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Segmented (weighted, gathered) row reduction — deterministic, no atomics.
+ *   out[s, :] = scale_s * sum_{j in [rowptr[s], rowptr[s+1])} w[i] * src[g(i), :],  i = perm[j]
+ *   g(i) = gather ? gather[i] : i ;  w[i] = weight ? weight[i] : 1 ;
+ *   scale_s = mean ? 1/max(count_s,1) : 1
+ * Replaces scatter_add / scatter_mean and the "w * X[idx] -> scatter" bipartite
+ * aggregations (gnn_utils.py:50,124-125,142-143; BC/Models/HGNN_GMM.py:251,269).
+ * Its adjoint w.r.t. src is the same call on the transposed plan.
+ * ------------------------------------------------------------------------ */
+int hgnn_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight,
+                        const int32_t* perm, const int32_t* rowptr, int64_t n_segments, int mean, float* out,
+                        void* stream);
+
+/* out[i, :] = w[i] * src[idx[i], :]  (idx NULL = identity). Adjoint of an
+ * ungathered segment reduce; also the row gather used by the encoders. */
+int hgnn_gather_rows(const float* src, int64_t width, const int32_t* idx, const float* weight, int64_t n_items,
+                     float* out, void* stream);
+
+/* out[i] = sum_d a[ai[i], d] * b[bi[i], d]   (ai / bi NULL = identity).
+ * Replaces einsum('ij,ij->i', src[g0], dst[g1]) (gnn_utils.py:208;
+ * BC/Models/HGNN_GMM.py:188) and gives d(weight) of a weighted segment reduce. */
+int hgnn_edge_dot(const float* a, const int32_t* ai, const float* b, const int32_t* bi, int64_t width,
+                  int64_t n_items, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused gathered-concat MLP (make_mlp, utils.py:169-196) applied row-wise:
+ *   in_row(r)  = concat_s seg_ptr[s][ seg_idx[s] ? seg_idx[s][r] : r , : ]
+ *   per layer l: h = a W_l^T + b_l ; optional LayerNorm(gamma_l, beta_l, eps) ; act_l
+ *   out[ out_idx ? out_idx[r] : r , : ] = a_last (+ seg_ptr[skip_seg] row if skip_seg >= 0)
+ * One kernel covers the edge step (gnn_utils.py:56-64,129-135,147-153: segments
+ * x[src] | x[dst] | e, skip = e), the node / supernode steps (gnn_utils.py:45-54,
+ * 119-127,137-145: segments x | agg [| agg2], skip = x), the encoders and heads
+ * (EC/Models/IN.py:84-85,126; BC/Models/HGNN_GMM.py:270-271,342-344).
+ * W_l is [out_width[l], in_width] row-major exactly as nn.Linear stores it.
+ * ------------------------------------------------------------------------ */
+#define HGNN_MLP_MAX_SEGS 3
+#define HGNN_MLP_MAX_LAYERS 4
+
+typedef struct {
+  int32_t n_seg;
+  int32_t n_layers;
+  int32_t skip_seg; /* -1: no skip connection */
+  float ln_eps;
+  const float* seg_ptr[HGNN_MLP_MAX_SEGS];
+  const int32_t* seg_idx[HGNN_MLP_MAX_SEGS];
+  int32_t seg_width[HGNN_MLP_MAX_SEGS];
+  int32_t out_width[HGNN_MLP_MAX_LAYERS];
+  int32_t act[HGNN_MLP_MAX_LAYERS];
+  const float* W[HGNN_MLP_MAX_LAYERS];
+  const float* b[HGNN_MLP_MAX_LAYERS];
+  const float* gamma[HGNN_MLP_MAX_LAYERS]; /* NULL: no LayerNorm after this layer */
+  const float* beta[HGNN_MLP_MAX_LAYERS];
+  const int32_t* out_idx; /* optional output row scatter */
+} hgnn_mlp_desc;
+
+int hgnn_mlp_forward(const hgnn_mlp_desc* d, int64_t rows, float* out, void* stream);
+
+/* Backward with in-kernel recompute (replaces torch.utils.checkpoint around
+ * every update, gnn_utils.py:14-15). Two launches:
+ *  (1) hgnn_mlp_backward_data: recomputes the forward per row tile, produces
+ *      - dseg[s]: per-ROW input gradients [rows, seg_width[s]] (NULL = skip);
+ *        for gathered segments the caller reduces them with the transposed
+ *        plan (hgnn_segment_reduce), keeping the result deterministic;
+ *      - per-layer row buffers in ws for the weight-gradient pass;
+ *      - dvec[l]: packed [3, out_width[l]] = (d bias, d gamma, d beta).
+ *  (2) hgnn_mlp_backward_weights: dW[l] = delta_l^T a_{l-1} as a split-K
+ *      reduction over rows with a deterministic second stage.
+ * grad_out is [rows, out_width[last]] indexed like `out` (through out_idx). */
+size_t hgnn_mlp_backward_workspace_bytes(const hgnn_mlp_desc* d, int64_t rows);
+int hgnn_mlp_backward_data(const hgnn_mlp_desc* d, int64_t rows, const float* grad_out,
+                           float* const dseg[HGNN_MLP_MAX_SEGS], float* const dvec[HGNN_MLP_MAX_LAYERS], void* ws,
+                           size_t ws_bytes, void* stream);
+int hgnn_mlp_backward_weights(const hgnn_mlp_desc* d, int64_t rows, float* const dW[HGNN_MLP_MAX_LAYERS], void* ws,
+                              size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Radius-limited k nearest neighbours, brute force, tiled through shared
+ * memory. Replaces frnn.frnn_grid_points as called by find_neighbors
+ * (utils.py:228-239): for each query row the up-to-k reference rows with
+ * squared distance < radius^2, ascending (ties: smaller index), -1 padded.
+ * Distances are direct fp32 sums of squared differences.
+ *   idx[n_query, k] int64 out;  dim <= 32, k <= 32.
+ * ------------------------------------------------------------------------ */
+int hgnn_knn_radius(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                    float radius, int64_t* idx, void* stream);
+
+/* Compacts idx (>= 0 entries, query-major, rank-minor: gnn_utils.py:195-202)
+ * into graph[2, n_query*k] (row 0 = query id, row 1 = neighbour id; only the
+ * first *count columns are valid). `count` is a device int64; ld = n_query*k. */
+size_t hgnn_knn_edges_workspace_bytes(int64_t n_query);
+int hgnn_knn_edges(const int64_t* idx, int64_t n_query, int64_t k, int64_t* graph, int64_t* count, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* Union of an edge list with its transpose, duplicates removed, columns in
+ * lexicographic order. Replaces cugraph symmetrize (gnn_utils.py:198-199).
+ *   graph_in[2, n_edges] (row stride ld_in) -> graph_out[2, 2*n_edges] (row
+ *   stride 2*n_edges), *count valid columns (device int64). */
+size_t hgnn_symmetrize_workspace_bytes(int64_t n_edges);
+int hgnn_symmetrize(const int64_t* graph_in, int64_t ld_in, int64_t n_edges, int64_t n_vertices, int64_t* graph_out,
+                    int64_t* count, void* ws, size_t ws_bytes, void* stream);
+
+/* max_i || a[ai[i]] - b[bi[i]] ||_2 over the edge list -> *out (device float);
+ * the radius tracker at gnn_utils.py:203-205. *out must be zeroed by caller. */
+int hgnn_edge_max_dist(const float* a, const int64_t* ai, const float* b, const int64_t* bi, int64_t width,
+                       int64_t n_items, float* out, void* stream);
+
+/* Weakly connected components over the kept edges (keep == NULL: all edges):
+ * labels[v] = smallest vertex id of v's component, -1 for vertices touched by
+ * no kept edge. Replaces cugraph.components.connected_components as used by
+ * HierarchicalGNNBlock.clustering (BC/Models/HGNN_GMM.py:215-232). */
+size_t hgnn_connected_components_workspace_bytes(int64_t n_vertices);
+int hgnn_connected_components(const int64_t* graph, int64_t ld, int64_t n_edges, const uint8_t* keep,
+                              int64_t n_vertices, int32_t* labels, void* ws, size_t ws_bytes, void* stream);
+
+/* 1-D two-component Gaussian mixture by EM, entirely on device (replaces the
+ * sklearn fit at BC/Models/HGNN_GMM.py:192). params[6] out (device):
+ * (pi0, mu0, var0, pi1, mu1, var1). ws: hgnn_gmm1d_workspace_bytes(). */
+size_t hgnn_gmm1d_workspace_bytes(void);
+int hgnn_gmm1d_fit(const float* x, int64_t n, int32_t max_iter, float tol, float* params, void* ws, size_t ws_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------
+ * Tensor-core (tcgen05 / TMEM) fused edge step — bf16 operands, fp32
+ * accumulate, fp32 storage. See hgnn_tc.h section below; available for
+ * latent in {32, 64, 128} with a 2-layer LayerNorm edge network.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t latent;     /* L */
+  int32_t hidden;     /* H */
+  int32_t act_hidden; /* hgnn_act of layer 0 */
+  int32_t act_out;    /* hgnn_act of layer 1 */
+  float ln_eps;
+  const void* w1_packed; /* bf16 UMMA smem images, from hgnn_tc_pack_weights */
+  const void* w2_packed;
+  const float* b1;
+  const float* gamma1;
+  const float* beta1;
+  const float* b2;
+  const float* gamma2;
+  const float* beta2;
+} hgnn_tc_edge_params;
+
+int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int layer_norm);
+size_t hgnn_tc_packed_weight_bytes(int64_t out_features, int64_t in_features);
+/* fp32 nn.Linear weight [out, in] -> bf16, K-major, 128B-swizzled UMMA smem image */
+int hgnn_tc_pack_weights(const float* W, int64_t out_features, int64_t in_features, void* packed, void* stream);
+/* e_out[i] = MLP([x[src_i] | x[dst_i] | e_i]) + e_i for i in row order `perm`
+ * (NULL = identity); if agg != NULL also agg[n] = sum_{dst_i = n} e_out[i],
+ * which requires perm/rowptr to be the destination-sorted plan. */
+size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges);
+int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
+                         const int32_t* dst, const int32_t* perm, int64_t n_edges, int64_t n_nodes, float* e_out,
+                         void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGNN_B200_H */

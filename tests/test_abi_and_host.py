@@ -1,0 +1,148 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol declared
+in include/hgnn_b200.h (no compute calls), and the host-side mirror of the
+reference interface (state-dict layout, init, hparams, cut solver) is right."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hgnn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hgnn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hierarchicalgnn_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 25
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in hgnn_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.lib().hgnn_abi_version() == 1
+
+
+def test_mlp_desc_struct_layout_matches_header():
+    from hierarchicalgnn_b200 import _lib
+    # 4 scalars (16 B) + 3+3 pointers + 3 ints (+pad) + 4+4 ints + 16 pointers + 1 pointer
+    assert ctypes.sizeof(_lib.MlpDesc) == 16 + 6 * 8 + 3 * 4 + 8 * 4 + 4 + 17 * 8
+
+
+def test_no_cpu_fallback():
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200._lib import HgnnError
+    with pytest.raises(HgnnError, match="no CPU fallback"):
+        ops.scatter_add(torch.randn(4, 4), torch.tensor([0, 1, 1, 0]), dim_size=2)
+    from hierarchicalgnn_b200.utils import make_mlp
+    with pytest.raises(HgnnError):
+        make_mlp(4, 8, 4, 2)(torch.randn(3, 4))
+
+
+def test_make_mlp_state_dict_layout_matches_reference(golden):
+    from hierarchicalgnn_b200.utils import make_mlp
+    for (n, ln, oa), rec in golden("make_mlp.pt").items():
+        net = make_mlp(6, 10, 4, n, hidden_activation="GELU", output_activation=oa, layer_norm=ln)
+        assert list(net.state_dict().keys()) == rec["keys"], (n, ln, oa)
+        net.load_state_dict(rec["state"], strict=True)
+
+
+def test_model_state_dict_keys_and_order_match_reference(golden):
+    from hierarchicalgnn_b200.training_utils import model_selector
+    ec = golden("ec_model.pt")
+    for tag in ("default", "shared_noln"):
+        hp = ec[tag]["hparams"]
+        over = {k: hp[k] for k in ("latent", "n_interaction_graph_iters", "share_weight", "layernorm", "hidden_output_activation")}
+        m = model_selector("EC-IN", over)
+        assert list(m.state_dict().keys()) == ec[tag]["keys"]
+        m.load_state_dict(ec[tag]["state"], strict=True)
+    bc = golden("bc_model.pt")
+    hp = bc["hparams"]
+    m = model_selector("4", {k: hp[k] for k in ("latent", "n_interaction_graph_iters", "n_hierarchical_graph_iters")})
+    assert list(m.state_dict().keys()) == bc["keys"]
+    m.load_state_dict(bc["train"]["state_before"], strict=True)
+    assert torch.isinf(m.hgnn_block.score_cut).all() and float(m.hgnn_block.super_graph_construction.knn_radius) == 1.0
+
+
+def test_full_size_parameter_counts_match_survey():
+    from hierarchicalgnn_b200.training_utils import model_selector
+    ec = model_selector("EC-IN")
+    assert len(ec.state_dict()) == 310 and sum(p.numel() for p in ec.parameters()) == 4441089
+    bc = model_selector("BC-HGNN-GMM", dict(latent=128))
+    assert len(bc.state_dict()) == 433 and sum(p.numel() for p in bc.parameters()) == 6358517
+
+
+def test_kaiming_init_matches_reference_rule():
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    from oracle import reference_harness as rh
+    a = model_selector("EC-IN", dict(latent=16, n_interaction_graph_iters=1))
+    b = model_selector("EC-IN", dict(latent=16, n_interaction_graph_iters=1))
+    torch.manual_seed(5)
+    kaiming_init(a)
+    torch.manual_seed(5)
+    rh.kaiming_init(b)
+    for (k, p), q in zip(a.named_parameters(), b.parameters()):
+        assert torch.equal(p, q), k
+    w0 = a.ignn_block.node_encoder[0].weight
+    assert abs(float(w0.std()) - 1 / math.sqrt(3)) < 0.2
+    assert float(a.ignn_block.node_encoder[0].bias.abs().max()) == 0.0
+
+
+def test_process_hparams_and_aliases():
+    from hierarchicalgnn_b200.training_utils import load_hparams
+    hp = load_hparams("1")
+    assert hp["hidden"] == 256 and hp["latent"] == 128 and hp["cluster_granularity"] == 0
+    hp = load_hparams("BC-HGNN-GMM", dict(latent=128))
+    assert hp["hidden"] == 256 and hp["emb_dim"] == 8 and hp["cluster_granularity"] == 5
+    with pytest.raises(ValueError):
+        load_hparams("nope")
+
+
+def test_gaussian_cut_agrees_with_reference_fsolve_formulation():
+    import numpy as np
+    from scipy.optimize import fsolve
+    from sklearn.mixture import GaussianMixture
+    from hierarchicalgnn_b200.BipartiteClassification.Models.HGNN_GMM import gaussian_cut
+    rng = np.random.RandomState(0)
+    x = np.concatenate([rng.normal(0.2, 0.3, 6000), rng.normal(2.4, 0.5, 4000)]).reshape(-1, 1)
+    gmm = GaussianMixture(2, random_state=0).fit(x)
+    for gran in (0, 5, -2):
+        sg = lambda v: 1 / (1 + np.exp(-v))
+        lo, hi = gmm.means_.argmin(), gmm.means_.argmax()
+        f = lambda t: sg(gran) * gmm.predict_proba(t.reshape(-1, 1))[:, lo] - sg(-gran) * gmm.predict_proba(t.reshape(-1, 1))[:, hi]
+        want = float(fsolve(f, gmm.means_.mean()).item())
+        params = []
+        for k in (0, 1):
+            params += [gmm.weights_[k], gmm.means_[k, 0], gmm.covariances_[k, 0, 0]]
+        cut, found = gaussian_cut(params, gran)
+        assert found and abs(cut - want) < 1e-4, (gran, cut, want)
+
+
+def test_synthetic_event_is_deterministic_and_shaped():
+    from hierarchicalgnn_b200.synth import synth_event, synth_edge_problem
+    a, b = synth_event(50, 10, 0.1, 4.0, seed=7), synth_event(50, 10, 0.1, 4.0, seed=7)
+    assert torch.equal(a.x, b.x) and torch.equal(a.edge_index, b.edge_index)
+    assert a.x.shape == (550, 3) and a.edge_index.shape[0] == 2 and a.x.dtype == torch.float32
+    assert int(a.y_pid.sum()) >= 50 * 9  # random fakes may join same-particle hits
+    n, e, g = synth_edge_problem(1000, 32)
+    assert n.shape == (100, 32) and e.shape == (1000, 32) and torch.equal(g[:, :500], g[:, 500:].flip(0))
+
+
+def test_lightning_compat_surface():
+    from hierarchicalgnn_b200.training_utils import model_selector
+    m = model_selector("EC-IN", dict(latent=16, n_interaction_graph_iters=1))
+    assert m.hparams["lr"] == 0.001 and "loss_schedule" not in m.hparams
+    m.log("a", 1.0)
+    m.log_dict({"b": 2.0})
+    assert m.trainer.current_epoch == 0 and m.trainer.global_step == 0
+    (opt,), (sched,) = m.configure_optimizers()
+    assert isinstance(opt, torch.optim.AdamW) and opt.defaults["amsgrad"] and sched["interval"] == "epoch"
+    for hook in ("training_step", "validation_step", "test_step", "optimizer_step", "configure_optimizers"):
+        assert callable(getattr(m, hook))
