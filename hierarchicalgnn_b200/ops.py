@@ -34,6 +34,35 @@ def _count(n=1):
     LAUNCHES["count"] += n
 
 
+# optional per-call CUDA-event profile: name -> [(start, end)], filled when not None
+PROFILE = None
+
+
+class _timed:
+    """Brackets one C-ABI call with CUDA events on the launch stream (bench.py)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
+def compute_dtype(module=None) -> str:
+    """Arithmetic type of the MLP contractions on the current path."""
+    return "f32"
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -125,9 +154,10 @@ def segment_reduce_raw(src: Tensor, plan: SegmentPlan, gather32: Optional[Tensor
         return torch.zeros((plan.n_segments, width), dtype=torch.float32, device=src.device)
     out = torch.empty((plan.n_segments, width), dtype=torch.float32, device=src.device)
     if plan.n_segments and width:
-        check(_lib.lib().hgnn_segment_reduce(_ptr(src), width, _ptr(gather32), _ptr(weight), _ptr(plan.perm),
-                                             _ptr(plan.rowptr), plan.n_segments, int(mean), _ptr(out), _stream()),
-              "segment_reduce")
+        with _timed("segment_reduce"):
+            check(_lib.lib().hgnn_segment_reduce(_ptr(src), width, _ptr(gather32), _ptr(weight), _ptr(plan.perm),
+                                                 _ptr(plan.rowptr), plan.n_segments, int(mean), _ptr(out), _stream()),
+                  "segment_reduce")
         _count()
     return out
 
@@ -137,8 +167,9 @@ def gather_rows_raw(src: Tensor, idx32: Optional[Tensor], weight: Optional[Tenso
     width = src.shape[1]
     out = torch.empty((n_items, width), dtype=torch.float32, device=src.device)
     if n_items and width:
-        check(_lib.lib().hgnn_gather_rows(_ptr(src), width, _ptr(idx32), _ptr(weight), n_items, _ptr(out), _stream()),
-              "gather_rows")
+        with _timed("gather_rows"):
+            check(_lib.lib().hgnn_gather_rows(_ptr(src), width, _ptr(idx32), _ptr(weight), n_items, _ptr(out), _stream()),
+                  "gather_rows")
         _count()
     return out
 
@@ -323,7 +354,8 @@ class _FusedMLP(torch.autograd.Function):
         d, rows, layers = _build_desc(meta, segs, params)
         out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=segs[0].device)
         if rows:
-            check(_lib.lib().hgnn_mlp_forward(C.byref(d), rows, _ptr(out), _stream()), "mlp_forward")
+            with _timed("mlp_forward"):
+                check(_lib.lib().hgnn_mlp_forward(C.byref(d), rows, _ptr(out), _stream()), "mlp_forward")
             _count()
         ctx.meta, ctx.n_seg = meta, n_seg
         ctx.save_for_backward(*segs, *params)
@@ -362,10 +394,12 @@ class _FusedMLP(torch.autograd.Function):
         if rows:
             nbytes = L.hgnn_mlp_backward_workspace_bytes(C.byref(d), rows)
             ws = _workspace(nbytes, dev)
-            check(L.hgnn_mlp_backward_data(C.byref(d), rows, _ptr(gout), C.byref(dseg_arr), C.byref(dvec_arr), _ptr(ws),
-                                           ws.numel(), _stream()), "mlp_backward_data")
-            check(L.hgnn_mlp_backward_weights(C.byref(d), rows, C.byref(dW_arr), _ptr(ws), ws.numel(), _stream()),
-                  "mlp_backward_weights")
+            with _timed("mlp_backward_data"):
+                check(L.hgnn_mlp_backward_data(C.byref(d), rows, _ptr(gout), C.byref(dseg_arr), C.byref(dvec_arr), _ptr(ws),
+                                               ws.numel(), _stream()), "mlp_backward_data")
+            with _timed("mlp_backward_weights"):
+                check(L.hgnn_mlp_backward_weights(C.byref(d), rows, C.byref(dW_arr), _ptr(ws), ws.numel(), _stream()),
+                      "mlp_backward_weights")
             _count(1 + len(layers) + 2 * len(layers))
         else:
             for v in dvec:

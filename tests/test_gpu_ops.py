@@ -174,11 +174,15 @@ def test_fused_mlp_is_deterministic(ops):
 @pytest.mark.parametrize("nq,nr,dim,k,radius", [(150, 23, 8, 5, 0.9), (400, 400, 8, 10, 0.6), (64, 7, 8, 10, 10.0),
                                                   (300, 90, 3, 4, 0.5), (100, 50, 16, 32, 2.0), (5, 0, 8, 3, 1.0)])
 def test_knn_radius_bit_exact_after_canonical_sort(ops, nq, nr, dim, k, radius):
-    g = torch.Generator().manual_seed(nq * 31 + nr)
-    q = torch.nn.functional.normalize(torch.randn(nq, dim, generator=g)) * 0.8
-    r = q.clone() if nq == nr else torch.nn.functional.normalize(torch.randn(nr, dim, generator=g)) * 0.8
-    if nr:
-        assert O.knn_margin(q, r, k, radius) > 1e-5  # certified: no fp32 near-ties on this seed
+    for seed in range(nq * 31 + nr, nq * 31 + nr + 200):
+        g = torch.Generator().manual_seed(seed)
+        q = torch.nn.functional.normalize(torch.randn(nq, dim, generator=g)) * 0.8
+        r = q.clone() if nq == nr else torch.nn.functional.normalize(torch.randn(nr, dim, generator=g)) * 0.8
+        # pin a seed certified to have no fp32 near-ties (rank gaps and radius gap)
+        if not nr or O.knn_margin(q, r, k, radius) > 2e-5:
+            break
+    else:
+        pytest.fail("no tie-free seed found")
     want = O.knn_radius(q, r, k, radius)
     got = ops.knn_radius(q.to(DEV), r.to(DEV), k, radius).cpu()
     assert torch.equal(got, want)
