@@ -90,6 +90,7 @@ SIGNATURES = {
     "hgnn_tc_supported": (C.c_int, [i64, i64, i64, C.c_int]),
     "hgnn_tc_packed_weight_bytes": (sz, [i64, i64]),
     "hgnn_tc_pack_weights": (C.c_int, [vp, i64, i64, vp, vp]),
+    "hgnn_tc_debug_gemm": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
     "hgnn_tc_edge_forward_workspace_bytes": (sz, [i64]),
     "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, i64, i64, vp, vp, sz, vp]),
 }

@@ -1,18 +1,454 @@
-// Tensor-core (tcgen05) fused edge step — placeholder entry points until the
-// kernel lands; they report "unsupported" so callers take the fp32 SIMT path.
+// Tensor-core fused edge step (forward), sm_100a:
+//   e'[i] = Tanh(LN2(W2 . GELU(LN1(W1 . [x[src_i] | x[dst_i] | e_i] + b1)) + b2)) + e_i
+// (InteractionGNNCell.edge_update, gnn_utils.py:56-64, with make_mlp's
+// LayerNorm/activation layout, utils.py:183-196.)
+//
+// One CTA owns a 128-edge tile (UMMA M = 128 = TMEM lanes); two CTAs are
+// resident per SM so that one tile's CUDA-core epilogue overlaps the other's
+// gathers and MMAs. Per tile:
+//   GEMM1  K-block by K-block (64 bf16): all threads gather the fp32 rows of
+//          x[src] / x[dst] / e (coalesced 256 B row pieces), convert to bf16 and
+//          write them 128B-swizzled into a 2-stage ring; the matching W1 K-block
+//          (pre-packed bf16 UMMA image) arrives by one bulk async copy; one thread
+//          issues 4 tcgen05.mma (128 x H x 16) into TMEM and commits to the
+//          stage's mbarrier, so block k's MMAs run under block k+1's gather.
+//   EPI1   each thread owns half a TMEM lane (row): bias + two-pass LayerNorm
+//          (Chan-combined across the two half-row threads) + activation, written
+//          as the bf16 K-major A operand of GEMM2 over the (now idle) ring.
+//   GEMM2  W2 K-blocks streamed through the tail of the ring; accumulator
+//          aliases the first L TMEM columns.
+//   EPI2   bias + LayerNorm + Tanh to a swizzled fp32 staging tile, then a
+//          coalesced pass adds the fp32 skip row and stores e' as full 512 B rows.
+// Weights are never resident in full: smem per CTA is ~105 KB at L = 128.
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 using namespace hgnn;
+using namespace hgnn::tc;
 
-extern "C" int hgnn_tc_supported(int64_t, int64_t, int64_t, int) { return 0; }
+namespace {
+
+constexpr int TC_THREADS = 256;
+
+template <int L>
+struct Cfg {
+  static constexpr int H = 2 * L;
+  static constexpr int K1 = 3 * L;
+  static constexpr int NKB1 = K1 / KBLK;
+  static constexpr int NKB2 = H / KBLK;
+  static constexpr int W1_BLK = H * ROW_BYTES;
+  static constexpr int W2_BLK = L * ROW_BYTES;
+  static constexpr int STAGE = A_BLK_BYTES + W1_BLK;
+  static constexpr int NSTAGE = 2;
+  static constexpr int A2_BYTES = NKB2 * A_BLK_BYTES;
+  static constexpr int SOUT_BYTES = TILE_M * L * 4;
+  static constexpr int R0 = NSTAGE * STAGE;
+  static constexpr int R1 = A2_BYTES + 2 * W2_BLK;
+  static constexpr int REGION = (R0 > R1 ? R0 : R1) > SOUT_BYTES ? (R0 > R1 ? R0 : R1) : SOUT_BYTES;
+  static constexpr int PARAM_FLOATS = 3 * H + 3 * L;
+  // region | params | row ids (3 x 128 int) | LN exchange (128 x 2 x 2 float) | 16 barriers | tmem slot
+  static constexpr int SMEM = REGION + PARAM_FLOATS * 4 + 3 * TILE_M * 4 + TILE_M * 4 * 4 + 16 * 8 + 16;
+  static constexpr int TMEM_COLS = H;  // power of two >= 32 for L in {64,128}
+  static_assert(L == 64 || L == 128, "tensor-core edge step is instantiated for latent 64 and 128");
+};
+
+// gather one K-block (64 fp32 columns starting at `col0` of rows rowid[r] of `base`) into a swizzled bf16 A block
+__device__ __forceinline__ void gather_a_block(uint8_t* __restrict__ blk, const float* __restrict__ base, int ld,
+                                               const int* __restrict__ rowid, int col0) {
+  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;  // 16 threads per row piece, 16 rows per pass
+  float4 v[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    int r = p * 16 + rr;
+    v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rowid[r] * ld + col0) + sub);
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    int r = p * 16 + rr;
+    uint2 pk = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
+    *reinterpret_cast<uint2*>(blk + sw128_off(r, sub >> 1) + (sub & 1) * 8) = pk;
+  }
+}
+
+struct LnStat { float mean, rstd; };
+
+// Chan-combine the two half-row partials (n each): returns mean / rstd of the full row
+__device__ __forceinline__ LnStat combine_halves(const float* red, int r, int n_half, float eps) {
+  float m0 = red[r * 4 + 0], q0 = red[r * 4 + 1], m1 = red[r * 4 + 2], q1 = red[r * 4 + 3];
+  float mean = 0.5f * (m0 + m1);
+  float d = m1 - m0;
+  float m2 = q0 + q1 + d * d * (0.5f * n_half);
+  LnStat s;
+  s.mean = mean;
+  s.rstd = rsqrtf(m2 / (2.0f * n_half) + eps);
+  return s;
+}
+
+template <int L>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,
+              const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out) {
+  using C = Cfg<L>;
+  constexpr int H = C::H;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* region = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_par = reinterpret_cast<float*>(region + C::REGION);
+  float *s_b1 = s_par, *s_g1 = s_par + H, *s_be1 = s_par + 2 * H, *s_b2 = s_par + 3 * H, *s_g2 = s_par + 3 * H + L,
+        *s_be2 = s_par + 3 * H + 2 * L;
+  int* s_eid = reinterpret_cast<int*>(s_par + C::PARAM_FLOATS);
+  int* s_src = s_eid + TILE_M;
+  int* s_dst = s_src + TILE_M;
+  float* s_red = reinterpret_cast<float*>(s_dst + TILE_M);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + TILE_M * 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t region_u = smem_u32(region);
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  enum { W_FULL = 0, ST_FREE = 2, W2_FULL = 4, W2_FREE = 6, ACC_FULL = 8 };
+
+  if (tid == 0) {
+    for (int i = 0; i < 9; ++i) mbar_init(BAR(i), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), C::TMEM_COLS);
+  for (int i = tid; i < H; i += TC_THREADS) { s_b1[i] = P.b1[i]; s_g1[i] = P.gamma1[i]; s_be1[i] = P.beta1[i]; }
+  for (int i = tid; i < L; i += TC_THREADS) { s_b2[i] = P.b2[i]; s_g2[i] = P.gamma2[i]; s_be2[i] = P.beta2[i]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t idesc1 = make_idesc(TILE_M, H), idesc2 = make_idesc(TILE_M, L);
+  const uint8_t* w1p = reinterpret_cast<const uint8_t*>(P.w1_packed);
+  const uint8_t* w2p = reinterpret_cast<const uint8_t*>(P.w2_packed);
+
+  uint32_t it1 = 0, it2 = 0, acc_par = 0;
+  const int q = warp & 3, hsel = warp >> 2;
+  const int row = q * 32 + lane;
+  const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+  const int n_tiles = (int)((n_edges + TILE_M - 1) / TILE_M);
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- row ids of this tile ----
+    if (tid < TILE_M) {
+      int64_t j = (int64_t)tile * TILE_M + tid;
+      if (j >= n_edges) j = n_edges - 1;  // padding rows recompute the last edge; never stored
+      int eid = perm ? perm[j] : (int)j;
+      s_eid[tid] = eid;
+      s_src[tid] = src[eid];
+      s_dst[tid] = dst[eid];
+    }
+    __syncthreads();
+
+    // ---- GEMM1: D1[128, H] = [x[src] | x[dst] | e] . W1^T ----
+    for (int kb = 0; kb < C::NKB1; ++kb, ++it1) {
+      const int s = it1 % C::NSTAGE;
+      const uint32_t ph = (it1 / C::NSTAGE) & 1;
+      uint8_t* stage = region + s * C::STAGE;
+      mbar_wait(BAR(ST_FREE + s), ph ^ 1);  // MMAs that last read this stage are done
+      if (tid == 0) {
+        mbar_expect_tx(BAR(W_FULL + s), C::W1_BLK);
+        bulk_g2s(region_u + s * C::STAGE + A_BLK_BYTES, w1p + (size_t)kb * C::W1_BLK, C::W1_BLK, BAR(W_FULL + s));
+      }
+      const int seg = (kb * KBLK) / L, col0 = (kb * KBLK) % L;
+      const float* base = seg == 2 ? e : x;
+      const int* rid = seg == 0 ? s_src : (seg == 1 ? s_dst : s_eid);
+      gather_a_block(stage, base, L, rid, col0);
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(BAR(W_FULL + s), ph);
+        tc_fence_after();
+        umma_kblock(tmem, region_u + s * C::STAGE, region_u + s * C::STAGE + A_BLK_BYTES, idesc1, kb == 0);
+        umma_commit(BAR(ST_FREE + s));
+        if (kb == C::NKB1 - 1) umma_commit(BAR(ACC_FULL));
+      }
+    }
+    mbar_wait(BAR(ACC_FULL), acc_par);
+    acc_par ^= 1;
+    tc_fence_after();
+
+    // W2 K-blocks 0/1 stream in behind EPI1 (their slots lie past the A2 image; GEMM1 no longer reads them)
+    if (tid == 0) {
+      for (int j = 0; j < 2 && j < C::NKB2; ++j) {
+        const uint32_t u = it2 + j, sl = u & 1, ph = (u >> 1) & 1;
+        mbar_wait(BAR(W2_FREE + sl), ph ^ 1);
+        mbar_expect_tx(BAR(W2_FULL + sl), C::W2_BLK);
+        bulk_g2s(region_u + C::A2_BYTES + sl * C::W2_BLK, w2p + (size_t)j * C::W2_BLK, C::W2_BLK, BAR(W2_FULL + sl));
+      }
+    }
+
+    // ---- EPI1: bias + LayerNorm + activation -> bf16 A2 (K-major, swizzled) ----
+    {
+      constexpr int NC = H / 2;  // columns per thread
+      const int c0 = hsel * NC;
+      float v[32];
+      float sum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        tmem_ld32(t_lane + c0 + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum += v[i] + s_b1[c0 + ch * 32 + i];
+      }
+      const float mloc = sum * (1.0f / NC);
+      float m2 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        tmem_ld32(t_lane + c0 + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float d = v[i] + s_b1[c0 + ch * 32 + i] - mloc; m2 = fmaf(d, d, m2); }
+      }
+      s_red[row * 4 + hsel * 2] = mloc;
+      s_red[row * 4 + hsel * 2 + 1] = m2;
+      __syncthreads();
+      const LnStat st = combine_halves(s_red, row, NC, P.ln_eps);
+#pragma unroll 1
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        tmem_ld32(t_lane + c0 + ch * 32, v);
+        const int cb = c0 + ch * 32;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = cb + g8 * 8 + i;
+            float y = (v[g8 * 8 + i] + s_b1[c] - st.mean) * st.rstd * s_g1[c] + s_be1[c];
+            o[i] = tc_act(P.act_hidden, y);
+          }
+          const int c = cb + g8 * 8;
+          uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          *reinterpret_cast<uint4*>(region + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) = pk;
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---- GEMM2: D2[128, L] = A2 . W2^T (accumulator aliases TMEM columns [0, L)) ----
+    if (tid == 0) {
+      tc_fence_after();
+      for (int j = 0; j < C::NKB2; ++j) {
+        const uint32_t u = it2 + j, sl = u & 1, ph = (u >> 1) & 1;
+        mbar_wait(BAR(W2_FULL + sl), ph);
+        tc_fence_after();
+        umma_kblock(tmem, region_u + j * A_BLK_BYTES, region_u + C::A2_BYTES + sl * C::W2_BLK, idesc2, j == 0);
+        umma_commit(BAR(W2_FREE + sl));
+        if (j + 2 < C::NKB2) {  // refill this slot with block j+2 once its MMAs retire
+          const uint32_t u2 = u + 2, ph2 = (u2 >> 1) & 1;
+          mbar_wait(BAR(W2_FREE + sl), ph2 ^ 1);
+          mbar_expect_tx(BAR(W2_FULL + sl), C::W2_BLK);
+          bulk_g2s(region_u + C::A2_BYTES + sl * C::W2_BLK, w2p + (size_t)(j + 2) * C::W2_BLK, C::W2_BLK, BAR(W2_FULL + sl));
+        }
+      }
+      umma_commit(BAR(ACC_FULL));
+    }
+    it2 += C::NKB2;
+    mbar_wait(BAR(ACC_FULL), acc_par);
+    acc_par ^= 1;
+    tc_fence_after();
+
+    // ---- EPI2: bias + LayerNorm + activation -> fp32 staging tile (swizzled 16 B chunks) ----
+    {
+      constexpr int NC = L / 2;
+      const int c0 = hsel * NC;
+      float v[32];
+      float sum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        tmem_ld32(t_lane + c0 + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum += v[i] + s_b2[c0 + ch * 32 + i];
+      }
+      const float mloc = sum * (1.0f / NC);
+      float m2 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        tmem_ld32(t_lane + c0 + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float d = v[i] + s_b2[c0 + ch * 32 + i] - mloc; m2 = fmaf(d, d, m2); }
+      }
+      __syncthreads();  // s_red reuse: every thread has consumed the EPI1 statistics
+      s_red[row * 4 + hsel * 2] = mloc;
+      s_red[row * 4 + hsel * 2 + 1] = m2;
+      __syncthreads();
+      const LnStat st = combine_halves(s_red, row, NC, P.ln_eps);
+#pragma unroll 1
+      for (int ch = 0; ch < NC / 32; ++ch) {
+        tmem_ld32(t_lane + c0 + ch * 32, v);
+        const int cb = c0 + ch * 32;
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = cb + g4 * 4 + i;
+            float y = (v[g4 * 4 + i] + s_b2[c] - st.mean) * st.rstd * s_g2[c] + s_be2[c];
+            o[i] = tc_act(P.act_out, y);
+          }
+          const int c4 = (cb >> 2) + g4;
+          *reinterpret_cast<float4*>(region + (size_t)row * (L * 4) + ((c4 ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- coalesced pass: + fp32 skip row, full-row stores ----
+    {
+      constexpr int CPR = L / 4;                       // float4 chunks per row
+      constexpr int ROWS_PER_WARP = TILE_M / (TC_THREADS / 32);
+#pragma unroll 4
+      for (int idx = lane; idx < ROWS_PER_WARP * CPR; idx += 32) {
+        const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
+        const int64_t j = (int64_t)tile * TILE_M + r;
+        if (j < n_edges) {
+          const float4 y = *reinterpret_cast<const float4*>(region + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
+          const size_t g = (size_t)s_eid[r] * L + c4 * 4;
+          const float4 sk = __ldg(reinterpret_cast<const float4*>(e + g));
+          *reinterpret_cast<float4*>(e_out + g) = make_float4(y.x + sk.x, y.y + sk.y, y.z + sk.z, y.w + sk.w);
+        }
+      }
+    }
+    __syncthreads();  // staging tile / row ids free for the next tile
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------
+// weight packing: fp32 [N, K] (nn.Linear layout) -> bf16 K-blocks of [N, 64], 128B-swizzled
+// ---------------------------------------------------------------------------
+__global__ void k_pack_weights(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (n, 8-column group)
+  int groups = K / 8;
+  if (t >= N * groups) return;
+  int n = t / groups, g = t % groups;
+  int kb = g / 8, c16 = g % 8;
+  const float* s = W + (size_t)n * K + g * 8;
+  uint4 pk = make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+  *reinterpret_cast<uint4*>(out + (size_t)kb * N * ROW_BYTES + sw128_off(n, c16)) = pk;
+}
+
+// ---------------------------------------------------------------------------
+// debug / unit-test GEMM: C[M, N] = bf16(A[M, K]) . bf16(W[N, K])^T with the same building blocks
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_debug_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Wp, int64_t M, int N, int K, float* __restrict__ Cout) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* region = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int wblk = N * ROW_BYTES;
+  int* s_rid = reinterpret_cast<int*>(region + A_BLK_BYTES + wblk);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rid + TILE_M);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t region_u = smem_u32(region), bar_w = smem_u32(s_bar), bar_mma = bar_w + 8;
+  int tcols = 32;
+  while (tcols < N) tcols <<= 1;
+  if (tid == 0) { mbar_init(bar_w, 1); mbar_init(bar_mma, 1); fence_mbar_init(); }
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), tcols);
+  if (tid < TILE_M) {
+    int64_t r = (int64_t)blockIdx.x * TILE_M + tid;
+    s_rid[tid] = (int)(r < M ? r : M - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t idesc = make_idesc(TILE_M, N);
+  uint32_t par = 0;
+  for (int kb = 0; kb < K / KBLK; ++kb) {
+    if (tid == 0) {
+      mbar_expect_tx(bar_w, wblk);
+      bulk_g2s(region_u + A_BLK_BYTES, Wp + (size_t)kb * wblk, wblk, bar_w);
+    }
+    gather_a_block(region, A, K, s_rid, kb * KBLK);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar_w, par);
+      tc_fence_after();
+      umma_kblock(tmem, region_u, region_u + A_BLK_BYTES, idesc, kb == 0);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, par);  // fully serialised: this kernel only checks layouts/descriptors
+    par ^= 1;
+    tc_fence_after();
+  }
+  const int q = warp & 3, hsel = warp >> 2;
+  const int row = q * 32 + lane;
+  const int64_t grow = (int64_t)blockIdx.x * TILE_M + row;
+  float v[32];
+  for (int c0 = hsel * 32; c0 < N; c0 += 64) {
+    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+    if (grow < M)
+      for (int i = 0; i < 32; ++i) Cout[grow * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, tcols);
+}
+
+}  // namespace
+
+extern "C" int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int layer_norm) {
+  return (latent == 64 || latent == 128) && hidden == 2 * latent && n_layers == 2 && layer_norm ? 1 : 0;
+}
+
 extern "C" size_t hgnn_tc_packed_weight_bytes(int64_t out_features, int64_t in_features) {
   return (size_t)out_features * in_features * 2;
 }
-extern "C" int hgnn_tc_pack_weights(const float*, int64_t, int64_t, void*, void*) {
-  return fail(HGNN_ERR_UNSUPPORTED, "tc_pack_weights: tensor-core path not built");
+
+extern "C" int hgnn_tc_pack_weights(const float* W, int64_t out_features, int64_t in_features, void* packed, void* stream) {
+  HGNN_REQUIRE(W && packed, "tc_pack_weights: NULL pointer");
+  HGNN_REQUIRE(in_features % KBLK == 0 && out_features % 8 == 0 && out_features <= 256,
+               "tc_pack_weights: need in_features %% 64 == 0, out_features %% 8 == 0 and <= 256 (got %lld x %lld)",
+               (long long)out_features, (long long)in_features);
+  int total = (int)(out_features * in_features / 8);
+  k_pack_weights<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, (int)out_features, (int)in_features, (uint8_t*)packed);
+  return check_launch("tc_pack_weights");
 }
+
+extern "C" int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t M, int64_t N, int64_t K, float* C, void* stream) {
+  HGNN_REQUIRE(A && w_packed && C && M > 0, "tc_debug_gemm: bad argument");
+  HGNN_REQUIRE(K % KBLK == 0 && N % 32 == 0 && N >= 32 && N <= 256, "tc_debug_gemm: need K %% 64 == 0, N %% 32 == 0, N <= 256");
+  size_t smem = 1024 + A_BLK_BYTES + (size_t)N * ROW_BYTES + TILE_M * 4 + 64;
+  HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_debug_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unsigned grid = (unsigned)((M + TILE_M - 1) / TILE_M);
+  k_tc_debug_gemm<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(A, (const uint8_t*)w_packed, M, (int)N, (int)K, C);
+  return check_launch("tc_debug_gemm");
+}
+
 extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t) { return 256; }
-extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params*, const float*, const float*, const int32_t*, const int32_t*,
-                                    const int32_t*, int64_t, int64_t, float*, void*, size_t, void*) {
-  return fail(HGNN_ERR_UNSUPPORTED, "tc_edge_forward: tensor-core path not built");
+
+template <int L>
+static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src, const int32_t* dst,
+                           const int32_t* perm, int64_t n_edges, float* e_out, cudaStream_t st) {
+  size_t smem = Cfg<L>::SMEM + 1024;
+  HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_edge_fwd<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
+  unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
+  k_tc_edge_fwd<L><<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out);
+  return check_launch("tc_edge_forward");
+}
+
+extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
+                                    const int32_t* dst, const int32_t* perm, int64_t n_edges, int64_t n_nodes, float* e_out,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes; (void)n_nodes;
+  HGNN_REQUIRE(p != nullptr, "tc_edge_forward: params is NULL");
+  if (n_edges <= 0) return HGNN_OK;
+  HGNN_REQUIRE(x && e && src && dst && e_out, "tc_edge_forward: NULL pointer");
+  HGNN_REQUIRE(p->w1_packed && p->w2_packed && p->b1 && p->gamma1 && p->beta1 && p->b2 && p->gamma2 && p->beta2,
+               "tc_edge_forward: NULL parameter pointer");
+  HGNN_REQUIRE(n_edges < INT32_MAX, "tc_edge_forward: too many edges");
+  if (!hgnn_tc_supported(p->latent, p->hidden, 2, 1))
+    return fail(HGNN_ERR_UNSUPPORTED, "tc_edge_forward: latent %d / hidden %d not supported (need latent in {64,128}, hidden = 2*latent)",
+                p->latent, p->hidden);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, st);
+  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, st);
 }

@@ -16,6 +16,7 @@ Reference call sites replaced (under /root/reference/Modules):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 from typing import List, Optional, Sequence
 
@@ -58,9 +59,28 @@ class _timed:
         return False
 
 
+# Precision of the MLP contractions: "fp32" = SIMT FFMA everywhere (bit-level parity mode);
+# "bf16" / "auto" = tcgen05 tensor cores (bf16 operands, fp32 accumulate, fp32 storage) wherever
+# a tensor-core kernel exists for the shape, fp32 SIMT elsewhere.
+_PRECISION = {"mode": os.environ.get("HGNN_PRECISION", "auto")}
+TC_CALLS = {"count": 0}
+
+
+def set_precision(mode: str) -> str:
+    if mode not in ("auto", "fp32", "bf16"):
+        raise _lib.HgnnError("precision must be one of auto / fp32 / bf16")
+    old = _PRECISION["mode"]
+    _PRECISION["mode"] = mode
+    return old
+
+
+def get_precision() -> str:
+    return _PRECISION["mode"]
+
+
 def compute_dtype(module=None) -> str:
-    """Arithmetic type of the MLP contractions on the current path."""
-    return "f32"
+    """Arithmetic type of the MLP contractions on the path that actually ran."""
+    return "bf16" if TC_CALLS["count"] else "f32"
 
 
 def _stream() -> int:
@@ -295,7 +315,8 @@ class MlpMeta:
     """Static description of one fused MLP call."""
 
     def __init__(self, seg_plans: Sequence[Optional[SegmentPlan]], acts: Sequence[Optional[str]],
-                 has_ln: Sequence[bool], skip_seg: int = -1, eps: float = 1e-5):
+                 has_ln: Sequence[bool], skip_seg: int = -1, eps: float = 1e-5, tc_pack=None):
+        self.tc_pack = tc_pack  # callable -> (w1_packed, w2_packed) when the tensor-core edge kernel applies
         self.seg_plans = list(seg_plans)
         self.acts = [ACT_CODES[a] for a in acts]
         self.has_ln = list(has_ln)
@@ -353,7 +374,9 @@ class _FusedMLP(torch.autograd.Function):
         params = [_f32(t) for t in tensors[n_seg:]]
         d, rows, layers = _build_desc(meta, segs, params)
         out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=segs[0].device)
-        if rows:
+        if rows and meta.tc_pack is not None:
+            tc_edge_forward_raw(meta, segs, layers, out)
+        elif rows:
             with _timed("mlp_forward"):
                 check(_lib.lib().hgnn_mlp_forward(C.byref(d), rows, _ptr(out), _stream()), "mlp_forward")
             _count()
@@ -420,6 +443,51 @@ class _FusedMLP(torch.autograd.Function):
             if gm is not None:
                 grads += [dvec[l][1], dvec[l][2]]
         return tuple(grads)
+
+
+def tc_supported(latent: int, hidden: int, n_layers: int, layer_norm: bool) -> bool:
+    return bool(_lib.lib().hgnn_tc_supported(int(latent), int(hidden), int(n_layers), int(bool(layer_norm))))
+
+
+def tc_pack_weight(W: Tensor) -> Tensor:
+    """fp32 nn.Linear weight [out, in] -> bf16 K-major 128B-swizzled UMMA image (uint8 tensor)."""
+    _need_cuda(W)
+    W = _f32(W.detach())
+    out = torch.empty(_lib.lib().hgnn_tc_packed_weight_bytes(W.shape[0], W.shape[1]), dtype=torch.uint8, device=W.device)
+    check(_lib.lib().hgnn_tc_pack_weights(_ptr(W), W.shape[0], W.shape[1], _ptr(out), _stream()), "tc_pack_weights")
+    _count()
+    return out
+
+
+def tc_debug_gemm(A: Tensor, W: Tensor) -> Tensor:
+    A = _f32(A)
+    Wp = tc_pack_weight(W)
+    out = torch.empty((A.shape[0], W.shape[0]), dtype=torch.float32, device=A.device)
+    check(_lib.lib().hgnn_tc_debug_gemm(_ptr(A), _ptr(Wp), A.shape[0], W.shape[0], W.shape[1], _ptr(out), _stream()),
+          "tc_debug_gemm")
+    _count()
+    return out
+
+
+def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor):
+    """e' = MLP([x[src] | x[dst] | e]) + e on tcgen05 tensor cores (segments: x|by_src, x|by_dst, e)."""
+    x, e = segs[0], segs[2]
+    plan_s, plan_d = meta.seg_plans[0], meta.seg_plans[1]
+    w1p, w2p = meta.tc_pack()
+    (W1, b1, g1, be1), (W2, b2, g2, be2) = layers
+    p = _lib.TcEdgeParams()
+    p.latent, p.hidden = W2.shape[0], W1.shape[0]
+    p.act_hidden, p.act_out = meta.acts[0], meta.acts[1]
+    p.ln_eps = meta.eps
+    p.w1_packed, p.w2_packed = w1p.data_ptr(), w2p.data_ptr()
+    p.b1, p.gamma1, p.beta1 = b1.data_ptr(), g1.data_ptr(), be1.data_ptr()
+    p.b2, p.gamma2, p.beta2 = b2.data_ptr(), g2.data_ptr(), be2.data_ptr()
+    n_edges = e.shape[0]
+    with _timed("tc_edge_forward"):
+        check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), None,
+                                              n_edges, x.shape[0], _ptr(out), None, 0, _stream()), "tc_edge_forward")
+    _count()
+    TC_CALLS["count"] += 1
 
 
 def fused_mlp(meta: MlpMeta, segs: Sequence[Tensor], params: Sequence[Tensor]) -> Tensor:

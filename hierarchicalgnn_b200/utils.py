@@ -63,8 +63,33 @@ class FusedMLP(nn.Sequential):
         if plans is None:
             plans = [None] * len(segs)
         ps, acts, lns, eps = self._params()
-        meta = ops.MlpMeta(plans, acts, lns, skip, eps)
+        meta = ops.MlpMeta(plans, acts, lns, skip, eps, tc_pack=self._tc_packer(segs, plans, skip, lns))
         return ops.fused_mlp(meta, list(segs), ps)
+
+    def _tc_packer(self, segs, plans, skip, lns):
+        """Returns a weight-image provider when this call is an edge step the tcgen05 kernel covers:
+        segments (x | by_src, x | by_dst, e), skip = e, two LayerNorm layers, latent in {64, 128}."""
+        if ops.get_precision() == "fp32" or len(segs) != 3 or skip != 2:
+            return None
+        layers = self._layers()
+        if len(layers) != 2 or not all(lns) or plans[0] is None or plans[1] is None or plans[2] is not None:
+            return None
+        if segs[0] is not segs[1] or not segs[0].is_cuda:
+            return None
+        L, H = layers[1][0].out_features, layers[0][0].out_features
+        if segs[0].shape[1] != L or segs[2].shape[1] != L or not ops.tc_supported(L, H, 2, True):
+            return None
+
+        def pack():
+            w1, w2 = layers[0][0].weight, layers[1][0].weight
+            key = (w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
+            cached = getattr(self, "_tc_cache", None)
+            if cached is None or cached[0] != key:
+                # bf16 shadow copies, rebuilt lazily when the fp32 parameters change; never registered
+                cached = (key, ops.tc_pack_weight(w1), ops.tc_pack_weight(w2))
+                object.__setattr__(self, "_tc_cache", cached)
+            return cached[1], cached[2]
+        return pack
 
     def forward(self, x):
         lead = x.shape[:-1]

@@ -212,6 +212,9 @@ int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int laye
 size_t hgnn_tc_packed_weight_bytes(int64_t out_features, int64_t in_features);
 /* fp32 nn.Linear weight [out, in] -> bf16, K-major, 128B-swizzled UMMA smem image */
 int hgnn_tc_pack_weights(const float* W, int64_t out_features, int64_t in_features, void* packed, void* stream);
+/* Unit-test entry: C[M,N] = bf16(A[M,K]) . bf16(W[N,K])^T, fp32 accumulate, built from
+ * the same gather / descriptor / tcgen05 / TMEM pieces as the fused kernels. */
+int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t M, int64_t N, int64_t K, float* C, void* stream);
 /* e_out[i] = MLP([x[src_i] | x[dst_i] | e_i]) + e_i for i in row order `perm`
  * (NULL = identity); if agg != NULL also agg[n] = sum_{dst_i = n} e_out[i],
  * which requires perm/rowptr to be the destination-sorted plan. */

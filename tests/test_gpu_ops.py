@@ -8,6 +8,15 @@ from oracle import hgnn_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def fp32_mode():
+    """These tests state fp32 tolerances: pin the SIMT fp32 path (tensor-core parity lives in test_gpu_tc.py)."""
+    from hierarchicalgnn_b200 import ops as _o
+    old = _o.set_precision("fp32")
+    yield
+    _o.set_precision(old)
+
 DEV = "cuda"
 
 

@@ -1,0 +1,111 @@
+"""GPU parity of the tcgen05 tensor-core path (bf16 operands, fp32 accumulate).
+Stated tolerances: against an oracle with the SAME operand rounding emulated the
+kernel must agree to fp32 accumulation noise (1e-3 on O(1) latents: bf16 ulp flips
+of the hidden activation); against the plain fp32 oracle to the bf16 tolerance of
+SURVEY.md §8c (2e-2 on latents)."""
+import pytest
+import torch
+
+from oracle import hgnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (128, 128, 128), (300, 256, 384), (1000, 64, 192), (77, 256, 64)])
+def test_tc_debug_gemm_layouts_and_descriptors(M, N, K):
+    from hierarchicalgnn_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    want = bf16r(A).double() @ bf16r(W).double().t()
+    got = ops.tc_debug_gemm(A.to(DEV), W.to(DEV)).cpu().double()
+    assert float((got - want).abs().max()) < 2e-5 * K ** 0.5 + 1e-5
+
+
+def test_tc_debug_gemm_structured_operands():
+    """One-hot operands expose any row/column/K-block permutation exactly."""
+    from hierarchicalgnn_b200 import ops
+    M, N, K = 128, 64, 128
+    A = torch.zeros(M, K)
+    A[torch.arange(M), torch.arange(M) % K] = 1.0
+    W = (torch.arange(N * K, dtype=torch.float32).reshape(N, K) % 251) / 256.0  # exactly representable in bf16
+    got = ops.tc_debug_gemm(A.to(DEV), W.to(DEV)).cpu()
+    assert torch.equal(got, W.t()[torch.arange(M) % K])
+
+
+def _edge_case(L, E, N, seed, hidden_act="GELU"):
+    from hierarchicalgnn_b200.utils import make_mlp
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    net = make_mlp(3 * L, 2 * L, L, 2, layer_norm=True, output_activation="Tanh", hidden_activation=hidden_act)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+    x, e = torch.randn(N, L, generator=g), torch.randn(E, L, generator=g)
+    graph = torch.randint(0, N, (2, E), generator=g)
+    return net, x, e, graph
+
+
+def _emulated(net, x, e, graph, L):
+    """fp64 oracle with the kernel's operand rounding: bf16 inputs/weights into GEMM1, bf16 hidden into GEMM2."""
+    sd = {k: v.detach().double() for k, v in net.state_dict().items()}
+    inp = torch.cat([x[graph[0]], x[graph[1]], e], -1)
+    h = bf16r(inp).double() @ bf16r(sd["0.weight"].float()).double().t() + sd["0.bias"]
+    h = torch.nn.functional.layer_norm(h, (2 * L,), sd["1.weight"], sd["1.bias"], 1e-5)
+    h = torch.nn.functional.gelu(h)
+    o = bf16r(h.float()).double() @ bf16r(sd["3.weight"].float()).double().t() + sd["3.bias"]
+    o = torch.tanh(torch.nn.functional.layer_norm(o, (L,), sd["4.weight"], sd["4.bias"], 1e-5))
+    return (o + e.double()).float()
+
+
+@pytest.mark.parametrize("L,E,N", [(128, 1000, 90), (128, 128, 7), (64, 777, 50), (128, 5, 3), (64, 4096, 400)])
+def test_tc_edge_forward_vs_emulated_and_fp32_oracle(L, E, N):
+    from hierarchicalgnn_b200 import ops
+    net, x, e, graph = _edge_case(L, E, N, seed=L + E)
+    want_emul = _emulated(net, x, e, graph, L)
+    sd = {"m." + k: v.detach() for k, v in net.state_dict().items()}
+    hp = dict(nb_edge_layer=2, hidden_activation="GELU", layernorm=True)
+    want_fp32 = O.edge_step(sd, "m", hp, x, e, graph)
+    net.to(DEV)
+    old = ops.set_precision("bf16")
+    try:
+        n0 = ops.TC_CALLS["count"]
+        gd = graph.to(DEV)
+        got = net.fused([x.to(DEV), x.to(DEV)][0:1] * 2 + [e.to(DEV)],
+                        [ops.plan_for(gd[0], N), ops.plan_for(gd[1], N), None], skip=2).cpu()
+        assert ops.TC_CALLS["count"] == n0 + 1, "tensor-core kernel was not used"
+    finally:
+        ops.set_precision(old)
+    assert float((got - want_emul).abs().max()) < 4e-3
+    assert float((got - want_emul).abs().mean()) < 2e-4
+    assert float((got - want_fp32).abs().max()) < 2e-2  # bf16 tolerance on latents
+
+
+def test_tc_edge_forward_backward_gradients_close_to_fp32():
+    """Forward on tensor cores, backward through the fp32 recompute kernels: gradients must
+    stay within bf16 tolerance of the all-fp32 oracle."""
+    from hierarchicalgnn_b200 import ops
+    L, E, N = 128, 600, 40
+    net, x, e, graph = _edge_case(L, E, N, seed=5)
+    sd = {"m." + k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    hp = dict(nb_edge_layer=2, hidden_activation="GELU", layernorm=True)
+    xr, er = x.clone().requires_grad_(True), e.clone().requires_grad_(True)
+    g = torch.Generator().manual_seed(1)
+    cot = torch.randn(E, L, generator=g)
+    (O.edge_step(sd, "m", hp, xr, er, graph) * cot).sum().backward()
+    net.to(DEV)
+    xd, ed, gd = x.to(DEV).requires_grad_(True), e.to(DEV).requires_grad_(True), graph.to(DEV)
+    old = ops.set_precision("bf16")
+    try:
+        out = net.fused([xd, xd, ed], [ops.plan_for(gd[0], N), ops.plan_for(gd[1], N), None], skip=2)
+    finally:
+        ops.set_precision(old)
+    (out * cot.to(DEV)).sum().backward()
+    torch.testing.assert_close(ed.grad.cpu(), er.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(net[0].weight.grad.cpu(), sd["m.0.weight"].grad, rtol=1e-3, atol=1e-3)
