@@ -91,6 +91,8 @@ SIGNATURES = {
     "hgnn_tc_packed_weight_bytes": (sz, [i64, i64]),
     "hgnn_tc_pack_weights": (C.c_int, [vp, i64, i64, vp, vp]),
     "hgnn_tc_debug_gemm": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
+    "hgnn_tc_debug_wgrad_workspace_bytes": (sz, [i64, i64, i64]),
+    "hgnn_tc_debug_wgrad": (C.c_int, [vp, vp, i64, i64, i64, vp, vp, sz, vp]),
     "hgnn_tc_edge_forward_workspace_bytes": (sz, [i64]),
     "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, i64, i64, vp, vp, sz, vp]),
 }

@@ -1,0 +1,230 @@
+// Tensor-core weight-gradient kernel (sm_100a):  dW[ca, cb] = sum_rows A[row, ca] * B[row, cb]
+// with rows = edges (the reduction dimension, K of the MMA).
+//
+// Operands arrive as "tile images": per 128-row tile, per 64-column block, one 16 KB
+// [128 rows x 128 B] bf16 array with the 128B XOR swizzle — exactly the layout the
+// backward-data kernel leaves in shared memory, bulk-copied to HBM as is. Here each
+// image is bulk-copied back into shared memory (no per-thread gather, no conversion)
+// and fed to tcgen05.mma as an MN-major operand, i.e. read transposed by the tensor
+// core itself. A CTA accumulates its tile range in TMEM (split-K over edges) and
+// writes one fp32 partial; a deterministic second stage sums the partials in order.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+using namespace hgnn;
+using namespace hgnn::tc;
+
+namespace {
+
+constexpr int WG_THREADS = 128;
+constexpr int WG_MAX_ROLES = 4;
+
+struct WgRole {
+  const uint8_t* img_a;  // [tiles][na_total][16 KB]
+  const uint8_t* img_b;
+  int na_total, a0, m_halves;   // A uses column blocks [a0, a0 + 2*m_halves): M = 128 per half
+  int nb_total, b0, nb;         // B uses column blocks [b0, b0 + nb): N = 64*nb <= 256
+  float* partial;               // [splits][M_total x N]
+};
+
+struct WgArgs {
+  WgRole role[WG_MAX_ROLES];
+  int n_roles, splits;
+  int n_tiles;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(WgArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int r = blockIdx.x / args.splits, split = blockIdx.x % args.splits;
+  const WgRole R = args.role[r];
+  const int na = 2 * R.m_halves, nb = R.nb;
+  const int N = 64 * nb;
+  const uint32_t stage_bytes = (uint32_t)(na + nb) * A_BLK_BYTES;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(base + 2 * stage_bytes);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 8);
+  const uint32_t base_u = smem_u32(base), bar0 = smem_u32(s_bar);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto FREE = [&](int s) { return bar0 + 16u + 8u * s; };
+  const uint32_t ACC = bar0 + 32u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tcols = 32;
+  while (tcols < N * R.m_halves) tcols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8u * i, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(s_tmem), tcols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int per = (args.n_tiles + args.splits - 1) / args.splits;
+  const int t0 = split * per, t1 = min(args.n_tiles, t0 + per);
+  const uint32_t idesc = make_idesc_mn(TILE_M, N);
+
+  if (tid == 0 && t0 < t1) {
+    auto load = [&](int t, int s) {
+      mbar_expect_tx(FULL(s), stage_bytes);
+      const uint32_t dst = base_u + s * stage_bytes;
+      bulk_g2s(dst, R.img_a + ((size_t)t * R.na_total + R.a0) * A_BLK_BYTES, na * A_BLK_BYTES, FULL(s));
+      bulk_g2s(dst + na * A_BLK_BYTES, R.img_b + ((size_t)t * R.nb_total + R.b0) * A_BLK_BYTES, nb * A_BLK_BYTES, FULL(s));
+    };
+    load(t0, 0);
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0, s = i & 1;
+      if (t + 1 < t1) {  // prefetch the next tile into the other stage once its previous MMAs retired
+        const int i2 = i + 1, s2 = i2 & 1;
+        mbar_wait(FREE(s2), ((i2 >> 1) & 1) ^ 1);
+        load(t + 1, s2);
+      }
+      mbar_wait(FULL(s), (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a_s = base_u + s * stage_bytes, b_s = a_s + na * A_BLK_BYTES;
+      for (int mh = 0; mh < R.m_halves; ++mh) {
+#pragma unroll
+        for (int k = 0; k < TILE_M / 16; ++k) {  // 16 K-rows (2 swizzle atoms = 2048 B) per MMA
+          uint64_t ad = make_smem_desc_mn(a_s + mh * 2 * A_BLK_BYTES + k * 2048, A_BLK_BYTES);
+          uint64_t bd = make_smem_desc_mn(b_s + k * 2048, A_BLK_BYTES);
+          umma_bf16(tmem + mh * N, ad, bd, idesc, (i == 0 && k == 0) ? 0u : 1u);
+        }
+      }
+      umma_commit(FREE(s));
+    }
+    umma_commit(ACC);
+  }
+  const int Mtot = 128 * R.m_halves;
+  float* out = R.partial + (size_t)split * Mtot * N;
+  if (t0 < t1) {
+    mbar_wait(ACC, 0);
+    tc_fence_after();
+    float v[32];
+    for (int mh = 0; mh < R.m_halves; ++mh) {
+      const int row = mh * 128 + warp * 32 + lane;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mh * N + c0, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(out + (size_t)row * N + c0 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+  } else {
+    for (int i = tid; i < Mtot * N; i += WG_THREADS) out[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, tcols);
+}
+
+// out[(row_off + m) * ld + col_off + n] (or transposed) = sum_splits partial[s][m][n]
+__global__ void k_wgrad_reduce(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ out, int ld,
+                               int row_off, int col_off, int transpose) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * M * N + i];
+  int m = i / N, n = i % N;
+  if (transpose) out[(size_t)(row_off + n) * ld + col_off + m] = s;
+  else out[(size_t)(row_off + m) * ld + col_off + n] = s;
+}
+
+// fp32 [rows, cols] -> tile images (test helper / generic producer); rows beyond `rows` are zero
+__global__ void k_make_image(const float* __restrict__ src, int64_t rows, int cols, uint8_t* __restrict__ img) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (padded row, 8-column group)
+  int groups = cols / 8;
+  int64_t prow = t / groups;
+  int g = (int)(t % groups);
+  int64_t n_tiles = (rows + TILE_M - 1) / TILE_M;
+  if (prow >= n_tiles * TILE_M) return;
+  int64_t tile = prow / TILE_M;
+  int r = (int)(prow % TILE_M);
+  float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (prow < rows)
+    for (int i = 0; i < 8; ++i) v[i] = src[prow * cols + g * 8 + i];
+  uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  *reinterpret_cast<uint4*>(img + ((size_t)tile * (cols / 64) + g / 8) * A_BLK_BYTES + sw128_off(r, g % 8)) = pk;
+}
+
+}  // namespace
+
+namespace hgnn {
+namespace tc {
+
+struct WgradProblem {  // dW[CA, CB] (+offsets into a larger matrix) = img_a^T img_b
+  const uint8_t* img_a; int ca_total, ca0, ca;   // columns of A used: [ca0, ca0+ca), ca multiple of 128
+  const uint8_t* img_b; int cb_total, cb0, cb;   // columns of B used, cb multiple of 64, <= 256
+  float* out; int ld, row_off, col_off, transpose;
+};
+
+size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits) {
+  size_t tot = 0;
+  for (int i = 0; i < n; ++i) tot += align_up((size_t)splits * probs[i].ca * probs[i].cb * 4, 256);
+  return tot + 256;
+}
+
+int wgrad_splits(int n_roles, int n_tiles) {
+  int s = std::max(1, num_sms() / std::max(1, n_roles));
+  return std::max(1, std::min(s, n_tiles));
+}
+
+int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st) {
+  HGNN_REQUIRE(n >= 1 && n <= WG_MAX_ROLES, "wgrad: 1..%d problems per launch", WG_MAX_ROLES);
+  WgArgs a{};
+  a.n_roles = n;
+  a.n_tiles = n_tiles;
+  a.splits = wgrad_splits(n, n_tiles);
+  if (ws_bytes < wgrad_workspace_bytes(probs, n, a.splits)) return fail(HGNN_ERR_WORKSPACE, "wgrad: workspace too small");
+  char* w = (char*)ws;
+  size_t max_stage = 0;
+  for (int i = 0; i < n; ++i) {
+    const WgradProblem& p = probs[i];
+    HGNN_REQUIRE(p.ca % 128 == 0 && p.ca >= 128 && p.ca <= 256 && p.cb % 64 == 0 && p.cb >= 64 && p.cb <= 256 &&
+                 (p.ca / 128) * p.cb <= 512, "wgrad: unsupported tile shape %d x %d", p.ca, p.cb);
+    WgRole& R = a.role[i];
+    R.img_a = p.img_a; R.na_total = p.ca_total / 64; R.a0 = p.ca0 / 64; R.m_halves = p.ca / 128;
+    R.img_b = p.img_b; R.nb_total = p.cb_total / 64; R.b0 = p.cb0 / 64; R.nb = p.cb / 64;
+    R.partial = (float*)w;
+    w += align_up((size_t)a.splits * p.ca * p.cb * 4, 256);
+    max_stage = std::max(max_stage, (size_t)(2 * R.m_halves + R.nb) * A_BLK_BYTES);
+  }
+  size_t smem = 1024 + 2 * max_stage + 128;
+  HGNN_REQUIRE(smem <= 227 * 1024, "wgrad: stage too large for shared memory");
+  HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_wgrad<<<n * a.splits, WG_THREADS, smem, st>>>(a);
+  for (int i = 0; i < n; ++i) {
+    const WgradProblem& p = probs[i];
+    int total = p.ca * p.cb;
+    k_wgrad_reduce<<<(total + 255) / 256, 256, 0, st>>>(a.role[i].partial, a.splits, p.ca, p.cb, p.out, p.ld, p.row_off, p.col_off,
+                                                         p.transpose);
+  }
+  return check_launch("tc_wgrad");
+}
+
+}  // namespace tc
+}  // namespace hgnn
+
+// Unit-test entry: out[CA, CB] = bf16(A[rows, CA])^T . bf16(B[rows, CB]) through tile images + MN-major UMMA.
+extern "C" size_t hgnn_tc_debug_wgrad_workspace_bytes(int64_t rows, int64_t ca, int64_t cb) {
+  int64_t tiles = (rows + TILE_M - 1) / TILE_M;
+  return (size_t)tiles * TILE_M * (ca + cb) * 2 + (size_t)num_sms() * ca * cb * 4 + 4096;
+}
+
+extern "C" int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca, int64_t cb, float* out, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  HGNN_REQUIRE(A && B && out && ws && rows > 0, "tc_debug_wgrad: bad argument");
+  HGNN_REQUIRE(ca % 128 == 0 && cb % 64 == 0, "tc_debug_wgrad: ca %% 128 == 0 and cb %% 64 == 0 required");
+  HGNN_REQUIRE(ws_bytes >= hgnn_tc_debug_wgrad_workspace_bytes(rows, ca, cb), "tc_debug_wgrad: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t tiles = (rows + TILE_M - 1) / TILE_M;
+  uint8_t* img_a = (uint8_t*)ws;
+  uint8_t* img_b = img_a + align_up((size_t)tiles * TILE_M * ca * 2, 1024);
+  char* rest = (char*)(img_b + align_up((size_t)tiles * TILE_M * cb * 2, 1024));
+  int64_t ta = tiles * TILE_M * (ca / 8), tb = tiles * TILE_M * (cb / 8);
+  k_make_image<<<(unsigned)((ta + 255) / 256), 256, 0, st>>>(A, rows, (int)ca, img_a);
+  k_make_image<<<(unsigned)((tb + 255) / 256), 256, 0, st>>>(B, rows, (int)cb, img_b);
+  hgnn::tc::WgradProblem p{img_a, (int)ca, 0, (int)ca, img_b, (int)cb, 0, (int)cb, out, (int)cb, 0, 0, 0};
+  return hgnn::tc::launch_wgrad(&p, 1, (int)tiles, rest, ws_bytes - (size_t)(rest - (char*)ws), st);
+}

@@ -469,6 +469,17 @@ def tc_debug_gemm(A: Tensor, W: Tensor) -> Tensor:
     return out
 
 
+def tc_debug_wgrad(A: Tensor, B: Tensor) -> Tensor:
+    A, B = _f32(A), _f32(B)
+    L = _lib.lib()
+    ws = _workspace(L.hgnn_tc_debug_wgrad_workspace_bytes(A.shape[0], A.shape[1], B.shape[1]), A.device)
+    out = torch.empty((A.shape[1], B.shape[1]), dtype=torch.float32, device=A.device)
+    check(L.hgnn_tc_debug_wgrad(_ptr(A), _ptr(B), A.shape[0], A.shape[1], B.shape[1], _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "tc_debug_wgrad")
+    _count(4)
+    return out
+
+
 def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor):
     """e' = MLP([x[src] | x[dst] | e]) + e on tcgen05 tensor cores (segments: x|by_src, x|by_dst, e)."""
     x, e = segs[0], segs[2]

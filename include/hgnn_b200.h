@@ -215,6 +215,11 @@ int hgnn_tc_pack_weights(const float* W, int64_t out_features, int64_t in_featur
 /* Unit-test entry: C[M,N] = bf16(A[M,K]) . bf16(W[N,K])^T, fp32 accumulate, built from
  * the same gather / descriptor / tcgen05 / TMEM pieces as the fused kernels. */
 int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t M, int64_t N, int64_t K, float* C, void* stream);
+/* Unit-test entry for the weight-gradient primitive: out[ca, cb] = bf16(A[rows, ca])^T . bf16(B[rows, cb]),
+ * through bf16 tile images read back as MN-major UMMA operands (split-K over rows, ordered reduce). */
+size_t hgnn_tc_debug_wgrad_workspace_bytes(int64_t rows, int64_t ca, int64_t cb);
+int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca, int64_t cb, float* out, void* ws,
+                        size_t ws_bytes, void* stream);
 /* e_out[i] = MLP([x[src_i] | x[dst_i] | e_i]) + e_i for i in row order `perm`
  * (NULL = identity); if agg != NULL also agg[n] = sum_{dst_i = n} e_out[i],
  * which requires perm/rowptr to be the destination-sorted plan. */

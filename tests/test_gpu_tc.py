@@ -37,6 +37,29 @@ def test_tc_debug_gemm_structured_operands():
     assert torch.equal(got, W.t()[torch.arange(M) % K])
 
 
+@pytest.mark.parametrize("rows,ca,cb", [(128, 128, 64), (1000, 128, 128), (5000, 256, 128), (300, 128, 256), (70000, 256, 128)])
+def test_tc_wgrad_mn_major_operands(rows, ca, cb):
+    from hierarchicalgnn_b200 import ops
+    g = torch.Generator().manual_seed(rows + ca)
+    A, B = torch.randn(rows, ca, generator=g), torch.randn(rows, cb, generator=g)
+    want = bf16r(A).double().t() @ bf16r(B).double()
+    got = ops.tc_debug_wgrad(A.to(DEV), B.to(DEV)).cpu().double()
+    assert float((got - want).abs().max()) < 3e-5 * rows ** 0.5 + 1e-4
+    again = ops.tc_debug_wgrad(A.to(DEV), B.to(DEV)).cpu().double()
+    assert torch.equal(got, again)  # split-K with ordered second stage: deterministic
+
+
+def test_tc_wgrad_structured():
+    from hierarchicalgnn_b200 import ops
+    rows, ca, cb = 256, 128, 64
+    A = torch.zeros(rows, ca)
+    A[torch.arange(rows), torch.arange(rows) % ca] = 1.0
+    B = ((torch.arange(rows * cb, dtype=torch.float32).reshape(rows, cb) * 7) % 127) / 128.0
+    want = A.t() @ B
+    got = ops.tc_debug_wgrad(A.to(DEV), B.to(DEV)).cpu()
+    assert torch.equal(got, want)
+
+
 def _edge_case(L, E, N, seed, hidden_act="GELU"):
     from hierarchicalgnn_b200.utils import make_mlp
     g = torch.Generator().manual_seed(seed)
