@@ -1,0 +1,689 @@
+// Tensor-core fused edge step, BACKWARD-DATA (sm_100a, latent 128):
+// recomputes the forward per 128-edge tile (replacing torch.utils.checkpoint,
+// gnn_utils.py:14-15) and back-propagates through Tanh/LayerNorm/Linear/GELU/
+// LayerNorm/Linear of InteractionGNNCell.edge_update (gnn_utils.py:56-64):
+//
+//   GEMM1  h1 = [x[src] | x[dst] | e] W1^T          (gather -> bf16 ring -> tcgen05, D1 kept in TMEM)
+//   EPI-A  LN1 stats, g = act(LN1(h1 + b1))  -> bf16 image (A operand of GEMM2, bulk-stored for wgrad)
+//   GEMM2  h2 = g W2^T
+//   EPI-B  LN2/Tanh forward, d(y2) = gout * act'(y2), LN2 adjoint -> delta2 (bf16 image), column sums
+//   GEMM3  dG = delta2 W2        (W2^T image as B operand)
+//   EPI-C  d(y1) = dG * act'(y1) (parked in TMEM), LN1 adjoint -> delta1 (bf16 image), column sums
+//   GEMM4  dA0 = delta1 W1       (W1^T image streamed in 16 KB (segment, K-block) pieces)
+//   EPI-D  per-edge rows d(x[src]), d(x[dst]) and d(e) = dA0_e + gout, as coalesced full rows
+//
+// gout = grad_eout[i] + grad_agg[dst_i] folds the adjoint of the scatter_add that follows the
+// edge step. The bf16 tile images of A0, g, delta1, delta2 go to HBM with bulk copies and are the
+// operands of the weight-gradient kernel (wgrad_tc.cu). Bias / LayerNorm-affine gradients are
+// reduced across rows with a register transpose-reduce and summed in a fixed order.
+// One CTA per SM (all 512 TMEM columns, ~205 KB of shared memory), 16 warps.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+using namespace hgnn;
+using namespace hgnn::tc;
+
+namespace hgnn { namespace tc {
+struct WgradProblem {
+  const uint8_t* img_a; int ca_total, ca0, ca;
+  const uint8_t* img_b; int cb_total, cb0, cb;
+  float* out; int ld, row_off, col_off, transpose;
+};
+size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits);
+int wgrad_splits(int n_roles, int n_tiles);
+int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st);
+}}
+
+namespace {
+
+constexpr int NT = 512;
+constexpr int L = 128, H = 256, K1 = 384;
+constexpr int NKB1 = K1 / KBLK, NKB2 = H / KBLK, NKBL = L / KBLK;  // 6, 4, 2
+constexpr int W1_BLK = H * ROW_BYTES;        // 32 KB : W1 image K-block ([H rows] of the [H, 3L] matrix)
+constexpr int W2_BLK = L * ROW_BYTES;        // 16 KB : W2 image K-block ([L rows] of [L, H])
+constexpr int W2T_BLK = H * ROW_BYTES;       // 32 KB : W2^T image K-block ([H rows] of [H, L])
+constexpr int W1T_BLK = K1 * ROW_BYTES;      // 48 KB : W1^T image K-block ([3L rows] of [3L, H])
+constexpr int SEG_BLK = L * ROW_BYTES;       // 16 KB : one segment's rows inside a W1^T K-block
+constexpr int STAGE = A_BLK_BYTES + W1_BLK;  // 48 KB
+constexpr int RING = 2 * STAGE;              // 96 KB
+constexpr int D2IMG_OFF = NKB2 * W2_BLK;     // delta2 image sits after the W2 / W2^T area: 64 KB
+constexpr int A2_OFF = RING;                 // g image -> delta1 image -> fp32 output staging (64 KB)
+constexpr int A2_BYTES = NKB2 * A_BLK_BYTES;
+constexpr int GS_OFF = A2_OFF + A2_BYTES;    // bf16 image of the upstream gradient tile (32 KB)
+constexpr int GS_BYTES = NKBL * A_BLK_BYTES;
+constexpr int PAR_OFF = GS_OFF + GS_BYTES;
+constexpr int PAR_FLOATS = 3 * H + 3 * L;
+constexpr int IDS_OFF = PAR_OFF + PAR_FLOATS * 4;
+constexpr int RED_OFF = IDS_OFF + 3 * TILE_M * 4;      // [128 rows][4 splits][2]
+constexpr int BAR_OFF = RED_OFF + TILE_M * 8 * 4;
+constexpr int NBAR = 2 + 2 + 6 + 6 + 1;
+constexpr int SMEM_BYTES = BAR_OFF + NBAR * 8 + 16;
+constexpr int NSLOT = 6;                                // 16 KB slots over the ring for GEMM4's weight stream
+constexpr uint32_t TM_D1 = 0, TM_D2 = H, TM_DGHI = H, TM_DGLO = H + L, TM_DA0 = 0;
+
+struct BwdArgs {
+  hgnn_tc_edge_params P;
+  const uint8_t* w1t;   // W1^T image: [3L rows, H cols]
+  const uint8_t* w2t;   // W2^T image: [H rows, L cols]
+  const float* x; const float* e; const int32_t* src; const int32_t* dst;
+  const float* g_e; const float* g_agg;   // upstream: d/d e_out [E, L], d/d agg [N, L] (may be NULL)
+  float* d_e; float* d_xs; float* d_xd;   // [E, L] each
+  uint8_t* a0_img; uint8_t* g_img; uint8_t* d1_img; uint8_t* d2_img;
+  float* colpart;                          // [grid][4][PAR_FLOATS]
+  int64_t n_edges;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// column sums over the 32 rows held by a warp: in v[c] = this lane's value for column c;
+// returns the sum over lanes of column `lane` (31 shuffles, log-step register transpose)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    bool up = lane & 16;
+    float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bool up = lane & 8;
+    float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bool up = lane & 4;
+    float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    bool up = lane & 2;
+    float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    bool up = lane & 1;
+    float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+// derivative of the activation w.r.t. its input, fast-math variants matching tc_act
+__device__ __forceinline__ float tc_act_bwd(int act, float y) {
+  switch (act) {
+    case HGNN_ACT_GELU: {
+      float ex = __expf(-0.5f * y * y);
+      float ax = fabsf(y) * 0.70710678118654752f;
+      float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+      float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+      float erf_abs = 1.0f - poly * ex;
+      float cdf = 0.5f * (1.0f + copysignf(erf_abs, y));
+      return fmaf(y * 0.3989422804014327f, ex, cdf);
+    }
+    case HGNN_ACT_TANH: { float t = fast_tanh(y); return 1.0f - t * t; }
+    case HGNN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case HGNN_ACT_SILU: { float s = __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f))); return s * (1.0f + y * (1.0f - s)); }
+    case HGNN_ACT_SIGMOID: { float s = __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f))); return s * (1.0f - s); }
+    default: return 1.f;
+  }
+}
+
+// mean / rstd of a row from 4 equal partial (mean, M2) pairs (Chan et al.), n values each
+__device__ __forceinline__ void combine4(const float* red, int r, int n, float eps, float& mean, float& rstd) {
+  float m[4], q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[i] = red[r * 8 + 2 * i]; q[i] = red[r * 8 + 2 * i + 1]; }
+  mean = 0.25f * (m[0] + m[1] + m[2] + m[3]);
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float d = m[i] - mean; m2 += q[i] + (float)n * d * d; }
+  rstd = rsqrtf(m2 / (4.0f * n) + eps);
+}
+
+__global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_par = reinterpret_cast<float*>(sm + PAR_OFF);
+  float *s_b1 = s_par, *s_g1 = s_par + H, *s_be1 = s_par + 2 * H, *s_b2 = s_par + 3 * H, *s_g2 = s_par + 3 * H + L,
+        *s_be2 = s_par + 3 * H + 2 * L;
+  int* s_eid = reinterpret_cast<int*>(sm + IDS_OFF);
+  int* s_src = s_eid + TILE_M;
+  int* s_dst = s_src + TILE_M;
+  float* s_red = reinterpret_cast<float*>(sm + RED_OFF);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + BAR_OFF + NBAR * 8);
+  const uint32_t sm_u = smem_u32(sm), bar0 = sm_u + BAR_OFF;
+  enum { W_FULL = 0, ST_FREE = 2, B_FULL = 4, B_FREE = 10, ACC = 16 };
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, cs = warp >> 2;  // TMEM lane quarter, column split
+  const int row = q * 32 + lane;
+  const hgnn_tc_edge_params& P = A.P;
+
+  if (tid == 0) {
+    for (int i = 0; i < NBAR; ++i) mbar_init(BAR(i), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
+  for (int i = tid; i < H; i += NT) { s_b1[i] = P.b1[i]; s_g1[i] = P.gamma1[i]; s_be1[i] = P.beta1[i]; }
+  for (int i = tid; i < L; i += NT) { s_b2[i] = P.b2[i]; s_g2[i] = P.gamma2[i]; s_be2[i] = P.beta2[i]; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+  const uint32_t idesc_h = make_idesc(TILE_M, H), idesc_l = make_idesc(TILE_M, L);
+  const uint8_t* w1p = reinterpret_cast<const uint8_t*>(P.w1_packed);
+  const uint8_t* w2p = reinterpret_cast<const uint8_t*>(P.w2_packed);
+
+  uint32_t it1 = 0, acc_par = 0;
+  uint32_t n_fill[NSLOT] = {0, 0, 0, 0, 0, 0}, n_commit[NSLOT] = {0, 0, 0, 0, 0, 0};  // thread 0 bookkeeping
+  // per-lane column-sum accumulators: lane c of warp (q, cs) owns columns cs*64 + {c, 32 + c} of H and cs*32 + c of L
+  float acc_db1[2] = {0.f, 0.f}, acc_dg1[2] = {0.f, 0.f}, acc_dbe1[2] = {0.f, 0.f};
+  float acc_db2 = 0.f, acc_dg2 = 0.f, acc_dbe2 = 0.f;
+
+  auto slot_fill = [&](int slot, uint32_t dst_off, const void* src, uint32_t bytes) {  // thread 0
+    if (n_commit[slot] > 0) mbar_wait(BAR(B_FREE + slot), (n_commit[slot] - 1) & 1);
+    mbar_expect_tx(BAR(B_FULL + slot), bytes);
+    bulk_g2s(sm_u + dst_off, src, bytes, BAR(B_FULL + slot));
+    n_fill[slot]++;
+  };
+  auto slot_wait_full = [&](int slot) { mbar_wait(BAR(B_FULL + slot), (n_fill[slot] - 1) & 1); tc_fence_after(); };
+  auto slot_commit = [&](int slot) { umma_commit(BAR(B_FREE + slot)); n_commit[slot]++; };
+
+  const int n_tiles = (int)((A.n_edges + TILE_M - 1) / TILE_M);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ================= tile setup: row ids =================
+    if (tid < TILE_M) {
+      int64_t j = (int64_t)tile * TILE_M + tid;
+      if (j >= A.n_edges) j = A.n_edges - 1;
+      s_eid[tid] = (int)j;
+      s_src[tid] = A.src[j];
+      s_dst[tid] = A.dst[j];
+    }
+    __syncthreads();
+    // upstream gradient tile -> bf16 image (zero for padding rows): 32 threads per row, 16 rows per pass
+    {
+      const int sub = tid & 31, rr = tid >> 5;
+#pragma unroll 2
+      for (int p = 0; p < TILE_M / 16; ++p) {
+        const int r = p * 16 + rr;
+        const int64_t j = (int64_t)tile * TILE_M + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < A.n_edges) {
+          v = __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + sub);
+          if (A.g_agg) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + sub);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+          }
+        }
+        const int c = sub * 4;
+        *reinterpret_cast<uint2*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(r, (c % KBLK) >> 3) + ((c >> 2) & 1) * 8) =
+            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      }
+    }
+
+    // ================= GEMM1 (recompute): D1 = A0 W1^T =================
+    for (int kb = 0; kb < NKB1; ++kb, ++it1) {
+      const int s = it1 & 1;
+      const uint32_t ph = (it1 >> 1) & 1;
+      mbar_wait(BAR(ST_FREE + s), ph ^ 1);
+      if (tid == 0) {
+        mbar_expect_tx(BAR(W_FULL + s), W1_BLK);
+        bulk_g2s(sm_u + s * STAGE + A_BLK_BYTES, w1p + (size_t)kb * W1_BLK, W1_BLK, BAR(W_FULL + s));
+      }
+      {
+        const int seg = (kb * KBLK) / L, col0 = (kb * KBLK) % L;
+        const float* base = seg == 2 ? A.e : A.x;
+        const int* rid = seg == 0 ? s_src : (seg == 1 ? s_dst : s_eid);
+        uint8_t* blk = sm + s * STAGE;
+        uint8_t* gimg = A.a0_img + ((size_t)tile * NKB1 + kb) * A_BLK_BYTES;
+        const int sub = tid & 15, rr = tid >> 4;  // 16 threads per 256 B row piece, 32 rows per pass
+        float4 v[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int r = p * 32 + rr;
+          v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rid[r] * L + col0) + sub);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int r = p * 32 + rr;
+          const uint2 pk = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
+          const uint32_t off = sw128_off(r, sub >> 1) + (sub & 1) * 8;
+          *reinterpret_cast<uint2*>(blk + off) = pk;
+          *reinterpret_cast<uint2*>(gimg + off) = pk;  // same image to HBM: B operand of the dW1 GEMM
+        }
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(BAR(W_FULL + s), ph);
+        tc_fence_after();
+        umma_kblock(tmem + TM_D1, sm_u + s * STAGE, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
+        umma_commit(BAR(ST_FREE + s));
+        if (kb == NKB1 - 1) umma_commit(BAR(ACC));
+      }
+    }
+    mbar_wait(BAR(ACC), acc_par);
+    acc_par ^= 1;
+    tc_fence_after();
+    // ring is idle: bring all of W2 in (4 x 16 KB slots) behind EPI-A
+    if (tid == 0) {
+      for (int j = 0; j < NKB2; ++j) slot_fill(j, j * W2_BLK, w2p + (size_t)j * W2_BLK, W2_BLK);
+    }
+
+    // ================= EPI-A: LN1 statistics, g = act(LN1(h1 + b1)) -> A2 image =================
+    float mean1, rstd1;
+    {
+      const int c0 = cs * 64;
+      float v[32];
+      float sum = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum += v[i] + s_b1[c0 + ch * 32 + i];
+      }
+      const float mloc = sum * (1.0f / 64);
+      float m2 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { float d = v[i] + s_b1[c0 + ch * 32 + i] - mloc; m2 = fmaf(d, d, m2); }
+      }
+      s_red[row * 8 + cs * 2] = mloc;
+      s_red[row * 8 + cs * 2 + 1] = m2;
+      __syncthreads();
+      combine4(s_red, row, 64, P.ln_eps, mean1, rstd1);
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
+        const int cb = c0 + ch * 32;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = cb + g8 * 8 + i;
+            o[i] = tc_act(P.act_hidden, (v[g8 * 8 + i] + s_b1[c] - mean1) * rstd1 * s_g1[c] + s_be1[c]);
+          }
+          const int c = cb + g8 * 8;
+          *reinterpret_cast<uint4*>(sm + A2_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
+              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ================= GEMM2 (recompute): D2 = g W2^T ; g image -> HBM =================
+    if (tid == 0) {
+      bulk_s2g(A.g_img + (size_t)tile * A2_BYTES, sm_u + A2_OFF, A2_BYTES);
+      bulk_commit();
+      tc_fence_after();
+      for (int j = 0; j < NKB2; ++j) {
+        slot_wait_full(j);
+        umma_kblock(tmem + TM_D2, sm_u + A2_OFF + j * A_BLK_BYTES, sm_u + j * W2_BLK, idesc_l, j == 0);
+        slot_commit(j);
+      }
+      umma_commit(BAR(ACC));
+    }
+    mbar_wait(BAR(ACC), acc_par);
+    acc_par ^= 1;
+    tc_fence_after();
+    // W2^T (2 x 32 KB) replaces W2 in the ring behind EPI-B
+    if (tid == 0) {
+      slot_fill(0, 0, A.w2t, W2T_BLK);
+      slot_fill(2, W2T_BLK, A.w2t + W2T_BLK, W2T_BLK);
+    }
+
+    // ================= EPI-B: LN2 + act forward, adjoint down to delta2 =================
+    {
+      const int c0 = cs * 32;
+      float v[32], dy[32];
+      tmem_ld32(t_lane + TM_D2 + c0, v);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { v[i] += s_b2[c0 + i]; sum += v[i]; }
+      const float mloc = sum * (1.0f / 32);
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { float d = v[i] - mloc; m2 = fmaf(d, d, m2); }
+      s_red[row * 8 + cs * 2] = mloc;      // EPI-A readers are past the pre-GEMM2 barrier
+      s_red[row * 8 + cs * 2 + 1] = m2;
+      __syncthreads();
+      float mean2, rstd2;
+      combine4(s_red, row, 32, P.ln_eps, mean2, rstd2);
+      // upstream gradient (bf16 image) for this quarter row: 4 chunks of 8
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const int c = c0 + g8 * 8;
+        const uint4 pk = *reinterpret_cast<const uint4*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3));
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float go = __uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
+          const int k = g8 * 8 + i;
+          const float xh = (v[k] - mean2) * rstd2;
+          const float y = xh * s_g2[c + i] + s_be2[c + i];
+          const float d = go * tc_act_bwd(P.act_out, y);
+          dy[k] = d;
+          v[k] = xh;
+          const float gd = s_g2[c + i] * d;
+          s1 += gd;
+          s2 = fmaf(gd, xh, s2);
+        }
+      }
+      __syncthreads();  // everyone has read the LN2 statistics
+      s_red[row * 8 + cs * 2] = s1;
+      s_red[row * 8 + cs * 2 + 1] = s2;
+      __syncthreads();
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { t1 += s_red[row * 8 + 2 * i]; t2 += s_red[row * 8 + 2 * i + 1]; }
+      t1 *= (1.0f / L);
+      t2 *= (1.0f / L);
+      float tmp[32];
+      // d gamma2 += dy * xhat ; d beta2 += dy
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tmp[i] = dy[i] * v[i];
+      acc_dg2 += warp_colsum32(tmp, lane);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) tmp[i] = dy[i];
+      acc_dbe2 += warp_colsum32(tmp, lane);
+      // delta2 = rstd (gamma dy - mean(gamma dy) - xhat mean(gamma dy xhat))
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dy[i] = rstd2 * (s_g2[c0 + i] * dy[i] - t1 - v[i] * t2);
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const int c = c0 + g8 * 8;
+        *reinterpret_cast<uint4*>(sm + D2IMG_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
+            make_uint4(pack_bf16(dy[g8 * 8], dy[g8 * 8 + 1]), pack_bf16(dy[g8 * 8 + 2], dy[g8 * 8 + 3]),
+                       pack_bf16(dy[g8 * 8 + 4], dy[g8 * 8 + 5]), pack_bf16(dy[g8 * 8 + 6], dy[g8 * 8 + 7]));
+      }
+      acc_db2 += warp_colsum32(dy, lane);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ================= GEMM3: dG = delta2 W2 (two N = 128 halves) ; delta2 image -> HBM =================
+    if (tid == 0) {
+      bulk_s2g(A.d2_img + (size_t)tile * GS_BYTES, sm_u + D2IMG_OFF, NKBL * A_BLK_BYTES);
+      bulk_commit();
+      tc_fence_after();
+      for (int kb = 0; kb < NKBL; ++kb) {
+        const int slot = kb * 2;
+        slot_wait_full(slot);
+        const uint32_t a_s = sm_u + D2IMG_OFF + kb * A_BLK_BYTES, b_s = sm_u + kb * W2T_BLK;
+        umma_kblock(tmem + TM_DGLO, a_s, b_s, idesc_l, kb == 0);                      // hidden units [0, 128)
+        umma_kblock(tmem + TM_DGHI, a_s, b_s + L * ROW_BYTES, idesc_l, kb == 0);      // hidden units [128, 256)
+        slot_commit(slot);
+      }
+      umma_commit(BAR(ACC));
+    }
+    mbar_wait(BAR(ACC), acc_par);
+    acc_par ^= 1;
+    tc_fence_after();
+    // start streaming W1^T (segment, K-block) pieces into the six 16 KB slots behind EPI-C
+    if (tid == 0) {
+      bulk_wait_read0();  // g / delta2 images have left shared memory
+      for (int b = 0; b < NSLOT; ++b) {
+        const int sg = b / NKB2, kb = b % NKB2;
+        slot_fill(b, b * SEG_BLK, A.w1t + (size_t)kb * W1T_BLK + (size_t)sg * SEG_BLK, SEG_BLK);
+      }
+    }
+
+    // ================= EPI-C: d(y1) = dG * act'(y1), LN1 adjoint -> delta1 image =================
+    {
+      const int c0 = cs * 64;
+      const uint32_t t_dg = t_lane + (cs < 2 ? TM_DGLO + c0 : TM_DGHI + (c0 - 128));
+      float v[32], u[32], tmp[32];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
+        tmem_ld32(t_dg + ch * 32, u);
+        const int cb = c0 + ch * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float xh = (v[i] + s_b1[cb + i] - mean1) * rstd1;
+          const float y = xh * s_g1[cb + i] + s_be1[cb + i];
+          const float d = u[i] * tc_act_bwd(P.act_hidden, y);
+          u[i] = d;
+          v[i] = xh;
+          const float gd = s_g1[cb + i] * d;
+          s1 += gd;
+          s2 = fmaf(gd, xh, s2);
+        }
+        tmem_st32(t_dg + ch * 32, u);  // park d(y1) where dG was
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tmp[i] = u[i] * v[i];
+        acc_dg1[ch] += warp_colsum32(tmp, lane);
+        acc_dbe1[ch] += warp_colsum32(u, lane);
+      }
+      __syncthreads();  // s_red free (EPI-B readers done)
+      s_red[row * 8 + cs * 2] = s1;
+      s_red[row * 8 + cs * 2 + 1] = s2;
+      __syncthreads();
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { t1 += s_red[row * 8 + 2 * i]; t2 += s_red[row * 8 + 2 * i + 1]; }
+      t1 *= (1.0f / H);
+      t2 *= (1.0f / H);
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
+        tmem_ld32(t_dg + ch * 32, u);
+        const int cb = c0 + ch * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float xh = (v[i] + s_b1[cb + i] - mean1) * rstd1;
+          u[i] = rstd1 * (s_g1[cb + i] * u[i] - t1 - xh * t2);
+        }
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int c = cb + g8 * 8;
+          *reinterpret_cast<uint4*>(sm + A2_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
+              make_uint4(pack_bf16(u[g8 * 8], u[g8 * 8 + 1]), pack_bf16(u[g8 * 8 + 2], u[g8 * 8 + 3]),
+                         pack_bf16(u[g8 * 8 + 4], u[g8 * 8 + 5]), pack_bf16(u[g8 * 8 + 6], u[g8 * 8 + 7]));
+        }
+        acc_db1[ch] += warp_colsum32(u, lane);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
+    // ================= GEMM4: dA0 = delta1 W1, one N = 128 accumulator per input segment =================
+    if (tid == 0) {
+      bulk_s2g(A.d1_img + (size_t)tile * A2_BYTES, sm_u + A2_OFF, A2_BYTES);
+      bulk_commit();
+      tc_fence_after();
+      constexpr int NB = 3 * NKB2;  // 12 pieces, segment-major
+      for (int b = 0; b < NB; ++b) {
+        const int slot = b % NSLOT, sg = b / NKB2, kb = b % NKB2;
+        slot_wait_full(slot);
+        umma_kblock(tmem + TM_DA0 + sg * L, sm_u + A2_OFF + kb * A_BLK_BYTES, sm_u + slot * SEG_BLK, idesc_l, kb == 0);
+        slot_commit(slot);
+        if (b >= 1 && b - 1 + NSLOT < NB) {  // refill the slot consumed one step ago
+          const int b2 = b - 1 + NSLOT, sl2 = b2 % NSLOT, sg2 = b2 / NKB2, kb2 = b2 % NKB2;
+          slot_fill(sl2, sl2 * SEG_BLK, A.w1t + (size_t)kb2 * W1T_BLK + (size_t)sg2 * SEG_BLK, SEG_BLK);
+        }
+      }
+      umma_commit(BAR(ACC));
+      bulk_wait_read0();  // delta1 image has left shared memory before EPI-D reuses the region
+    }
+    mbar_wait(BAR(ACC), acc_par);
+    acc_par ^= 1;
+    tc_fence_after();
+    __syncthreads();  // orders thread 0's bulk_wait_read0 before the staging writes below
+
+    // ================= EPI-D: rows of d(x[src]), d(x[dst]), d(e) through a swizzled fp32 staging tile =================
+#pragma unroll 1
+    for (int sg = 0; sg < 3; ++sg) {
+      {
+        float v[32];
+        tmem_ld32(t_lane + TM_DA0 + sg * L + cs * 32, v);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const int c4 = cs * 8 + g4;
+          *reinterpret_cast<float4*>(sm + A2_OFF + (size_t)row * (L * 4) + ((c4 ^ (row & 7)) << 4)) =
+              make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
+        }
+      }
+      __syncthreads();
+      float* outp = sg == 0 ? A.d_xs : (sg == 1 ? A.d_xd : A.d_e);
+#pragma unroll 2
+      for (int idx = lane; idx < 8 * 32; idx += 32) {  // 8 rows per warp, 32 float4 per row
+        const int r = warp * 8 + (idx >> 5), c4 = idx & 31;
+        const int64_t j = (int64_t)tile * TILE_M + r;
+        if (j < A.n_edges) {
+          float4 y = *reinterpret_cast<const float4*>(sm + A2_OFF + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
+          const size_t g = (size_t)s_eid[r] * L + c4 * 4;
+          if (sg == 2) {  // skip connection: d(e) += gout (fp32, re-read)
+            float4 go = __ldg(reinterpret_cast<const float4*>(A.g_e + g));
+            if (A.g_agg) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L + c4 * 4));
+              go.x += a.x; go.y += a.y; go.z += a.z; go.w += a.w;
+            }
+            y.x += go.x; y.y += go.y; y.z += go.z; y.w += go.w;
+          }
+          *reinterpret_cast<float4*>(outp + g) = y;
+        }
+      }
+      __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---- ordered hand-off of the column sums: [cta][q][PAR_FLOATS], lane c owns its columns ----
+  {
+    float* o = A.colpart + ((size_t)blockIdx.x * 4 + q) * PAR_FLOATS;
+    // layout mirrors s_par: db1 | dgamma1 | dbeta1 | db2 | dgamma2 | dbeta2
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int c = cs * 64 + ch * 32 + lane;
+      o[c] = acc_db1[ch];
+      o[H + c] = acc_dg1[ch];
+      o[2 * H + c] = acc_dbe1[ch];
+    }
+    const int c = cs * 32 + lane;
+    o[3 * H + c] = acc_db2;
+    o[3 * H + L + c] = acc_dg2;
+    o[3 * H + 2 * L + c] = acc_dbe2;
+  }
+  if (tid == 0) bulk_wait0();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// dvec1[3, H] = (db1, dgamma1, dbeta1), dvec2[3, L]: ordered sum over [grid * 4] partial vectors
+__global__ void k_colpart_reduce(const float* __restrict__ part, int n_part, float* __restrict__ dvec1, float* __restrict__ dvec2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= PAR_FLOATS) return;
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) s += part[(size_t)p * PAR_FLOATS + i];
+  if (i < 3 * H) dvec1[i] = s; else dvec2[i - 3 * H] = s;
+}
+
+struct Layout {
+  size_t a0, g, d1, d2, colpart, wgrad, total;
+  int grid, tiles;
+  size_t wgrad_bytes;
+};
+
+Layout make_layout(int64_t n_edges) {
+  Layout Y{};
+  Y.tiles = (int)((n_edges + TILE_M - 1) / TILE_M);
+  Y.grid = std::max(1, std::min(Y.tiles, num_sms()));
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = align_up(off, 1024); off = o + b; return o; };
+  Y.a0 = take((size_t)Y.tiles * NKB1 * A_BLK_BYTES);
+  Y.g = take((size_t)Y.tiles * NKB2 * A_BLK_BYTES);
+  Y.d1 = take((size_t)Y.tiles * NKB2 * A_BLK_BYTES);
+  Y.d2 = take((size_t)Y.tiles * NKBL * A_BLK_BYTES);
+  Y.colpart = take((size_t)Y.grid * 4 * PAR_FLOATS * 4);
+  // wgrad partials: 3 roles of [256 x 128] + 1 role of [128 x 256]
+  int splits = hgnn::tc::wgrad_splits(4, Y.tiles);
+  Y.wgrad_bytes = (size_t)4 * align_up((size_t)splits * 256 * 128 * 4, 256) + 256;
+  Y.wgrad = take(Y.wgrad_bytes);
+  Y.total = align_up(off, 1024);
+  return Y;
+}
+
+}  // namespace
+
+extern "C" size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges) {
+  return make_layout(n_edges > 0 ? n_edges : 1).total + 1024;
+}
+
+extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed,
+                                     const float* x, const float* e, const int32_t* src, const int32_t* dst, int64_t n_edges,
+                                     const float* grad_eout, const float* grad_agg, float* d_e, float* d_xsrc_rows,
+                                     float* d_xdst_rows, float* dW1, float* dW2, float* dvec1, float* dvec2, void* ws,
+                                     size_t ws_bytes, void* stream) {
+  HGNN_REQUIRE(p != nullptr, "tc_edge_backward: params is NULL");
+  HGNN_REQUIRE(p->latent == 128 && p->hidden == 256, "tc_edge_backward: only latent 128 / hidden 256 is built (got %d / %d)",
+               p->latent, p->hidden);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_edges <= 0) {
+    if (dW1) HGNN_CUDA_TRY(cudaMemsetAsync(dW1, 0, (size_t)H * K1 * 4, st));
+    if (dW2) HGNN_CUDA_TRY(cudaMemsetAsync(dW2, 0, (size_t)L * H * 4, st));
+    if (dvec1) HGNN_CUDA_TRY(cudaMemsetAsync(dvec1, 0, (size_t)3 * H * 4, st));
+    if (dvec2) HGNN_CUDA_TRY(cudaMemsetAsync(dvec2, 0, (size_t)3 * L * 4, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(w1t_packed && w2t_packed && x && e && src && dst && grad_eout && d_e && d_xsrc_rows && d_xdst_rows && dW1 && dW2 &&
+               dvec1 && dvec2 && ws, "tc_edge_backward: NULL pointer");
+  HGNN_REQUIRE(n_edges < INT32_MAX, "tc_edge_backward: too many edges");
+  Layout Y = make_layout(n_edges);
+  uintptr_t base = align_up((uintptr_t)ws, 1024);
+  if (ws_bytes < (base - (uintptr_t)ws) + Y.total) return fail(HGNN_ERR_WORKSPACE, "tc_edge_backward: workspace too small");
+  uint8_t* w = (uint8_t*)base;
+  BwdArgs A{};
+  A.P = *p;
+  A.w1t = (const uint8_t*)w1t_packed;
+  A.w2t = (const uint8_t*)w2t_packed;
+  A.x = x; A.e = e; A.src = src; A.dst = dst;
+  A.g_e = grad_eout; A.g_agg = grad_agg;
+  A.d_e = d_e; A.d_xs = d_xsrc_rows; A.d_xd = d_xdst_rows;
+  A.a0_img = w + Y.a0; A.g_img = w + Y.g; A.d1_img = w + Y.d1; A.d2_img = w + Y.d2;
+  A.colpart = (float*)(w + Y.colpart);
+  A.n_edges = n_edges;
+  size_t smem = SMEM_BYTES + 1024;
+  HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_edge_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tc_edge_bwd<<<Y.grid, NT, smem, st>>>(A);
+  int rc = check_launch("tc_edge_backward");
+  if (rc) return rc;
+  k_colpart_reduce<<<(PAR_FLOATS + 255) / 256, 256, 0, st>>>(A.colpart, Y.grid * 4, dvec1, dvec2);
+  // weight gradients: dW1[:, seg] = delta1^T A0[:, seg] (3 problems), dW2 = delta2^T g
+  hgnn::tc::WgradProblem pr[4];
+  for (int s = 0; s < 3; ++s)
+    pr[s] = hgnn::tc::WgradProblem{A.d1_img, H, 0, H, A.a0_img, K1, s * L, L, dW1, K1, 0, s * L, 0};
+  pr[3] = hgnn::tc::WgradProblem{A.d2_img, L, 0, L, A.g_img, H, 0, H, dW2, H, 0, 0, 0};
+  return hgnn::tc::launch_wgrad(pr, 4, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, st);
+}

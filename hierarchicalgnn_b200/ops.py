@@ -392,6 +392,13 @@ class _FusedMLP(torch.autograd.Function):
         d, rows, layers = _build_desc(meta, segs, params)
         dev = segs[0].device
         gout = _f32(gout)
+        if rows and tc_backward_available(meta, layers):
+            d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, gout)
+            need = ctx.needs_input_grad[2:]
+            gx_s = segment_reduce_raw(d_xs, meta.seg_plans[0]) if need[0] else None
+            gx_d = segment_reduce_raw(d_xd, meta.seg_plans[1]) if need[1] else None
+            return (None, None, gx_s, gx_d, d_e if need[2] else None,
+                    dW1, dv1[0], dv1[1], dv1[2], dW2, dv2[0], dv2[1], dv2[2])
         L = _lib.lib()
         need = ctx.needs_input_grad[2:]
         dseg_rows: List[Optional[Tensor]] = []
@@ -459,6 +466,19 @@ def tc_pack_weight(W: Tensor) -> Tensor:
     return out
 
 
+def tc_pack_weight_t(W: Tensor) -> Tensor:
+    """UMMA image of W^T ([in, out] rows), the B operand of the data-gradient GEMMs. in-features > 256
+    (W1^T: 3L rows) exceed one MMA's N and are consumed in 128-row pieces, so pack in row chunks."""
+    Wt = W.detach().t().contiguous()
+    if Wt.shape[0] <= 256:
+        return tc_pack_weight(Wt)
+    # image layout is per K-block [rows x 128 B]; build it from <=256-row packs and interleave per K-block
+    rows, cols = Wt.shape
+    nkb = cols // 64
+    parts = [tc_pack_weight(Wt[r0:r0 + 128].contiguous()).reshape(nkb, 128 * 128) for r0 in range(0, rows, 128)]
+    return torch.cat(parts, dim=1).reshape(-1).contiguous()
+
+
 def tc_debug_gemm(A: Tensor, W: Tensor) -> Tensor:
     A = _f32(A)
     Wp = tc_pack_weight(W)
@@ -480,11 +500,53 @@ def tc_debug_wgrad(A: Tensor, B: Tensor) -> Tensor:
     return out
 
 
+def _tc_params(meta: MlpMeta, layers, w1p, w2p):
+    (W1, b1, g1, be1), (W2, b2, g2, be2) = layers
+    p = _lib.TcEdgeParams()
+    p.latent, p.hidden = W2.shape[0], W1.shape[0]
+    p.act_hidden, p.act_out = meta.acts[0], meta.acts[1]
+    p.ln_eps = meta.eps
+    p.w1_packed, p.w2_packed = w1p.data_ptr(), w2p.data_ptr()
+    p.b1, p.gamma1, p.beta1 = b1.data_ptr(), g1.data_ptr(), be1.data_ptr()
+    p.b2, p.gamma2, p.beta2 = b2.data_ptr(), g2.data_ptr(), be2.data_ptr()
+    return p
+
+
+def tc_backward_available(meta: MlpMeta, layers) -> bool:
+    return meta.tc_pack is not None and layers[1][0].shape[0] == 128 and layers[0][0].shape[0] == 256
+
+
+def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, grad_agg: Optional[Tensor] = None):
+    """Backward of the tensor-core edge step. Returns (d_xsrc_rows, d_xdst_rows, d_e, dW1, dW2, dvec1, dvec2)."""
+    x, e = segs[0], segs[2]
+    plan_s, plan_d = meta.seg_plans[0], meta.seg_plans[1]
+    w1p, w2p, w1tp, w2tp = meta.tc_pack()
+    p = _tc_params(meta, layers, w1p, w2p)
+    E, Lw = e.shape
+    dev = e.device
+    d_e = torch.empty_like(e)
+    d_xs = torch.empty((E, Lw), dtype=torch.float32, device=dev)
+    d_xd = torch.empty((E, Lw), dtype=torch.float32, device=dev)
+    dW1, dW2 = torch.empty_like(layers[0][0]), torch.empty_like(layers[1][0])
+    dv1 = torch.empty((3, layers[0][0].shape[0]), dtype=torch.float32, device=dev)
+    dv2 = torch.empty((3, layers[1][0].shape[0]), dtype=torch.float32, device=dev)
+    L_ = _lib.lib()
+    ws = _workspace(L_.hgnn_tc_edge_backward_workspace_bytes(E), dev)
+    with _timed("tc_edge_backward"):
+        check(L_.hgnn_tc_edge_backward(C.byref(p), _ptr(w1tp), _ptr(w2tp), _ptr(x), _ptr(e), _ptr(plan_s.keys32),
+                                       _ptr(plan_d.keys32), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_xs), _ptr(d_xd),
+                                       _ptr(dW1), _ptr(dW2), _ptr(dv1), _ptr(dv2), _ptr(ws), ws.numel(), _stream()),
+              "tc_edge_backward")
+    _count(1 + 1 + 1 + 4)
+    TC_CALLS["count"] += 1
+    return d_xs, d_xd, d_e, dW1, dW2, dv1, dv2
+
+
 def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor):
     """e' = MLP([x[src] | x[dst] | e]) + e on tcgen05 tensor cores (segments: x|by_src, x|by_dst, e)."""
     x, e = segs[0], segs[2]
     plan_s, plan_d = meta.seg_plans[0], meta.seg_plans[1]
-    w1p, w2p = meta.tc_pack()
+    w1p, w2p = meta.tc_pack()[:2]
     (W1, b1, g1, be1), (W2, b2, g2, be2) = layers
     p = _lib.TcEdgeParams()
     p.latent, p.hidden = W2.shape[0], W1.shape[0]

@@ -86,9 +86,10 @@ class FusedMLP(nn.Sequential):
             cached = getattr(self, "_tc_cache", None)
             if cached is None or cached[0] != key:
                 # bf16 shadow copies, rebuilt lazily when the fp32 parameters change; never registered
-                cached = (key, ops.tc_pack_weight(w1), ops.tc_pack_weight(w2))
+                cached = (key, ops.tc_pack_weight(w1), ops.tc_pack_weight(w2),
+                          ops.tc_pack_weight_t(w1), ops.tc_pack_weight_t(w2))
                 object.__setattr__(self, "_tc_cache", cached)
-            return cached[1], cached[2]
+            return cached[1:]
         return pack
 
     def forward(self, x):

@@ -228,6 +228,18 @@ int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const flo
                          const int32_t* dst, const int32_t* perm, int64_t n_edges, int64_t n_nodes, float* e_out,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* Backward of the tensor-core edge step (latent 128): in-kernel recompute (no saved activations),
+ * data gradients as per-edge rows (d_e final; d_xsrc_rows / d_xdst_rows are reduced by the caller
+ * with hgnn_segment_reduce over the by-source / by-destination plans), weight gradients by the
+ * tcgen05 split-K kernel, bias/LayerNorm gradients dvec{1,2} = [3, width] (d bias, d gamma, d beta).
+ * grad_agg (optional, [n_nodes, L]) is the cotangent of agg = scatter_add(e_out, dst): the kernel uses
+ * grad_eout[i] + grad_agg[dst_i]. w1t/w2t_packed are hgnn_tc_pack_weights images of W1^T / W2^T. */
+size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges);
+int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const float* x,
+                          const float* e, const int32_t* src, const int32_t* dst, int64_t n_edges, const float* grad_eout,
+                          const float* grad_agg, float* d_e, float* d_xsrc_rows, float* d_xdst_rows, float* dW1, float* dW2,
+                          float* dvec1, float* dvec2, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
