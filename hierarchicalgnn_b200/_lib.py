@@ -87,7 +87,7 @@ SIGNATURES = {
     "hgnn_connected_components": (C.c_int, [vp, i64, i64, vp, i64, vp, vp, sz, vp]),
     "hgnn_gmm1d_workspace_bytes": (sz, []),
     "hgnn_gmm1d_fit": (C.c_int, [vp, i64, i32, f32, vp, vp, sz, vp]),
-    "hgnn_tc_supported": (C.c_int, [i64, i64, i64, C.c_int]),
+    "hgnn_tc_supported": (C.c_int, [i64, i64, i64, C.c_int, C.c_int, C.c_int]),
     "hgnn_tc_packed_weight_bytes": (sz, [i64, i64]),
     "hgnn_tc_pack_weights": (C.c_int, [vp, i64, i64, vp, vp]),
     "hgnn_tc_debug_gemm": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),

@@ -126,26 +126,6 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// derivative of the activation w.r.t. its input, fast-math variants matching tc_act
-__device__ __forceinline__ float tc_act_bwd(int act, float y) {
-  switch (act) {
-    case HGNN_ACT_GELU: {
-      float ex = __expf(-0.5f * y * y);
-      float ax = fabsf(y) * 0.70710678118654752f;
-      float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-      float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-      float erf_abs = 1.0f - poly * ex;
-      float cdf = 0.5f * (1.0f + copysignf(erf_abs, y));
-      return fmaf(y * 0.3989422804014327f, ex, cdf);
-    }
-    case HGNN_ACT_TANH: { float t = fast_tanh(y); return 1.0f - t * t; }
-    case HGNN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
-    case HGNN_ACT_SILU: { float s = __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f))); return s * (1.0f + y * (1.0f - s)); }
-    case HGNN_ACT_SIGMOID: { float s = __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f))); return s * (1.0f - s); }
-    default: return 1.f;
-  }
-}
-
 // mean / rstd of a row from 4 equal partial (mean, M2) pairs (Chan et al.), n values each
 __device__ __forceinline__ void combine4(const float* red, int r, int n, float eps, float& mean, float& rstd) {
   float m[4], q[4];
@@ -158,9 +138,10 @@ __device__ __forceinline__ void combine4(const float* red, int r, int n, float e
   rstd = rsqrtf(m2 / (4.0f * n) + eps);
 }
 
+template <int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* const sm = smem_raw;
   float* s_par = reinterpret_cast<float*>(sm + PAR_OFF);
   float *s_b1 = s_par, *s_g1 = s_par + H, *s_be1 = s_par + 2 * H, *s_b2 = s_par + 3 * H, *s_g2 = s_par + 3 * H + L,
         *s_be2 = s_par + 3 * H + 2 * L;
@@ -170,6 +151,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   float* s_red = reinterpret_cast<float*>(sm + RED_OFF);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + BAR_OFF + NBAR * 8);
   const uint32_t sm_u = smem_u32(sm), bar0 = sm_u + BAR_OFF;
+  if ((sm_u & 1023u) != 0) __trap();
   enum { W_FULL = 0, ST_FREE = 2, B_FULL = 4, B_FREE = 10, ACC = 16 };
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -324,7 +306,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int c = cb + g8 * 8 + i;
-            o[i] = tc_act(P.act_hidden, (v[g8 * 8 + i] + s_b1[c] - mean1) * rstd1 * s_g1[c] + s_be1[c]);
+            o[i] = tc_act<ACT_H>((v[g8 * 8 + i] + s_b1[c] - mean1) * rstd1 * s_g1[c] + s_be1[c]);
           }
           const int c = cb + g8 * 8;
           *reinterpret_cast<uint4*>(sm + A2_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
@@ -387,7 +369,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
           const int k = g8 * 8 + i;
           const float xh = (v[k] - mean2) * rstd2;
           const float y = xh * s_g2[c + i] + s_be2[c + i];
-          const float d = go * tc_act_bwd(P.act_out, y);
+          const float d = go * tc_act_bwd<ACT_O>(y);
           dy[k] = d;
           v[k] = xh;
           const float gd = s_g2[c + i] * d;
@@ -470,7 +452,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
         for (int i = 0; i < 32; ++i) {
           const float xh = (v[i] + s_b1[cb + i] - mean1) * rstd1;
           const float y = xh * s_g1[cb + i] + s_be1[cb + i];
-          const float d = u[i] * tc_act_bwd(P.act_hidden, y);
+          const float d = u[i] * tc_act_bwd<ACT_H>(y);
           u[i] = d;
           v[i] = xh;
           const float gd = s_g1[cb + i] * d;
@@ -674,9 +656,11 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   A.a0_img = w + Y.a0; A.g_img = w + Y.g; A.d1_img = w + Y.d1; A.d2_img = w + Y.d2;
   A.colpart = (float*)(w + Y.colpart);
   A.n_edges = n_edges;
-  size_t smem = SMEM_BYTES + 1024;
-  HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_edge_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tc_edge_bwd<<<Y.grid, NT, smem, st>>>(A);
+  HGNN_REQUIRE(p->act_hidden == HGNN_ACT_GELU && p->act_out == HGNN_ACT_TANH, "tc_edge_backward: only GELU / Tanh is built");
+  size_t smem = SMEM_BYTES;
+  auto kern = k_tc_edge_bwd<HGNN_ACT_GELU, HGNN_ACT_TANH>;
+  HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<Y.grid, NT, smem, st>>>(A);
   int rc = check_launch("tc_edge_backward");
   if (rc) return rc;
   k_colpart_reduce<<<(PAR_FLOATS + 255) / 256, 256, 0, st>>>(A.colpart, Y.grid * 4, dvec1, dvec2);

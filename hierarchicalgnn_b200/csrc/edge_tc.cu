@@ -85,14 +85,14 @@ __device__ __forceinline__ LnStat combine_halves(const float* red, int r, int n_
   return s;
 }
 
-template <int L>
+template <int L, int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,
               const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out) {
   using C = Cfg<L>;
   constexpr int H = C::H;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* region = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // declared alignment keeps the shared address space visible (LDS/STS)
+  uint8_t* const region = smem_raw;
   float* s_par = reinterpret_cast<float*>(region + C::REGION);
   float *s_b1 = s_par, *s_g1 = s_par + H, *s_be1 = s_par + 2 * H, *s_b2 = s_par + 3 * H, *s_g2 = s_par + 3 * H + L,
         *s_be2 = s_par + 3 * H + 2 * L;
@@ -105,6 +105,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t region_u = smem_u32(region);
+  if ((region_u & 1023u) != 0) __trap();  // swizzled operand images need 1024 B alignment
   const uint32_t bar0 = smem_u32(s_bar);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   enum { W_FULL = 0, ST_FREE = 2, W2_FULL = 4, W2_FREE = 6, ACC_FULL = 8 };
@@ -215,7 +216,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
           for (int i = 0; i < 8; ++i) {
             const int c = cb + g8 * 8 + i;
             float y = (v[g8 * 8 + i] + s_b1[c] - st.mean) * st.rstd * s_g1[c] + s_be1[c];
-            o[i] = tc_act(P.act_hidden, y);
+            o[i] = tc_act<ACT_H>(y);
           }
           const int c = cb + g8 * 8;
           uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
@@ -286,7 +287,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
           for (int i = 0; i < 4; ++i) {
             const int c = cb + g4 * 4 + i;
             float y = (v[g4 * 4 + i] + s_b2[c] - st.mean) * st.rstd * s_g2[c] + s_be2[c];
-            o[i] = tc_act(P.act_out, y);
+            o[i] = tc_act<ACT_O>(y);
           }
           const int c4 = (cb >> 2) + g4;
           *reinterpret_cast<float4*>(region + (size_t)row * (L * 4) + ((c4 ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
@@ -338,8 +339,8 @@ __global__ void k_pack_weights(const float* __restrict__ W, int N, int K, uint8_
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_debug_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Wp, int64_t M, int N, int K, float* __restrict__ Cout) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* region = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* const region = smem_raw;
   const int wblk = N * ROW_BYTES;
   int* s_rid = reinterpret_cast<int*>(region + A_BLK_BYTES + wblk);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rid + TILE_M);
@@ -394,8 +395,9 @@ k_tc_debug_gemm(const float* __restrict__ A, const uint8_t* __restrict__ Wp, int
 
 }  // namespace
 
-extern "C" int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int layer_norm) {
-  return (latent == 64 || latent == 128) && hidden == 2 * latent && n_layers == 2 && layer_norm ? 1 : 0;
+extern "C" int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int layer_norm, int act_hidden, int act_out) {
+  return (latent == 64 || latent == 128) && hidden == 2 * latent && n_layers == 2 && layer_norm &&
+         act_hidden == HGNN_ACT_GELU && act_out == HGNN_ACT_TANH ? 1 : 0;
 }
 
 extern "C" size_t hgnn_tc_packed_weight_bytes(int64_t out_features, int64_t in_features) {
@@ -415,7 +417,7 @@ extern "C" int hgnn_tc_pack_weights(const float* W, int64_t out_features, int64_
 extern "C" int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t M, int64_t N, int64_t K, float* C, void* stream) {
   HGNN_REQUIRE(A && w_packed && C && M > 0, "tc_debug_gemm: bad argument");
   HGNN_REQUIRE(K % KBLK == 0 && N % 32 == 0 && N >= 32 && N <= 256, "tc_debug_gemm: need K %% 64 == 0, N %% 32 == 0, N <= 256");
-  size_t smem = 1024 + A_BLK_BYTES + (size_t)N * ROW_BYTES + TILE_M * 4 + 64;
+  size_t smem = A_BLK_BYTES + (size_t)N * ROW_BYTES + TILE_M * 4 + 64;
   HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_debug_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned grid = (unsigned)((M + TILE_M - 1) / TILE_M);
   k_tc_debug_gemm<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(A, (const uint8_t*)w_packed, M, (int)N, (int)K, C);
@@ -427,11 +429,12 @@ extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t) { return 256; }
 template <int L>
 static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src, const int32_t* dst,
                            const int32_t* perm, int64_t n_edges, float* e_out, cudaStream_t st) {
-  size_t smem = Cfg<L>::SMEM + 1024;
-  HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_edge_fwd<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  size_t smem = Cfg<L>::SMEM;
+  auto kern = k_tc_edge_fwd<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
+  HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
-  k_tc_edge_fwd<L><<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out);
+  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out);
   return check_launch("tc_edge_forward");
 }
 
@@ -445,9 +448,10 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
   HGNN_REQUIRE(p->w1_packed && p->w2_packed && p->b1 && p->gamma1 && p->beta1 && p->b2 && p->gamma2 && p->beta2,
                "tc_edge_forward: NULL parameter pointer");
   HGNN_REQUIRE(n_edges < INT32_MAX, "tc_edge_forward: too many edges");
-  if (!hgnn_tc_supported(p->latent, p->hidden, 2, 1))
-    return fail(HGNN_ERR_UNSUPPORTED, "tc_edge_forward: latent %d / hidden %d not supported (need latent in {64,128}, hidden = 2*latent)",
-                p->latent, p->hidden);
+  if (!hgnn_tc_supported(p->latent, p->hidden, 2, 1, p->act_hidden, p->act_out))
+    return fail(HGNN_ERR_UNSUPPORTED,
+                "tc_edge_forward: latent %d / hidden %d / activations (%d, %d) not built (need latent in {64,128}, hidden = 2*latent, GELU/Tanh)",
+                p->latent, p->hidden, p->act_hidden, p->act_out);
   cudaStream_t st = (cudaStream_t)stream;
   if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, st);
   return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, st);

@@ -157,7 +157,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one rcp + one ex2 + 6 fma
 __device__ __forceinline__ float fast_erf(float x) {
   float ax = fabsf(x);
-  float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
   float r = 1.0f - poly * __expf(-ax * ax);
   return copysignf(r, x);
@@ -166,14 +166,39 @@ __device__ __forceinline__ float fast_tanh(float x) {
   float t = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));  // tanh(15) == 1 in fp32; keeps the divide in range
   return 1.0f - __fdividef(2.0f, t + 1.0f);
 }
-__device__ __forceinline__ float tc_act(int act, float y) {
-  switch (act) {
-    case HGNN_ACT_GELU: return 0.5f * y * (1.0f + fast_erf(y * 0.70710678118654752f));
-    case HGNN_ACT_TANH: return fast_tanh(y);
-    case HGNN_ACT_RELU: return fmaxf(y, 0.f);
-    case HGNN_ACT_SILU: return __fdividef(y, 1.0f + __expf(fminf(-y, 80.0f)));
-    case HGNN_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f)));
-    default: return y;
+// compile-time activation: one code path per kernel instantiation (keeps the SASS inside the I-cache)
+template <int ACT>
+__device__ __forceinline__ float tc_act(float y) {
+  if constexpr (ACT == HGNN_ACT_GELU) return 0.5f * y * (1.0f + fast_erf(y * 0.70710678118654752f));
+  else if constexpr (ACT == HGNN_ACT_TANH) return fast_tanh(y);
+  else if constexpr (ACT == HGNN_ACT_RELU) return fmaxf(y, 0.f);
+  else if constexpr (ACT == HGNN_ACT_SILU) return __fdividef(y, 1.0f + __expf(fminf(-y, 80.0f)));
+  else if constexpr (ACT == HGNN_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f)));
+  else return y;
+}
+// derivative w.r.t. the pre-activation, same fast-math pieces
+template <int ACT>
+__device__ __forceinline__ float tc_act_bwd(float y) {
+  if constexpr (ACT == HGNN_ACT_GELU) {
+    float ex = __expf(-0.5f * y * y);
+    float ax = fabsf(y) * 0.70710678118654752f;
+    float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+    float cdf = 0.5f * (1.0f + copysignf(1.0f - poly * ex, y));
+    return fmaf(y * 0.3989422804014327f, ex, cdf);
+  } else if constexpr (ACT == HGNN_ACT_TANH) {
+    float t = fast_tanh(y);
+    return 1.0f - t * t;
+  } else if constexpr (ACT == HGNN_ACT_RELU) {
+    return y > 0.f ? 1.f : 0.f;
+  } else if constexpr (ACT == HGNN_ACT_SILU) {
+    float sg = __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f)));
+    return sg * (1.0f + y * (1.0f - sg));
+  } else if constexpr (ACT == HGNN_ACT_SIGMOID) {
+    float sg = __fdividef(1.0f, 1.0f + __expf(fminf(-y, 80.0f)));
+    return sg * (1.0f - sg);
+  } else {
+    return 1.f;
   }
 }
 

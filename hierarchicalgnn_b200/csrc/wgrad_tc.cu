@@ -35,8 +35,8 @@ struct WgArgs {
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(WgArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* const base = smem_raw;
   const int r = blockIdx.x / args.splits, split = blockIdx.x % args.splits;
   const WgRole R = args.role[r];
   const int na = 2 * R.m_halves, nb = R.nb;
@@ -190,7 +190,7 @@ int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t
     w += align_up((size_t)a.splits * p.ca * p.cb * 4, 256);
     max_stage = std::max(max_stage, (size_t)(2 * R.m_halves + R.nb) * A_BLK_BYTES);
   }
-  size_t smem = 1024 + 2 * max_stage + 128;
+  size_t smem = 2 * max_stage + 128;
   HGNN_REQUIRE(smem <= 227 * 1024, "wgrad: stage too large for shared memory");
   HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_tc_wgrad<<<n * a.splits, WG_THREADS, smem, st>>>(a);

@@ -452,8 +452,9 @@ class _FusedMLP(torch.autograd.Function):
         return tuple(grads)
 
 
-def tc_supported(latent: int, hidden: int, n_layers: int, layer_norm: bool) -> bool:
-    return bool(_lib.lib().hgnn_tc_supported(int(latent), int(hidden), int(n_layers), int(bool(layer_norm))))
+def tc_supported(latent: int, hidden: int, n_layers: int, layer_norm: bool, act_hidden="GELU", act_out="Tanh") -> bool:
+    return bool(_lib.lib().hgnn_tc_supported(int(latent), int(hidden), int(n_layers), int(bool(layer_norm)),
+                                             ACT_CODES.get(act_hidden, -1), ACT_CODES.get(act_out, -1)))
 
 
 def tc_pack_weight(W: Tensor) -> Tensor:

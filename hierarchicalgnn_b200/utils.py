@@ -77,7 +77,7 @@ class FusedMLP(nn.Sequential):
         if segs[0] is not segs[1] or not segs[0].is_cuda:
             return None
         L, H = layers[1][0].out_features, layers[0][0].out_features
-        if segs[0].shape[1] != L or segs[2].shape[1] != L or not ops.tc_supported(L, H, 2, True):
+        if segs[0].shape[1] != L or segs[2].shape[1] != L or not ops.tc_supported(L, H, 2, True, layers[0][2], layers[1][2]):
             return None
 
         def pack():

@@ -190,7 +190,7 @@ int hgnn_gmm1d_fit(const float* x, int64_t n, int32_t max_iter, float tol, float
 /* ------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM) fused edge step — bf16 operands, fp32
  * accumulate, fp32 storage. See hgnn_tc.h section below; available for
- * latent in {32, 64, 128} with a 2-layer LayerNorm edge network.
+ * latent in {64, 128} with the 2-layer LayerNorm GELU/Tanh edge network of the HGNN configs.
  * ------------------------------------------------------------------------ */
 typedef struct {
   int32_t latent;     /* L */
@@ -208,7 +208,7 @@ typedef struct {
   const float* beta2;
 } hgnn_tc_edge_params;
 
-int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int layer_norm);
+int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int layer_norm, int act_hidden, int act_out);
 size_t hgnn_tc_packed_weight_bytes(int64_t out_features, int64_t in_features);
 /* fp32 nn.Linear weight [out, in] -> bf16, K-major, 128B-swizzled UMMA smem image */
 int hgnn_tc_pack_weights(const float* W, int64_t out_features, int64_t in_features, void* packed, void* stream);
