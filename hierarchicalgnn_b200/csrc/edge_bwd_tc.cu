@@ -276,43 +276,13 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     float mean1, rstd1;
     {
       const int c0 = cs * 64;
-      float v[32];
-      float sum = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sum += v[i] + s_b1[c0 + ch * 32 + i];
-      }
-      const float mloc = sum * (1.0f / 64);
-      float m2 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { float d = v[i] + s_b1[c0 + ch * 32 + i] - mloc; m2 = fmaf(d, d, m2); }
-      }
+      float mloc, m2;
+      ln_partial<2>(t_lane + TM_D1 + c0, s_b1 + c0, mloc, m2);
       s_red[row * 8 + cs * 2] = mloc;
       s_red[row * 8 + cs * 2 + 1] = m2;
       __syncthreads();
       combine4(s_red, row, 64, P.ln_eps, mean1, rstd1);
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_ld32(t_lane + TM_D1 + c0 + ch * 32, v);
-        const int cb = c0 + ch * 32;
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = cb + g8 * 8 + i;
-            o[i] = tc_act<ACT_H>((v[g8 * 8 + i] + s_b1[c] - mean1) * rstd1 * s_g1[c] + s_be1[c]);
-          }
-          const int c = cb + g8 * 8;
-          *reinterpret_cast<uint4*>(sm + A2_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
-              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-        }
-      }
+      ln_act_to_image<ACT_H, 2>(t_lane + TM_D1 + c0, s_b1, s_g1, s_be1, c0, mean1, rstd1, sm + A2_OFF, row);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -344,18 +314,24 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       const int c0 = cs * 32;
       float v[32], dy[32];
       tmem_ld32(t_lane + TM_D2 + c0, v);
-      float sum = 0.f;
+      const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c0);
+      const float4* g4 = reinterpret_cast<const float4*>(s_g2 + c0);
+      const float4* e4 = reinterpret_cast<const float4*>(s_be2 + c0);
+      float sum = 0.f, sq = 0.f;
+      const float pv = v[0] + s_b2[c0];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { v[i] += s_b2[c0 + i]; sum += v[i]; }
-      const float mloc = sum * (1.0f / 32);
-      float m2 = 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = b4[i];
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { float d = v[i] - mloc; m2 = fmaf(d, d, m2); }
-      s_red[row * 8 + cs * 2] = mloc;      // EPI-A readers are past the pre-GEMM2 barrier
-      s_red[row * 8 + cs * 2 + 1] = m2;
+        for (int k = 0; k < 4; ++k) { const float d = v[4 * i + k] - pv; sum += d; sq = fmaf(d, d, sq); }
+      }
+      s_red[row * 8 + cs * 2] = fmaf(sum, 1.0f / 32, pv);      // EPI-A readers are past the pre-GEMM2 barrier
+      s_red[row * 8 + cs * 2 + 1] = fmaxf(sq - sum * sum * (1.0f / 32), 0.f);
       __syncthreads();
       float mean2, rstd2;
       combine4(s_red, row, 32, P.ln_eps, mean2, rstd2);
+      const float nmr = -mean2 * rstd2;
       // upstream gradient (bf16 image) for this quarter row: 4 chunks of 8
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -363,16 +339,18 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
         const int c = c0 + g8 * 8;
         const uint4 pk = *reinterpret_cast<const uint4*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3));
         const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+        const float4 ga = g4[2 * g8], gb = g4[2 * g8 + 1], ea = e4[2 * g8], eb = e4[2 * g8 + 1];
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float ee[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float go = __uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
           const int k = g8 * 8 + i;
-          const float xh = (v[k] - mean2) * rstd2;
-          const float y = xh * s_g2[c + i] + s_be2[c + i];
-          const float d = go * tc_act_bwd<ACT_O>(y);
+          const float xh = fmaf(v[k], rstd2, nmr);
+          const float d = go * tc_act_bwd<ACT_O>(fmaf(xh, gg[i], ee[i]));
+          const float gd = gg[i] * d;
           dy[k] = d;
           v[k] = xh;
-          const float gd = s_g2[c + i] * d;
           s1 += gd;
           s2 = fmaf(gd, xh, s2);
         }
@@ -396,7 +374,13 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       acc_dbe2 += warp_colsum32(tmp, lane);
       // delta2 = rstd (gamma dy - mean(gamma dy) - xhat mean(gamma dy xhat))
 #pragma unroll
-      for (int i = 0; i < 32; ++i) dy[i] = rstd2 * (s_g2[c0 + i] * dy[i] - t1 - v[i] * t2);
+      for (int i = 0; i < 8; ++i) {
+        const float4 g = g4[i];
+        dy[4 * i] = rstd2 * (g.x * dy[4 * i] - t1 - v[4 * i] * t2);
+        dy[4 * i + 1] = rstd2 * (g.y * dy[4 * i + 1] - t1 - v[4 * i + 1] * t2);
+        dy[4 * i + 2] = rstd2 * (g.z * dy[4 * i + 2] - t1 - v[4 * i + 2] * t2);
+        dy[4 * i + 3] = rstd2 * (g.w * dy[4 * i + 3] - t1 - v[4 * i + 3] * t2);
+      }
 #pragma unroll
       for (int g8 = 0; g8 < 4; ++g8) {
         const int c = c0 + g8 * 8;
@@ -441,6 +425,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     {
       const int c0 = cs * 64;
       const uint32_t t_dg = t_lane + (cs < 2 ? TM_DGLO + c0 : TM_DGHI + (c0 - 128));
+      const float nmr1 = -mean1 * rstd1;
       float v[32], u[32], tmp[32];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -449,15 +434,22 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
         tmem_ld32(t_dg + ch * 32, u);
         const int cb = c0 + ch * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float xh = (v[i] + s_b1[cb + i] - mean1) * rstd1;
-          const float y = xh * s_g1[cb + i] + s_be1[cb + i];
-          const float d = u[i] * tc_act_bwd<ACT_H>(y);
-          u[i] = d;
-          v[i] = xh;
-          const float gd = s_g1[cb + i] * d;
-          s1 += gd;
-          s2 = fmaf(gd, xh, s2);
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 b = *reinterpret_cast<const float4*>(s_b1 + cb + 4 * i4);
+          const float4 g = *reinterpret_cast<const float4*>(s_g1 + cb + 4 * i4);
+          const float4 be = *reinterpret_cast<const float4*>(s_be1 + cb + 4 * i4);
+          const float bb[4] = {b.x, b.y, b.z, b.w}, gg[4] = {g.x, g.y, g.z, g.w}, ee[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * i4 + k;
+            const float xh = fmaf(v[i] + bb[k], rstd1, nmr1);
+            const float d = u[i] * tc_act_bwd<ACT_H>(fmaf(xh, gg[k], ee[k]));
+            const float gd = gg[k] * d;
+            u[i] = d;
+            v[i] = xh;
+            s1 += gd;
+            s2 = fmaf(gd, xh, s2);
+          }
         }
         tmem_st32(t_dg + ch * 32, u);  // park d(y1) where dG was
 #pragma unroll
@@ -480,9 +472,16 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
         tmem_ld32(t_dg + ch * 32, u);
         const int cb = c0 + ch * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float xh = (v[i] + s_b1[cb + i] - mean1) * rstd1;
-          u[i] = rstd1 * (s_g1[cb + i] * u[i] - t1 - xh * t2);
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 b = *reinterpret_cast<const float4*>(s_b1 + cb + 4 * i4);
+          const float4 g = *reinterpret_cast<const float4*>(s_g1 + cb + 4 * i4);
+          const float bb[4] = {b.x, b.y, b.z, b.w}, gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * i4 + k;
+            const float xh = fmaf(v[i] + bb[k], rstd1, nmr1);
+            u[i] = rstd1 * (gg[k] * u[i] - t1 - xh * t2);
+          }
         }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {

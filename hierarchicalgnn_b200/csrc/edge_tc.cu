@@ -78,7 +78,7 @@ __device__ __forceinline__ LnStat combine_halves(const float* red, int r, int n_
   float m0 = red[r * 4 + 0], q0 = red[r * 4 + 1], m1 = red[r * 4 + 2], q1 = red[r * 4 + 3];
   float mean = 0.5f * (m0 + m1);
   float d = m1 - m0;
-  float m2 = q0 + q1 + d * d * (0.5f * n_half);
+  float m2 = q0 + q1 + d * d * (0.5f * n_half);  // Chan: M2 = M2a + M2b + delta^2 * na*nb/(na+nb)
   LnStat s;
   s.mean = mean;
   s.rstd = rsqrtf(m2 / (2.0f * n_half) + eps);
@@ -185,44 +185,13 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     {
       constexpr int NC = H / 2;  // columns per thread
       const int c0 = hsel * NC;
-      float v[32];
-      float sum = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        tmem_ld32(t_lane + c0 + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sum += v[i] + s_b1[c0 + ch * 32 + i];
-      }
-      const float mloc = sum * (1.0f / NC);
-      float m2 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        tmem_ld32(t_lane + c0 + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { float d = v[i] + s_b1[c0 + ch * 32 + i] - mloc; m2 = fmaf(d, d, m2); }
-      }
+      float mloc, m2;
+      ln_partial<NC / 32>(t_lane + c0, s_b1 + c0, mloc, m2);
       s_red[row * 4 + hsel * 2] = mloc;
       s_red[row * 4 + hsel * 2 + 1] = m2;
       __syncthreads();
       const LnStat st = combine_halves(s_red, row, NC, P.ln_eps);
-#pragma unroll 1
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        tmem_ld32(t_lane + c0 + ch * 32, v);
-        const int cb = c0 + ch * 32;
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = cb + g8 * 8 + i;
-            float y = (v[g8 * 8 + i] + s_b1[c] - st.mean) * st.rstd * s_g1[c] + s_be1[c];
-            o[i] = tc_act<ACT_H>(y);
-          }
-          const int c = cb + g8 * 8;
-          uint4 pk = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-          *reinterpret_cast<uint4*>(region + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) = pk;
-        }
-      }
+      ln_act_to_image<ACT_H, NC / 32>(t_lane + c0, s_b1, s_g1, s_be1, c0, st.mean, st.rstd, region, row);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -255,42 +224,30 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     {
       constexpr int NC = L / 2;
       const int c0 = hsel * NC;
-      float v[32];
-      float sum = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        tmem_ld32(t_lane + c0 + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sum += v[i] + s_b2[c0 + ch * 32 + i];
-      }
-      const float mloc = sum * (1.0f / NC);
-      float m2 = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < NC / 32; ++ch) {
-        tmem_ld32(t_lane + c0 + ch * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { float d = v[i] + s_b2[c0 + ch * 32 + i] - mloc; m2 = fmaf(d, d, m2); }
-      }
-      __syncthreads();  // s_red reuse: every thread has consumed the EPI1 statistics
-      s_red[row * 4 + hsel * 2] = mloc;
+      float mloc, m2;
+      ln_partial<NC / 32>(t_lane + c0, s_b2 + c0, mloc, m2);
+      s_red[row * 4 + hsel * 2] = mloc;   // EPI1's readers passed the pre-GEMM2 barrier long ago
       s_red[row * 4 + hsel * 2 + 1] = m2;
       __syncthreads();
       const LnStat st = combine_halves(s_red, row, NC, P.ln_eps);
+      const float nmr = -st.mean * st.rstd;
+      float v[32];
 #pragma unroll 1
       for (int ch = 0; ch < NC / 32; ++ch) {
         tmem_ld32(t_lane + c0 + ch * 32, v);
         const int cb = c0 + ch * 32;
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
-          float o[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = cb + g4 * 4 + i;
-            float y = (v[g4 * 4 + i] + s_b2[c] - st.mean) * st.rstd * s_g2[c] + s_be2[c];
-            o[i] = tc_act<ACT_O>(y);
-          }
-          const int c4 = (cb >> 2) + g4;
-          *reinterpret_cast<float4*>(region + (size_t)row * (L * 4) + ((c4 ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+          const int c = cb + g4 * 4;
+          const float4 b = *reinterpret_cast<const float4*>(s_b2 + c);
+          const float4 g = *reinterpret_cast<const float4*>(s_g2 + c);
+          const float4 be = *reinterpret_cast<const float4*>(s_be2 + c);
+          float4 o;
+          o.x = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 0] + b.x, st.rstd, nmr), g.x, be.x));
+          o.y = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 1] + b.y, st.rstd, nmr), g.y, be.y));
+          o.z = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 2] + b.z, st.rstd, nmr), g.z, be.z));
+          o.w = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 3] + b.w, st.rstd, nmr), g.w, be.w));
+          *reinterpret_cast<float4*>(region + (size_t)row * (L * 4) + (((c >> 2) ^ (row & 7)) << 4)) = o;
         }
       }
     }

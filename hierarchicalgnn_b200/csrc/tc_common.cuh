@@ -153,23 +153,43 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// ---- fast, accurate-enough transcendental pieces for the epilogues ----
-// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one rcp + one ex2 + 6 fma
+// ---- transcendental pieces for the epilogues (bf16 path: error budget << bf16 rounding of the outputs) ----
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }  // rcp(+inf) = +0
+
+// GELU(y) = y * Phi(y) with Phi(y) ~= sigmoid(y * (c0 + c1 y^2 + c2 y^4)), y^2 clamped to 64.
+// Coefficients fitted against the exact erf form: max |error| of GELU = 2.8e-5 over the reals
+// (profiles/fit_gelu.py). 7 FP32 ops + ex2 + rcp; the erf/exp form cost ~3x as many issue slots.
+constexpr float kG0 = 1.5949518066125585f, kG1 = 0.07406933810902123f, kG2 = -0.0007124377042967553f;
+constexpr float kLog2e = 1.4426950408889634f;
+struct GeluParts { float sig, y2; };
+__device__ __forceinline__ GeluParts gelu_sigmoid(float y) {
+  GeluParts g;
+  g.y2 = fminf(y * y, 64.0f);
+  const float zn = y * fmaf(fmaf(-kG2 * kLog2e, g.y2, -kG1 * kLog2e), g.y2, -kG0 * kLog2e);  // -z * log2(e)
+  g.sig = rcp_approx(1.0f + ex2_approx(zn));
+  return g;
+}
+__device__ __forceinline__ float fast_gelu(float y) { return y * gelu_sigmoid(y).sig; }
+// exact derivative of fast_gelu: sig * (1 + y (1 - sig) z'(y)),  z' = c0 + 3 c1 y^2 + 5 c2 y^4
+__device__ __forceinline__ float fast_gelu_bwd(float y) {
+  const GeluParts g = gelu_sigmoid(y);
+  const float zp = fmaf(fmaf(5.0f * kG2, g.y2, 3.0f * kG1), g.y2, kG0);
+  return g.sig * fmaf(y * (1.0f - g.sig), zp, 1.0f);
+}
+// tanh(y) = 1 - 2 / (1 + e^{2y}); saturates correctly through ex2 -> inf / 0
+__device__ __forceinline__ float fast_tanh(float y) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(y * (2.0f * kLog2e))), 1.0f); }
+// A&S 7.1.26 erf (|err| <= 1.5e-7) kept for activations that need it
 __device__ __forceinline__ float fast_erf(float x) {
   float ax = fabsf(x);
-  float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-  float r = 1.0f - poly * __expf(-ax * ax);
-  return copysignf(r, x);
-}
-__device__ __forceinline__ float fast_tanh(float x) {
-  float t = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));  // tanh(15) == 1 in fp32; keeps the divide in range
-  return 1.0f - __fdividef(2.0f, t + 1.0f);
+  return copysignf(1.0f - poly * __expf(-ax * ax), x);
 }
 // compile-time activation: one code path per kernel instantiation (keeps the SASS inside the I-cache)
 template <int ACT>
 __device__ __forceinline__ float tc_act(float y) {
-  if constexpr (ACT == HGNN_ACT_GELU) return 0.5f * y * (1.0f + fast_erf(y * 0.70710678118654752f));
+  if constexpr (ACT == HGNN_ACT_GELU) return fast_gelu(y);
   else if constexpr (ACT == HGNN_ACT_TANH) return fast_tanh(y);
   else if constexpr (ACT == HGNN_ACT_RELU) return fmaxf(y, 0.f);
   else if constexpr (ACT == HGNN_ACT_SILU) return __fdividef(y, 1.0f + __expf(fminf(-y, 80.0f)));
@@ -180,12 +200,7 @@ __device__ __forceinline__ float tc_act(float y) {
 template <int ACT>
 __device__ __forceinline__ float tc_act_bwd(float y) {
   if constexpr (ACT == HGNN_ACT_GELU) {
-    float ex = __expf(-0.5f * y * y);
-    float ax = fabsf(y) * 0.70710678118654752f;
-    float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-    float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-    float cdf = 0.5f * (1.0f + copysignf(1.0f - poly * ex, y));
-    return fmaf(y * 0.3989422804014327f, ex, cdf);
+    return fast_gelu_bwd(y);
   } else if constexpr (ACT == HGNN_ACT_TANH) {
     float t = fast_tanh(y);
     return 1.0f - t * t;
@@ -199,6 +214,63 @@ __device__ __forceinline__ float tc_act_bwd(float y) {
     return sg * (1.0f - sg);
   } else {
     return 1.f;
+  }
+}
+
+// ---- LayerNorm epilogue pieces over a TMEM row (lane = row, this thread owns NCH*32 consecutive columns) ----
+// partial statistics of (accumulator + bias): single pass around a pivot taken from the row itself
+// (no catastrophic cancellation: |pivot - mean| is of the order of the row's spread)
+template <int NCH>
+__device__ __forceinline__ void ln_partial(uint32_t taddr, const float* __restrict__ sbias, float& mean_loc, float& m2_loc) {
+  float v[32];
+  float pv = 0.f, sum = 0.f, sq = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    tmem_ld32(taddr + ch * 32, v);
+    const float4* b4 = reinterpret_cast<const float4*>(sbias + ch * 32);
+    if (ch == 0) pv = v[0] + sbias[0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = b4[i];
+      const float d0 = v[4 * i] + b.x - pv, d1 = v[4 * i + 1] + b.y - pv, d2 = v[4 * i + 2] + b.z - pv, d3 = v[4 * i + 3] + b.w - pv;
+      sum += (d0 + d1) + (d2 + d3);
+      sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+    }
+  }
+  constexpr float inv = 1.0f / (NCH * 32);
+  mean_loc = fmaf(sum, inv, pv);
+  m2_loc = fmaxf(sq - sum * sum * inv, 0.f);
+}
+
+// act(LayerNorm(accumulator + bias)) -> bf16, written as the K-major swizzled A-operand image of the next GEMM.
+// sb / sg / sbe are the full per-column parameter arrays; c0 = first column owned by this thread.
+template <int ACT, int NCH>
+__device__ __forceinline__ void ln_act_to_image(uint32_t taddr, const float* __restrict__ sb, const float* __restrict__ sg,
+                                                const float* __restrict__ sbe, int c0, float mean, float rstd,
+                                                uint8_t* __restrict__ img, int row) {
+  float v[32];
+  const float nmr = -mean * rstd;
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    tmem_ld32(taddr + ch * 32, v);
+    const int cb = c0 + ch * 32;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const int c = cb + g8 * 8;
+      float o[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + c + 4 * h);
+        const float4 g = *reinterpret_cast<const float4*>(sg + c + 4 * h);
+        const float4 be = *reinterpret_cast<const float4*>(sbe + c + 4 * h);
+        o[4 * h + 0] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 0] + b.x, rstd, nmr), g.x, be.x));
+        o[4 * h + 1] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 1] + b.y, rstd, nmr), g.y, be.y));
+        o[4 * h + 2] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 2] + b.z, rstd, nmr), g.z, be.z));
+        o[4 * h + 3] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 3] + b.w, rstd, nmr), g.w, be.w));
+      }
+      *reinterpret_cast<uint4*>(img + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
+          make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
   }
 }
 
