@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--cpu-edges", type=int, default=40_000, help="bounded CPU-baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="dp", choices=["dp", "partition"],
+                    help="dp: every rank owns a batch of edges (weak scaling, default); partition: ONE full-pile-up "
+                         "event split by destination node across ranks (strong scaling, BASELINE config 5)")
     return ap.parse_args()
 
 
@@ -139,7 +142,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
@@ -230,10 +233,10 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None  # started before warm-up so short timed regions are covered
     for _ in range(max(args.warmup, 3)):
         step(nodes, edges, gp)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.LAUNCHES["count"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -340,10 +343,96 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_partition(args):
+    """BASELINE config 5: one full-pile-up shaped event (N = 0.04 E), one InteractionGNNCell fwd+bwd, destination-
+    partitioned over the ranks: all-gather of node rows forward, reduce-scatter of node gradients backward,
+    all-reduce of weight gradients. Strong scaling: value = E_total / time."""
+    import torch.distributed as dist
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.gnn_utils import InteractionGNNCell
+    from hierarchicalgnn_b200.parallel import (allreduce_gradients, cuda_cell_callables, pad_rows, partition_by_destination,
+                                               partitioned_interaction_cell)
+    from hierarchicalgnn_b200.synth import synth_edge_problem
+    from hierarchicalgnn_b200.training_utils import kaiming_init
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = args.latent
+    E = args.edges if args.edges != 1_000_000 else 3_000_000
+    torch.manual_seed(0)
+    cell = InteractionGNNCell(hparams(L))
+    kaiming_init(cell)
+    cell.to(dev)
+    nodes_h, edges_h, graph_h = synth_edge_problem(E, L, seed=2000, nodes_per_edge=0.04)
+    N = nodes_h.shape[0]
+    part = partition_by_destination(graph_h, N, world, rank)
+    g = torch.Generator().manual_seed(11)
+    cot_n, cot_e = torch.randn(N, L, generator=g), torch.randn(E, L, generator=g)
+    own = slice(part.node_lo, part.node_hi)
+    cot_n_d, cot_e_d = cot_n[own].to(dev), cot_e[part.edge_ids].to(dev)
+    nodes = pad_rows(nodes_h, world * part.block).to(dev).requires_grad_(True)
+    e_loc = edges_h[part.edge_ids].to(dev).requires_grad_(True)
+    part.graph, part.dst_local, part.edge_ids = part.graph.to(dev), part.dst_local.to(dev), part.edge_ids.to(dev)
+    node_fn, edge_fn, seg = cuda_cell_callables(cell)
+    params = list(cell.parameters())
+
+    def step():
+        n2, e2 = partitioned_interaction_cell(part, nodes, e_loc, node_fn, edge_fn, seg)
+        grads = torch.autograd.grad([n2[own], e2], [nodes, e_loc] + params, [cot_n_d, cot_e_d])
+        if world > 1:
+            flat = torch.cat([x.reshape(-1) for x in grads[2:]])
+            dist.all_reduce(flat)
+            dist.all_reduce(grads[0])  # replicated input nodes: gradient partials summed over ranks
+        return n2, e2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.LAUNCHES["count"]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": E / (ms / args.steps * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": ops.compute_dtype(), "data": "synthetic",
+            "config": {"workload": f"InteractionGNNCell fwd+bwd on one full-pile-up shaped event, L={L} E={E} N={N}, "
+                                   f"destination-partitioned (BASELINE config 5)", "latent": L, "edges_total": E,
+                       "nodes_total": N, "parallelism": f"dst-partition x{world}", "l2_policy": "inputs larger than L2",
+                       "edges_rank0": int(part.edge_ids.numel())},
+            "clocks": clocks, "e2e": None, "gpu_launches": ops.LAUNCHES["count"] - l0, "roofline": None, "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "partition":
+        if args.precision != "auto":
+            os.environ["HGNN_PRECISION"] = args.precision
+        run_partition(args)
     else:
         if args.precision != "auto":
             os.environ["HGNN_PRECISION"] = args.precision

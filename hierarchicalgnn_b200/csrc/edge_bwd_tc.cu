@@ -224,44 +224,47 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     }
 
     // ================= GEMM1 (recompute): D1 = A0 W1^T =================
-    for (int kb = 0; kb < NKB1; ++kb, ++it1) {
-      const int s = it1 & 1;
-      const uint32_t ph = (it1 >> 1) & 1;
-      mbar_wait(BAR(ST_FREE + s), ph ^ 1);
-      if (tid == 0) {
-        mbar_expect_tx(BAR(W_FULL + s), W1_BLK);
-        bulk_g2s(sm_u + s * STAGE + A_BLK_BYTES, w1p + (size_t)kb * W1_BLK, W1_BLK, BAR(W_FULL + s));
-      }
-      {
+    {
+      const int sub = tid & 15, rr = tid >> 4;  // 16 threads per 256 B row piece, 32 rows per pass
+      auto load_blk = [&](int kb, float4 (&v)[4]) {
         const int seg = (kb * KBLK) / L, col0 = (kb * KBLK) % L;
         const float* base = seg == 2 ? A.e : A.x;
         const int* rid = seg == 0 ? s_src : (seg == 1 ? s_dst : s_eid);
-        uint8_t* blk = sm + s * STAGE;
-        uint8_t* gimg = A.a0_img + ((size_t)tile * NKB1 + kb) * A_BLK_BYTES;
-        const int sub = tid & 15, rr = tid >> 4;  // 16 threads per 256 B row piece, 32 rows per pass
-        float4 v[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int r = p * 32 + rr;
-          v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rid[r] * L + col0) + sub);
+        for (int p = 0; p < 4; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rid[p * 32 + rr] * L + col0) + sub);
+      };
+      float4 pre[4];
+      load_blk(0, pre);
+      for (int kb = 0; kb < NKB1; ++kb, ++it1) {
+        const int s = it1 & 1;
+        const uint32_t ph = (it1 >> 1) & 1;
+        mbar_wait(BAR(ST_FREE + s), ph ^ 1);
+        if (tid == 0) {
+          mbar_expect_tx(BAR(W_FULL + s), W1_BLK);
+          bulk_g2s(sm_u + s * STAGE + A_BLK_BYTES, w1p + (size_t)kb * W1_BLK, W1_BLK, BAR(W_FULL + s));
         }
+        {
+          uint8_t* blk = sm + s * STAGE;
+          uint8_t* gimg = A.a0_img + ((size_t)tile * NKB1 + kb) * A_BLK_BYTES;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int r = p * 32 + rr;
-          const uint2 pk = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
-          const uint32_t off = sw128_off(r, sub >> 1) + (sub & 1) * 8;
-          *reinterpret_cast<uint2*>(blk + off) = pk;
-          *reinterpret_cast<uint2*>(gimg + off) = pk;  // same image to HBM: B operand of the dW1 GEMM
+          for (int p = 0; p < 4; ++p) {
+            const int r = p * 32 + rr;
+            const uint2 pk = make_uint2(pack_bf16(pre[p].x, pre[p].y), pack_bf16(pre[p].z, pre[p].w));
+            const uint32_t off = sw128_off(r, sub >> 1) + (sub & 1) * 8;
+            *reinterpret_cast<uint2*>(blk + off) = pk;
+            *reinterpret_cast<uint2*>(gimg + off) = pk;  // same image to HBM: B operand of the dW1 GEMM
+          }
         }
-      }
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(BAR(W_FULL + s), ph);
-        tc_fence_after();
-        umma_kblock(tmem + TM_D1, sm_u + s * STAGE, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
-        umma_commit(BAR(ST_FREE + s));
-        if (kb == NKB1 - 1) umma_commit(BAR(ACC));
+        if (kb + 1 < NKB1) load_blk(kb + 1, pre);  // next block's rows in flight under the barrier + MMA issue
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          mbar_wait(BAR(W_FULL + s), ph);
+          tc_fence_after();
+          umma_kblock(tmem + TM_D1, sm_u + s * STAGE, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
+          umma_commit(BAR(ST_FREE + s));
+          if (kb == NKB1 - 1) umma_commit(BAR(ACC));
+        }
       }
     }
     mbar_wait(BAR(ACC), acc_par);

@@ -53,22 +53,26 @@ struct Cfg {
   static_assert(L == 64 || L == 128, "tensor-core edge step is instantiated for latent 64 and 128");
 };
 
-// gather one K-block (64 fp32 columns starting at `col0` of rows rowid[r] of `base`) into a swizzled bf16 A block
+// gather one K-block (64 fp32 columns starting at `col0` of rows rowid[r] of `base`): 16 threads per 256 B row piece,
+// 16 rows per pass. Split in two so the loads of block k+1 are in flight while block k is converted, stored and multiplied.
+__device__ __forceinline__ void gather_load(float4 (&v)[8], const float* __restrict__ base, int ld, const int* __restrict__ rowid, int col0) {
+  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rowid[p * 16 + rr] * ld + col0) + sub);
+}
+__device__ __forceinline__ void gather_store(uint8_t* __restrict__ blk, const float4 (&v)[8]) {
+  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int r = p * 16 + rr;
+    *reinterpret_cast<uint2*>(blk + sw128_off(r, sub >> 1) + (sub & 1) * 8) = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
+  }
+}
 __device__ __forceinline__ void gather_a_block(uint8_t* __restrict__ blk, const float* __restrict__ base, int ld,
                                                const int* __restrict__ rowid, int col0) {
-  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;  // 16 threads per row piece, 16 rows per pass
   float4 v[8];
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    int r = p * 16 + rr;
-    v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rowid[r] * ld + col0) + sub);
-  }
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    int r = p * 16 + rr;
-    uint2 pk = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
-    *reinterpret_cast<uint2*>(blk + sw128_off(r, sub >> 1) + (sub & 1) * 8) = pk;
-  }
+  gather_load(v, base, ld, rowid, col0);
+  gather_store(blk, v);
 }
 
 struct LnStat { float mean, rstd; };
@@ -144,6 +148,10 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     __syncthreads();
 
     // ---- GEMM1: D1[128, H] = [x[src] | x[dst] | e] . W1^T ----
+    auto seg_base = [&](int kb) { return (kb * KBLK) / L == 2 ? e : x; };
+    auto seg_rows = [&](int kb) { const int sg = (kb * KBLK) / L; return sg == 0 ? s_src : (sg == 1 ? s_dst : s_eid); };
+    float4 pre[8];
+    gather_load(pre, seg_base(0), L, seg_rows(0), 0);
     for (int kb = 0; kb < C::NKB1; ++kb, ++it1) {
       const int s = it1 % C::NSTAGE;
       const uint32_t ph = (it1 / C::NSTAGE) & 1;
@@ -153,10 +161,8 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
         mbar_expect_tx(BAR(W_FULL + s), C::W1_BLK);
         bulk_g2s(region_u + s * C::STAGE + A_BLK_BYTES, w1p + (size_t)kb * C::W1_BLK, C::W1_BLK, BAR(W_FULL + s));
       }
-      const int seg = (kb * KBLK) / L, col0 = (kb * KBLK) % L;
-      const float* base = seg == 2 ? e : x;
-      const int* rid = seg == 0 ? s_src : (seg == 1 ? s_dst : s_eid);
-      gather_a_block(stage, base, L, rid, col0);
+      gather_store(stage, pre);
+      if (kb + 1 < C::NKB1) gather_load(pre, seg_base(kb + 1), L, seg_rows(kb + 1), ((kb + 1) * KBLK) % L);  // next block in flight
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
@@ -257,7 +263,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     {
       constexpr int CPR = L / 4;                       // float4 chunks per row
       constexpr int ROWS_PER_WARP = TILE_M / (TC_THREADS / 32);
-#pragma unroll 4
+#pragma unroll 8
       for (int idx = lane; idx < ROWS_PER_WARP * CPR; idx += 32) {
         const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
         const int64_t j = (int64_t)tile * TILE_M + r;

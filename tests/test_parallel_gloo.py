@@ -1,0 +1,143 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: gradient all-reduce for the data-parallel mode and
+the destination-partitioned interaction cell (all-gather forward / reduce-scatter backward) against the
+single-process oracle."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import hgnn_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(fn, world=2):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert r[1] is None, r[1]
+    return dict(res)
+
+
+def _entry(fn, rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.set_num_threads(1)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        out = fn(rank, world)
+        dist.destroy_process_group()
+        q.put((rank, None, out) if False else (rank, None))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
+def _dp_case(rank, world):
+    from hierarchicalgnn_b200.parallel import allreduce_gradients, clip_grad_norm_
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    dead = torch.nn.Linear(3, 3)  # never used: grad stays None on every rank
+    data = torch.randn(world, 7, 6, generator=torch.Generator().manual_seed(1))
+    net(data[rank]).square().mean().backward()
+    params = list(net.parameters()) + list(dead.parameters())
+    allreduce_gradients(params, bucket_bytes=64)  # tiny buckets: exercises the flush path
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    ref.load_state_dict(net.state_dict())
+    sum(ref(data[r]).square().mean() for r in range(world)).div(world).backward()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        torch.testing.assert_close(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+    for p in dead.parameters():
+        assert float(p.grad.abs().max()) == 0.0
+    total = clip_grad_norm_(list(net.parameters()), 1e-3)
+    after = torch.sqrt(sum(p.grad.square().sum() for p in net.parameters()))
+    assert float(after) <= 1e-3 * 1.001 and float(total) > 0
+
+
+def _partition_case(rank, world):
+    from hierarchicalgnn_b200.parallel import (allreduce_gradients, pad_rows, partition_by_destination,
+                                               partitioned_interaction_cell)
+    from hierarchicalgnn_b200.synth import synth_edge_problem
+    from oracle.reference_harness import kaiming_init
+    from hierarchicalgnn_b200.utils import make_mlp
+    L, E = 16, 600
+    hp = dict(latent=L, hidden=2 * L, nb_edge_layer=2, nb_node_layer=3, layernorm=True, hidden_activation="GELU")
+    torch.manual_seed(0)
+    nets = torch.nn.ModuleDict({"edge_network": make_mlp(3 * L, 2 * L, L, 2, layer_norm=True, output_activation="Tanh"),
+                                "node_network": make_mlp(2 * L, 2 * L, L, 3, layer_norm=True)})
+    kaiming_init(nets)
+    nodes, edges, graph = synth_edge_problem(E, L, seed=3)
+    N = nodes.shape[0] - 1                     # odd node count: the last block is padded
+    nodes = nodes[:N]
+    graph = graph.clamp(max=N - 1)
+    cot_n, cot_e = torch.randn(N, L, generator=torch.Generator().manual_seed(5)), torch.randn(E, L, generator=torch.Generator().manual_seed(6))
+
+    # single-process oracle, two stacked cells with shared weights
+    sd_ref = O.leaf_state({"c." + k: v for k, v in nets.state_dict().items()})
+    n_ref, e_ref = nodes.clone().requires_grad_(True), edges.clone().requires_grad_(True)
+    n2, e2 = n_ref, e_ref
+    for _ in range(2):
+        n2, e2 = O.interaction_cell(sd_ref, "c", hp, n2, e2, graph)
+    ((n2 * cot_n).sum() + (e2 * cot_e).sum()).backward()
+
+    # partitioned run
+    part = partition_by_destination(graph, N, world, rank)
+    assert int(part.dst_local.min()) >= 0 and int(part.dst_local.max()) < part.block
+    sd = O.leaf_state({"c." + k: v for k, v in nets.state_dict().items()})
+    node_fn = lambda x, agg: O.mlp_apply(sd, "c.node_network", torch.cat([x, agg], -1), 3, "GELU", "GELU", True) + x
+    edge_fn = lambda x, e, g: O.edge_step(sd, "c.edge_network", hp, x, e, g)
+    n_full = pad_rows(nodes, world * part.block).clone().requires_grad_(True)
+    e_loc = edges[part.edge_ids].clone().requires_grad_(True)
+    pn, pe = n_full, e_loc
+    for _ in range(2):
+        pn, pe = partitioned_interaction_cell(part, pn, pe, node_fn, edge_fn, O.scatter_add)
+    torch.testing.assert_close(pn[:N], n2.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pe, e2.detach()[part.edge_ids], rtol=1e-5, atol=1e-6)
+    # each rank back-propagates its share of the objective: owned nodes + owned edges
+    own = slice(part.node_lo, part.node_hi)
+    loss = (pn[own] * cot_n[own]).sum() + (pe * cot_e[part.edge_ids]).sum()
+    loss.backward()
+    torch.testing.assert_close(e_loc.grad, e_ref.grad[part.edge_ids], rtol=1e-4, atol=1e-5)
+    # the input-node gradient is a sum over ranks (x is replicated): reduce and compare
+    g = n_full.grad.clone()
+    dist.all_reduce(g)
+    torch.testing.assert_close(g[:N], n_ref.grad, rtol=1e-4, atol=1e-5)
+    params = [v for v in sd.values() if v.requires_grad]
+    allreduce_gradients(params, average=False)
+    for k, v in sd.items():
+        if v.requires_grad:
+            torch.testing.assert_close(v.grad, sd_ref[k].grad, rtol=1e-4, atol=1e-5, msg=lambda m: f"{k}: {m}")
+
+
+def test_data_parallel_gradient_allreduce_world2():
+    _run(_dp_case)
+
+
+def test_destination_partitioned_cells_match_single_process_world2():
+    _run(_partition_case)
+
+
+def test_partition_covers_every_edge_once():
+    from hierarchicalgnn_b200.parallel import partition_by_destination
+    g = torch.Generator().manual_seed(0)
+    graph = torch.randint(0, 101, (2, 5000), generator=g)
+    for world in (1, 2, 4, 8):
+        parts = [partition_by_destination(graph, 101, world, r) for r in range(world)]
+        ids = torch.cat([p.edge_ids for p in parts])
+        assert torch.equal(ids.sort().values, torch.arange(5000))
+        assert all(p.block == parts[0].block for p in parts) and sum(p.n_owned for p in parts) == 101
+        for p in parts:
+            assert torch.equal(p.graph, graph[:, p.edge_ids])
