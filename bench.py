@@ -256,13 +256,13 @@ def run_gpu(args):
 
     # ---- per-kernel timing of the step (CUDA events around each C-ABI call on the launch stream) ----
     roof = None
+    ops.PROFILE = {}
+    for _ in range(3):  # every rank runs these steps (they contain the gradient all-reduce); rank 0 reports
+        step(nodes, edges, gp)
+    torch.cuda.synchronize()
+    prof = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in ops.PROFILE.items()}
+    ops.PROFILE = None
     if rank == 0:
-        ops.PROFILE = {}
-        for _ in range(3):
-            step(nodes, edges, gp)
-        torch.cuda.synchronize()
-        prof = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in ops.PROFILE.items()}
-        ops.PROFILE = None
         pk = peaks()
         fwd_b, bwd_b = alg_bytes_per_edge(L, N / E)
         # dominant kernel of the step by measured time
