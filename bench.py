@@ -219,8 +219,9 @@ def run_gpu(args):
 
     def step(nodes, edges, gp):
         """edge step fwd (+ the scatter_add feeding the next node update) and its backward."""
-        e2 = cell.edge_update(nodes, edges, gp)
-        agg = ops.scatter_add(e2, gp.graph[1], dim_size=N, plan=gp.by_dst)
+        e2, agg = net.edge_step(nodes, edges, gp.by_src, gp.by_dst)  # (e', agg) from one autograd node on the TC path
+        if agg is None:
+            agg = ops.scatter_add(e2, gp.graph[1], dim_size=N, plan=gp.by_dst)
         grads = torch.autograd.grad([e2, agg], [nodes, edges] + params, [cot_e, cot_a])
         if world > 1:
             nonlocal flat
@@ -268,7 +269,7 @@ def run_gpu(args):
         # dominant kernel of the step by measured time
         top = max(prof, key=prof.get) if prof else None
         flops_edge = {"mlp_forward": 16 * L * L, "mlp_backward_data": 32 * L * L, "mlp_backward_weights": 16 * L * L,
-                      "tc_edge_forward": 16 * L * L}
+                      "tc_edge_forward": 16 * L * L, "tc_edge_backward": 48 * L * L}
         if top in flops_edge:
             ach = flops_edge[top] * E / (prof[top] * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]

@@ -205,18 +205,19 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     // upstream gradient tile -> bf16 image (zero for padding rows): 32 threads per row, 16 rows per pass
     {
       const int sub = tid & 31, rr = tid >> 5;
-#pragma unroll 2
+      float4 gv[TILE_M / 16], ga[TILE_M / 16];
+#pragma unroll
+      for (int p = 0; p < TILE_M / 16; ++p) {  // issue every load of the tile before touching any
+        const int r = p * 16 + rr;
+        const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
+        gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + sub)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
       for (int p = 0; p < TILE_M / 16; ++p) {
         const int r = p * 16 + rr;
-        const int64_t j = (int64_t)tile * TILE_M + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < A.n_edges) {
-          v = __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + sub);
-          if (A.g_agg) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + sub);
-            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-          }
-        }
+        const float4 v = make_float4(gv[p].x + ga[p].x, gv[p].y + ga[p].y, gv[p].z + ga[p].z, gv[p].w + ga[p].w);
         const int c = sub * 4;
         *reinterpret_cast<uint2*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(r, (c % KBLK) >> 3) + ((c >> 2) & 1) * 8) =
             make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
@@ -233,9 +234,12 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rid[p * 32 + rr] * L + col0) + sub);
       };
-      float4 pre[4];
-      load_blk(0, pre);
+      float4 preA[4], preB[4];  // two K-blocks of loads in flight
+      load_blk(0, preA);
+      load_blk(1, preB);
+#pragma unroll
       for (int kb = 0; kb < NKB1; ++kb, ++it1) {
+        float4 (&pre)[4] = (kb & 1) ? preB : preA;
         const int s = it1 & 1;
         const uint32_t ph = (it1 >> 1) & 1;
         mbar_wait(BAR(ST_FREE + s), ph ^ 1);
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
             *reinterpret_cast<uint2*>(gimg + off) = pk;  // same image to HBM: B operand of the dW1 GEMM
           }
         }
-        if (kb + 1 < NKB1) load_blk(kb + 1, pre);  // next block's rows in flight under the barrier + MMA issue
+        if (kb + 2 < NKB1) load_blk(kb + 2, pre);  // refill this register set: two blocks stay in flight
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -525,6 +529,18 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     __syncthreads();  // orders thread 0's bulk_wait_read0 before the staging writes below
 
     // ================= EPI-D: rows of d(x[src]), d(x[dst]), d(e) through a swizzled fp32 staging tile =================
+    float4 skipg[8];  // fp32 upstream gradient of this lane's 8 output chunks (skip path of d(e)), loaded early
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = warp * 8 + k;
+      const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
+      float4 go = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live && A.g_agg) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + lane);
+        go.x += a.x; go.y += a.y; go.z += a.z; go.w += a.w;
+      }
+      skipg[k] = go;
+    }
 #pragma unroll 1
     for (int sg = 0; sg < 3; ++sg) {
       {
@@ -539,22 +555,16 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       }
       __syncthreads();
       float* outp = sg == 0 ? A.d_xs : (sg == 1 ? A.d_xd : A.d_e);
-#pragma unroll 2
-      for (int idx = lane; idx < 8 * 32; idx += 32) {  // 8 rows per warp, 32 float4 per row
-        const int r = warp * 8 + (idx >> 5), c4 = idx & 31;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {  // 8 rows per warp, one float4 chunk per lane
+        const int r = warp * 8 + k, c4 = lane;
         const int64_t j = (int64_t)tile * TILE_M + r;
         if (j < A.n_edges) {
           float4 y = *reinterpret_cast<const float4*>(sm + A2_OFF + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
-          const size_t g = (size_t)s_eid[r] * L + c4 * 4;
-          if (sg == 2) {  // skip connection: d(e) += gout (fp32, re-read)
-            float4 go = __ldg(reinterpret_cast<const float4*>(A.g_e + g));
-            if (A.g_agg) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L + c4 * 4));
-              go.x += a.x; go.y += a.y; go.z += a.z; go.w += a.w;
-            }
-            y.x += go.x; y.y += go.y; y.z += go.z; y.w += go.w;
+          if (sg == 2) {  // skip connection: d(e) += gout (fp32)
+            y.x += skipg[k].x; y.y += skipg[k].y; y.z += skipg[k].z; y.w += skipg[k].w;
           }
-          *reinterpret_cast<float4*>(outp + g) = y;
+          *reinterpret_cast<float4*>(outp + (size_t)s_eid[r] * L + c4 * 4) = y;
         }
       }
       __syncthreads();

@@ -11,6 +11,8 @@ state-dict keys as the reference; the arithmetic runs in hand-written CUDA:
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -43,9 +45,27 @@ def _plans(graph, n_src, n_dst):
     return graph if isinstance(graph, GraphPlans) else GraphPlans(graph, n_src, n_dst)
 
 
+# agg = scatter_add(e', dst) produced as a by-product of the edge step that created e' (cell i), consumed by the node
+# update that opens cell i+1 (SURVEY §3.2 "fusion crosses the cell boundary"). Keyed on the identity of e'.
+_AGG_CACHE = {}
+_AGG_CACHE_MAX = 4
+
+
 def _edge_update(network, nodes, edges, gp: GraphPlans):
     # e' = MLP([x[src] | x[dst] | e]) + e      (gnn_utils.py:56-64)
-    return network.fused([nodes, nodes, edges], [gp.by_src, gp.by_dst, None], skip=2)
+    new_edges, agg = network.edge_step(nodes, edges, gp.by_src, gp.by_dst)
+    if agg is not None:
+        while len(_AGG_CACHE) >= _AGG_CACHE_MAX:
+            _AGG_CACHE.pop(next(iter(_AGG_CACHE)))
+        _AGG_CACHE[id(new_edges)] = (weakref.ref(new_edges), gp.by_dst, agg)
+    return new_edges
+
+
+def _incoming_sum(edges, gp: GraphPlans, n_nodes):
+    hit = _AGG_CACHE.pop(id(edges), None)
+    if hit is not None and hit[0]() is edges and hit[1] is gp.by_dst:
+        return hit[2]
+    return ops.scatter_add(edges, gp.graph[1], dim_size=n_nodes, plan=gp.by_dst)
 
 
 class InteractionGNNCell(nn.Module):
@@ -61,7 +81,7 @@ class InteractionGNNCell(nn.Module):
 
     def node_update(self, nodes, edges, graph):
         gp = _plans(graph, nodes.shape[0], nodes.shape[0])
-        messages = ops.scatter_add(edges, gp.graph[1], dim_size=nodes.shape[0], plan=gp.by_dst)
+        messages = _incoming_sum(edges, gp, nodes.shape[0])
         return self.node_network.fused([nodes, messages], skip=0)
 
     def edge_update(self, nodes, edges, graph):
@@ -90,7 +110,7 @@ class HierarchicalGNNCell(nn.Module):
         gp = _plans(graph, nodes.shape[0], nodes.shape[0])
         bp = _plans(bipartite_graph, nodes.shape[0], supernodes.shape[0])
         down = ops.gather_scatter(supernodes, bipartite_edge_weights, bp.by_dst, bp.by_src)
-        messages = ops.scatter_add(edges, gp.graph[1], dim_size=nodes.shape[0], plan=gp.by_dst)
+        messages = _incoming_sum(edges, gp, nodes.shape[0])
         return self.node_network.fused([nodes, messages, down], skip=0)
 
     def edge_update(self, nodes, edges, graph):

@@ -564,6 +564,46 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor):
     TC_CALLS["count"] += 1
 
 
+class _TcEdgeStepAgg(torch.autograd.Function):
+    """(e', agg) = (MLP([x[src] | x[dst] | e]) + e,  scatter_add(e', dst)) as ONE autograd node on the tensor-core
+    path: the backward kernel consumes grad_e' and grad_agg[dst] together (no gather / add kernels in between) —
+    the edge step of cell i and the aggregation that opens cell i+1 (gnn_utils.py:68-69 then :50)."""
+
+    @staticmethod
+    def forward(ctx, meta: MlpMeta, x, e, *params):
+        _need_cuda(x, e, *params)
+        segs = [_f32(x), _f32(x), _f32(e)]
+        segs[1] = segs[0]
+        ps = [_f32(t) for t in params]
+        d, rows, layers = _build_desc(meta, segs, ps)
+        out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=e.device)
+        tc_edge_forward_raw(meta, segs, layers, out)
+        agg = segment_reduce_raw(out, meta.seg_plans[1])
+        ctx.meta = meta
+        ctx.save_for_backward(segs[0], segs[2], *ps)
+        return out, agg
+
+    @staticmethod
+    def backward(ctx, g_out, g_agg):
+        meta = ctx.meta
+        saved = ctx.saved_tensors
+        x, e, ps = saved[0], saved[1], list(saved[2:])
+        segs = [x, x, e]
+        d, rows, layers = _build_desc(meta, segs, ps)
+        g_out = torch.zeros_like(e) if g_out is None else _f32(g_out)
+        g_agg = None if g_agg is None else _f32(g_agg)
+        d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, g_agg)
+        gx = None
+        if ctx.needs_input_grad[1]:
+            gx = segment_reduce_raw(d_xs, meta.seg_plans[0])
+            gx.add_(segment_reduce_raw(d_xd, meta.seg_plans[1]))
+        return (None, gx, d_e if ctx.needs_input_grad[2] else None, dW1, dv1[0], dv1[1], dv1[2], dW2, dv2[0], dv2[1], dv2[2])
+
+
+def tc_edge_step_with_agg(meta: MlpMeta, x: Tensor, e: Tensor, params: Sequence[Tensor]):
+    return _TcEdgeStepAgg.apply(meta, x, e, *params)
+
+
 def fused_mlp(meta: MlpMeta, segs: Sequence[Tensor], params: Sequence[Tensor]) -> Tensor:
     """Row-wise MLP on the concatenation of (optionally gathered) segments, with
     LayerNorm/activation per layer and an optional skip connection — one kernel

@@ -66,6 +66,17 @@ class FusedMLP(nn.Sequential):
         meta = ops.MlpMeta(plans, acts, lns, skip, eps, tc_pack=self._tc_packer(segs, plans, skip, lns))
         return ops.fused_mlp(meta, list(segs), ps)
 
+    def edge_step(self, nodes, edges, plan_src, plan_dst):
+        """e' = MLP([x[src] | x[dst] | e]) + e. Returns (e', agg) where agg = scatter_add(e', dst) comes out of the
+        same autograd node when the tensor-core forward+backward kernels cover this network, else (e', None)."""
+        segs, plans = [nodes, nodes, edges], [plan_src, plan_dst, None]
+        ps, acts, lns, eps = self._params()
+        packer = self._tc_packer(segs, plans, 2, lns)
+        if packer is not None and self._layers()[1][0].out_features == 128:
+            meta = ops.MlpMeta(plans, acts, lns, 2, eps, tc_pack=packer)
+            return ops.tc_edge_step_with_agg(meta, nodes, edges, ps)
+        return self.fused(segs, plans, skip=2), None
+
     def _tc_packer(self, segs, plans, skip, lns):
         """Returns a weight-image provider when this call is an edge step the tcgen05 kernel covers:
         segments (x | by_src, x | by_dst, e), skip = e, two LayerNorm layers, latent in {64, 128}."""
