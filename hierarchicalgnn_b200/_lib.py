@@ -97,7 +97,7 @@ SIGNATURES = {
     "hgnn_tc_edge_backward_workspace_bytes": (sz, [i64]),
     "hgnn_tc_edge_backward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                         vp, sz, vp]),
-    "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, i64, i64, vp, vp, sz, vp]),
+    "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, sz, vp]),
 }
 
 _lib = None

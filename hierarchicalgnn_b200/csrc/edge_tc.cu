@@ -48,7 +48,7 @@ struct Cfg {
   static constexpr int REGION = (R0 > R1 ? R0 : R1) > SOUT_BYTES ? (R0 > R1 ? R0 : R1) : SOUT_BYTES;
   static constexpr int PARAM_FLOATS = 3 * H + 3 * L;
   // region | params | row ids (3 x 128 int) | LN exchange (128 x 2 x 2 float) | 16 barriers | tmem slot
-  static constexpr int SMEM = REGION + PARAM_FLOATS * 4 + 3 * TILE_M * 4 + TILE_M * 4 * 4 + 16 * 8 + 16;
+  static constexpr int SMEM = REGION + PARAM_FLOATS * 4 + 4 * TILE_M * 4 + TILE_M * 4 * 4 + 16 * 8 + 16;
   static constexpr int TMEM_COLS = H;  // power of two >= 32 for L in {64,128}
   static_assert(L == 64 || L == 128, "tensor-core edge step is instantiated for latent 64 and 128");
 };
@@ -92,7 +92,8 @@ __device__ __forceinline__ LnStat combine_halves(const float* red, int r, int n_
 template <int L, int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,
-              const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out) {
+              const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out,
+              const int32_t* __restrict__ rowptr, float* __restrict__ agg) {
   using C = Cfg<L>;
   constexpr int H = C::H;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // declared alignment keeps the shared address space visible (LDS/STS)
@@ -103,7 +104,9 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
   int* s_eid = reinterpret_cast<int*>(s_par + C::PARAM_FLOATS);
   int* s_src = s_eid + TILE_M;
   int* s_dst = s_src + TILE_M;
-  float* s_red = reinterpret_cast<float*>(s_dst + TILE_M);
+  int* s_flag = s_dst + TILE_M;  // per row: 1 = last row of a segment that lies inside this row group (store the sum),
+                                 //          2 = last row of a run that continues elsewhere (drop it; fix-up pass owns it), 0 = inside a run
+  float* s_red = reinterpret_cast<float*>(s_flag + TILE_M);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + TILE_M * 4);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
 
@@ -143,7 +146,21 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
       int eid = perm ? perm[j] : (int)j;
       s_eid[tid] = eid;
       s_src[tid] = src[eid];
-      s_dst[tid] = dst[eid];
+      const int d = dst[eid];
+      s_dst[tid] = d;
+      if (agg) {  // rows arrive destination-sorted (perm = the by-destination plan): classify run ends
+        constexpr int G = TILE_M / (TC_THREADS / L);           // rows per reduction group
+        const int64_t j0 = (int64_t)tile * TILE_M + tid;       // true sorted position (may be >= n_edges: padding)
+        const int64_t gbeg = j0 / G * G, gend = gbeg + G < n_edges ? gbeg + G : n_edges;
+        int flag = 0;
+        if (j0 < n_edges) {
+          const bool last = (j0 + 1 >= gend) || (dst[perm ? perm[j0 + 1] : (int)(j0 + 1)] != d);
+          if (last) flag = (rowptr[d] >= gbeg && rowptr[d + 1] <= gend) ? 1 : 2;
+        } else {
+          flag = 2;
+        }
+        s_flag[tid] = flag;
+      }
     }
     __syncthreads();
 
@@ -271,7 +288,36 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
           const float4 y = *reinterpret_cast<const float4*>(region + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
           const size_t g = (size_t)s_eid[r] * L + c4 * 4;
           const float4 sk = __ldg(reinterpret_cast<const float4*>(e + g));
-          *reinterpret_cast<float4*>(e_out + g) = make_float4(y.x + sk.x, y.y + sk.y, y.z + sk.z, y.w + sk.w);
+          const float4 o = make_float4(y.x + sk.x, y.y + sk.y, y.z + sk.z, y.w + sk.w);
+          *reinterpret_cast<float4*>(e_out + g) = o;
+          if (agg) *reinterpret_cast<float4*>(region + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4)) = o;
+        }
+      }
+    }
+    if (agg) {
+      // ---- fused scatter_add: destination-sorted segmented reduce of the finished tile, ordered, no atomics.
+      // One thread per (row group, column): runs of equal destination are summed in row order; a run that lies
+      // inside the group is stored, runs crossing a group boundary are left to the fix-up pass.
+      __syncthreads();
+      constexpr int G = TILE_M / (TC_THREADS / L);
+      const int grp = tid / L, col = tid % L;
+      // run-end / store masks of this row group, gathered once (warp-uniform control flow below)
+      uint64_t endm = 0, storem = 0;
+#pragma unroll
+      for (int w = 0; w < G / 32; ++w) {
+        const int f = s_flag[grp * G + w * 32 + lane];
+        endm |= (uint64_t)__ballot_sync(0xffffffffu, f != 0) << (32 * w);
+        storem |= (uint64_t)__ballot_sync(0xffffffffu, f == 1) << (32 * w);
+      }
+      const uint8_t* colp = region + (((col >> 2) << 4) | ((col & 3) << 2));
+      float acc = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < G; ++i) {
+        const int r = grp * G + i;
+        acc += *reinterpret_cast<const float*>(colp + (size_t)r * (L * 4) - (((col >> 2) << 4)) + ((((col >> 2) ^ (r & 7)) << 4)));
+        if ((endm >> i) & 1) {
+          if ((storem >> i) & 1) agg[(size_t)s_dst[r] * L + col] = acc;
+          acc = 0.f;
         }
       }
     }
@@ -281,6 +327,26 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// segments the fused reduce did not finish: empty (-> zeros) or spanning a row-group boundary (-> ordered sum of e_out rows)
+template <int L>
+__global__ void __launch_bounds__(256) k_agg_fixup(const float* __restrict__ e_out, const int32_t* __restrict__ perm,
+                                                   const int32_t* __restrict__ rowptr, int64_t n_nodes, float* __restrict__ agg) {
+  constexpr int G = TILE_M / (TC_THREADS / L);
+  constexpr int CH = L / 4;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t s = t / CH;
+  int c = (int)(t % CH);
+  if (s >= n_nodes) return;
+  const int beg = rowptr[s], end = rowptr[s + 1];
+  if (end > beg && beg / G == (end - 1) / G) return;  // finished inside the edge kernel
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = beg; j < end; ++j) {
+    const float4 v = *(reinterpret_cast<const float4*>(e_out + (size_t)(perm ? perm[j] : j) * L) + c);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  reinterpret_cast<float4*>(agg + (size_t)s * L)[c] = acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -391,20 +457,30 @@ extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t) { return 256; }
 
 template <int L>
 static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src, const int32_t* dst,
-                           const int32_t* perm, int64_t n_edges, float* e_out, cudaStream_t st) {
+                           const int32_t* perm, int64_t n_edges, float* e_out, const int32_t* rowptr, int64_t n_nodes, float* agg,
+                           cudaStream_t st) {
   size_t smem = Cfg<L>::SMEM;
   auto kern = k_tc_edge_fwd<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
   HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
-  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out);
+  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg);
+  if (agg) {
+    int64_t threads = n_nodes * (L / 4);
+    k_agg_fixup<L><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(e_out, perm, rowptr, n_nodes, agg);
+  }
   return check_launch("tc_edge_forward");
 }
 
 extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
-                                    const int32_t* dst, const int32_t* perm, int64_t n_edges, int64_t n_nodes, float* e_out,
-                                    void* ws, size_t ws_bytes, void* stream) {
-  (void)ws; (void)ws_bytes; (void)n_nodes;
+                                    const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges,
+                                    int64_t n_nodes, float* e_out, float* agg, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  HGNN_REQUIRE(agg == nullptr || (perm != nullptr && rowptr != nullptr && n_nodes > 0),
+               "tc_edge_forward: the fused aggregate needs the destination-sorted plan (perm, rowptr) and n_nodes");
+  if (n_edges <= 0 && agg != nullptr) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(agg, 0, (size_t)n_nodes * p->latent * 4, (cudaStream_t)stream));
+  }
   HGNN_REQUIRE(p != nullptr, "tc_edge_forward: params is NULL");
   if (n_edges <= 0) return HGNN_OK;
   HGNN_REQUIRE(x && e && src && dst && e_out, "tc_edge_forward: NULL pointer");
@@ -416,6 +492,6 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
                 "tc_edge_forward: latent %d / hidden %d / activations (%d, %d) not built (need latent in {64,128}, hidden = 2*latent, GELU/Tanh)",
                 p->latent, p->hidden, p->act_hidden, p->act_out);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, st);
-  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, st);
+  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, st);
+  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, st);
 }

@@ -543,24 +543,22 @@ def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, grad_agg: Op
     return d_xs, d_xd, d_e, dW1, dW2, dv1, dv2
 
 
-def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor):
-    """e' = MLP([x[src] | x[dst] | e]) + e on tcgen05 tensor cores (segments: x|by_src, x|by_dst, e)."""
+def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[Tensor] = None):
+    """e' = MLP([x[src] | x[dst] | e]) + e on tcgen05 tensor cores (segments: x|by_src, x|by_dst, e); with ``agg``
+    the same launch also leaves scatter_add(e', dst) there (edges visited in destination-sorted order)."""
     x, e = segs[0], segs[2]
     plan_s, plan_d = meta.seg_plans[0], meta.seg_plans[1]
     w1p, w2p = meta.tc_pack()[:2]
-    (W1, b1, g1, be1), (W2, b2, g2, be2) = layers
-    p = _lib.TcEdgeParams()
-    p.latent, p.hidden = W2.shape[0], W1.shape[0]
-    p.act_hidden, p.act_out = meta.acts[0], meta.acts[1]
-    p.ln_eps = meta.eps
-    p.w1_packed, p.w2_packed = w1p.data_ptr(), w2p.data_ptr()
-    p.b1, p.gamma1, p.beta1 = b1.data_ptr(), g1.data_ptr(), be1.data_ptr()
-    p.b2, p.gamma2, p.beta2 = b2.data_ptr(), g2.data_ptr(), be2.data_ptr()
+    p = _tc_params(meta, layers, w1p, w2p)
     n_edges = e.shape[0]
+    perm = rowptr = None
+    if agg is not None:
+        perm, rowptr = plan_d.perm, plan_d.rowptr
     with _timed("tc_edge_forward"):
-        check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), None,
-                                              n_edges, x.shape[0], _ptr(out), None, 0, _stream()), "tc_edge_forward")
-    _count()
+        check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), _ptr(perm),
+                                              _ptr(rowptr), n_edges, x.shape[0], _ptr(out), _ptr(agg), None, 0, _stream()),
+              "tc_edge_forward")
+    _count(1 if agg is None else 2)
     TC_CALLS["count"] += 1
 
 
@@ -577,8 +575,8 @@ class _TcEdgeStepAgg(torch.autograd.Function):
         ps = [_f32(t) for t in params]
         d, rows, layers = _build_desc(meta, segs, ps)
         out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=e.device)
-        tc_edge_forward_raw(meta, segs, layers, out)
-        agg = segment_reduce_raw(out, meta.seg_plans[1])
+        agg = torch.empty((segs[0].shape[0], out.shape[1]), dtype=torch.float32, device=e.device)
+        tc_edge_forward_raw(meta, segs, layers, out, agg)  # one launch: edge MLP + skip + destination-sorted reduce
         ctx.meta = meta
         ctx.save_for_backward(segs[0], segs[2], *ps)
         return out, agg

@@ -220,13 +220,16 @@ int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t M, int64_t 
 size_t hgnn_tc_debug_wgrad_workspace_bytes(int64_t rows, int64_t ca, int64_t cb);
 int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca, int64_t cb, float* out, void* ws,
                         size_t ws_bytes, void* stream);
-/* e_out[i] = MLP([x[src_i] | x[dst_i] | e_i]) + e_i for i in row order `perm`
- * (NULL = identity); if agg != NULL also agg[n] = sum_{dst_i = n} e_out[i],
- * which requires perm/rowptr to be the destination-sorted plan. */
+/* The fused edge step:  e_out[i] = MLP([x[src_i] | x[dst_i] | e_i]) + e_i, edges visited in row order `perm`
+ * (NULL = identity). If agg != NULL the same launch also produces agg[n] = sum_{dst_i = n} e_out[i] — the
+ * scatter_add that opens the next cell (gnn_utils.py:50) — by a destination-sorted, ordered segmented reduce of
+ * each finished tile in shared memory (no atomics); this needs perm/rowptr = the by-destination plan of
+ * hgnn_csr_build. Segments crossing a row-group boundary (hub nodes) and empty segments are completed by a small
+ * second kernel inside the same call. */
 size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges);
 int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
-                         const int32_t* dst, const int32_t* perm, int64_t n_edges, int64_t n_nodes, float* e_out,
-                         void* ws, size_t ws_bytes, void* stream);
+                         const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges, int64_t n_nodes,
+                         float* e_out, float* agg, void* ws, size_t ws_bytes, void* stream);
 
 /* Backward of the tensor-core edge step (latent 128): in-kernel recompute (no saved activations),
  * data gradients as per-edge rows (d_e final; d_xsrc_rows / d_xdst_rows are reduced by the caller

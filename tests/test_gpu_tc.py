@@ -252,3 +252,24 @@ def test_tc_cell_stack_with_cached_aggregate_matches_oracle():
     assert rel(nd.grad, nr.grad) < 3e-2 and rel(ed.grad, er.grad) < 3e-2
     for k, p in cells.named_parameters():
         assert rel(p.grad, sd[k].grad) < 3e-2, k
+
+
+@pytest.mark.parametrize("L,E,N", [(128, 5000, 300), (128, 700, 1000), (128, 64, 5), (128, 2000, 3)])
+def test_tc_fused_scatter_add_matches_ordered_oracle(L, E, N):
+    """The destination-sorted segmented reduce fused into the edge kernel (+ fix-up for hubs / empty nodes):
+    agg must equal scatter_add(e', dst) of the kernel's own e' to fp32 summation noise, and be bit-reproducible."""
+    from hierarchicalgnn_b200 import ops
+    net, x, e, graph = _edge_case(L, E, N, seed=E + N)
+    graph[1, : E // 3] = 1 % N          # a hub: more rows than one row group
+    net.to(DEV)
+    gd = graph.to(DEV)
+    old = ops.set_precision("auto")
+    try:
+        ps, pd = ops.plan_for(gd[0], N), ops.plan_for(gd[1], N)
+        e1, agg1 = net.edge_step(x.to(DEV), e.to(DEV), ps, pd)
+        e2, agg2 = net.edge_step(x.to(DEV), e.to(DEV), ps, pd)
+    finally:
+        ops.set_precision(old)
+    assert agg1 is not None and torch.equal(agg1, agg2) and torch.equal(e1, e2)
+    want = O.scatter_add(e1.detach().cpu().double(), graph[1], N)
+    assert float((agg1.detach().cpu().double() - want).abs().max()) <= 2e-6 * float(want.abs().max()) + 1e-6
