@@ -202,27 +202,30 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       s_dst[tid] = A.dst[j];
     }
     __syncthreads();
-    // upstream gradient tile -> bf16 image (zero for padding rows): 32 threads per row, 16 rows per pass
-    {
-      const int sub = tid & 31, rr = tid >> 5;
-      float4 gv[TILE_M / 16], ga[TILE_M / 16];
+    // The upstream gradient tile (-> bf16 image, zero for padding rows; 32 threads per row, 16 rows per pass) is
+    // staged in four pieces interleaved with GEMM1's K-block iterations, so its load latency hides under them.
+    const int g_sub = tid & 31, g_rr = tid >> 5;
+    float4 gq[4];
+    auto g_load = [&](int part) {  // rows (2*part) * 16 + rr and (2*part + 1) * 16 + rr
 #pragma unroll
-      for (int p = 0; p < TILE_M / 16; ++p) {  // issue every load of the tile before touching any
-        const int r = p * 16 + rr;
+      for (int h = 0; h < 2; ++h) {
+        const int r = (2 * part + h) * 16 + g_rr;
         const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-        gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + sub)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        gq[2 * h] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gq[2 * h + 1] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + g_sub)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    auto g_store = [&](int part) {
 #pragma unroll
-      for (int p = 0; p < TILE_M / 16; ++p) {
-        const int r = p * 16 + rr;
-        const float4 v = make_float4(gv[p].x + ga[p].x, gv[p].y + ga[p].y, gv[p].z + ga[p].z, gv[p].w + ga[p].w);
-        const int c = sub * 4;
+      for (int h = 0; h < 2; ++h) {
+        const int r = (2 * part + h) * 16 + g_rr;
+        const float4 a = gq[2 * h], b = gq[2 * h + 1];
+        const int c = g_sub * 4;
         *reinterpret_cast<uint2*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(r, (c % KBLK) >> 3) + ((c >> 2) & 1) * 8) =
-            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            make_uint2(pack_bf16(a.x + b.x, a.y + b.y), pack_bf16(a.z + b.z, a.w + b.w));
       }
-    }
+    };
 
     // ================= GEMM1 (recompute): D1 = A0 W1^T =================
     {
@@ -259,6 +262,8 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
             *reinterpret_cast<uint2*>(gimg + off) = pk;  // same image to HBM: B operand of the dW1 GEMM
           }
         }
+        if (kb >= 1 && kb <= 4) g_store(kb - 1);   // upstream-gradient piece loaded one iteration ago
+        if (kb <= 3) g_load(kb);
         if (kb + 2 < NKB1) load_blk(kb + 2, pre);  // refill this register set: two blocks stay in flight
         fence_proxy_async();
         __syncthreads();
@@ -271,7 +276,8 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
         }
       }
     }
-    mbar_wait(BAR(ACC), acc_par);
+    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
+    __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
     // ring is idle: bring all of W2 in (4 x 16 KB slots) behind EPI-A
@@ -307,7 +313,8 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       }
       umma_commit(BAR(ACC));
     }
-    mbar_wait(BAR(ACC), acc_par);
+    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
+    __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
     // W2^T (2 x 32 KB) replaces W2 in the ring behind EPI-B
@@ -416,7 +423,8 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       }
       umma_commit(BAR(ACC));
     }
-    mbar_wait(BAR(ACC), acc_par);
+    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
+    __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
     // start streaming W1^T (segment, K-block) pieces into the six 16 KB slots behind EPI-C
@@ -523,7 +531,8 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       umma_commit(BAR(ACC));
       bulk_wait_read0();  // delta1 image has left shared memory before EPI-D reuses the region
     }
-    mbar_wait(BAR(ACC), acc_par);
+    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
+    __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
     __syncthreads();  // orders thread 0's bulk_wait_read0 before the staging writes below

@@ -190,7 +190,8 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
         if (kb == C::NKB1 - 1) umma_commit(BAR(ACC_FULL));
       }
     }
-    mbar_wait(BAR(ACC_FULL), acc_par);
+    if (warp == 0) mbar_wait(BAR(ACC_FULL), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
+    __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
 
@@ -239,7 +240,8 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
       umma_commit(BAR(ACC_FULL));
     }
     it2 += C::NKB2;
-    mbar_wait(BAR(ACC_FULL), acc_par);
+    if (warp == 0) mbar_wait(BAR(ACC_FULL), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
+    __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
 
