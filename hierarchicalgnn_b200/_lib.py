@@ -96,8 +96,10 @@ SIGNATURES = {
     "hgnn_tc_edge_forward_workspace_bytes": (sz, [i64]),
     "hgnn_tc_edge_backward_workspace_bytes": (sz, [i64]),
     "hgnn_tc_edge_backward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                        vp, sz, vp]),
-    "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, sz, vp]),
+                                        vp, sz, vp]),  # (p, w1t, w2t, a0_img, src, dst, perm, n_edges, g_e, g_agg, d_e, d_xs, d_xd, dW1, dW2, dv1, dv2, ws, n, st)
+    "hgnn_tc_debug_set_phase_clock": (None, [vp]),
+    "hgnn_tc_edge_a0_image_bytes": (sz, [i64, i64]),
+    "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz, vp]),
 }
 
 _lib = None

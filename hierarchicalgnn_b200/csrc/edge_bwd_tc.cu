@@ -66,12 +66,14 @@ struct BwdArgs {
   hgnn_tc_edge_params P;
   const uint8_t* w1t;   // W1^T image: [3L rows, H cols]
   const uint8_t* w2t;   // W2^T image: [H rows, L cols]
-  const float* x; const float* e; const int32_t* src; const int32_t* dst;
+  const int32_t* src; const int32_t* dst; const int32_t* perm;  // perm: tile row j -> edge id (NULL = identity)
   const float* g_e; const float* g_agg;   // upstream: d/d e_out [E, L], d/d agg [N, L] (may be NULL)
   float* d_e; float* d_xs; float* d_xd;   // [E, L] each
-  uint8_t* a0_img; uint8_t* g_img; uint8_t* d1_img; uint8_t* d2_img;
+  const uint8_t* a0_img;  // [tiles][6][16 KB] bf16 image of [x[src] | x[dst] | e], written by the forward kernel in the same row order
+  uint8_t* g_img; uint8_t* d1_img; uint8_t* d2_img;
   float* colpart;                          // [grid][4][PAR_FLOATS]
   int64_t n_edges;
+  unsigned long long* phase_clk;  // optional [16] per-phase cycle accumulators (CTA 0, thread 0); NULL in production
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
@@ -191,89 +193,70 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   auto slot_wait_full = [&](int slot) { mbar_wait(BAR(B_FULL + slot), (n_fill[slot] - 1) & 1); tc_fence_after(); };
   auto slot_commit = [&](int slot) { umma_commit(BAR(B_FREE + slot)); n_commit[slot]++; };
 
+  long long t_prev = clock64();
+  auto MARK = [&](int ph) {
+    if (A.phase_clk && tid == 0 && blockIdx.x == 0) { long long t = clock64(); atomicAdd(A.phase_clk + ph, (unsigned long long)(t - t_prev)); t_prev = t; }
+  };
+  // GEMM1 operand request: A0 image block + W1 block into ring stage (it & 1), one transaction barrier for both
+  auto g1_issue = [&](int t, int kb, uint32_t it) {  // thread 0
+    const int s = it & 1;
+    mbar_wait(BAR(ST_FREE + s), ((it >> 1) & 1) ^ 1);
+    mbar_expect_tx(BAR(W_FULL + s), A_BLK_BYTES + W1_BLK);
+    bulk_g2s(sm_u + s * STAGE, A.a0_img + ((size_t)t * NKB1 + kb) * A_BLK_BYTES, A_BLK_BYTES, BAR(W_FULL + s));
+    bulk_g2s(sm_u + s * STAGE + A_BLK_BYTES, w1p + (size_t)kb * W1_BLK, W1_BLK, BAR(W_FULL + s));
+  };
   const int n_tiles = (int)((A.n_edges + TILE_M - 1) / TILE_M);
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    g1_issue(blockIdx.x, 0, 0);
+    g1_issue(blockIdx.x, 1, 1);
+  }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ================= tile setup: row ids =================
     if (tid < TILE_M) {
       int64_t j = (int64_t)tile * TILE_M + tid;
       if (j >= A.n_edges) j = A.n_edges - 1;
-      s_eid[tid] = (int)j;
-      s_src[tid] = A.src[j];
-      s_dst[tid] = A.dst[j];
+      const int eid = A.perm ? A.perm[j] : (int)j;
+      s_eid[tid] = eid;
+      s_src[tid] = A.src[eid];
+      s_dst[tid] = A.dst[eid];
     }
     __syncthreads();
-    // The upstream gradient tile (-> bf16 image, zero for padding rows; 32 threads per row, 16 rows per pass) is
-    // staged in four pieces interleaved with GEMM1's K-block iterations, so its load latency hides under them.
-    const int g_sub = tid & 31, g_rr = tid >> 5;
-    float4 gq[4];
-    auto g_load = [&](int part) {  // rows (2*part) * 16 + rr and (2*part + 1) * 16 + rr
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = (2 * part + h) * 16 + g_rr;
-        const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-        gq[2 * h] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-        gq[2 * h + 1] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + g_sub)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    MARK(0);
+    // ================= GEMM1 (recompute): D1 = A0 W1^T, operands by bulk copy only =================
+    // Thread 0 streams the saved bf16 image of A0 and the W1 K-blocks through the two ring stages and issues the MMAs;
+    // the first two K-blocks of this tile were already requested at the end of the previous tile.
+    if (tid == 0) {
+      for (int kb = 0; kb < NKB1; ++kb) {
+        const uint32_t it = it1 + kb;
+        const int s = it & 1;
+        mbar_wait(BAR(W_FULL + s), (it >> 1) & 1);
+        tc_fence_after();
+        umma_kblock(tmem + TM_D1, sm_u + s * STAGE, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
+        umma_commit(BAR(ST_FREE + s));
+        if (kb == NKB1 - 1) umma_commit(BAR(ACC));
+        if (kb + 2 < NKB1) g1_issue(tile, kb + 2, it + 2);
       }
-    };
-    auto g_store = [&](int part) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = (2 * part + h) * 16 + g_rr;
-        const float4 a = gq[2 * h], b = gq[2 * h + 1];
-        const int c = g_sub * 4;
-        *reinterpret_cast<uint2*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(r, (c % KBLK) >> 3) + ((c >> 2) & 1) * 8) =
-            make_uint2(pack_bf16(a.x + b.x, a.y + b.y), pack_bf16(a.z + b.z, a.w + b.w));
-      }
-    };
-
-    // ================= GEMM1 (recompute): D1 = A0 W1^T =================
+    }
+    it1 += NKB1;
+    // meanwhile every thread stages the upstream gradient tile as a bf16 image (zero for padding rows):
+    // 32 threads per row, 16 rows per pass, all loads of the tile in flight before the first is consumed
     {
-      const int sub = tid & 15, rr = tid >> 4;  // 16 threads per 256 B row piece, 32 rows per pass
-      auto load_blk = [&](int kb, float4 (&v)[4]) {
-        const int seg = (kb * KBLK) / L, col0 = (kb * KBLK) % L;
-        const float* base = seg == 2 ? A.e : A.x;
-        const int* rid = seg == 0 ? s_src : (seg == 1 ? s_dst : s_eid);
+      const int sub = tid & 31, rr = tid >> 5;
+      float4 gv[TILE_M / 16], ga[TILE_M / 16];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rid[p * 32 + rr] * L + col0) + sub);
-      };
-      float4 preA[4], preB[4];  // two K-blocks of loads in flight
-      load_blk(0, preA);
-      load_blk(1, preB);
+      for (int p = 0; p < TILE_M / 16; ++p) {
+        const int r = p * 16 + rr;
+        const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
+        gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + sub)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-      for (int kb = 0; kb < NKB1; ++kb, ++it1) {
-        float4 (&pre)[4] = (kb & 1) ? preB : preA;
-        const int s = it1 & 1;
-        const uint32_t ph = (it1 >> 1) & 1;
-        mbar_wait(BAR(ST_FREE + s), ph ^ 1);
-        if (tid == 0) {
-          mbar_expect_tx(BAR(W_FULL + s), W1_BLK);
-          bulk_g2s(sm_u + s * STAGE + A_BLK_BYTES, w1p + (size_t)kb * W1_BLK, W1_BLK, BAR(W_FULL + s));
-        }
-        {
-          uint8_t* blk = sm + s * STAGE;
-          uint8_t* gimg = A.a0_img + ((size_t)tile * NKB1 + kb) * A_BLK_BYTES;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int r = p * 32 + rr;
-            const uint2 pk = make_uint2(pack_bf16(pre[p].x, pre[p].y), pack_bf16(pre[p].z, pre[p].w));
-            const uint32_t off = sw128_off(r, sub >> 1) + (sub & 1) * 8;
-            *reinterpret_cast<uint2*>(blk + off) = pk;
-            *reinterpret_cast<uint2*>(gimg + off) = pk;  // same image to HBM: B operand of the dW1 GEMM
-          }
-        }
-        if (kb >= 1 && kb <= 4) g_store(kb - 1);   // upstream-gradient piece loaded one iteration ago
-        if (kb <= 3) g_load(kb);
-        if (kb + 2 < NKB1) load_blk(kb + 2, pre);  // refill this register set: two blocks stay in flight
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-          mbar_wait(BAR(W_FULL + s), ph);
-          tc_fence_after();
-          umma_kblock(tmem + TM_D1, sm_u + s * STAGE, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
-          umma_commit(BAR(ST_FREE + s));
-          if (kb == NKB1 - 1) umma_commit(BAR(ACC));
-        }
+      for (int p = 0; p < TILE_M / 16; ++p) {
+        const int r = p * 16 + rr;
+        const int c = sub * 4;
+        *reinterpret_cast<uint2*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(r, (c % KBLK) >> 3) + ((c >> 2) & 1) * 8) =
+            make_uint2(pack_bf16(gv[p].x + ga[p].x, gv[p].y + ga[p].y), pack_bf16(gv[p].z + ga[p].z, gv[p].w + ga[p].w));
       }
     }
     if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
@@ -285,6 +268,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       for (int j = 0; j < NKB2; ++j) slot_fill(j, j * W2_BLK, w2p + (size_t)j * W2_BLK, W2_BLK);
     }
 
+    MARK(1);
     // ================= EPI-A: LN1 statistics, g = act(LN1(h1 + b1)) -> A2 image =================
     float mean1, rstd1;
     {
@@ -301,6 +285,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     tc_fence_before();
     __syncthreads();
 
+    MARK(2);
     // ================= GEMM2 (recompute): D2 = g W2^T ; g image -> HBM =================
     if (tid == 0) {
       bulk_s2g(A.g_img + (size_t)tile * A2_BYTES, sm_u + A2_OFF, A2_BYTES);
@@ -323,6 +308,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       slot_fill(2, W2T_BLK, A.w2t + W2T_BLK, W2T_BLK);
     }
 
+    MARK(3);
     // ================= EPI-B: LN2 + act forward, adjoint down to delta2 =================
     {
       const int c0 = cs * 32;
@@ -408,6 +394,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     tc_fence_before();
     __syncthreads();
 
+    MARK(4);
     // ================= GEMM3: dG = delta2 W2 (two N = 128 halves) ; delta2 image -> HBM =================
     if (tid == 0) {
       bulk_s2g(A.d2_img + (size_t)tile * GS_BYTES, sm_u + D2IMG_OFF, NKBL * A_BLK_BYTES);
@@ -436,6 +423,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       }
     }
 
+    MARK(5);
     // ================= EPI-C: d(y1) = dG * act'(y1), LN1 adjoint -> delta1 image =================
     {
       const int c0 = cs * 64;
@@ -512,6 +500,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     tc_fence_before();
     __syncthreads();
 
+    MARK(6);
     // ================= GEMM4: dA0 = delta1 W1, one N = 128 accumulator per input segment =================
     if (tid == 0) {
       bulk_s2g(A.d1_img + (size_t)tile * A2_BYTES, sm_u + A2_OFF, A2_BYTES);
@@ -532,11 +521,16 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       bulk_wait_read0();  // delta1 image has left shared memory before EPI-D reuses the region
     }
     if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
-    __syncthreads();
+    __syncthreads();  // also orders thread 0's bulk_wait_read0 before the staging writes below
     acc_par ^= 1;
     tc_fence_after();
-    __syncthreads();  // orders thread 0's bulk_wait_read0 before the staging writes below
+    // every MMA that read the ring has retired: request the next tile's first two GEMM1 K-blocks under EPI-D
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
+      g1_issue(tile + gridDim.x, 0, it1);
+      g1_issue(tile + gridDim.x, 1, it1 + 1);
+    }
 
+    MARK(7);
     // ================= EPI-D: rows of d(x[src]), d(x[dst]), d(e) through a swizzled fp32 staging tile =================
     float4 skipg[8];  // fp32 upstream gradient of this lane's 8 output chunks (skip path of d(e)), loaded early
 #pragma unroll
@@ -580,6 +574,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     }
     tc_fence_before();
     __syncthreads();
+    MARK(8);
   }
 
   // ---- ordered hand-off of the column sums: [cta][q][PAR_FLOATS], lane c owns its columns ----
@@ -614,7 +609,7 @@ __global__ void k_colpart_reduce(const float* __restrict__ part, int n_part, flo
 }
 
 struct Layout {
-  size_t a0, g, d1, d2, colpart, wgrad, total;
+  size_t g, d1, d2, colpart, wgrad, total;
   int grid, tiles;
   size_t wgrad_bytes;
 };
@@ -625,7 +620,6 @@ Layout make_layout(int64_t n_edges) {
   Y.grid = std::max(1, std::min(Y.tiles, num_sms()));
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = align_up(off, 1024); off = o + b; return o; };
-  Y.a0 = take((size_t)Y.tiles * NKB1 * A_BLK_BYTES);
   Y.g = take((size_t)Y.tiles * NKB2 * A_BLK_BYTES);
   Y.d1 = take((size_t)Y.tiles * NKB2 * A_BLK_BYTES);
   Y.d2 = take((size_t)Y.tiles * NKBL * A_BLK_BYTES);
@@ -640,13 +634,17 @@ Layout make_layout(int64_t n_edges) {
 
 }  // namespace
 
+static void* g_phase_clk = nullptr;
+// debug hook (not part of the stable ABI): device buffer of 16 uint64 that CTA 0 fills with per-phase cycle counts
+extern "C" void hgnn_tc_debug_set_phase_clock(void* dev_u64x16) { g_phase_clk = dev_u64x16; }
+
 extern "C" size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges) {
   return make_layout(n_edges > 0 ? n_edges : 1).total + 1024;
 }
 
 extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed,
-                                     const float* x, const float* e, const int32_t* src, const int32_t* dst, int64_t n_edges,
-                                     const float* grad_eout, const float* grad_agg, float* d_e, float* d_xsrc_rows,
+                                     const void* a0_img, const int32_t* src, const int32_t* dst, const int32_t* perm,
+                                     int64_t n_edges, const float* grad_eout, const float* grad_agg, float* d_e, float* d_xsrc_rows,
                                      float* d_xdst_rows, float* dW1, float* dW2, float* dvec1, float* dvec2, void* ws,
                                      size_t ws_bytes, void* stream) {
   HGNN_REQUIRE(p != nullptr, "tc_edge_backward: params is NULL");
@@ -660,7 +658,7 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
     if (dvec2) HGNN_CUDA_TRY(cudaMemsetAsync(dvec2, 0, (size_t)3 * L * 4, st));
     return HGNN_OK;
   }
-  HGNN_REQUIRE(w1t_packed && w2t_packed && x && e && src && dst && grad_eout && d_e && d_xsrc_rows && d_xdst_rows && dW1 && dW2 &&
+  HGNN_REQUIRE(w1t_packed && w2t_packed && a0_img && src && dst && grad_eout && d_e && d_xsrc_rows && d_xdst_rows && dW1 && dW2 &&
                dvec1 && dvec2 && ws, "tc_edge_backward: NULL pointer");
   HGNN_REQUIRE(n_edges < INT32_MAX, "tc_edge_backward: too many edges");
   Layout Y = make_layout(n_edges);
@@ -671,12 +669,13 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   A.P = *p;
   A.w1t = (const uint8_t*)w1t_packed;
   A.w2t = (const uint8_t*)w2t_packed;
-  A.x = x; A.e = e; A.src = src; A.dst = dst;
+  A.src = src; A.dst = dst; A.perm = perm;
   A.g_e = grad_eout; A.g_agg = grad_agg;
   A.d_e = d_e; A.d_xs = d_xsrc_rows; A.d_xd = d_xdst_rows;
-  A.a0_img = w + Y.a0; A.g_img = w + Y.g; A.d1_img = w + Y.d1; A.d2_img = w + Y.d2;
+  A.a0_img = (const uint8_t*)a0_img; A.g_img = w + Y.g; A.d1_img = w + Y.d1; A.d2_img = w + Y.d2;
   A.colpart = (float*)(w + Y.colpart);
   A.n_edges = n_edges;
+  A.phase_clk = (unsigned long long*)g_phase_clk;
   HGNN_REQUIRE(p->act_hidden == HGNN_ACT_GELU && p->act_out == HGNN_ACT_TANH, "tc_edge_backward: only GELU / Tanh is built");
   size_t smem = SMEM_BYTES;
   auto kern = k_tc_edge_bwd<HGNN_ACT_GELU, HGNN_ACT_TANH>;

@@ -60,12 +60,17 @@ __device__ __forceinline__ void gather_load(float4 (&v)[8], const float* __restr
 #pragma unroll
   for (int p = 0; p < 8; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rowid[p * 16 + rr] * ld + col0) + sub);
 }
-__device__ __forceinline__ void gather_store(uint8_t* __restrict__ blk, const float4 (&v)[8]) {
+// gimg (optional): the same swizzled bf16 block is also left in HBM — the backward pass and the weight-gradient GEMM
+// read these tile images back with bulk copies instead of re-gathering
+__device__ __forceinline__ void gather_store(uint8_t* __restrict__ blk, const float4 (&v)[8], uint8_t* __restrict__ gimg = nullptr) {
   const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
     const int r = p * 16 + rr;
-    *reinterpret_cast<uint2*>(blk + sw128_off(r, sub >> 1) + (sub & 1) * 8) = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
+    const uint2 pk = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
+    const uint32_t off = sw128_off(r, sub >> 1) + (sub & 1) * 8;
+    *reinterpret_cast<uint2*>(blk + off) = pk;
+    if (gimg) *reinterpret_cast<uint2*>(gimg + off) = pk;
   }
 }
 __device__ __forceinline__ void gather_a_block(uint8_t* __restrict__ blk, const float* __restrict__ base, int ld,
@@ -93,7 +98,7 @@ template <int L, int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,
               const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out,
-              const int32_t* __restrict__ rowptr, float* __restrict__ agg) {
+              const int32_t* __restrict__ rowptr, float* __restrict__ agg, uint8_t* __restrict__ a0_img) {
   using C = Cfg<L>;
   constexpr int H = C::H;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // declared alignment keeps the shared address space visible (LDS/STS)
@@ -178,7 +183,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
         mbar_expect_tx(BAR(W_FULL + s), C::W1_BLK);
         bulk_g2s(region_u + s * C::STAGE + A_BLK_BYTES, w1p + (size_t)kb * C::W1_BLK, C::W1_BLK, BAR(W_FULL + s));
       }
-      gather_store(stage, pre);
+      gather_store(stage, pre, a0_img ? a0_img + ((size_t)tile * C::NKB1 + kb) * A_BLK_BYTES : nullptr);
       if (kb + 1 < C::NKB1) gather_load(pre, seg_base(kb + 1), L, seg_rows(kb + 1), ((kb + 1) * KBLK) % L);  // next block in flight
       fence_proxy_async();
       __syncthreads();
@@ -456,17 +461,21 @@ extern "C" int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t 
 }
 
 extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t) { return 256; }
+extern "C" size_t hgnn_tc_edge_a0_image_bytes(int64_t n_edges, int64_t latent) {
+  int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
+  return (size_t)tiles * (3 * latent / KBLK) * A_BLK_BYTES;
+}
 
 template <int L>
 static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src, const int32_t* dst,
                            const int32_t* perm, int64_t n_edges, float* e_out, const int32_t* rowptr, int64_t n_nodes, float* agg,
-                           cudaStream_t st) {
+                           uint8_t* a0_img, cudaStream_t st) {
   size_t smem = Cfg<L>::SMEM;
   auto kern = k_tc_edge_fwd<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
   HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
-  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg);
+  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg, a0_img);
   if (agg) {
     int64_t threads = n_nodes * (L / 4);
     k_agg_fixup<L><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(e_out, perm, rowptr, n_nodes, agg);
@@ -476,7 +485,8 @@ static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const f
 
 extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
                                     const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges,
-                                    int64_t n_nodes, float* e_out, float* agg, void* ws, size_t ws_bytes, void* stream) {
+                                    int64_t n_nodes, float* e_out, float* agg, void* a0_img, void* ws, size_t ws_bytes,
+                                    void* stream) {
   (void)ws; (void)ws_bytes;
   HGNN_REQUIRE(agg == nullptr || (perm != nullptr && rowptr != nullptr && n_nodes > 0),
                "tc_edge_forward: the fused aggregate needs the destination-sorted plan (perm, rowptr) and n_nodes");
@@ -494,6 +504,6 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
                 "tc_edge_forward: latent %d / hidden %d / activations (%d, %d) not built (need latent in {64,128}, hidden = 2*latent, GELU/Tanh)",
                 p->latent, p->hidden, p->act_hidden, p->act_out);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, st);
-  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, st);
+  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)a0_img, st);
+  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)a0_img, st);
 }

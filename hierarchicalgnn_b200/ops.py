@@ -374,8 +374,10 @@ class _FusedMLP(torch.autograd.Function):
         params = [_f32(t) for t in tensors[n_seg:]]
         d, rows, layers = _build_desc(meta, segs, params)
         out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=segs[0].device)
+        ctx.a0 = None
         if rows and meta.tc_pack is not None:
-            tc_edge_forward_raw(meta, segs, layers, out)
+            ctx.a0 = tc_edge_forward_raw(meta, segs, layers, out,
+                                         save_image=any(ctx.needs_input_grad[2:]) and tc_backward_available(meta, layers))
         elif rows:
             with _timed("mlp_forward"):
                 check(_lib.lib().hgnn_mlp_forward(C.byref(d), rows, _ptr(out), _stream()), "mlp_forward")
@@ -392,8 +394,8 @@ class _FusedMLP(torch.autograd.Function):
         d, rows, layers = _build_desc(meta, segs, params)
         dev = segs[0].device
         gout = _f32(gout)
-        if rows and tc_backward_available(meta, layers):
-            d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, gout)
+        if rows and tc_backward_available(meta, layers) and ctx.a0 is not None:
+            d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, gout, ctx.a0)
             need = ctx.needs_input_grad[2:]
             gx_s = segment_reduce_raw(d_xs, meta.seg_plans[0]) if need[0] else None
             gx_d = segment_reduce_raw(d_xd, meta.seg_plans[1]) if need[1] else None
@@ -517,8 +519,10 @@ def tc_backward_available(meta: MlpMeta, layers) -> bool:
     return meta.tc_pack is not None and layers[1][0].shape[0] == 128 and layers[0][0].shape[0] == 256
 
 
-def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, grad_agg: Optional[Tensor] = None):
-    """Backward of the tensor-core edge step. Returns (d_xsrc_rows, d_xdst_rows, d_e, dW1, dW2, dvec1, dvec2)."""
+def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, a0_img: Tensor, perm: Optional[Tensor] = None,
+                         grad_agg: Optional[Tensor] = None):
+    """Backward of the tensor-core edge step from the forward's saved A0 image (same row order ``perm``).
+    Returns (d_xsrc_rows, d_xdst_rows, d_e, dW1, dW2, dvec1, dvec2)."""
     x, e = segs[0], segs[2]
     plan_s, plan_d = meta.seg_plans[0], meta.seg_plans[1]
     w1p, w2p, w1tp, w2tp = meta.tc_pack()
@@ -534,8 +538,8 @@ def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, grad_agg: Op
     L_ = _lib.lib()
     ws = _workspace(L_.hgnn_tc_edge_backward_workspace_bytes(E), dev)
     with _timed("tc_edge_backward"):
-        check(L_.hgnn_tc_edge_backward(C.byref(p), _ptr(w1tp), _ptr(w2tp), _ptr(x), _ptr(e), _ptr(plan_s.keys32),
-                                       _ptr(plan_d.keys32), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_xs), _ptr(d_xd),
+        check(L_.hgnn_tc_edge_backward(C.byref(p), _ptr(w1tp), _ptr(w2tp), _ptr(a0_img), _ptr(plan_s.keys32),
+                                       _ptr(plan_d.keys32), _ptr(perm), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_xs), _ptr(d_xd),
                                        _ptr(dW1), _ptr(dW2), _ptr(dv1), _ptr(dv2), _ptr(ws), ws.numel(), _stream()),
               "tc_edge_backward")
     _count(1 + 1 + 1 + 4)
@@ -543,7 +547,7 @@ def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, grad_agg: Op
     return d_xs, d_xd, d_e, dW1, dW2, dv1, dv2
 
 
-def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[Tensor] = None):
+def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[Tensor] = None, save_image: bool = False):
     """e' = MLP([x[src] | x[dst] | e]) + e on tcgen05 tensor cores (segments: x|by_src, x|by_dst, e); with ``agg``
     the same launch also leaves scatter_add(e', dst) there (edges visited in destination-sorted order)."""
     x, e = segs[0], segs[2]
@@ -554,12 +558,16 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[
     perm = rowptr = None
     if agg is not None:
         perm, rowptr = plan_d.perm, plan_d.rowptr
+    a0 = None
+    if save_image:  # bf16 tile image of [x[src] | x[dst] | e] for the backward pass (768 B/edge at L = 128)
+        a0 = torch.empty(_lib.lib().hgnn_tc_edge_a0_image_bytes(n_edges, e.shape[1]), dtype=torch.uint8, device=e.device)
     with _timed("tc_edge_forward"):
         check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), _ptr(perm),
-                                              _ptr(rowptr), n_edges, x.shape[0], _ptr(out), _ptr(agg), None, 0, _stream()),
-              "tc_edge_forward")
+                                              _ptr(rowptr), n_edges, x.shape[0], _ptr(out), _ptr(agg), _ptr(a0), None, 0,
+                                              _stream()), "tc_edge_forward")
     _count(1 if agg is None else 2)
     TC_CALLS["count"] += 1
+    return a0
 
 
 class _TcEdgeStepAgg(torch.autograd.Function):
@@ -576,8 +584,11 @@ class _TcEdgeStepAgg(torch.autograd.Function):
         d, rows, layers = _build_desc(meta, segs, ps)
         out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=e.device)
         agg = torch.empty((segs[0].shape[0], out.shape[1]), dtype=torch.float32, device=e.device)
-        tc_edge_forward_raw(meta, segs, layers, out, agg)  # one launch: edge MLP + skip + destination-sorted reduce
+        need_bwd = any(ctx.needs_input_grad[1:])
+        # one launch: edge MLP + skip + destination-sorted reduce (+ the bf16 input image the backward will stream)
+        a0 = tc_edge_forward_raw(meta, segs, layers, out, agg, save_image=need_bwd)
         ctx.meta = meta
+        ctx.a0 = a0
         ctx.save_for_backward(segs[0], segs[2], *ps)
         return out, agg
 
@@ -590,7 +601,7 @@ class _TcEdgeStepAgg(torch.autograd.Function):
         d, rows, layers = _build_desc(meta, segs, ps)
         g_out = torch.zeros_like(e) if g_out is None else _f32(g_out)
         g_agg = None if g_agg is None else _f32(g_agg)
-        d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, g_agg)
+        d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, ctx.a0, meta.seg_plans[1].perm, g_agg)
         gx = None
         if ctx.needs_input_grad[1]:
             gx = segment_reduce_raw(d_xs, meta.seg_plans[0])

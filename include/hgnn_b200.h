@@ -225,23 +225,32 @@ int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca
  * scatter_add that opens the next cell (gnn_utils.py:50) — by a destination-sorted, ordered segmented reduce of
  * each finished tile in shared memory (no atomics); this needs perm/rowptr = the by-destination plan of
  * hgnn_csr_build. Segments crossing a row-group boundary (hub nodes) and empty segments are completed by a small
- * second kernel inside the same call. */
+ * second kernel inside the same call.
+ * a0_img (optional, hgnn_tc_edge_a0_image_bytes): the bf16 tile image of the gathered input [x[src] | x[dst] | e]
+ * that the kernel builds anyway is also left in HBM; the backward pass and the weight-gradient GEMM consume it with
+ * bulk copies instead of gathering again (pass it when a backward will follow). */
 size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges);
+size_t hgnn_tc_edge_a0_image_bytes(int64_t n_edges, int64_t latent);
 int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
                          const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges, int64_t n_nodes,
-                         float* e_out, float* agg, void* ws, size_t ws_bytes, void* stream);
+                         float* e_out, float* agg, void* a0_img, void* ws, size_t ws_bytes, void* stream);
 
 /* Backward of the tensor-core edge step (latent 128): in-kernel recompute (no saved activations),
  * data gradients as per-edge rows (d_e final; d_xsrc_rows / d_xdst_rows are reduced by the caller
  * with hgnn_segment_reduce over the by-source / by-destination plans), weight gradients by the
  * tcgen05 split-K kernel, bias/LayerNorm gradients dvec{1,2} = [3, width] (d bias, d gamma, d beta).
+ * a0_img / perm must be the image and row order of the matching hgnn_tc_edge_forward call.
  * grad_agg (optional, [n_nodes, L]) is the cotangent of agg = scatter_add(e_out, dst): the kernel uses
  * grad_eout[i] + grad_agg[dst_i]. w1t/w2t_packed are hgnn_tc_pack_weights images of W1^T / W2^T. */
 size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges);
-int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const float* x,
-                          const float* e, const int32_t* src, const int32_t* dst, int64_t n_edges, const float* grad_eout,
+int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const void* a0_img,
+                          const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_edges, const float* grad_eout,
                           const float* grad_agg, float* d_e, float* d_xsrc_rows, float* d_xdst_rows, float* dW1, float* dW2,
                           float* dvec1, float* dvec2, void* ws, size_t ws_bytes, void* stream);
+
+/* Profiling hook: when set (device buffer of 16 uint64), CTA 0 of hgnn_tc_edge_backward accumulates the cycles it
+ * spends in each phase of the tile loop (GEMM1, EPI-A, GEMM2, EPI-B, GEMM3, EPI-C, GEMM4, EPI-D). NULL disables. */
+void hgnn_tc_debug_set_phase_clock(void* dev_u64x16);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,28 @@
+"""Per-phase cycle breakdown of the tensor-core backward kernel (CTA 0), via the hgnn_tc_debug_set_phase_clock hook."""
+import sys, torch
+sys.path.insert(0, '.')
+from hierarchicalgnn_b200 import ops, _lib
+from hierarchicalgnn_b200.gnn_utils import GraphPlans, InteractionGNNCell
+from hierarchicalgnn_b200.synth import synth_edge_problem
+from hierarchicalgnn_b200.training_utils import kaiming_init
+L, E = 128, 1_000_000
+hp = dict(latent=L, hidden=2 * L, nb_edge_layer=2, nb_node_layer=3, layernorm=True, hidden_activation="GELU")
+torch.manual_seed(0); cell = InteractionGNNCell(hp); kaiming_init(cell); cell.cuda()
+n, e, g = synth_edge_problem(E, L); n, e, g = n.cuda().requires_grad_(True), e.cuda().requires_grad_(True), g.cuda()
+gp = GraphPlans(g, n.shape[0], n.shape[0]); gp.by_src; gp.by_dst
+cot_e, cot_a = torch.randn_like(e), torch.randn(n.shape[0], L, device="cuda")
+def step():
+    e2, agg = cell.edge_network.edge_step(n, e, gp.by_src, gp.by_dst)
+    torch.autograd.grad([e2, agg], [n, e] + list(cell.edge_network.parameters()), [cot_e, cot_a])
+for _ in range(3): step()
+clk = torch.zeros(16, dtype=torch.int64, device="cuda")
+_lib.lib().hgnn_tc_debug_set_phase_clock(clk.data_ptr())
+step(); torch.cuda.synchronize()
+_lib.lib().hgnn_tc_debug_set_phase_clock(None)
+c = clk.cpu().tolist()
+names = ["setup+G", "GEMM1(gather)", "EPI-A", "GEMM2", "EPI-B", "GEMM3", "EPI-C", "GEMM4", "EPI-D"]
+tiles = (E + 127) // 128 // 148 + 1
+tot = sum(c[:9])
+for nm, v in zip(names, c[:9]):
+    print(f"{nm:14s} {v / tiles:9.0f} cyc/tile  {100 * v / tot:5.1f}%")
+print(f"total {tot / tiles:.0f} cycles/tile over ~{tiles} tiles")
