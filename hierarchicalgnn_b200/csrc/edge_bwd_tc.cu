@@ -57,7 +57,7 @@ constexpr int PAR_FLOATS = 3 * H + 3 * L;
 constexpr int IDS_OFF = PAR_OFF + PAR_FLOATS * 4;
 constexpr int RED_OFF = IDS_OFF + 3 * TILE_M * 4;      // [128 rows][4 splits][2]
 constexpr int BAR_OFF = RED_OFF + TILE_M * 8 * 4;
-constexpr int NBAR = 2 + 2 + 6 + 6 + 1;
+constexpr int NBAR = 2 + 2 + 6 + 6 + 1 + 1;
 constexpr int SMEM_BYTES = BAR_OFF + NBAR * 8 + 16;
 constexpr int NSLOT = 6;                                // 16 KB slots over the ring for GEMM4's weight stream
 constexpr uint32_t TM_D1 = 0, TM_D2 = H, TM_DGHI = H, TM_DGLO = H + L, TM_DA0 = 0;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + BAR_OFF + NBAR * 8);
   const uint32_t sm_u = smem_u32(sm), bar0 = sm_u + BAR_OFF;
   if ((sm_u & 1023u) != 0) __trap();
-  enum { W_FULL = 0, ST_FREE = 2, B_FULL = 4, B_FREE = 10, ACC = 16 };
+  enum { W_FULL = 0, ST_FREE = 2, B_FULL = 4, B_FREE = 10, ACC = 16, A_REST = 17 };
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   const uint8_t* w2p = reinterpret_cast<const uint8_t*>(P.w2_packed);
 
   uint32_t it1 = 0, acc_par = 0;
+  int nx_eid = 0, nx_src = 0, nx_dst = 0;  // row ids of the next tile, prefetched
   uint32_t n_fill[NSLOT] = {0, 0, 0, 0, 0, 0}, n_commit[NSLOT] = {0, 0, 0, 0, 0, 0};  // thread 0 bookkeeping
   // per-lane column-sum accumulators: lane c of warp (q, cs) owns columns cs*64 + {c, 32 + c} of H and cs*32 + c of L
   float acc_db1[2] = {0.f, 0.f}, acc_dg1[2] = {0.f, 0.f}, acc_dbe1[2] = {0.f, 0.f};
@@ -197,64 +198,88 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   auto MARK = [&](int ph) {
     if (A.phase_clk && tid == 0 && blockIdx.x == 0) { long long t = clock64(); atomicAdd(A.phase_clk + ph, (unsigned long long)(t - t_prev)); t_prev = t; }
   };
-  // GEMM1 operand request: A0 image block + W1 block into ring stage (it & 1), one transaction barrier for both
-  auto g1_issue = [&](int t, int kb, uint32_t it) {  // thread 0
+  // GEMM1 operand requests (thread 0). K-blocks 0/1: A0 image block + W1 block into ring stage (it & 1), one
+  // transaction barrier for both; they are requested a tile ahead. K-blocks 2..5: the four A0 blocks land together in
+  // the A2 region (idle until EPI-A) at tile start, only their W1 blocks go through the ring.
+  auto g1_issue = [&](int t, int kb, uint32_t it) {
     const int s = it & 1;
     mbar_wait(BAR(ST_FREE + s), ((it >> 1) & 1) ^ 1);
-    mbar_expect_tx(BAR(W_FULL + s), A_BLK_BYTES + W1_BLK);
-    bulk_g2s(sm_u + s * STAGE, A.a0_img + ((size_t)t * NKB1 + kb) * A_BLK_BYTES, A_BLK_BYTES, BAR(W_FULL + s));
+    if (kb < 2) {
+      mbar_expect_tx(BAR(W_FULL + s), A_BLK_BYTES + W1_BLK);
+      bulk_g2s(sm_u + s * STAGE, A.a0_img + ((size_t)t * NKB1 + kb) * A_BLK_BYTES, A_BLK_BYTES, BAR(W_FULL + s));
+    } else {
+      mbar_expect_tx(BAR(W_FULL + s), W1_BLK);
+    }
     bulk_g2s(sm_u + s * STAGE + A_BLK_BYTES, w1p + (size_t)kb * W1_BLK, W1_BLK, BAR(W_FULL + s));
   };
+  uint32_t rest_par = 0;
   const int n_tiles = (int)((A.n_edges + TILE_M - 1) / TILE_M);
   if (tid == 0 && (int)blockIdx.x < n_tiles) {
     g1_issue(blockIdx.x, 0, 0);
     g1_issue(blockIdx.x, 1, 1);
   }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ================= tile setup: row ids =================
+    // ================= tile setup: row ids (fetched one tile ahead into registers; see the end of the loop) ==========
     if (tid < TILE_M) {
-      int64_t j = (int64_t)tile * TILE_M + tid;
-      if (j >= A.n_edges) j = A.n_edges - 1;
-      const int eid = A.perm ? A.perm[j] : (int)j;
-      s_eid[tid] = eid;
-      s_src[tid] = A.src[eid];
-      s_dst[tid] = A.dst[eid];
+      if (tile == (int)blockIdx.x) {
+        int64_t j = (int64_t)tile * TILE_M + tid;
+        if (j >= A.n_edges) j = A.n_edges - 1;
+        nx_eid = A.perm ? A.perm[j] : (int)j;
+        nx_src = A.src[nx_eid];
+        nx_dst = A.dst[nx_eid];
+      }
+      s_eid[tid] = nx_eid;
+      s_src[tid] = nx_src;
+      s_dst[tid] = nx_dst;
     }
     __syncthreads();
+    const bool has_next = tile + (int)gridDim.x < n_tiles;
+    if (tid < TILE_M && has_next) {  // first link of the dependent chain perm -> src/dst for the next tile
+      int64_t j = (int64_t)(tile + gridDim.x) * TILE_M + tid;
+      if (j >= A.n_edges) j = A.n_edges - 1;
+      nx_eid = A.perm ? A.perm[j] : (int)j;
+    }
     MARK(0);
     // ================= GEMM1 (recompute): D1 = A0 W1^T, operands by bulk copy only =================
     // Thread 0 streams the saved bf16 image of A0 and the W1 K-blocks through the two ring stages and issues the MMAs;
     // the first two K-blocks of this tile were already requested at the end of the previous tile.
+    // upstream-gradient loads first (every warp, including the issuing one), so they fly under the MMA loop
+    const int g_sub = tid & 31, g_rr = tid >> 5;
+    float4 gv[TILE_M / 16], ga[TILE_M / 16];
+#pragma unroll
+    for (int p = 0; p < TILE_M / 16; ++p) {
+      const int r = p * 16 + g_rr;
+      const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
+      gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + g_sub)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (tid == 0) {
+      // the A2 region is free (previous tile's EPI-D staging was drained before the closing barrier)
+      fence_proxy_async();
+      mbar_expect_tx(BAR(A_REST), 4 * A_BLK_BYTES);
+      bulk_g2s(sm_u + A2_OFF, A.a0_img + ((size_t)tile * NKB1 + 2) * A_BLK_BYTES, 4 * A_BLK_BYTES, BAR(A_REST));
       for (int kb = 0; kb < NKB1; ++kb) {
         const uint32_t it = it1 + kb;
         const int s = it & 1;
         mbar_wait(BAR(W_FULL + s), (it >> 1) & 1);
+        if (kb == 2) mbar_wait(BAR(A_REST), rest_par);
         tc_fence_after();
-        umma_kblock(tmem + TM_D1, sm_u + s * STAGE, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
+        umma_kblock(tmem + TM_D1, kb < 2 ? sm_u + s * STAGE : sm_u + A2_OFF + (kb - 2) * A_BLK_BYTES, sm_u + s * STAGE + A_BLK_BYTES,
+                    idesc_h, kb == 0);
         umma_commit(BAR(ST_FREE + s));
         if (kb == NKB1 - 1) umma_commit(BAR(ACC));
         if (kb + 2 < NKB1) g1_issue(tile, kb + 2, it + 2);
       }
     }
     it1 += NKB1;
-    // meanwhile every thread stages the upstream gradient tile as a bf16 image (zero for padding rows):
-    // 32 threads per row, 16 rows per pass, all loads of the tile in flight before the first is consumed
+    rest_par ^= 1;
+    // stage the upstream gradient tile as a bf16 image (zero for padding rows): 32 threads per row, 16 rows per pass
     {
-      const int sub = tid & 31, rr = tid >> 5;
-      float4 gv[TILE_M / 16], ga[TILE_M / 16];
 #pragma unroll
       for (int p = 0; p < TILE_M / 16; ++p) {
-        const int r = p * 16 + rr;
-        const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-        gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + sub)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int p = 0; p < TILE_M / 16; ++p) {
-        const int r = p * 16 + rr;
-        const int c = sub * 4;
+        const int r = p * 16 + g_rr;
+        const int c = g_sub * 4;
         *reinterpret_cast<uint2*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(r, (c % KBLK) >> 3) + ((c >> 2) & 1) * 8) =
             make_uint2(pack_bf16(gv[p].x + ga[p].x, gv[p].y + ga[p].y), pack_bf16(gv[p].z + ga[p].z, gv[p].w + ga[p].w));
       }
@@ -309,6 +334,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     }
 
     MARK(3);
+    if (tid < TILE_M && has_next) { nx_src = A.src[nx_eid]; nx_dst = A.dst[nx_eid]; }  // second link, consumed next tile
     // ================= EPI-B: LN2 + act forward, adjoint down to delta2 =================
     {
       const int c0 = cs * 32;

@@ -488,8 +488,8 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
                                     int64_t n_nodes, float* e_out, float* agg, void* a0_img, void* ws, size_t ws_bytes,
                                     void* stream) {
   (void)ws; (void)ws_bytes;
-  HGNN_REQUIRE(agg == nullptr || (perm != nullptr && rowptr != nullptr && n_nodes > 0),
-               "tc_edge_forward: the fused aggregate needs the destination-sorted plan (perm, rowptr) and n_nodes");
+  HGNN_REQUIRE(agg == nullptr || (rowptr != nullptr && n_nodes > 0),
+               "tc_edge_forward: the fused aggregate needs the destination-sorted plan (rowptr; perm unless the edges are stored sorted) and n_nodes");
   if (n_edges <= 0 && agg != nullptr) {
     HGNN_CUDA_TRY(cudaMemsetAsync(agg, 0, (size_t)n_nodes * p->latent * 4, (cudaStream_t)stream));
   }

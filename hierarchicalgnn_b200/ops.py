@@ -131,6 +131,15 @@ class SegmentPlan:
                                _ptr(ws), ws.numel(), _stream()), "csr_build")
         _count(4)
         self._counts_inv = None
+        self._identity = None
+
+    def is_identity(self) -> bool:
+        """True when the items already arrive segment-sorted (perm == arange): kernels then stream rows in place
+        instead of following perm (one host sync, cached)."""
+        if self._identity is None:
+            k = self.keys32
+            self._identity = bool(self.n_items < 2 or bool((k[1:] >= k[:-1]).all()))
+        return self._identity
 
     def inv_counts(self) -> Tensor:
         if self._counts_inv is None:
@@ -557,7 +566,7 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[
     n_edges = e.shape[0]
     perm = rowptr = None
     if agg is not None:
-        perm, rowptr = plan_d.perm, plan_d.rowptr
+        perm, rowptr = (None if plan_d.is_identity() else plan_d.perm), plan_d.rowptr
     a0 = None
     if save_image:  # bf16 tile image of [x[src] | x[dst] | e] for the backward pass (768 B/edge at L = 128)
         a0 = torch.empty(_lib.lib().hgnn_tc_edge_a0_image_bytes(n_edges, e.shape[1]), dtype=torch.uint8, device=e.device)
@@ -601,7 +610,7 @@ class _TcEdgeStepAgg(torch.autograd.Function):
         d, rows, layers = _build_desc(meta, segs, ps)
         g_out = torch.zeros_like(e) if g_out is None else _f32(g_out)
         g_agg = None if g_agg is None else _f32(g_agg)
-        d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, ctx.a0, meta.seg_plans[1].perm, g_agg)
+        d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, ctx.a0, None if meta.seg_plans[1].is_identity() else meta.seg_plans[1].perm, g_agg)
         gx = None
         if ctx.needs_input_grad[1]:
             gx = segment_reduce_raw(d_xs, meta.seg_plans[0])

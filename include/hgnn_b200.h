@@ -224,7 +224,7 @@ int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca
  * (NULL = identity). If agg != NULL the same launch also produces agg[n] = sum_{dst_i = n} e_out[i] — the
  * scatter_add that opens the next cell (gnn_utils.py:50) — by a destination-sorted, ordered segmented reduce of
  * each finished tile in shared memory (no atomics); this needs perm/rowptr = the by-destination plan of
- * hgnn_csr_build. Segments crossing a row-group boundary (hub nodes) and empty segments are completed by a small
+ * hgnn_csr_build (perm may be NULL when the edges are already stored destination-sorted: rows then stream in place). Segments crossing a row-group boundary (hub nodes) and empty segments are completed by a small
  * second kernel inside the same call.
  * a0_img (optional, hgnn_tc_edge_a0_image_bytes): the bf16 tile image of the gathered input [x[src] | x[dst] | e]
  * that the kernel builds anyway is also left in HBM; the backward pass and the weight-gradient GEMM consume it with
