@@ -57,7 +57,7 @@ constexpr int PAR_FLOATS = 3 * H + 3 * L;
 constexpr int IDS_OFF = PAR_OFF + PAR_FLOATS * 4;
 constexpr int RED_OFF = IDS_OFF + 3 * TILE_M * 4;      // [128 rows][4 splits][2]
 constexpr int BAR_OFF = RED_OFF + TILE_M * 8 * 4;
-constexpr int NBAR = 2 + 2 + 6 + 6 + 1 + 1;
+constexpr int NBAR = 2 + 2 + 6 + 6 + 1 + 1 + 1 + 1;
 constexpr int SMEM_BYTES = BAR_OFF + NBAR * 8 + 16;
 constexpr int NSLOT = 6;                                // 16 KB slots over the ring for GEMM4's weight stream
 constexpr uint32_t TM_D1 = 0, TM_D2 = H, TM_DGHI = H, TM_DGLO = H + L, TM_DA0 = 0;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + BAR_OFF + NBAR * 8);
   const uint32_t sm_u = smem_u32(sm), bar0 = sm_u + BAR_OFF;
   if ((sm_u & 1023u) != 0) __trap();
-  enum { W_FULL = 0, ST_FREE = 2, B_FULL = 4, B_FREE = 10, ACC = 16, A_REST = 17 };
+  enum { W_FULL = 0, ST_FREE = 2, B_FULL = 4, B_FREE = 10, ACC = 16, A_REST = 17, W_KB2 = 18, KB2_DONE = 19 };
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -212,11 +212,18 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     }
     bulk_g2s(sm_u + s * STAGE + A_BLK_BYTES, w1p + (size_t)kb * W1_BLK, W1_BLK, BAR(W_FULL + s));
   };
+  // W1 K-block 2 is parked in the upstream-gradient staging region (idle from EPI-B of one tile to the end of the next
+  // tile's GEMM1) so that GEMM1 itself only streams K-blocks 3..5
+  auto w1_kb2_prefetch = [&]() {  // thread 0
+    mbar_expect_tx(BAR(W_KB2), W1_BLK);
+    bulk_g2s(sm_u + GS_OFF, w1p + (size_t)2 * W1_BLK, W1_BLK, BAR(W_KB2));
+  };
   uint32_t rest_par = 0;
   const int n_tiles = (int)((A.n_edges + TILE_M - 1) / TILE_M);
   if (tid == 0 && (int)blockIdx.x < n_tiles) {
     g1_issue(blockIdx.x, 0, 0);
     g1_issue(blockIdx.x, 1, 1);
+    w1_kb2_prefetch();
   }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ================= tile setup: row ids (fetched one tile ahead into registers; see the end of the loop) ==========
@@ -259,22 +266,36 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
       fence_proxy_async();
       mbar_expect_tx(BAR(A_REST), 4 * A_BLK_BYTES);
       bulk_g2s(sm_u + A2_OFF, A.a0_img + ((size_t)tile * NKB1 + 2) * A_BLK_BYTES, 4 * A_BLK_BYTES, BAR(A_REST));
+      uint32_t it = it1;  // ring use counter: K-blocks 0, 1, 3, 4, 5 go through the two ring stages
       for (int kb = 0; kb < NKB1; ++kb) {
-        const uint32_t it = it1 + kb;
+        const uint32_t a_s = kb < 2 ? 0u : sm_u + A2_OFF + (kb - 2) * A_BLK_BYTES;
+        if (kb == 2) {
+          mbar_wait(BAR(A_REST), rest_par);
+          mbar_wait(BAR(W_KB2), rest_par);
+          tc_fence_after();
+          umma_kblock(tmem + TM_D1, a_s, sm_u + GS_OFF, idesc_h, false);
+          umma_commit(BAR(KB2_DONE));
+          continue;
+        }
         const int s = it & 1;
         mbar_wait(BAR(W_FULL + s), (it >> 1) & 1);
-        if (kb == 2) mbar_wait(BAR(A_REST), rest_par);
         tc_fence_after();
-        umma_kblock(tmem + TM_D1, kb < 2 ? sm_u + s * STAGE : sm_u + A2_OFF + (kb - 2) * A_BLK_BYTES, sm_u + s * STAGE + A_BLK_BYTES,
-                    idesc_h, kb == 0);
+        umma_kblock(tmem + TM_D1, kb < 2 ? sm_u + s * STAGE : a_s, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
         umma_commit(BAR(ST_FREE + s));
         if (kb == NKB1 - 1) umma_commit(BAR(ACC));
-        if (kb + 2 < NKB1) g1_issue(tile, kb + 2, it + 2);
+        // keep two W1 blocks in flight: after kb = 0 request 3, after 1 request 4, after 3 request 5
+        const int nxt = kb < 2 ? kb + 3 : kb + 2;
+        if (nxt < NKB1) g1_issue(tile, nxt, it + 2);
+        ++it;
       }
     }
-    it1 += NKB1;
+    it1 += NKB1 - 1;
     rest_par ^= 1;
-    // stage the upstream gradient tile as a bf16 image (zero for padding rows): 32 threads per row, 16 rows per pass
+    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
+    __syncthreads();
+    acc_par ^= 1;
+    tc_fence_after();
+    // GEMM1 has retired (W1 K-block 2 no longer needed in this region): stage the upstream gradient tile as a bf16 image (zero for padding rows): 32 threads per row, 16 rows per pass
     {
 #pragma unroll
       for (int p = 0; p < TILE_M / 16; ++p) {
@@ -284,10 +305,6 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
             make_uint2(pack_bf16(gv[p].x + ga[p].x, gv[p].y + ga[p].y), pack_bf16(gv[p].z + ga[p].z, gv[p].w + ga[p].w));
       }
     }
-    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
-    __syncthreads();
-    acc_par ^= 1;
-    tc_fence_after();
     // ring is idle: bring all of W2 in (4 x 16 KB slots) behind EPI-A
     if (tid == 0) {
       for (int j = 0; j < NKB2; ++j) slot_fill(j, j * W2_BLK, w2p + (size_t)j * W2_BLK, W2_BLK);
@@ -423,6 +440,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     MARK(4);
     // ================= GEMM3: dG = delta2 W2 (two N = 128 halves) ; delta2 image -> HBM =================
     if (tid == 0) {
+      if (has_next) { fence_proxy_async(); w1_kb2_prefetch(); }  // gradient image consumed by EPI-B: region free again
       bulk_s2g(A.d2_img + (size_t)tile * GS_BYTES, sm_u + D2IMG_OFF, NKBL * A_BLK_BYTES);
       bulk_commit();
       tc_fence_after();
