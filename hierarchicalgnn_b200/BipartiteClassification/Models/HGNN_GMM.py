@@ -19,7 +19,8 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...gnn_utils import DynamicGraphConstruction, GraphPlans, HierarchicalGNNCell, InteractionGNNCell
+from ...gnn_utils import (DynamicGraphConstruction, GraphPlans, HierarchicalGNNCell, InteractionGNNCell,
+                          sort_edges_by_destination)
 from ...utils import make_mlp
 from ..bipartite_classification_base import BipartiteClassificationBase
 
@@ -186,7 +187,8 @@ class BC_HierarchicalGNN_GMM(BipartiteClassificationBase):
 
     def forward(self, x, graph, clusters=None):
         N = x.shape[0]
-        directed = GraphPlans(torch.cat([graph, graph.flip(0)], dim=1), N, N)
+        # destination-sorted once per event; nothing downstream depends on the edge order (HGNN_GMM.py:328-346)
+        directed = GraphPlans(sort_edges_by_destination(torch.cat([graph, graph.flip(0)], dim=1))[0], N, N)
         embeddings, nodes, edges = self.ignn_block(x, directed)
         nodes, supernodes, bipartite_graph = self.hgnn_block(x, embeddings, nodes, edges, directed, clusters=clusters)
         bp = GraphPlans(bipartite_graph, N, supernodes.shape[0])

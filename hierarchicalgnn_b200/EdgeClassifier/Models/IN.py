@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...gnn_utils import GraphPlans, InteractionGNNCell
+from ...gnn_utils import GraphPlans, InteractionGNNCell, sort_edges_by_destination
 from ...utils import make_mlp
 from ..edge_classifier_base import EdgeClassifierBase
 
@@ -61,8 +61,12 @@ class EC_InteractionGNN(EdgeClassifierBase):
 
     def forward(self, x, graph):
         E = graph.shape[1]
-        directed = torch.cat([graph, graph.flip(0)], dim=1)
+        directed = torch.cat([graph, graph.flip(0)], dim=1)          # edge k and k+E are mutual reverses (IN.py:122)
+        directed, _, where = sort_edges_by_destination(directed)     # one sort per event; cells stream rows in place
         nodes, edges = self.ignn_block(x, GraphPlans(directed, x.shape[0], x.shape[0]))
-        # classifier input = [e_forward | e_reverse]: two contiguous row blocks, no concat materialised
-        scores = self.edge_classifier.fused([edges[:E], edges[E:]]).squeeze()
+        # classifier input = [e_forward | e_reverse] (IN.py:126): rows where[k] and where[k+E] of the sorted edge
+        # latents, gathered inside the fused MLP kernel — no concat, no un-sort pass
+        fwd = ops.plan_for(where[:E].contiguous(), 2 * E)
+        rev = ops.plan_for(where[E:].contiguous(), 2 * E)
+        scores = self.edge_classifier.fused([edges, edges], [fwd, rev]).squeeze()
         return torch.sigmoid(scores)

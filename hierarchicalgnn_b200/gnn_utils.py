@@ -41,6 +41,16 @@ class GraphPlans:
         return self._dst
 
 
+def sort_edges_by_destination(graph: torch.Tensor):
+    """Returns (sorted_graph, order, inverse): the edge list reordered so destinations ascend (stable), the permutation
+    that produced it and its inverse. The models do this once per event: every cell then streams edge rows in place
+    (identity plan permutation) and the fused segmented reduce sees contiguous runs."""
+    order = torch.argsort(graph[1], stable=True)
+    inverse = torch.empty_like(order)
+    inverse[order] = torch.arange(order.numel(), device=order.device)
+    return graph[:, order].contiguous(), order, inverse
+
+
 def _plans(graph, n_src, n_dst):
     return graph if isinstance(graph, GraphPlans) else GraphPlans(graph, n_src, n_dst)
 
