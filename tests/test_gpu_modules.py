@@ -222,3 +222,30 @@ def test_ec_model_medium_event_auc_and_scores_vs_oracle():
         got = model(ev.x.to(DEV), ev.edge_index.to(DEV)).cpu()
     assert float((got - want).abs().max()) < 5e-5  # fp32 path vs fp64 oracle
     assert abs(O.roc_auc(got, ev.y_pid) - O.roc_auc(want, ev.y_pid)) <= 1e-3
+
+
+def test_ec_full_config_tensor_core_path_scores_and_auc_vs_fp64_oracle():
+    """BASELINE config 1 shape at half size (N=6000, E~27k; full EC-IN config: latent 128, 14 cells) on the DEFAULT
+    (tensor-core) path: scores within the bf16 tolerance of the fp64 oracle (1e-2 on sigmoid scores),
+    AUC difference <= 1e-3."""
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.synth import synth_event
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    torch.manual_seed(0)
+    model = model_selector("EC-IN")
+    kaiming_init(model)
+    ev = synth_event(600, 10, 0.0, 4.0, seed=1000)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        want = O.ec_forward(O.cast_state(sd, torch.float64), dict(model.hparams), ev.x.double(), ev.edge_index).float()
+    model.to(DEV).eval()
+    old = ops.set_precision("auto")
+    try:
+        n0 = ops.TC_CALLS["count"]
+        with torch.no_grad():
+            got = model(ev.x.to(DEV), ev.edge_index.to(DEV)).cpu()
+        assert ops.TC_CALLS["count"] - n0 == 14  # every cell's edge step ran on tensor cores
+    finally:
+        ops.set_precision(old)
+    assert float((got - want).abs().max()) < 1e-2
+    assert abs(O.roc_auc(got, ev.y_pid) - O.roc_auc(want, ev.y_pid)) <= 1e-3
