@@ -296,26 +296,43 @@ def run_gpu(args):
         h2d = sum(t.numel() * t.element_size() for t in (nodes_p, edges_p, graph_p))
         out_host = torch.empty(2, dtype=torch.float32).pin_memory()
 
-        def e2e_step():
-            n_d = nodes_p.to(dev, non_blocking=True).requires_grad_(True)
-            e_d = edges_p.to(dev, non_blocking=True).requires_grad_(True)
-            g_d = graph_p.to(dev, non_blocking=True)
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def upload():
+            """H2D copy of one step's inputs from pinned host memory, on the copy stream (double buffered: step i+1's
+            upload runs under step i's kernels; every step's copy is inside the timed region)."""
+            with torch.cuda.stream(copy_stream):
+                bufs = (nodes_p.to(dev, non_blocking=True), edges_p.to(dev, non_blocking=True), graph_p.to(dev, non_blocking=True))
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            return bufs, done
+
+        def e2e_step(cur):
+            (n_d, e_d, g_d), done = cur
+            torch.cuda.current_stream().wait_event(done)
+            n_d.requires_grad_(True)
+            e_d.requires_grad_(True)
             plans = GraphPlans(g_d, N, N)  # a new graph arrives with every event: plan build is inside the step
             e2, agg, grads = step(n_d, e_d, plans)
             metric = torch.stack([e2.sum() + agg.sum(), grads[1].abs().sum()])
             out_host.copy_(metric, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+
+        def e2e_run(k):
+            cur = upload()
+            for i in range(k):
+                nxt = upload() if i + 1 < k else None
+                e2e_step(cur)
+                torch.cuda.current_stream().synchronize()  # the host reads the step's result before the next step
+                cur = nxt
             return out_host
 
-        for _ in range(3):
-            e2e_step()
+        e2e_run(3)
         barrier()
         k = max(3, min(args.steps, 10))
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        for _ in range(k):
-            e2e_step()
+        e2e_run(k)
         t1.record()
         barrier()
         ems = t0.elapsed_time(t1)
@@ -324,7 +341,8 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         e2e = {"value": world * E / (ems / k * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-               "ms_per_step": ems / k, "steps": k}
+               "ms_per_step": ems / k, "steps": k,
+               "pipeline": "double-buffered H2D on a copy stream, host sync + 8 B D2H per step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -67,7 +67,9 @@ def _edge_update(network, nodes, edges, gp: GraphPlans):
     if agg is not None:
         while len(_AGG_CACHE) >= _AGG_CACHE_MAX:
             _AGG_CACHE.pop(next(iter(_AGG_CACHE)))
-        _AGG_CACHE[id(new_edges)] = (weakref.ref(new_edges), gp.by_dst, agg)
+        key = id(new_edges)
+        # the entry dies with e' (an aggregate nobody consumed, e.g. the last cell's, must not pin device memory)
+        _AGG_CACHE[key] = (weakref.ref(new_edges, lambda _r, k=key: _AGG_CACHE.pop(k, None)), gp.by_dst, agg)
     return new_edges
 
 

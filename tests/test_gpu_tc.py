@@ -237,6 +237,7 @@ def test_tc_cell_stack_with_cached_aggregate_matches_oracle():
     old = ops.set_precision("auto")
     try:
         gp = gnn_utils.GraphPlans(gd, nodes.shape[0], nodes.shape[0])
+        gnn_utils._AGG_CACHE.clear()
         a, b = nd, ed
         calls0 = ops.LAUNCHES["count"]
         for c in cells:
