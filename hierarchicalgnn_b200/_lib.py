@@ -60,6 +60,23 @@ class TcEdgeParams(C.Structure):
     ]
 
 
+class TcRowLayer(C.Structure):
+    _fields_ = [
+        ("n_seg", C.c_int32),
+        ("n_out", C.c_int32),
+        ("act", C.c_int32),
+        ("ln_eps", C.c_float),
+        ("seg_ptr", C.c_void_p * MAX_SEGS),
+        ("seg_idx", C.c_void_p * MAX_SEGS),
+        ("seg_width", C.c_int32 * MAX_SEGS),
+        ("w_packed", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("gamma", C.c_void_p),
+        ("beta", C.c_void_p),
+        ("skip", C.c_void_p),
+    ]
+
+
 i64, i32, f32, sz, vp = C.c_int64, C.c_int32, C.c_float, C.c_size_t, C.c_void_p
 
 # name -> (restype, argtypes); must list every symbol include/hgnn_b200.h declares
@@ -98,6 +115,11 @@ SIGNATURES = {
     "hgnn_tc_edge_backward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                         vp, sz, vp]),  # (p, w1t, w2t, a0_img, src, dst, perm, n_edges, g_e, g_agg, d_e, d_xs, d_xd, dW1, dW2, dv1, dv2, ws, n, st)
     "hgnn_tc_debug_set_phase_clock": (None, [vp]),
+    "hgnn_tc_row_supported": (C.c_int, [C.POINTER(TcRowLayer)]),
+    "hgnn_tc_row_image_bytes": (sz, [i64, i64]),
+    "hgnn_tc_row_forward": (C.c_int, [C.POINTER(TcRowLayer), i64, vp, vp, vp]),
+    "hgnn_tc_row_backward_workspace_bytes": (sz, [i64, i64, i64]),
+    "hgnn_tc_row_backward": (C.c_int, [C.POINTER(TcRowLayer), vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]),
     "hgnn_tc_edge_a0_image_bytes": (sz, [i64, i64]),
     "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz, vp]),
 }

@@ -24,17 +24,6 @@
 using namespace hgnn;
 using namespace hgnn::tc;
 
-namespace hgnn { namespace tc {
-struct WgradProblem {
-  const uint8_t* img_a; int ca_total, ca0, ca;
-  const uint8_t* img_b; int cb_total, cb0, cb;
-  float* out; int ld, row_off, col_off, transpose;
-};
-size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits);
-int wgrad_splits(int n_roles, int n_tiles);
-int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st);
-}}
-
 namespace {
 
 constexpr int NT = 512;
@@ -75,70 +64,6 @@ struct BwdArgs {
   int64_t n_edges;
   unsigned long long* phase_clk;  // optional [16] per-phase cycle accumulators (CTA 0, thread 0); NULL in production
 };
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// column sums over the 32 rows held by a warp: in v[c] = this lane's value for column c;
-// returns the sum over lanes of column `lane` (31 shuffles, log-step register transpose)
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    bool up = lane & 16;
-    float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    bool up = lane & 8;
-    float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bool up = lane & 4;
-    float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    bool up = lane & 2;
-    float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  {
-    bool up = lane & 1;
-    float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  return v[0];
-}
-
-// mean / rstd of a row from 4 equal partial (mean, M2) pairs (Chan et al.), n values each
-__device__ __forceinline__ void combine4(const float* red, int r, int n, float eps, float& mean, float& rstd) {
-  float m[4], q[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { m[i] = red[r * 8 + 2 * i]; q[i] = red[r * 8 + 2 * i + 1]; }
-  mean = 0.25f * (m[0] + m[1] + m[2] + m[3]);
-  float m2 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float d = m[i] - mean; m2 += q[i] + (float)n * d * d; }
-  rstd = rsqrtf(m2 / (4.0f * n) + eps);
-}
 
 template <int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {

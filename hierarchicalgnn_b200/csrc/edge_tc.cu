@@ -53,47 +53,6 @@ struct Cfg {
   static_assert(L == 64 || L == 128, "tensor-core edge step is instantiated for latent 64 and 128");
 };
 
-// gather one K-block (64 fp32 columns starting at `col0` of rows rowid[r] of `base`): 16 threads per 256 B row piece,
-// 16 rows per pass. Split in two so the loads of block k+1 are in flight while block k is converted, stored and multiplied.
-__device__ __forceinline__ void gather_load(float4 (&v)[8], const float* __restrict__ base, int ld, const int* __restrict__ rowid, int col0) {
-  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
-#pragma unroll
-  for (int p = 0; p < 8; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rowid[p * 16 + rr] * ld + col0) + sub);
-}
-// gimg (optional): the same swizzled bf16 block is also left in HBM — the backward pass and the weight-gradient GEMM
-// read these tile images back with bulk copies instead of re-gathering
-__device__ __forceinline__ void gather_store(uint8_t* __restrict__ blk, const float4 (&v)[8], uint8_t* __restrict__ gimg = nullptr) {
-  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
-#pragma unroll
-  for (int p = 0; p < 8; ++p) {
-    const int r = p * 16 + rr;
-    const uint2 pk = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
-    const uint32_t off = sw128_off(r, sub >> 1) + (sub & 1) * 8;
-    *reinterpret_cast<uint2*>(blk + off) = pk;
-    if (gimg) *reinterpret_cast<uint2*>(gimg + off) = pk;
-  }
-}
-__device__ __forceinline__ void gather_a_block(uint8_t* __restrict__ blk, const float* __restrict__ base, int ld,
-                                               const int* __restrict__ rowid, int col0) {
-  float4 v[8];
-  gather_load(v, base, ld, rowid, col0);
-  gather_store(blk, v);
-}
-
-struct LnStat { float mean, rstd; };
-
-// Chan-combine the two half-row partials (n each): returns mean / rstd of the full row
-__device__ __forceinline__ LnStat combine_halves(const float* red, int r, int n_half, float eps) {
-  float m0 = red[r * 4 + 0], q0 = red[r * 4 + 1], m1 = red[r * 4 + 2], q1 = red[r * 4 + 3];
-  float mean = 0.5f * (m0 + m1);
-  float d = m1 - m0;
-  float m2 = q0 + q1 + d * d * (0.5f * n_half);  // Chan: M2 = M2a + M2b + delta^2 * na*nb/(na+nb)
-  LnStat s;
-  s.mean = mean;
-  s.rstd = rsqrtf(m2 / (2.0f * n_half) + eps);
-  return s;
-}
-
 template <int L, int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,

@@ -274,5 +274,124 @@ __device__ __forceinline__ void ln_act_to_image(uint32_t taddr, const float* __r
   }
 }
 
+
+// ---- pieces shared by the fused edge kernels and the per-layer row kernels ----
+// (gathers assume 256-thread CTAs: 16 threads per 256 B row piece, 16 rows per pass)
+// gather one K-block (64 fp32 columns starting at `col0` of rows rowid[r] of `base`): 16 threads per 256 B row piece,
+// 16 rows per pass. Split in two so the loads of block k+1 are in flight while block k is converted, stored and multiplied.
+__device__ __forceinline__ void gather_load(float4 (&v)[8], const float* __restrict__ base, int ld, const int* __restrict__ rowid, int col0) {
+  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rowid[p * 16 + rr] * ld + col0) + sub);
+}
+// gimg (optional): the same swizzled bf16 block is also left in HBM — the backward pass and the weight-gradient GEMM
+// read these tile images back with bulk copies instead of re-gathering
+__device__ __forceinline__ void gather_store(uint8_t* __restrict__ blk, const float4 (&v)[8], uint8_t* __restrict__ gimg = nullptr) {
+  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int r = p * 16 + rr;
+    const uint2 pk = make_uint2(pack_bf16(v[p].x, v[p].y), pack_bf16(v[p].z, v[p].w));
+    const uint32_t off = sw128_off(r, sub >> 1) + (sub & 1) * 8;
+    *reinterpret_cast<uint2*>(blk + off) = pk;
+    if (gimg) *reinterpret_cast<uint2*>(gimg + off) = pk;
+  }
+}
+__device__ __forceinline__ void gather_a_block(uint8_t* __restrict__ blk, const float* __restrict__ base, int ld,
+                                               const int* __restrict__ rowid, int col0) {
+  float4 v[8];
+  gather_load(v, base, ld, rowid, col0);
+  gather_store(blk, v);
+}
+
+struct LnStat { float mean, rstd; };
+
+// Chan-combine the two half-row partials (n each): returns mean / rstd of the full row
+__device__ __forceinline__ LnStat combine_halves(const float* red, int r, int n_half, float eps) {
+  float m0 = red[r * 4 + 0], q0 = red[r * 4 + 1], m1 = red[r * 4 + 2], q1 = red[r * 4 + 3];
+  float mean = 0.5f * (m0 + m1);
+  float d = m1 - m0;
+  float m2 = q0 + q1 + d * d * (0.5f * n_half);  // Chan: M2 = M2a + M2b + delta^2 * na*nb/(na+nb)
+  LnStat s;
+  s.mean = mean;
+  s.rstd = rsqrtf(m2 / (2.0f * n_half) + eps);
+  return s;
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// column sums over the 32 rows held by a warp: in v[c] = this lane's value for column c;
+// returns the sum over lanes of column `lane` (31 shuffles, log-step register transpose)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    bool up = lane & 16;
+    float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bool up = lane & 8;
+    float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bool up = lane & 4;
+    float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    bool up = lane & 2;
+    float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    bool up = lane & 1;
+    float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+// mean / rstd of a row from 4 equal partial (mean, M2) pairs (Chan et al.), n values each
+__device__ __forceinline__ void combine4(const float* red, int r, int n, float eps, float& mean, float& rstd) {
+  float m[4], q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[i] = red[r * 8 + 2 * i]; q[i] = red[r * 8 + 2 * i + 1]; }
+  mean = 0.25f * (m[0] + m[1] + m[2] + m[3]);
+  float m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float d = m[i] - mean; m2 += q[i] + (float)n * d * d; }
+  rstd = rsqrtf(m2 / (4.0f * n) + eps);
+}
+
+
+// weight-gradient GEMM over tile images (wgrad_tc.cu): dW[CA, CB] (+offsets into a larger matrix) = img_a^T img_b
+struct WgradProblem {
+  const uint8_t* img_a; int ca_total, ca0, ca;   // columns of A used: [ca0, ca0+ca), ca multiple of 128
+  const uint8_t* img_b; int cb_total, cb0, cb;   // columns of B used, cb multiple of 64, <= 256
+  float* out; int ld, row_off, col_off, transpose;
+};
+size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits);
+int wgrad_splits(int n_roles, int n_tiles);
+int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace tc
 }  // namespace hgnn

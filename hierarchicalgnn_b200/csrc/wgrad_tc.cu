@@ -153,12 +153,6 @@ __global__ void k_make_image(const float* __restrict__ src, int64_t rows, int co
 namespace hgnn {
 namespace tc {
 
-struct WgradProblem {  // dW[CA, CB] (+offsets into a larger matrix) = img_a^T img_b
-  const uint8_t* img_a; int ca_total, ca0, ca;   // columns of A used: [ca0, ca0+ca), ca multiple of 128
-  const uint8_t* img_b; int cb_total, cb0, cb;   // columns of B used, cb multiple of 64, <= 256
-  float* out; int ld, row_off, col_off, transpose;
-};
-
 size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits) {
   size_t tot = 0;
   for (int i = 0; i < n; ++i) tot += align_up((size_t)splits * probs[i].ca * probs[i].cb * 4, 256);

@@ -16,6 +16,7 @@ Reference call sites replaced (under /root/reference/Modules):
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from collections import OrderedDict
 from typing import List, Optional, Sequence
@@ -63,7 +64,8 @@ class _timed:
 # "bf16" / "auto" = tcgen05 tensor cores (bf16 operands, fp32 accumulate, fp32 storage) wherever
 # a tensor-core kernel exists for the shape, fp32 SIMT elsewhere.
 _PRECISION = {"mode": os.environ.get("HGNN_PRECISION", "auto")}
-TC_CALLS = {"count": 0}
+TC_CALLS = {"count": 0}       # fused tensor-core edge-step launches (forward / backward)
+TC_ROW_CALLS = {"count": 0}   # tensor-core row-layer launches
 
 
 def set_precision(mode: str) -> str:
@@ -80,7 +82,7 @@ def get_precision() -> str:
 
 def compute_dtype(module=None) -> str:
     """Arithmetic type of the MLP contractions on the path that actually ran."""
-    return "bf16" if TC_CALLS["count"] else "f32"
+    return "bf16" if (TC_CALLS["count"] or TC_ROW_CALLS["count"]) else "f32"
 
 
 def _stream() -> int:
@@ -620,6 +622,140 @@ class _TcEdgeStepAgg(torch.autograd.Function):
 
 def tc_edge_step_with_agg(meta: MlpMeta, x: Tensor, e: Tensor, params: Sequence[Tensor]):
     return _TcEdgeStepAgg.apply(meta, x, e, *params)
+
+
+# ---------------------------------------------------------------------------
+# tensor-core row layer (one Linear + LayerNorm + activation on a gathered concatenation)
+# ---------------------------------------------------------------------------
+class RowLayerMeta:
+    """Static description of one tensor-core row-layer call: gather plans per segment, activation, LayerNorm eps,
+    whether a residual tensor follows the segments, and the provider of the packed bf16 weight images."""
+
+    def __init__(self, seg_plans, act: Optional[str], eps: float, has_skip: bool, pack):
+        self.seg_plans = list(seg_plans)
+        self.act = ACT_CODES[act]
+        self.eps = float(eps)
+        self.has_skip = bool(has_skip)
+        self.pack = pack  # callable -> (W image, W^T image)
+
+
+def _row_desc(meta: RowLayerMeta, segs, W, b, g, be, w_packed, skip=None):
+    d = _lib.TcRowLayer()
+    d.n_seg, d.n_out, d.act, d.ln_eps = len(segs), W.shape[0], meta.act, meta.eps
+    rows = None
+    for s, t in enumerate(segs):
+        plan = meta.seg_plans[s]
+        d.seg_ptr[s] = t.data_ptr() if t is not None else None
+        d.seg_width[s] = t.shape[1] if t is not None else 0
+        d.seg_idx[s] = plan.keys32.data_ptr() if plan is not None else None
+        n = plan.n_items if plan is not None else (t.shape[0] if t is not None else None)
+        if rows is None:
+            rows = n
+        elif n is not None and rows != n:
+            raise _lib.HgnnError(f"row layer: segment {s} yields {n} rows, expected {rows}")
+    d.w_packed = _ptr(w_packed)
+    d.bias, d.gamma, d.beta = b.data_ptr(), g.data_ptr(), be.data_ptr()
+    d.skip = _ptr(skip)
+    return d, rows
+
+
+def tc_row_supported(seg_widths: Sequence[int], n_out: int, act: Optional[str]) -> bool:
+    """Whether hgnn_tc_row_forward/backward are built for this layer shape (include/hgnn_b200.h)."""
+    return _tc_row_supported(tuple(int(w) for w in seg_widths), int(n_out), act)
+
+
+@functools.lru_cache(maxsize=256)
+def _tc_row_supported(seg_widths, n_out, act) -> bool:
+    if len(seg_widths) < 1 or len(seg_widths) > MAX_SEGS or act not in ACT_CODES:
+        return False
+    d = _lib.TcRowLayer()
+    d.n_seg, d.n_out, d.act = len(seg_widths), int(n_out), ACT_CODES[act]
+    for s, w in enumerate(seg_widths):
+        d.seg_width[s] = int(w)
+    return bool(_lib.lib().hgnn_tc_row_supported(C.byref(d)))
+
+
+class _TcRowLayer(torch.autograd.Function):
+    """out = act(LayerNorm(W . concat(gathered segments) + b)) (+ skip) on tcgen05 tensor cores. The forward leaves the
+    bf16 image of its gathered input in HBM; the backward recomputes the layer from that image (no fp32 inputs or
+    activations are kept alive by this node) and emits d_in, dW, d bias / gamma / beta."""
+
+    @staticmethod
+    def forward(ctx, meta: RowLayerMeta, n_seg: int, *tensors):
+        _need_cuda(*tensors)
+        segs = [_f32(t) for t in tensors[:n_seg]]
+        skip = _f32(tensors[n_seg]) if meta.has_skip else None
+        W, b, g, be = [_f32(t) for t in tensors[n_seg + int(meta.has_skip):]]
+        w_packed, _ = meta.pack()
+        d, rows = _row_desc(meta, segs, W, b, g, be, w_packed, skip)
+        K = sum(t.shape[1] for t in segs)
+        out = torch.empty((rows, W.shape[0]), dtype=torch.float32, device=W.device)
+        if skip is not None and tuple(skip.shape) != tuple(out.shape):
+            raise _lib.HgnnError(f"row layer: residual has shape {tuple(skip.shape)}, output {tuple(out.shape)}")
+        need_bwd = any(ctx.needs_input_grad[2:])
+        a_img = None
+        if need_bwd and rows:
+            a_img = torch.empty(_lib.lib().hgnn_tc_row_image_bytes(rows, K), dtype=torch.uint8, device=W.device)
+        if rows:
+            with _timed("tc_row_forward"):
+                check(_lib.lib().hgnn_tc_row_forward(C.byref(d), rows, _ptr(out), _ptr(a_img), _stream()), "tc_row_forward")
+            _count()
+            TC_ROW_CALLS["count"] += 1
+        ctx.meta, ctx.n_seg, ctx.rows, ctx.a_img = meta, n_seg, rows, a_img
+        ctx.widths = [t.shape[1] for t in segs]
+        ctx.seg_rows = [t.shape[0] for t in segs]
+        ctx.save_for_backward(W, b, g, be)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        meta, n_seg, rows = ctx.meta, ctx.n_seg, ctx.rows
+        W, b, g, be = ctx.saved_tensors
+        gout = _f32(gout)
+        dev = W.device
+        N, K = W.shape
+        w_packed, wt_packed = meta.pack()
+        d, _ = _row_desc(meta, [None] * n_seg, W, b, g, be, w_packed)
+        for s in range(n_seg):
+            d.seg_width[s] = ctx.widths[s]
+        d_in = torch.empty((rows, K), dtype=torch.float32, device=dev)
+        dW = torch.empty_like(W)
+        dvec = torch.empty((3, N), dtype=torch.float32, device=dev)
+        L_ = _lib.lib()
+        if rows:
+            ws = _workspace(L_.hgnn_tc_row_backward_workspace_bytes(rows, K, N), dev)
+            with _timed("tc_row_backward"):
+                check(L_.hgnn_tc_row_backward(C.byref(d), _ptr(wt_packed), _ptr(ctx.a_img), rows, _ptr(gout), _ptr(d_in), _ptr(dW),
+                                              _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "tc_row_backward")
+            _count(2 + 1 + K // 128)
+            TC_ROW_CALLS["count"] += 1
+        else:
+            dW.zero_()
+            dvec.zero_()
+        grads: List[Optional[Tensor]] = [None, None]
+        need = ctx.needs_input_grad[2:]
+        off = 0
+        for s in range(n_seg):
+            w = ctx.widths[s]
+            gs = None
+            if need[s]:
+                gs = d_in if n_seg == 1 else d_in[:, off:off + w]
+                plan = meta.seg_plans[s]
+                if plan is not None:
+                    if plan.n_segments != ctx.seg_rows[s]:
+                        raise _lib.HgnnError("row layer: gather plan does not cover the gathered tensor")
+                    gs = segment_reduce_raw(gs.contiguous(), plan)
+            grads.append(gs)
+            off += w
+        if meta.has_skip:
+            grads.append(gout if need[n_seg] else None)  # d(out)/d(skip) = identity
+        grads += [dW, dvec[0], dvec[1], dvec[2]]
+        return tuple(grads)
+
+
+def tc_row_layer(meta: RowLayerMeta, segs: Sequence[Tensor], skip: Optional[Tensor], W, b, gamma, beta) -> Tensor:
+    extra = [skip] if meta.has_skip else []
+    return _TcRowLayer.apply(meta, len(segs), *segs, *extra, W, b, gamma, beta)
 
 
 def fused_mlp(meta: MlpMeta, segs: Sequence[Tensor], params: Sequence[Tensor]) -> Tensor:

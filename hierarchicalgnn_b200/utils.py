@@ -63,8 +63,89 @@ class FusedMLP(nn.Sequential):
         if plans is None:
             plans = [None] * len(segs)
         ps, acts, lns, eps = self._params()
-        meta = ops.MlpMeta(plans, acts, lns, skip, eps, tc_pack=self._tc_packer(segs, plans, skip, lns))
+        packer = self._tc_packer(segs, plans, skip, lns)
+        if packer is None:
+            groups = self._row_groups(segs, plans, skip)
+            if groups is not None:
+                return self._run_groups(groups, list(segs), list(plans), skip)
+        meta = ops.MlpMeta(plans, acts, lns, skip, eps, tc_pack=packer)
         return ops.fused_mlp(meta, list(segs), ps)
+
+    # ---- layer-wise execution: tensor-core row layers where a kernel exists, fp32 SIMT groups elsewhere ----
+    def _row_groups(self, segs, plans, skip):
+        """[("tc", l) | ("simt", l0, l1)] covering the layers in order, or None when no layer can use the tensor-core
+        row kernel (precision fp32, CPU tensors, odd shapes): the whole stack then runs as one fp32 kernel."""
+        if ops.get_precision() == "fp32" or not all(t.is_cuda for t in segs):
+            return None
+        if skip >= 0 and plans[skip] is not None:
+            return None  # a gathered residual only exists in the fused fp32 kernel
+        layers = self._layers()
+        groups, any_tc, cur = [], False, None
+        widths = [t.shape[1] for t in segs]
+        for l, (lin, ln, act) in enumerate(layers):
+            w_in = widths if l == 0 else [layers[l - 1][0].out_features]
+            ok = ln is not None and ops.tc_row_supported(w_in, lin.out_features, act)
+            if ok:
+                if cur is not None:
+                    groups.append(("simt", cur, l))
+                    cur = None
+                groups.append(("tc", l))
+                any_tc = True
+            elif cur is None:
+                cur = l
+        if cur is not None:
+            groups.append(("simt", cur, len(layers)))
+        return groups if any_tc else None
+
+    def _row_pack(self, l):
+        lin = self._layers()[l][0]
+
+        def pack():
+            w = lin.weight
+            key = (w.data_ptr(), w._version)
+            cache = self.__dict__.setdefault("_row_cache", {})
+            hit = cache.get(l)
+            if hit is None or hit[0] != key:  # bf16 shadow images, rebuilt lazily when the fp32 parameter changes
+                hit = (key, ops.tc_pack_weight(w), ops.tc_pack_weight_t(w))
+                cache[l] = hit
+            return hit[1], hit[2]
+        return pack
+
+    def _run_groups(self, groups, segs, plans, skip):
+        layers = self._layers()
+        last = len(layers) - 1
+        cur_segs, cur_plans = segs, plans
+        residual = segs[skip] if skip >= 0 else None
+        for grp in groups:
+            if grp[0] == "tc":
+                l = grp[1]
+                lin, ln, act = layers[l]
+                res = residual if l == last else None
+                meta = ops.RowLayerMeta(cur_plans, act, ln.eps, res is not None, self._row_pack(l))
+                y = ops.tc_row_layer(meta, cur_segs, res, lin.weight, lin.bias, ln.weight, ln.bias)
+            else:
+                l0, l1 = grp[1], grp[2]
+                ps, acts, lns, eps = [], [], [], 1e-5
+                for lin, ln, act in layers[l0:l1]:
+                    ps += [lin.weight, lin.bias]
+                    if ln is not None:
+                        ps += [ln.weight, ln.bias]
+                        eps = ln.eps
+                    acts.append(act)
+                    lns.append(ln is not None)
+                sk = -1
+                call_segs, call_plans = list(cur_segs), list(cur_plans)
+                if l1 - 1 == last and residual is not None:
+                    if l0 == 0:
+                        sk = skip
+                    else:  # the residual is not an input of this trailing fp32 group: added after it
+                        sk = -2
+                meta = ops.MlpMeta(call_plans, acts, lns, sk if sk >= 0 else -1, eps)
+                y = ops.fused_mlp(meta, call_segs, ps)
+                if sk == -2:
+                    y = y + residual
+            cur_segs, cur_plans = [y], [None]
+        return y
 
     def edge_step(self, nodes, edges, plan_src, plan_dst):
         """e' = MLP([x[src] | x[dst] | e]) + e. Returns (e', agg) where agg = scatter_add(e', dst) comes out of the

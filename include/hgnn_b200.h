@@ -248,6 +248,45 @@ int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, 
                           const float* grad_agg, float* d_e, float* d_xsrc_rows, float* d_xdst_rows, float* dW1, float* dW2,
                           float* dvec1, float* dvec2, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Tensor-core row layer: ONE make_mlp layer (utils.py:183-196) on a gathered concatenation,
+ *   out[r] = act(LayerNorm(W . [seg0[i0(r)] | seg1[i1(r)] | seg2[i2(r)]] + b)) (+ skip[r])
+ * bf16 operands / fp32 accumulate in TMEM / fp32 storage. Covers the node and supernode updates
+ * (gnn_utils.py:45-54,119-127,137-145), the encoder layers past the first and the hidden layers of the heads
+ * (EC/Models/IN.py:29-48,126; BC/Models/HGNN_GMM.py:37-82,342-344). Built for: 1..3 segments of width % 64 == 0,
+ * fan-in % 128 == 0 and <= 384, fan-out 128 or 256, LayerNorm present, activation GELU/Tanh/ReLU/SiLU. `skip`
+ * (optional) is any fp32 [rows, fan_out] matrix added after the activation (the residual of the node updates);
+ * its gradient is grad_out itself, so the backward entry does not return it.
+ * hgnn_tc_row_supported() answers exactly that; other layers run on the fp32 kernels above.
+ * a_img (optional, hgnn_tc_row_image_bytes(rows, fan_in)): bf16 tile image of the gathered input, left in HBM for
+ * the backward (which recomputes the layer from it and never touches the fp32 inputs again).
+ * Backward: d_in[rows, fan_in] per-row input gradients (the caller splits columns per segment and reduces gathered
+ * segments with hgnn_segment_reduce), dW[fan_out, fan_in], dvec[3, fan_out] = (d bias, d gamma, d beta).
+ * wt_packed = hgnn_tc_pack_weights image of W^T (fan-in rows; > 256 rows: 128-row packs interleaved per K-block).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_seg;
+  int32_t n_out;
+  int32_t act; /* hgnn_act after the LayerNorm */
+  float ln_eps;
+  const float* seg_ptr[HGNN_MLP_MAX_SEGS];
+  const int32_t* seg_idx[HGNN_MLP_MAX_SEGS]; /* NULL: rows used in place */
+  int32_t seg_width[HGNN_MLP_MAX_SEGS];
+  const void* w_packed; /* hgnn_tc_pack_weights image of W [n_out, fan_in] */
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  const float* skip; /* NULL: no residual */
+} hgnn_tc_row_layer;
+
+int hgnn_tc_row_supported(const hgnn_tc_row_layer* d);
+size_t hgnn_tc_row_image_bytes(int64_t rows, int64_t fan_in);
+int hgnn_tc_row_forward(const hgnn_tc_row_layer* d, int64_t rows, float* out, void* a_img, void* stream);
+size_t hgnn_tc_row_backward_workspace_bytes(int64_t rows, int64_t fan_in, int64_t n_out);
+int hgnn_tc_row_backward(const hgnn_tc_row_layer* d, const void* wt_packed, const void* a_img, int64_t rows,
+                         const float* grad_out, float* d_in, float* dW, float* dvec, void* ws, size_t ws_bytes,
+                         void* stream);
+
 /* Profiling hook: when set (device buffer of 16 uint64), CTA 0 of hgnn_tc_edge_backward accumulates the cycles it
  * spends in each phase of the tile loop (GEMM1, EPI-A, GEMM2, EPI-B, GEMM3, EPI-C, GEMM4, EPI-D). NULL disables. */
 void hgnn_tc_debug_set_phase_clock(void* dev_u64x16);
