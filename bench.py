@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-edges", type=int, default=40_000, help="bounded CPU-baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "serial"],
+                    help="pipelined: step i+1's H2D upload runs on a copy stream under step i's kernels; serial: same stream")
     ap.add_argument("--mode", default="dp", choices=["dp", "partition"],
                     help="dp: every rank owns a batch of edges (weak scaling, default); partition: ONE full-pile-up "
                          "event split by destination node across ranks (strong scaling, BASELINE config 5)")
@@ -317,10 +319,15 @@ def run_gpu(args):
             metric = torch.stack([e2.sum() + agg.sum(), grads[1].abs().sum()])
             out_host.copy_(metric, non_blocking=True)
 
+        if args.e2e_mode == "serial":
+            copy_stream = torch.cuda.current_stream()
+
         def e2e_run(k):
             cur = upload()
             for i in range(k):
-                nxt = upload() if i + 1 < k else None
+                nxt = upload() if (i + 1 < k and args.e2e_mode == "pipelined") else None
+                if args.e2e_mode == "serial" and i > 0:
+                    cur = upload()
                 e2e_step(cur)
                 torch.cuda.current_stream().synchronize()  # the host reads the step's result before the next step
                 cur = nxt
@@ -342,7 +349,8 @@ def run_gpu(args):
             ems = float(t.item())
         e2e = {"value": world * E / (ems / k * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                "ms_per_step": ems / k, "steps": k,
-               "pipeline": "double-buffered H2D on a copy stream, host sync + 8 B D2H per step"}
+               "pipeline": ("double-buffered H2D on a copy stream" if args.e2e_mode == "pipelined" else "H2D on the compute stream")
+                           + ", host sync + 8 B D2H per step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,494 @@
+// Skinny make_mlp layers (utils.py:183-196), fp32 SIMT, one warp per row — the two layer shapes that are pure
+// bandwidth and have no business in a GEMM kernel:
+//   narrow-in :  fan-in <= 8  (the encoders' first Linear on x[N,3] / [x[src] | x[dst]], EC/Models/IN.py:29-33,84-85;
+//                BC/Models/HGNN_GMM.py:37-41) -> out[r, :] = act(LayerNorm(W a_r + b)), write-bound
+//   narrow-out:  fan-out <= 8 (edge classifier / bipartite score / embedding heads, EC/Models/IN.py:126,
+//                BC/Models/HGNN_GMM.py:45-48,342-344) -> out[r, n] = <W[n, :], a_r> + b[n], read-bound
+// Backward passes recompute what they need per row, keep the weight / bias / LayerNorm-affine gradient partials in
+// registers across the rows a warp owns, and sum them warp by warp, CTA by CTA in a fixed order (bit-reproducible).
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace hgnn;
+
+namespace {
+
+constexpr int SK_THREADS = 256;
+constexpr int SK_WARPS = SK_THREADS / 32;
+constexpr int NI_MAX_K = 8;
+
+struct NarrowInArgs {
+  const float* seg_ptr[HGNN_MLP_MAX_SEGS];
+  const int32_t* seg_idx[HGNN_MLP_MAX_SEGS];
+  int seg_width[HGNN_MLP_MAX_SEGS];
+  int n_seg, K, N, act;
+  float eps;
+  const float *W, *bias, *gamma, *beta;  // gamma == NULL: no LayerNorm
+  int64_t rows;
+};
+
+// lane k < K fetches input column k of row r (through the segment gathers); everyone gets all K values by shuffle
+__device__ __forceinline__ void load_row(const NarrowInArgs& A, int64_t r, int lane, int my_seg, int my_col, float (&a)[NI_MAX_K]) {
+  float mine = 0.f;
+  if (lane < A.K) {
+    const int64_t sr = A.seg_idx[my_seg] ? (int64_t)A.seg_idx[my_seg][r] : r;
+    mine = __ldg(A.seg_ptr[my_seg] + sr * A.seg_width[my_seg] + my_col);
+  }
+#pragma unroll
+  for (int k = 0; k < NI_MAX_K; ++k) a[k] = __shfl_sync(0xffffffffu, mine, k);
+}
+
+__device__ __forceinline__ void lane_source(const NarrowInArgs& A, int lane, int& seg, int& col) {
+  int c = lane, s = 0;
+  while (s + 1 < A.n_seg && c >= A.seg_width[s]) { c -= A.seg_width[s]; ++s; }
+  seg = s;
+  col = c;
+}
+
+// shared: Wt[K][N] | bias[N] | gamma[N] | beta[N]
+template <int NJ>
+__device__ __forceinline__ void stage_params(const NarrowInArgs& A, float* sm) {
+  const int N = A.N;
+  for (int i = threadIdx.x; i < N * A.K; i += SK_THREADS) {
+    const int n = i / A.K, k = i % A.K;
+    sm[k * N + n] = A.W[i];
+  }
+  float* sb = sm + NI_MAX_K * N;
+  for (int i = threadIdx.x; i < N; i += SK_THREADS) {
+    sb[i] = A.bias[i];
+    sb[N + i] = A.gamma ? A.gamma[i] : 1.f;
+    sb[2 * N + i] = A.beta ? A.beta[i] : 0.f;
+  }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(SK_THREADS) k_narrow_in_fwd(NarrowInArgs A, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int N = A.N;
+  stage_params<NJ>(A, sm);
+  __syncthreads();
+  const float *sb = sm + NI_MAX_K * N, *sg = sb + N, *sbe = sb + 2 * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int my_seg, my_col;
+  lane_source(A, lane, my_seg, my_col);
+  const float invN = 1.0f / N;
+  for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < A.rows; r += (int64_t)gridDim.x * SK_WARPS) {
+    float a[NI_MAX_K];
+    load_row(A, r, lane, my_seg, my_col, a);
+    float h[NJ];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane + 32 * j;
+      float v = sb[c];
+#pragma unroll
+      for (int k = 0; k < NI_MAX_K; ++k)
+        if (k < A.K) v = fmaf(sm[k * N + c], a[k], v);
+      h[j] = v;
+      sum += v;
+    }
+    if (A.gamma) {
+      const float mean = warp_sum(sum) * invN;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const float d = h[j] - mean; sq = fmaf(d, d, sq); }
+      const float rstd = rsqrtf(warp_sum(sq) * invN + A.eps);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int c = lane + 32 * j; h[j] = fmaf((h[j] - mean) * rstd, sg[c], sbe[c]); }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) out[(size_t)r * N + lane + 32 * j] = act_fwd(A.act, h[j]);
+  }
+}
+
+// partial layout per CTA: [K + 3][N] = dW^T rows (k-major) | d bias | d gamma | d beta
+template <int NJ>
+__global__ void __launch_bounds__(SK_THREADS) k_narrow_in_bwd(NarrowInArgs A, const float* __restrict__ gout, float* __restrict__ d_in,
+                                                              float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  const int N = A.N;
+  stage_params<NJ>(A, sm);
+  float* s_acc = sm + (NI_MAX_K + 3) * N;  // [K + 3][N] CTA accumulator
+  for (int i = threadIdx.x; i < (NI_MAX_K + 3) * N; i += SK_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const float *sb = sm + NI_MAX_K * N, *sg = sb + N, *sbe = sb + 2 * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int my_seg, my_col;
+  lane_source(A, lane, my_seg, my_col);
+  const float invN = 1.0f / N;
+  float aW[NJ][NI_MAX_K], ab[NJ], ag[NJ], abe[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    ab[j] = ag[j] = abe[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NI_MAX_K; ++k) aW[j][k] = 0.f;
+  }
+  for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < A.rows; r += (int64_t)gridDim.x * SK_WARPS) {
+    float a[NI_MAX_K];
+    load_row(A, r, lane, my_seg, my_col, a);
+    float h[NJ], go[NJ];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane + 32 * j;
+      go[j] = __ldg(gout + (size_t)r * N + c);
+      float v = sb[c];
+#pragma unroll
+      for (int k = 0; k < NI_MAX_K; ++k)
+        if (k < A.K) v = fmaf(sm[k * N + c], a[k], v);
+      h[j] = v;
+      sum += v;
+    }
+    float delta[NJ];
+    if (A.gamma) {
+      const float mean = warp_sum(sum) * invN;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const float d = h[j] - mean; sq = fmaf(d, d, sq); }
+      const float rstd = rsqrtf(warp_sum(sq) * invN + A.eps);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int c = lane + 32 * j;
+        const float xh = (h[j] - mean) * rstd;
+        const float d = go[j] * act_bwd(A.act, fmaf(xh, sg[c], sbe[c]));
+        ag[j] = fmaf(d, xh, ag[j]);
+        abe[j] += d;
+        const float gd = sg[c] * d;
+        h[j] = xh;
+        delta[j] = gd;
+        s1 += gd;
+        s2 = fmaf(gd, xh, s2);
+      }
+      s1 = warp_sum(s1) * invN;
+      s2 = warp_sum(s2) * invN;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) delta[j] = rstd * (delta[j] - s1 - h[j] * s2);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) delta[j] = go[j] * act_bwd(A.act, h[j]);
+    }
+    float da[NI_MAX_K];
+#pragma unroll
+    for (int k = 0; k < NI_MAX_K; ++k) da[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane + 32 * j;
+      ab[j] += delta[j];
+#pragma unroll
+      for (int k = 0; k < NI_MAX_K; ++k) {
+        if (k < A.K) {
+          aW[j][k] = fmaf(delta[j], a[k], aW[j][k]);
+          da[k] = fmaf(delta[j], sm[k * N + c], da[k]);
+        }
+      }
+    }
+    if (d_in) {
+      float mine = 0.f;
+#pragma unroll
+      for (int k = 0; k < NI_MAX_K; ++k) {
+        if (k < A.K) {
+          const float s = warp_sum(da[k]);
+          if (lane == k) mine = s;
+        }
+      }
+      if (lane < A.K) d_in[(size_t)r * A.K + lane] = mine;
+    }
+  }
+  // ordered accumulation: warp 0, 1, ... 7 add their registers into the CTA accumulator in turn
+  for (int w = 0; w < SK_WARPS; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int c = lane + 32 * j;
+#pragma unroll
+        for (int k = 0; k < NI_MAX_K; ++k)
+          if (k < A.K) s_acc[k * N + c] += aW[j][k];
+        s_acc[(NI_MAX_K + 0) * N + c] += ab[j];
+        s_acc[(NI_MAX_K + 1) * N + c] += ag[j];
+        s_acc[(NI_MAX_K + 2) * N + c] += abe[j];
+      }
+    }
+    __syncthreads();
+  }
+  float* o = partial + (size_t)blockIdx.x * (NI_MAX_K + 3) * N;
+  for (int i = threadIdx.x; i < (NI_MAX_K + 3) * N; i += SK_THREADS) o[i] = s_acc[i];
+}
+
+// dW[n, k] = sum_cta partial[cta][k][n];  dvec[3, N] = (d bias, d gamma, d beta)
+__global__ void k_narrow_in_reduce(const float* __restrict__ partial, int n_part, int N, int K, float* __restrict__ dW,
+                                   float* __restrict__ dvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (NI_MAX_K + 3) * N) return;
+  const int k = i / N, n = i % N;
+  if (k < NI_MAX_K && k >= K) return;
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) s += partial[(size_t)p * (NI_MAX_K + 3) * N + i];
+  if (k < NI_MAX_K) dW[(size_t)n * K + k] = s;
+  else dvec[(size_t)(k - NI_MAX_K) * N + n] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NO_MAX_N = 8;
+
+// out[r, n] = <W[n, :], a[r, :]> + b[n];  KCH = K / 128 float4 chunks per lane
+template <int KCH>
+__global__ void __launch_bounds__(SK_THREADS) k_narrow_out_fwd(const float* __restrict__ a, int64_t rows, int K, const float* __restrict__ W,
+                                                               const float* __restrict__ bias, int n_out, float* __restrict__ out) {
+  extern __shared__ float sm[];  // W [n_out][K]
+  for (int i = threadIdx.x; i < n_out * K; i += SK_THREADS) sm[i] = W[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < rows; r += (int64_t)gridDim.x * SK_WARPS) {
+    float4 av[KCH];
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) av[c] = __ldg(reinterpret_cast<const float4*>(a + (size_t)r * K) + lane + 32 * c);
+    float acc[NO_MAX_N];
+#pragma unroll
+    for (int n = 0; n < NO_MAX_N; ++n) {
+      acc[n] = 0.f;
+      if (n < n_out) {
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          const float4 w = *reinterpret_cast<const float4*>(sm + (size_t)n * K + (lane + 32 * c) * 4);
+          acc[n] = fmaf(av[c].x, w.x, fmaf(av[c].y, w.y, fmaf(av[c].z, w.z, fmaf(av[c].w, w.w, acc[n]))));
+        }
+        acc[n] = warp_sum(acc[n]);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < NO_MAX_N; ++n)
+        if (n < n_out) out[(size_t)r * n_out + n] = acc[n] + bias[n];
+    }
+  }
+}
+
+// d_a[r, :] = sum_n gout[r, n] W[n, :];  partial per CTA: [n_out][K] dW | [n_out] db
+template <int KCH, int NMAX>
+__global__ void __launch_bounds__(SK_THREADS) k_narrow_out_bwd(const float* __restrict__ a, int64_t rows, int K, const float* __restrict__ W,
+                                                               int n_out, const float* __restrict__ gout, float* __restrict__ d_a,
+                                                               float* __restrict__ partial) {
+  extern __shared__ float sm[];  // W [n_out][K] | acc [n_out][K] | db [NO_MAX_N]
+  float* s_acc = sm + n_out * K;
+  for (int i = threadIdx.x; i < n_out * K; i += SK_THREADS) { sm[i] = W[i]; s_acc[i] = 0.f; }
+  if (threadIdx.x < NO_MAX_N) s_acc[n_out * K + threadIdx.x] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 aw[NMAX][KCH];
+  float ab[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    ab[n] = 0.f;
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) aw[n][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < rows; r += (int64_t)gridDim.x * SK_WARPS) {
+    float4 av[KCH], da[KCH];
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      av[c] = __ldg(reinterpret_cast<const float4*>(a + (size_t)r * K) + lane + 32 * c);
+      da[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      if (n < n_out) {
+        const float g = __ldg(gout + (size_t)r * n_out + n);
+        ab[n] += g;
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          const float4 w = *reinterpret_cast<const float4*>(sm + (size_t)n * K + (lane + 32 * c) * 4);
+          da[c].x = fmaf(g, w.x, da[c].x); da[c].y = fmaf(g, w.y, da[c].y);
+          da[c].z = fmaf(g, w.z, da[c].z); da[c].w = fmaf(g, w.w, da[c].w);
+          aw[n][c].x = fmaf(g, av[c].x, aw[n][c].x); aw[n][c].y = fmaf(g, av[c].y, aw[n][c].y);
+          aw[n][c].z = fmaf(g, av[c].z, aw[n][c].z); aw[n][c].w = fmaf(g, av[c].w, aw[n][c].w);
+        }
+      }
+    }
+    if (d_a) {
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) *(reinterpret_cast<float4*>(d_a + (size_t)r * K) + lane + 32 * c) = da[c];
+    }
+  }
+  for (int w = 0; w < SK_WARPS; ++w) {  // ordered accumulation over the warps
+    if (warp == w) {
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n) {
+        if (n < n_out) {
+#pragma unroll
+          for (int c = 0; c < KCH; ++c) {
+            float4* p = reinterpret_cast<float4*>(s_acc + (size_t)n * K + (lane + 32 * c) * 4);
+            float4 v = *p;
+            v.x += aw[n][c].x; v.y += aw[n][c].y; v.z += aw[n][c].z; v.w += aw[n][c].w;
+            *p = v;
+          }
+          if (lane == 0) s_acc[n_out * K + n] += ab[n];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* o = partial + (size_t)blockIdx.x * (n_out * K + NO_MAX_N);
+  for (int i = threadIdx.x; i < n_out * K + NO_MAX_N; i += SK_THREADS) o[i] = s_acc[i];
+}
+
+__global__ void k_narrow_out_reduce(const float* __restrict__ partial, int n_part, int stride, int n_w, int n_out, float* __restrict__ dW,
+                                    float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_w + n_out) return;
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) s += partial[(size_t)p * stride + i];
+  if (i < n_w) dW[i] = s; else db[i - n_w] = s;
+}
+
+int narrow_in_args(const hgnn_mlp_desc* d, int64_t rows, NarrowInArgs& a, const char* who) {
+  HGNN_REQUIRE(d != nullptr, "%s: desc is NULL", who);
+  if (!hgnn_narrow_in_supported(d))
+    return fail(HGNN_ERR_UNSUPPORTED, "%s: needs one layer, fan-in <= %d, fan-out in {32, 64, 128, 256}", who, NI_MAX_K);
+  HGNN_REQUIRE(rows >= 0 && rows < INT32_MAX, "%s: rows out of range", who);
+  a = NarrowInArgs{};
+  a.n_seg = d->n_seg;
+  int k = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    HGNN_REQUIRE(d->seg_ptr[s] != nullptr, "%s: segment %d is NULL", who, s);
+    a.seg_ptr[s] = d->seg_ptr[s]; a.seg_idx[s] = d->seg_idx[s]; a.seg_width[s] = d->seg_width[s];
+    k += d->seg_width[s];
+  }
+  a.K = k; a.N = d->out_width[0]; a.act = d->act[0]; a.eps = d->ln_eps;
+  a.W = d->W[0]; a.bias = d->b[0]; a.gamma = d->gamma[0]; a.beta = d->beta[0];
+  a.rows = rows;
+  HGNN_REQUIRE(a.W && a.bias && ((a.gamma == nullptr) == (a.beta == nullptr)), "%s: NULL parameter", who);
+  return HGNN_OK;
+}
+
+int skinny_grid(int64_t rows, int rows_per_cta) {
+  int64_t want = (rows + rows_per_cta - 1) / rows_per_cta;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, 2 * (int64_t)num_sms()));
+}
+
+}  // namespace
+
+extern "C" int hgnn_narrow_in_supported(const hgnn_mlp_desc* d) {
+  if (!d || d->n_layers != 1 || d->n_seg < 1 || d->n_seg > HGNN_MLP_MAX_SEGS || d->skip_seg >= 0 || d->out_idx) return 0;
+  int k = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    if (d->seg_width[s] <= 0) return 0;
+    k += d->seg_width[s];
+  }
+  const int n = d->out_width[0];
+  return k <= NI_MAX_K && (n == 32 || n == 64 || n == 128 || n == 256);
+}
+
+extern "C" int hgnn_narrow_in_forward(const hgnn_mlp_desc* d, int64_t rows, float* out, void* stream) {
+  NarrowInArgs a;
+  int rc = narrow_in_args(d, rows, a, "narrow_in_forward");
+  if (rc) return rc;
+  if (rows == 0) return HGNN_OK;
+  HGNN_REQUIRE(out != nullptr, "narrow_in_forward: out is NULL");
+  const size_t smem = (size_t)(NI_MAX_K + 3) * a.N * 4;
+  const int grid = skinny_grid(rows, SK_WARPS * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a.N / 32) {
+    case 1: k_narrow_in_fwd<1><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+    case 2: k_narrow_in_fwd<2><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+    case 4: k_narrow_in_fwd<4><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+    default: k_narrow_in_fwd<8><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+  }
+  return check_launch("narrow_in_forward");
+}
+
+extern "C" size_t hgnn_narrow_in_backward_workspace_bytes(int64_t n_out) {
+  return (size_t)2 * num_sms() * (NI_MAX_K + 3) * n_out * 4 + 256;
+}
+
+extern "C" int hgnn_narrow_in_backward(const hgnn_mlp_desc* d, int64_t rows, const float* grad_out, float* d_in, float* dW,
+                                       float* dvec, void* ws, size_t ws_bytes, void* stream) {
+  NarrowInArgs a;
+  int rc = narrow_in_args(d, rows, a, "narrow_in_backward");
+  if (rc) return rc;
+  HGNN_REQUIRE(dW && dvec, "narrow_in_backward: NULL output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(dW, 0, (size_t)a.N * a.K * 4, st));
+    HGNN_CUDA_TRY(cudaMemsetAsync(dvec, 0, (size_t)3 * a.N * 4, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(grad_out && ws, "narrow_in_backward: NULL pointer");
+  const int grid = skinny_grid(rows, SK_WARPS * 8);
+  HGNN_REQUIRE(ws_bytes >= (size_t)grid * (NI_MAX_K + 3) * a.N * 4, "narrow_in_backward: workspace too small");
+  float* partial = (float*)ws;
+  const size_t smem = (size_t)2 * (NI_MAX_K + 3) * a.N * 4;
+  switch (a.N / 32) {
+    case 1: k_narrow_in_bwd<1><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    case 2: k_narrow_in_bwd<2><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    case 4: k_narrow_in_bwd<4><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    default: k_narrow_in_bwd<8><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+  }
+  rc = check_launch("narrow_in_backward");
+  if (rc) return rc;
+  const int total = (NI_MAX_K + 3) * a.N;
+  k_narrow_in_reduce<<<(total + 255) / 256, 256, 0, st>>>(partial, grid, a.N, a.K, dW, dvec);
+  if (!a.gamma) {  // no LayerNorm: d gamma / d beta rows are meaningless -> zero
+    HGNN_CUDA_TRY(cudaMemsetAsync(dvec + a.N, 0, (size_t)2 * a.N * 4, st));
+  }
+  return check_launch("narrow_in_backward (reduce)");
+}
+
+extern "C" int hgnn_narrow_out_supported(int64_t k, int64_t n_out) {
+  return (k == 128 || k == 256 || k == 512) && n_out >= 1 && n_out <= NO_MAX_N && k * n_out <= 2048;
+}
+
+extern "C" int hgnn_narrow_out_forward(const float* a, int64_t rows, int64_t k, const float* W, const float* bias, int64_t n_out,
+                                       float* out, void* stream) {
+  if (!hgnn_narrow_out_supported(k, n_out))
+    return fail(HGNN_ERR_UNSUPPORTED, "narrow_out_forward: needs fan-in in {128, 256, 512}, fan-out <= 8, fan-in * fan-out <= 2048");
+  if (rows <= 0) return HGNN_OK;
+  HGNN_REQUIRE(a && W && bias && out, "narrow_out_forward: NULL pointer");
+  const size_t smem = (size_t)n_out * k * 4;
+  const int grid = skinny_grid(rows, SK_WARPS * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (k / 128) {
+    case 1: k_narrow_out_fwd<1><<<grid, SK_THREADS, smem, st>>>(a, rows, (int)k, W, bias, (int)n_out, out); break;
+    case 2: k_narrow_out_fwd<2><<<grid, SK_THREADS, smem, st>>>(a, rows, (int)k, W, bias, (int)n_out, out); break;
+    default: k_narrow_out_fwd<4><<<grid, SK_THREADS, smem, st>>>(a, rows, (int)k, W, bias, (int)n_out, out); break;
+  }
+  return check_launch("narrow_out_forward");
+}
+
+extern "C" size_t hgnn_narrow_out_backward_workspace_bytes(int64_t k, int64_t n_out) {
+  return (size_t)2 * num_sms() * (n_out * k + NO_MAX_N) * 4 + 256;
+}
+
+extern "C" int hgnn_narrow_out_backward(const float* a, int64_t rows, int64_t k, const float* W, int64_t n_out, const float* grad_out,
+                                        float* d_a, float* dW, float* db, void* ws, size_t ws_bytes, void* stream) {
+  if (!hgnn_narrow_out_supported(k, n_out))
+    return fail(HGNN_ERR_UNSUPPORTED, "narrow_out_backward: needs fan-in in {128, 256, 512}, fan-out <= 8, fan-in * fan-out <= 2048");
+  HGNN_REQUIRE(dW && db, "narrow_out_backward: NULL output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(dW, 0, (size_t)n_out * k * 4, st));
+    HGNN_CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)n_out * 4, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(a && W && grad_out && ws, "narrow_out_backward: NULL pointer");
+  const int grid = skinny_grid(rows, SK_WARPS * 8);
+  const int stride = (int)(n_out * k) + NO_MAX_N;
+  HGNN_REQUIRE(ws_bytes >= (size_t)grid * stride * 4, "narrow_out_backward: workspace too small");
+  float* partial = (float*)ws;
+  const size_t smem = ((size_t)2 * n_out * k + NO_MAX_N) * 4;
+  const int K = (int)k, NO = (int)n_out;
+  // register accumulators: n_out x K/32 floats per lane (<= 64)
+  if (k == 128) {
+    k_narrow_out_bwd<1, 8><<<grid, SK_THREADS, smem, st>>>(a, rows, K, W, NO, grad_out, d_a, partial);
+  } else if (k == 256) {
+    k_narrow_out_bwd<2, 8><<<grid, SK_THREADS, smem, st>>>(a, rows, K, W, NO, grad_out, d_a, partial);
+  } else {
+    k_narrow_out_bwd<4, 4><<<grid, SK_THREADS, smem, st>>>(a, rows, K, W, NO, grad_out, d_a, partial);
+  }
+  int rc = check_launch("narrow_out_backward");
+  if (rc) return rc;
+  const int total = NO * K + NO;
+  k_narrow_out_reduce<<<(total + 255) / 256, 256, 0, st>>>(partial, grid, stride, NO * K, NO, dW, db);
+  return check_launch("narrow_out_backward (reduce)");
+}

@@ -625,6 +625,120 @@ def tc_edge_step_with_agg(meta: MlpMeta, x: Tensor, e: Tensor, params: Sequence[
 
 
 # ---------------------------------------------------------------------------
+# skinny layers: fan-in <= 8 (encoder first layers) and fan-out <= 8 (heads' last layers), fp32, one warp per row
+# ---------------------------------------------------------------------------
+@functools.lru_cache(maxsize=256)
+def narrow_in_supported(seg_widths, n_out: int) -> bool:
+    return 1 <= len(seg_widths) <= MAX_SEGS and sum(seg_widths) <= 8 and n_out in (32, 64, 128, 256)
+
+
+@functools.lru_cache(maxsize=256)
+def narrow_out_supported(fan_in: int, n_out: int) -> bool:
+    return bool(_lib.lib().hgnn_narrow_out_supported(int(fan_in), int(n_out)))
+
+
+class _NarrowIn(torch.autograd.Function):
+    """act(LayerNorm(W . concat(gathered segments) + b)) for fan-in <= 8 (one-layer MlpMeta)."""
+
+    @staticmethod
+    def forward(ctx, meta: MlpMeta, n_seg: int, *tensors):
+        _need_cuda(*tensors)
+        segs = [_f32(t) for t in tensors[:n_seg]]
+        params = [_f32(t) for t in tensors[n_seg:]]
+        d, rows, layers = _build_desc(meta, segs, params)
+        out = torch.empty((rows, layers[0][0].shape[0]), dtype=torch.float32, device=params[0].device)
+        if rows:
+            with _timed("narrow_in_forward"):
+                check(_lib.lib().hgnn_narrow_in_forward(C.byref(d), rows, _ptr(out), _stream()), "narrow_in_forward")
+            _count()
+        ctx.meta, ctx.n_seg = meta, n_seg
+        ctx.save_for_backward(*segs, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        meta, n_seg = ctx.meta, ctx.n_seg
+        saved = ctx.saved_tensors
+        segs, params = list(saved[:n_seg]), list(saved[n_seg:])
+        d, rows, layers = _build_desc(meta, segs, params)
+        W = layers[0][0]
+        dev = W.device
+        N, K = W.shape
+        gout = _f32(gout)
+        need = ctx.needs_input_grad[2:2 + n_seg]
+        d_in = torch.empty((rows, K), dtype=torch.float32, device=dev) if any(need) else None
+        dW = torch.empty_like(W)
+        dvec = torch.empty((3, N), dtype=torch.float32, device=dev)
+        L_ = _lib.lib()
+        ws = _workspace(L_.hgnn_narrow_in_backward_workspace_bytes(N), dev)
+        with _timed("narrow_in_backward"):
+            check(L_.hgnn_narrow_in_backward(C.byref(d), rows, _ptr(gout), _ptr(d_in), _ptr(dW), _ptr(dvec), _ptr(ws), ws.numel(),
+                                             _stream()), "narrow_in_backward")
+        _count(2)
+        grads: List[Optional[Tensor]] = [None, None]
+        off = 0
+        for s in range(n_seg):
+            w = segs[s].shape[1]
+            gs = None
+            if need[s]:
+                gs = d_in if n_seg == 1 else d_in[:, off:off + w]
+                plan = meta.seg_plans[s]
+                if plan is not None:
+                    if plan.n_segments != segs[s].shape[0]:
+                        raise _lib.HgnnError("narrow-in layer: gather plan does not cover the gathered tensor")
+                    gs = segment_reduce_raw(gs.contiguous(), plan)
+            grads.append(gs)
+            off += w
+        grads += [dW, dvec[0]]
+        if meta.has_ln[0]:
+            grads += [dvec[1], dvec[2]]
+        return tuple(grads)
+
+
+def narrow_in(meta: MlpMeta, segs: Sequence[Tensor], params: Sequence[Tensor]) -> Tensor:
+    return _NarrowIn.apply(meta, len(segs), *segs, *params)
+
+
+class _NarrowOut(torch.autograd.Function):
+    """out = a W^T + b for fan-out <= 8."""
+
+    @staticmethod
+    def forward(ctx, a, W, b):
+        _need_cuda(a, W, b)
+        a, W, b = _f32(a), _f32(W), _f32(b)
+        rows, K = a.shape
+        out = torch.empty((rows, W.shape[0]), dtype=torch.float32, device=a.device)
+        if rows:
+            with _timed("narrow_out_forward"):
+                check(_lib.lib().hgnn_narrow_out_forward(_ptr(a), rows, K, _ptr(W), _ptr(b), W.shape[0], _ptr(out), _stream()),
+                      "narrow_out_forward")
+            _count()
+        ctx.save_for_backward(a, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, W = ctx.saved_tensors
+        gout = _f32(gout)
+        rows, K = a.shape
+        n_out = W.shape[0]
+        d_a = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(W)
+        db = torch.empty(n_out, dtype=torch.float32, device=a.device)
+        L_ = _lib.lib()
+        ws = _workspace(L_.hgnn_narrow_out_backward_workspace_bytes(K, n_out), a.device)
+        with _timed("narrow_out_backward"):
+            check(L_.hgnn_narrow_out_backward(_ptr(a), rows, K, _ptr(W), n_out, _ptr(gout), _ptr(d_a), _ptr(dW), _ptr(db), _ptr(ws),
+                                              ws.numel(), _stream()), "narrow_out_backward")
+        _count(2)
+        return d_a, dW, db
+
+
+def narrow_out(a: Tensor, W: Tensor, b: Tensor) -> Tensor:
+    return _NarrowOut.apply(a, W, b)
+
+
+# ---------------------------------------------------------------------------
 # tensor-core row layer (one Linear + LayerNorm + activation on a gathered concatenation)
 # ---------------------------------------------------------------------------
 class RowLayerMeta:

@@ -73,29 +73,39 @@ class FusedMLP(nn.Sequential):
 
     # ---- layer-wise execution: tensor-core row layers where a kernel exists, fp32 SIMT groups elsewhere ----
     def _row_groups(self, segs, plans, skip):
-        """[("tc", l) | ("simt", l0, l1)] covering the layers in order, or None when no layer can use the tensor-core
-        row kernel (precision fp32, CPU tensors, odd shapes): the whole stack then runs as one fp32 kernel."""
+        """[("tc", l) | ("nin", l) | ("nout", l) | ("simt", l0, l1)] covering the layers in order, or None when no layer
+        has a specialised kernel (precision fp32, CPU tensors, odd shapes): the whole stack then runs as one fp32 kernel.
+        tc = tensor-core row layer, nin / nout = skinny fan-in / fan-out layers, simt = generic fused fp32 group."""
         if ops.get_precision() == "fp32" or not all(t.is_cuda for t in segs):
             return None
         if skip >= 0 and plans[skip] is not None:
             return None  # a gathered residual only exists in the fused fp32 kernel
         layers = self._layers()
-        groups, any_tc, cur = [], False, None
-        widths = [t.shape[1] for t in segs]
+        last = len(layers) - 1
+        groups, special, cur = [], False, None
+        widths = tuple(t.shape[1] for t in segs)
         for l, (lin, ln, act) in enumerate(layers):
-            w_in = widths if l == 0 else [layers[l - 1][0].out_features]
-            ok = ln is not None and ops.tc_row_supported(w_in, lin.out_features, act)
-            if ok:
+            w_in = widths if l == 0 else (layers[l - 1][0].out_features,)
+            has_res = l == last and skip >= 0
+            kind = None
+            if ln is not None and ops.tc_row_supported(w_in, lin.out_features, act):
+                kind = "tc"
+            elif l == 0 and not has_res and ops.narrow_in_supported(w_in, lin.out_features):
+                kind = "nin"
+            elif (not has_res and ln is None and act is None and len(w_in) == 1 and (l > 0 or plans[0] is None)
+                  and ops.narrow_out_supported(w_in[0], lin.out_features)):
+                kind = "nout"
+            if kind is not None:
                 if cur is not None:
                     groups.append(("simt", cur, l))
                     cur = None
-                groups.append(("tc", l))
-                any_tc = True
+                groups.append((kind, l))
+                special = True
             elif cur is None:
                 cur = l
         if cur is not None:
             groups.append(("simt", cur, len(layers)))
-        return groups if any_tc else None
+        return groups if special else None
 
     def _row_pack(self, l):
         lin = self._layers()[l][0]
@@ -123,6 +133,14 @@ class FusedMLP(nn.Sequential):
                 res = residual if l == last else None
                 meta = ops.RowLayerMeta(cur_plans, act, ln.eps, res is not None, self._row_pack(l))
                 y = ops.tc_row_layer(meta, cur_segs, res, lin.weight, lin.bias, ln.weight, ln.bias)
+            elif grp[0] == "nin":
+                lin, ln, act = layers[grp[1]]
+                ps = [lin.weight, lin.bias] + ([ln.weight, ln.bias] if ln is not None else [])
+                meta = ops.MlpMeta(cur_plans, [act], [ln is not None], -1, ln.eps if ln is not None else 1e-5)
+                y = ops.narrow_in(meta, cur_segs, ps)
+            elif grp[0] == "nout":
+                lin = layers[grp[1]][0]
+                y = ops.narrow_out(cur_segs[0], lin.weight, lin.bias)
             else:
                 l0, l1 = grp[1], grp[2]
                 ps, acts, lns, eps = [], [], [], 1e-5

@@ -287,6 +287,29 @@ int hgnn_tc_row_backward(const hgnn_tc_row_layer* d, const void* wt_packed, cons
                          const float* grad_out, float* d_in, float* dW, float* dvec, void* ws, size_t ws_bytes,
                          void* stream);
 
+/* ------------------------------------------------------------------------
+ * Skinny layers (fp32, one warp per row) — the make_mlp layers that are pure bandwidth:
+ *  narrow-in : a one-layer hgnn_mlp_desc with fan-in <= 8 and fan-out in {32, 64, 128, 256} (the encoders' first
+ *              Linear on x[N,3] / [x[src] | x[dst]]: EC/Models/IN.py:29-33,84-85; BC/Models/HGNN_GMM.py:37-41),
+ *              optional LayerNorm + activation; backward gives d_in[rows, fan_in] (optional), dW[fan_out, fan_in],
+ *              dvec[3, fan_out] = (d bias, d gamma, d beta).
+ *  narrow-out: out[r, n] = <W[n, :], a[r, :]> + b[n] with fan-out <= 8, fan-in in {128, 256, 512}, fan-in * fan-out
+ *              <= 2048 and no LayerNorm / activation (the score and embedding heads' last Linear: EC/Models/IN.py:126;
+ *              BC/Models/HGNN_GMM.py:45-48,342-344); backward gives d_a[rows, fan_in] (optional), dW, db.
+ * All reductions over rows are ordered (warp by warp, CTA by CTA): bit-reproducible.
+ * ------------------------------------------------------------------------ */
+int hgnn_narrow_in_supported(const hgnn_mlp_desc* d);
+int hgnn_narrow_in_forward(const hgnn_mlp_desc* d, int64_t rows, float* out, void* stream);
+size_t hgnn_narrow_in_backward_workspace_bytes(int64_t n_out);
+int hgnn_narrow_in_backward(const hgnn_mlp_desc* d, int64_t rows, const float* grad_out, float* d_in, float* dW, float* dvec,
+                            void* ws, size_t ws_bytes, void* stream);
+int hgnn_narrow_out_supported(int64_t fan_in, int64_t n_out);
+int hgnn_narrow_out_forward(const float* a, int64_t rows, int64_t fan_in, const float* W, const float* bias, int64_t n_out,
+                            float* out, void* stream);
+size_t hgnn_narrow_out_backward_workspace_bytes(int64_t fan_in, int64_t n_out);
+int hgnn_narrow_out_backward(const float* a, int64_t rows, int64_t fan_in, const float* W, int64_t n_out, const float* grad_out,
+                             float* d_a, float* dW, float* db, void* ws, size_t ws_bytes, void* stream);
+
 /* Profiling hook: when set (device buffer of 16 uint64), CTA 0 of hgnn_tc_edge_backward accumulates the cycles it
  * spends in each phase of the tile loop (GEMM1, EPI-A, GEMM2, EPI-B, GEMM3, EPI-C, GEMM4, EPI-D). NULL disables. */
 void hgnn_tc_debug_set_phase_clock(void* dev_u64x16);

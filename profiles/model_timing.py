@@ -55,3 +55,15 @@ ops.PROFILE = None
 print(f"EC-IN fwd+bwd wall {wall:.1f} ms; per-op GPU ms:")
 for k, (n, t) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
     print(f"   {k:24s} calls {n:4d}  total {t:8.2f} ms")
+
+ops.PROFILE = {}
+bc.zero_grad(set_to_none=True)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+bg, sc, emb = bc(x.clone(), g, clusters=clusters)
+(sc.sum() + emb.sum()).backward()
+torch.cuda.synchronize(); wall = (time.perf_counter() - t0) * 1e3
+prof = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in ops.PROFILE.items()}
+ops.PROFILE = None
+print(f"BC-HGNN fwd+bwd wall {wall:.1f} ms; per-op GPU ms (sum {sum(t for _, t in prof.values()):.2f}):")
+for k, (n, t) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+    print(f"   {k:24s} calls {n:4d}  total {t:8.2f} ms")
