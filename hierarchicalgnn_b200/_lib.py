@@ -115,6 +115,7 @@ SIGNATURES = {
     "hgnn_tc_edge_backward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                         vp, sz, vp]),  # (p, w1t, w2t, a0_img, src, dst, perm, n_edges, g_e, g_agg, d_e, d_xs, d_xd, dW1, dW2, dv1, dv2, ws, n, st)
     "hgnn_tc_debug_set_phase_clock": (None, [vp]),
+    "hgnn_tc_debug_set_fwd_phase_clock": (None, [vp]),
     "hgnn_narrow_in_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "hgnn_narrow_in_forward": (C.c_int, [C.POINTER(MlpDesc), i64, vp, vp]),
     "hgnn_narrow_in_backward_workspace_bytes": (sz, [i64]),

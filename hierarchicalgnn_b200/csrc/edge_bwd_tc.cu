@@ -18,6 +18,7 @@
 // reduced across rows with a register transpose-reduce and summed in a fixed order.
 // One CTA per SM (all 512 TMEM columns, ~205 KB of shared memory), 16 warps.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -62,6 +63,7 @@ struct BwdArgs {
   uint8_t* g_img; uint8_t* d1_img; uint8_t* d2_img;
   float* colpart;                          // [grid][4][PAR_FLOATS]
   int64_t n_edges;
+  int stagger_cycles;             // start offset between the four CTA groups (0 = none)
   unsigned long long* phase_clk;  // optional [16] per-phase cycle accumulators (CTA 0, thread 0); NULL in production
 };
 
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   const uint8_t* w1p = reinterpret_cast<const uint8_t*>(P.w1_packed);
   const uint8_t* w2p = reinterpret_cast<const uint8_t*>(P.w2_packed);
 
-  uint32_t it1 = 0, acc_par = 0;
+  uint32_t it1 = 0, acc_par = 0, tl = 0;  // ring use counter, accumulator-barrier parity, tiles done by this CTA
   int nx_eid = 0, nx_src = 0, nx_dst = 0;  // row ids of the next tile, prefetched
   uint32_t n_fill[NSLOT] = {0, 0, 0, 0, 0, 0}, n_commit[NSLOT] = {0, 0, 0, 0, 0, 0};  // thread 0 bookkeeping
   // per-lane column-sum accumulators: lane c of warp (q, cs) owns columns cs*64 + {c, 32 + c} of H and cs*32 + c of L
@@ -122,6 +124,11 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   long long t_prev = clock64();
   auto MARK = [&](int ph) {
     if (A.phase_clk && tid == 0 && blockIdx.x == 0) { long long t = clock64(); atomicAdd(A.phase_clk + ph, (unsigned long long)(t - t_prev)); t_prev = t; }
+  };
+  long long t_sub = 0;
+  auto SUB0 = [&]() { if (A.phase_clk && tid == 0 && blockIdx.x == 0) t_sub = clock64(); };
+  auto SUB = [&](int i) {
+    if (A.phase_clk && tid == 0 && blockIdx.x == 0) { long long t = clock64(); atomicAdd(A.phase_clk + 9 + i, (unsigned long long)(t - t_sub)); t_sub = t; }
   };
   // GEMM1 operand requests (thread 0). K-blocks 0/1: A0 image block + W1 block into ring stage (it & 1), one
   // transaction barrier for both; they are requested a tile ahead. K-blocks 2..5: the four A0 blocks land together in
@@ -145,6 +152,13 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   };
   uint32_t rest_par = 0;
   const int n_tiles = (int)((A.n_edges + TILE_M - 1) / TILE_M);
+  // All CTAs start together and every tile costs the same, so without this the SMs stay in lock-step and their
+  // HBM-heavy phases (operand images + gradient rows in, gradient rows out) coincide: stagger the start by a fraction
+  // of a tile so the memory system sees a steady demand instead of bursts.
+  if (A.stagger_cycles > 0 && n_tiles > (int)gridDim.x) {
+    const long long t0 = clock64(), wait = (long long)(blockIdx.x % 4) * A.stagger_cycles;
+    while (clock64() - t0 < wait) {}
+  }
   if (tid == 0 && (int)blockIdx.x < n_tiles) {
     g1_issue(blockIdx.x, 0, 0);
     g1_issue(blockIdx.x, 1, 1);
@@ -173,53 +187,71 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     }
     MARK(0);
     // ================= GEMM1 (recompute): D1 = A0 W1^T, operands by bulk copy only =================
-    // Thread 0 streams the saved bf16 image of A0 and the W1 K-blocks through the two ring stages and issues the MMAs;
-    // the first two K-blocks of this tile were already requested at the end of the previous tile.
-    // upstream-gradient loads first (every warp, including the issuing one), so they fly under the MMA loop
-    const int g_sub = tid & 31, g_rr = tid >> 5;
-    float4 gv[TILE_M / 16], ga[TILE_M / 16];
-#pragma unroll
-    for (int p = 0; p < TILE_M / 16; ++p) {
-      const int r = p * 16 + g_rr;
-      const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-      gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-      ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + g_sub)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    // Two single-thread roles in different warps: thread 0 only waits for operands and issues MMAs; thread 32 (the
+    // "producer") waits for ring stages to retire and refills them, so the issuing thread never blocks on an MMA's
+    // completion. K-blocks 0/1 were requested a tile ahead and W1 K-block 2 is parked in the gradient staging region.
+    SUB0();
     if (tid == 0) {
       // the A2 region is free (previous tile's EPI-D staging was drained before the closing barrier)
       fence_proxy_async();
       mbar_expect_tx(BAR(A_REST), 4 * A_BLK_BYTES);
       bulk_g2s(sm_u + A2_OFF, A.a0_img + ((size_t)tile * NKB1 + 2) * A_BLK_BYTES, 4 * A_BLK_BYTES, BAR(A_REST));
-      uint32_t it = it1;  // ring use counter: K-blocks 0, 1, 3, 4, 5 go through the two ring stages
-      for (int kb = 0; kb < NKB1; ++kb) {
-        const uint32_t a_s = kb < 2 ? 0u : sm_u + A2_OFF + (kb - 2) * A_BLK_BYTES;
-        if (kb == 2) {
-          mbar_wait(BAR(A_REST), rest_par);
-          mbar_wait(BAR(W_KB2), rest_par);
-          tc_fence_after();
-          umma_kblock(tmem + TM_D1, a_s, sm_u + GS_OFF, idesc_h, false);
-          umma_commit(BAR(KB2_DONE));
-          continue;
-        }
-        const int s = it & 1;
-        mbar_wait(BAR(W_FULL + s), (it >> 1) & 1);
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint32_t u = it1 + kb;
+        const int s = u & 1;
+        mbar_wait(BAR(W_FULL + s), (u >> 1) & 1);
         tc_fence_after();
-        umma_kblock(tmem + TM_D1, kb < 2 ? sm_u + s * STAGE : a_s, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
+        umma_kblock(tmem + TM_D1, sm_u + s * STAGE, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, kb == 0);
         umma_commit(BAR(ST_FREE + s));
-        if (kb == NKB1 - 1) umma_commit(BAR(ACC));
-        // keep two W1 blocks in flight: after kb = 0 request 3, after 1 request 4, after 3 request 5
-        const int nxt = kb < 2 ? kb + 3 : kb + 2;
-        if (nxt < NKB1) g1_issue(tile, nxt, it + 2);
-        ++it;
       }
     }
+    if (tid == 32) {  // ring uses of this tile: K-blocks 0, 1, 3, 4, 5 -> it1 .. it1 + 4
+      g1_issue(tile, 3, it1 + 2);
+      g1_issue(tile, 4, it1 + 3);
+    }
+    SUB(0);
+    // upstream-gradient loads (every warp): 128 KB of register-staged loads per tile, in flight under the MMA loop
+    const int g_sub = tid & 31, g_rr = tid >> 5;
+    float4 gv[TILE_M / 16], ga[TILE_M / 16];
+    auto gout_loads = [&]() {
+#pragma unroll
+      for (int p = 0; p < TILE_M / 16; ++p) {
+        const int r = p * 16 + g_rr;
+        const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
+        gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + g_sub)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    gout_loads();
+    SUB(1);
+    if (tid == 0) {
+      mbar_wait(BAR(A_REST), rest_par);
+      SUB(2);
+      mbar_wait(BAR(W_KB2), rest_par);
+      tc_fence_after();
+      umma_kblock(tmem + TM_D1, sm_u + A2_OFF, sm_u + GS_OFF, idesc_h, false);
+      umma_commit(BAR(KB2_DONE));
+      SUB(3);
+      for (int kb = 3; kb < NKB1; ++kb) {
+        const uint32_t u = it1 + kb - 1;
+        const int s = u & 1;
+        mbar_wait(BAR(W_FULL + s), (u >> 1) & 1);
+        tc_fence_after();
+        umma_kblock(tmem + TM_D1, sm_u + A2_OFF + (kb - 2) * A_BLK_BYTES, sm_u + s * STAGE + A_BLK_BYTES, idesc_h, false);
+        umma_commit(BAR(ST_FREE + s));
+        if (kb == NKB1 - 1) umma_commit(BAR(ACC));
+      }
+    }
+    if (tid == 32) g1_issue(tile, 5, it1 + 4);  // as soon as K-block 3's MMAs retire
+    SUB(4);
     it1 += NKB1 - 1;
     rest_par ^= 1;
     if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
     __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
+    SUB(5);
     // GEMM1 has retired (W1 K-block 2 no longer needed in this region): stage the upstream gradient tile as a bf16 image (zero for padding rows): 32 threads per row, 16 rows per pass
     {
 #pragma unroll
@@ -481,13 +513,23 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
         slot_wait_full(slot);
         umma_kblock(tmem + TM_DA0 + sg * L, sm_u + A2_OFF + kb * A_BLK_BYTES, sm_u + slot * SEG_BLK, idesc_l, kb == 0);
         slot_commit(slot);
-        if (b >= 1 && b - 1 + NSLOT < NB) {  // refill the slot consumed one step ago
-          const int b2 = b - 1 + NSLOT, sl2 = b2 % NSLOT, sg2 = b2 / NKB2, kb2 = b2 % NKB2;
-          slot_fill(sl2, sl2 * SEG_BLK, A.w1t + (size_t)kb2 * W1T_BLK + (size_t)sg2 * SEG_BLK, SEG_BLK);
-        }
+        if (b < NSLOT) n_fill[slot]++;  // pieces 6..11 are requested by the producer thread below
       }
       umma_commit(BAR(ACC));
       bulk_wait_read0();  // delta1 image has left shared memory before EPI-D reuses the region
+    }
+    if (tid == 32) {
+      // producer: refill slot sl with piece sl + 6 once the MMAs of piece sl have retired. Completions of B_FREE[sl]
+      // before this point: 4 / 3 / 4 / 3 / 2 / 2 per earlier tile (GEMM2 + GEMM3 + 2 x GEMM4) plus 2 / 1 / 2 / 1 / 0 / 0 in
+      // this tile, so the awaited completion has parity 0 except on slots 1 and 3, where it alternates with the tile.
+#pragma unroll 1
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int b2 = sl + NSLOT, sg2 = b2 / NKB2, kb2 = b2 % NKB2;
+        const uint32_t par = (sl == 1 || sl == 3) ? ((tl + 1) & 1u) : 0u;
+        mbar_wait(BAR(B_FREE + sl), par);
+        mbar_expect_tx(BAR(B_FULL + sl), SEG_BLK);
+        bulk_g2s(sm_u + sl * SEG_BLK, A.w1t + (size_t)kb2 * W1T_BLK + (size_t)sg2 * SEG_BLK, SEG_BLK, BAR(B_FULL + sl));
+      }
     }
     if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
     __syncthreads();  // also orders thread 0's bulk_wait_read0 before the staging writes below
@@ -543,6 +585,7 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     }
     tc_fence_before();
     __syncthreads();
+    ++tl;
     MARK(8);
   }
 
@@ -645,6 +688,11 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   A.colpart = (float*)(w + Y.colpart);
   A.n_edges = n_edges;
   A.phase_clk = (unsigned long long*)g_phase_clk;
+  {
+    static int stagger = -1;
+    if (stagger < 0) { const char* e = getenv("HGNN_BWD_STAGGER"); stagger = e ? atoi(e) : 17000; }
+    A.stagger_cycles = stagger;
+  }
   HGNN_REQUIRE(p->act_hidden == HGNN_ACT_GELU && p->act_out == HGNN_ACT_TANH, "tc_edge_backward: only GELU / Tanh is built");
   size_t smem = SMEM_BYTES;
   auto kern = k_tc_edge_bwd<HGNN_ACT_GELU, HGNN_ACT_TANH>;

@@ -57,7 +57,8 @@ template <int L, int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,
               const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out,
-              const int32_t* __restrict__ rowptr, float* __restrict__ agg, uint8_t* __restrict__ a0_img) {
+              const int32_t* __restrict__ rowptr, float* __restrict__ agg, uint8_t* __restrict__ a0_img,
+              unsigned long long* __restrict__ phase_clk) {
   using C = Cfg<L>;
   constexpr int H = C::H;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // declared alignment keeps the shared address space visible (LDS/STS)
@@ -102,6 +103,10 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
   const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
   const int n_tiles = (int)((n_edges + TILE_M - 1) / TILE_M);
 
+  long long t_prev = clock64();
+  auto MARK = [&](int ph) {  // optional per-phase cycle accounting (CTA 0, thread 0)
+    if (phase_clk && tid == 0 && blockIdx.x == 0) { long long t = clock64(); atomicAdd(phase_clk + ph, (unsigned long long)(t - t_prev)); t_prev = t; }
+  };
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // ---- row ids of this tile ----
     if (tid < TILE_M) {
@@ -127,6 +132,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
       }
     }
     __syncthreads();
+    MARK(0);
 
     // ---- GEMM1: D1[128, H] = [x[src] | x[dst] | e] . W1^T ----
     auto seg_base = [&](int kb) { return (kb * KBLK) / L == 2 ? e : x; };
@@ -158,6 +164,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
+    MARK(1);
 
     // W2 K-blocks 0/1 stream in behind EPI1 (their slots lie past the A2 image; GEMM1 no longer reads them)
     if (tid == 0) {
@@ -184,6 +191,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    MARK(2);
 
     // ---- GEMM2: D2[128, L] = A2 . W2^T (accumulator aliases TMEM columns [0, L)) ----
     if (tid == 0) {
@@ -208,6 +216,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     __syncthreads();
     acc_par ^= 1;
     tc_fence_after();
+    MARK(3);
 
     // ---- EPI2: bias + LayerNorm + activation -> fp32 staging tile (swizzled 16 B chunks) ----
     {
@@ -242,6 +251,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     }
     tc_fence_before();
     __syncthreads();
+    MARK(4);
     // ---- coalesced pass: + fp32 skip row, full-row stores ----
     {
       constexpr int CPR = L / 4;                       // float4 chunks per row
@@ -260,6 +270,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
         }
       }
     }
+    MARK(5);
     if (agg) {
       // ---- fused scatter_add: destination-sorted segmented reduce of the finished tile, ordered, no atomics.
       // One thread per (row group, column): runs of equal destination are summed in row order; a run that lies
@@ -288,6 +299,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
       }
     }
     __syncthreads();  // staging tile / row ids free for the next tile
+    MARK(6);
   }
 
   tc_fence_before();
@@ -419,6 +431,10 @@ extern "C" int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t 
   return check_launch("tc_debug_gemm");
 }
 
+static void* g_fwd_phase_clk = nullptr;
+// debug hook (not part of the stable ABI): device buffer of 16 uint64 that CTA 0 of the forward kernel fills with per-phase cycles
+extern "C" void hgnn_tc_debug_set_fwd_phase_clock(void* dev_u64x16) { g_fwd_phase_clk = dev_u64x16; }
+
 extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t) { return 256; }
 extern "C" size_t hgnn_tc_edge_a0_image_bytes(int64_t n_edges, int64_t latent) {
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
@@ -434,7 +450,8 @@ static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const f
   HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
-  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg, a0_img);
+  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg, a0_img,
+                                        (unsigned long long*)g_fwd_phase_clk);
   if (agg) {
     int64_t threads = n_nodes * (L / 4);
     k_agg_fixup<L><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(e_out, perm, rowptr, n_nodes, agg);

@@ -313,6 +313,8 @@ int hgnn_narrow_out_backward(const float* a, int64_t rows, int64_t fan_in, const
 /* Profiling hook: when set (device buffer of 16 uint64), CTA 0 of hgnn_tc_edge_backward accumulates the cycles it
  * spends in each phase of the tile loop (GEMM1, EPI-A, GEMM2, EPI-B, GEMM3, EPI-C, GEMM4, EPI-D). NULL disables. */
 void hgnn_tc_debug_set_phase_clock(void* dev_u64x16);
+/* Same for hgnn_tc_edge_forward: tile setup, GEMM1 (gather), EPI1, GEMM2, EPI2, store pass, fused aggregate. */
+void hgnn_tc_debug_set_fwd_phase_clock(void* dev_u64x16);
 
 #ifdef __cplusplus
 }

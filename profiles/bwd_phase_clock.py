@@ -8,7 +8,9 @@ from hierarchicalgnn_b200.training_utils import kaiming_init
 L, E = 128, 1_000_000
 hp = dict(latent=L, hidden=2 * L, nb_edge_layer=2, nb_node_layer=3, layernorm=True, hidden_activation="GELU")
 torch.manual_seed(0); cell = InteractionGNNCell(hp); kaiming_init(cell); cell.cuda()
-n, e, g = synth_edge_problem(E, L); n, e, g = n.cuda().requires_grad_(True), e.cuda().requires_grad_(True), g.cuda()
+n, e, g = synth_edge_problem(E, L)
+order = torch.argsort(g[1], stable=True); g, e = g[:, order].contiguous(), e[order].contiguous()  # as bench.py / the models
+n, e, g = n.cuda().requires_grad_(True), e.cuda().requires_grad_(True), g.cuda()
 gp = GraphPlans(g, n.shape[0], n.shape[0]); gp.by_src; gp.by_dst
 cot_e, cot_a = torch.randn_like(e), torch.randn(n.shape[0], L, device="cuda")
 def step():
@@ -26,3 +28,20 @@ tot = sum(c[:9])
 for nm, v in zip(names, c[:9]):
     print(f"{nm:14s} {v / tiles:9.0f} cyc/tile  {100 * v / tot:5.1f}%")
 print(f"total {tot / tiles:.0f} cycles/tile over ~{tiles} tiles")
+sub = ["gout loads issued", "kb0-1 issued", "wait A_REST", "wait W_KB2 + kb2", "kb3-5", "drain: ACC + barrier"]
+for nm, v in zip(sub, c[9:15]):
+    print(f"   GEMM1 / {nm:24s} {v / tiles:9.0f} cyc/tile")
+
+# forward kernel
+clk.zero_()
+_lib.lib().hgnn_tc_debug_set_fwd_phase_clock(clk.data_ptr())
+step(); torch.cuda.synchronize()
+_lib.lib().hgnn_tc_debug_set_fwd_phase_clock(None)
+c = clk.cpu().tolist()
+names = ["setup", "GEMM1(gather)", "EPI1", "GEMM2", "EPI2", "store pass", "aggregate"]
+tiles_f = (E + 127) // 128 // 296 + 1
+tot = sum(c[:7])
+print("forward kernel (2 CTAs / SM):")
+for nm, v in zip(names, c[:7]):
+    print(f"{nm:14s} {v / tiles_f:9.0f} cyc/tile  {100 * v / tot:5.1f}%")
+print(f"total {tot / tiles_f:.0f} cycles/tile over ~{tiles_f} tiles")
