@@ -119,16 +119,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_tc_wgrad(WgArgs args) {
   if (warp == 0) tmem_dealloc(tmem, tcols);
 }
 
-// out[(row_off + m) * ld + col_off + n] (or transposed) = sum_splits partial[s][m][n]
-__global__ void k_wgrad_reduce(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ out, int ld,
-                               int row_off, int col_off, int transpose) {
+// out[(row_off + m) * ld + col_off + n] (or transposed) = sum_splits partial[s][m][n]; one launch, blockIdx.y = problem
+struct WgReduceArgs {
+  const float* partial[WG_MAX_ROLES];
+  float* out[WG_MAX_ROLES];
+  int M[WG_MAX_ROLES], N[WG_MAX_ROLES], ld[WG_MAX_ROLES], row_off[WG_MAX_ROLES], col_off[WG_MAX_ROLES], transpose[WG_MAX_ROLES];
+  int splits;
+};
+__global__ void k_wgrad_reduce(WgReduceArgs a) {
+  const int p = blockIdx.y;
+  const int M = a.M[p], N = a.N[p];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
+  const float* partial = a.partial[p];
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * M * N + i];
+  for (int k = 0; k < a.splits; ++k) s += partial[(size_t)k * M * N + i];
   int m = i / N, n = i % N;
-  if (transpose) out[(size_t)(row_off + n) * ld + col_off + m] = s;
-  else out[(size_t)(row_off + m) * ld + col_off + n] = s;
+  if (a.transpose[p]) a.out[p][(size_t)(a.row_off[p] + n) * a.ld[p] + a.col_off[p] + m] = s;
+  else a.out[p][(size_t)(a.row_off[p] + m) * a.ld[p] + a.col_off[p] + n] = s;
 }
 
 // fp32 [rows, cols] -> tile images (test helper / generic producer); rows beyond `rows` are zero
@@ -188,12 +196,16 @@ int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t
   HGNN_REQUIRE(smem <= 227 * 1024, "wgrad: stage too large for shared memory");
   HGNN_CUDA_TRY(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_tc_wgrad<<<n * a.splits, WG_THREADS, smem, st>>>(a);
+  WgReduceArgs ra{};
+  ra.splits = a.splits;
+  int max_total = 0;
   for (int i = 0; i < n; ++i) {
     const WgradProblem& p = probs[i];
-    int total = p.ca * p.cb;
-    k_wgrad_reduce<<<(total + 255) / 256, 256, 0, st>>>(a.role[i].partial, a.splits, p.ca, p.cb, p.out, p.ld, p.row_off, p.col_off,
-                                                         p.transpose);
+    ra.partial[i] = a.role[i].partial; ra.out[i] = p.out;
+    ra.M[i] = p.ca; ra.N[i] = p.cb; ra.ld[i] = p.ld; ra.row_off[i] = p.row_off; ra.col_off[i] = p.col_off; ra.transpose[i] = p.transpose;
+    max_total = std::max(max_total, p.ca * p.cb);
   }
+  k_wgrad_reduce<<<dim3((max_total + 255) / 256, n), 256, 0, st>>>(ra);
   return check_launch("tc_wgrad");
 }
 

@@ -553,7 +553,7 @@ def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, a0_img: Tens
                                        _ptr(plan_d.keys32), _ptr(perm), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_xs), _ptr(d_xd),
                                        _ptr(dW1), _ptr(dW2), _ptr(dv1), _ptr(dv2), _ptr(ws), ws.numel(), _stream()),
               "tc_edge_backward")
-    _count(1 + 1 + 1 + 4)
+    _count(4)  # data-gradient kernel, column-sum reduce, weight-gradient GEMM, its ordered reduce
     TC_CALLS["count"] += 1
     return d_xs, d_xd, d_e, dW1, dW2, dv1, dv2
 
@@ -841,7 +841,7 @@ class _TcRowLayer(torch.autograd.Function):
             with _timed("tc_row_backward"):
                 check(L_.hgnn_tc_row_backward(C.byref(d), _ptr(wt_packed), _ptr(ctx.a_img), rows, _ptr(gout), _ptr(d_in), _ptr(dW),
                                               _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "tc_row_backward")
-            _count(2 + 1 + K // 128)
+            _count(4)  # data-gradient kernel, column-sum reduce, weight-gradient GEMM, its ordered reduce
             TC_ROW_CALLS["count"] += 1
         else:
             dW.zero_()
