@@ -417,7 +417,10 @@ def run_partition(args):
         if world > 1:
             flat = torch.cat([x.reshape(-1) for x in grads[2:]])
             dist.all_reduce(flat)
-            dist.all_reduce(grads[0])  # replicated input nodes: gradient partials summed over ranks
+            # replicated input nodes: each rank holds the gradient of its own block only (the other rows are zero),
+            # so the sum over ranks is an all-gather of the owned blocks
+            gfull = torch.empty_like(grads[0])
+            dist.all_gather_into_tensor(gfull, grads[0][part.node_lo:part.node_lo + part.block].contiguous())
         return n2, e2
 
     def barrier():

@@ -188,7 +188,7 @@ class BC_HierarchicalGNN_GMM(BipartiteClassificationBase):
     def forward(self, x, graph, clusters=None):
         N = x.shape[0]
         # destination-sorted once per event; nothing downstream depends on the edge order (HGNN_GMM.py:328-346)
-        directed = GraphPlans(sort_edges_by_destination(torch.cat([graph, graph.flip(0)], dim=1))[0], N, N)
+        directed = GraphPlans(sort_edges_by_destination(torch.cat([graph, graph.flip(0)], dim=1))[0], N, N, dst_sorted=True)
         embeddings, nodes, edges = self.ignn_block(x, directed)
         nodes, supernodes, bipartite_graph = self.hgnn_block(x, embeddings, nodes, edges, directed, clusters=clusters)
         bp = GraphPlans(bipartite_graph, N, supernodes.shape[0])

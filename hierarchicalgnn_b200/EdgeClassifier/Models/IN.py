@@ -63,7 +63,7 @@ class EC_InteractionGNN(EdgeClassifierBase):
         E = graph.shape[1]
         directed = torch.cat([graph, graph.flip(0)], dim=1)          # edge k and k+E are mutual reverses (IN.py:122)
         directed, _, where = sort_edges_by_destination(directed)     # one sort per event; cells stream rows in place
-        nodes, edges = self.ignn_block(x, GraphPlans(directed, x.shape[0], x.shape[0]))
+        nodes, edges = self.ignn_block(x, GraphPlans(directed, x.shape[0], x.shape[0], dst_sorted=True))
         # classifier input = [e_forward | e_reverse] (IN.py:126): rows where[k] and where[k+E] of the sorted edge
         # latents, gathered inside the fused MLP kernel — no concat, no un-sort pass
         fwd = ops.plan_for(where[:E].contiguous(), 2 * E)

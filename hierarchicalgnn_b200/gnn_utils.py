@@ -24,9 +24,10 @@ class GraphPlans:
     """Segment plans of one edge list [2, E]: by destination (row 1, over n_dst
     segments) and by source (row 0, over n_src segments). Built lazily, cached."""
 
-    def __init__(self, graph: torch.Tensor, n_src: int, n_dst: int):
+    def __init__(self, graph: torch.Tensor, n_src: int, n_dst: int, dst_sorted: bool = False):
         self.graph, self.n_src, self.n_dst = graph, int(n_src), int(n_dst)
         self._src = self._dst = None
+        self.dst_sorted = bool(dst_sorted)  # caller guarantees graph[1] ascends (sort_edges_by_destination): no host check
 
     @property
     def by_src(self) -> ops.SegmentPlan:
@@ -38,6 +39,8 @@ class GraphPlans:
     def by_dst(self) -> ops.SegmentPlan:
         if self._dst is None:
             self._dst = ops.plan_for(self.graph[1], self.n_dst)
+            if self.dst_sorted:
+                self._dst._identity = True
         return self._dst
 
 

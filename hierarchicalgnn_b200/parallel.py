@@ -117,7 +117,7 @@ class EdgePartition:
     block: int              # padded node block size B (equal on every rank)
     node_lo: int            # first owned node
     node_hi: int            # one past the last owned node (<= n_nodes)
-    edge_ids: Tensor        # [E_g] ids (into the global directed edge list) of the owned edges, ascending
+    edge_ids: Tensor        # [E_g] ids (into the global directed edge list) of the owned edges, ordered by destination
     graph: Tensor           # [2, E_g] owned edges, GLOBAL node ids
     dst_local: Tensor       # [E_g] destination ids relative to node_lo (segment ids of the local aggregate)
 
@@ -132,6 +132,7 @@ def partition_by_destination(graph: Tensor, n_nodes: int, world: int, rank: int)
     lo, hi = rank * block, min(n_nodes, (rank + 1) * block)
     dst = graph[1]
     mine = ((dst >= lo) & (dst < hi)).nonzero().squeeze(1)
+    mine = mine[torch.argsort(dst[mine], stable=True)]  # destination-sorted: the kernels stream rows in place
     g = graph[:, mine].contiguous()
     return EdgePartition(rank, world, n_nodes, block, lo, hi, mine, g, (g[1] - lo).contiguous())
 
@@ -209,7 +210,7 @@ def cuda_cell_callables(cell):
         return cell.node_network.fused([x_owned, agg], skip=0)
 
     def edge_fn(x_full, e_local, graph_local):
-        gp = GraphPlans(graph_local, x_full.shape[0], x_full.shape[0])
+        gp = GraphPlans(graph_local, x_full.shape[0], x_full.shape[0], dst_sorted=True)  # partition_by_destination sorts
         return cell.edge_network.fused([x_full, x_full, e_local], [gp.by_src, gp.by_dst, None], skip=2)
 
     def segment_sum(rows, seg, n):
