@@ -113,7 +113,7 @@ SIGNATURES = {
     "hgnn_tc_edge_forward_workspace_bytes": (sz, [i64]),
     "hgnn_tc_edge_backward_workspace_bytes": (sz, [i64]),
     "hgnn_tc_edge_backward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                        vp, sz, vp]),  # (p, w1t, w2t, a0_img, src, dst, perm, n_edges, g_e, g_agg, d_e, d_xs, d_xd, dW1, dW2, dv1, dv2, ws, n, st)
+                                        vp, sz, vp]),  # (p, w1t, w2t, stash, src, dst, perm, n_edges, g_e, g_agg, d_e, d_xs, d_xd, dW1, dW2, dv1, dv2, ws, n, st)
     "hgnn_tc_debug_set_phase_clock": (None, [vp]),
     "hgnn_tc_debug_set_fwd_phase_clock": (None, [vp]),
     "hgnn_narrow_in_supported": (C.c_int, [C.POINTER(MlpDesc)]),
@@ -129,7 +129,7 @@ SIGNATURES = {
     "hgnn_tc_row_forward": (C.c_int, [C.POINTER(TcRowLayer), i64, vp, vp, vp]),
     "hgnn_tc_row_backward_workspace_bytes": (sz, [i64, i64, i64]),
     "hgnn_tc_row_backward": (C.c_int, [C.POINTER(TcRowLayer), vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]),
-    "hgnn_tc_edge_a0_image_bytes": (sz, [i64, i64]),
+    "hgnn_tc_edge_stash_bytes": (sz, [i64, i64]),
     "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz, vp]),
 }
 

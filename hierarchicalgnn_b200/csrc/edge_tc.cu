@@ -21,6 +21,7 @@
 //          coalesced pass adds the fp32 skip row and stores e' as full 512 B rows.
 // Weights are never resident in full: smem per CTA is ~105 KB at L = 128.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -57,8 +58,8 @@ template <int L, int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,
               const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out,
-              const int32_t* __restrict__ rowptr, float* __restrict__ agg, uint8_t* __restrict__ a0_img,
-              unsigned long long* __restrict__ phase_clk) {
+              const int32_t* __restrict__ rowptr, float* __restrict__ agg, uint8_t* __restrict__ stash, EdgeStash SL,
+              unsigned long long* __restrict__ phase_clk, int stagger_cycles) {
   using C = Cfg<L>;
   constexpr int H = C::H;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // declared alignment keeps the shared address space visible (LDS/STS)
@@ -96,6 +97,12 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
   const uint32_t idesc1 = make_idesc(TILE_M, H), idesc2 = make_idesc(TILE_M, L);
   const uint8_t* w1p = reinterpret_cast<const uint8_t*>(P.w1_packed);
   const uint8_t* w2p = reinterpret_cast<const uint8_t*>(P.w2_packed);
+  // activations kept for the backward pass (NULL in inference): see EdgeStash in tc_common.cuh
+  uint8_t* const a0_img = stash ? stash + SL.a0 : nullptr;
+  uint8_t* const g_img = stash ? stash + SL.g : nullptr;
+  uint4* const xh1_st = stash ? reinterpret_cast<uint4*>(stash + SL.xh1) : nullptr;
+  uint4* const xh2_st = stash ? reinterpret_cast<uint4*>(stash + SL.xh2) : nullptr;
+  float* const rstd_st = stash ? reinterpret_cast<float*>(stash + SL.rstd) : nullptr;
 
   uint32_t it1 = 0, it2 = 0, acc_par = 0;
   const int q = warp & 3, hsel = warp >> 2;
@@ -103,6 +110,11 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
   const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
   const int n_tiles = (int)((n_edges + TILE_M - 1) / TILE_M);
 
+  // desynchronise the CTAs' HBM-heavy phases (see the backward kernel): a fraction-of-a-tile start offset per CTA group
+  if (stagger_cycles > 0 && n_tiles > (int)gridDim.x) {
+    const long long t0 = clock64(), wait = (long long)(blockIdx.x % 4) * stagger_cycles;
+    while (clock64() - t0 < wait) {}
+  }
   long long t_prev = clock64();
   auto MARK = [&](int ph) {  // optional per-phase cycle accounting (CTA 0, thread 0)
     if (phase_clk && tid == 0 && blockIdx.x == 0) { long long t = clock64(); atomicAdd(phase_clk + ph, (unsigned long long)(t - t_prev)); t_prev = t; }
@@ -186,7 +198,9 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
       s_red[row * 4 + hsel * 2 + 1] = m2;
       __syncthreads();
       const LnStat st = combine_halves(s_red, row, NC, P.ln_eps);
-      ln_act_to_image<ACT_H, NC / 32>(t_lane + c0, s_b1, s_g1, s_be1, c0, st.mean, st.rstd, region, row);
+      ln_act_to_image<ACT_H, NC / 32>(t_lane + c0, s_b1, s_g1, s_be1, c0, st.mean, st.rstd, region, row,
+                                      xh1_st ? xh1_st + (size_t)tile * (H / 8) * TILE_M : nullptr);
+      if (rstd_st && hsel == 0) rstd_st[(size_t)tile * 2 * TILE_M + row] = st.rstd;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -195,6 +209,10 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
 
     // ---- GEMM2: D2[128, L] = A2 . W2^T (accumulator aliases TMEM columns [0, L)) ----
     if (tid == 0) {
+      if (g_img) {  // the finished A2 image is also the weight-gradient operand of layer 2: one bulk copy to HBM
+        bulk_s2g(g_img + (size_t)tile * C::A2_BYTES, region_u, C::A2_BYTES);
+        bulk_commit();
+      }
       tc_fence_after();
       for (int j = 0; j < C::NKB2; ++j) {
         const uint32_t u = it2 + j, sl = u & 1, ph = (u >> 1) & 1;
@@ -226,26 +244,40 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
       ln_partial<NC / 32>(t_lane + c0, s_b2 + c0, mloc, m2);
       s_red[row * 4 + hsel * 2] = mloc;   // EPI1's readers passed the pre-GEMM2 barrier long ago
       s_red[row * 4 + hsel * 2 + 1] = m2;
+      if (tid == 0 && g_img) bulk_wait_read0();  // the g image has left shared memory before the region becomes staging
       __syncthreads();
       const LnStat st = combine_halves(s_red, row, NC, P.ln_eps);
       const float nmr = -st.mean * st.rstd;
+      if (rstd_st && hsel == 0) rstd_st[(size_t)tile * 2 * TILE_M + TILE_M + row] = st.rstd;
+      uint4* const xh2_t = xh2_st ? xh2_st + (size_t)tile * (L / 8) * TILE_M : nullptr;
       float v[32];
 #pragma unroll 1
       for (int ch = 0; ch < NC / 32; ++ch) {
         tmem_ld32(t_lane + c0 + ch * 32, v);
         const int cb = c0 + ch * 32;
 #pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          const int c = cb + g4 * 4;
-          const float4 b = *reinterpret_cast<const float4*>(s_b2 + c);
-          const float4 g = *reinterpret_cast<const float4*>(s_g2 + c);
-          const float4 be = *reinterpret_cast<const float4*>(s_be2 + c);
-          float4 o;
-          o.x = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 0] + b.x, st.rstd, nmr), g.x, be.x));
-          o.y = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 1] + b.y, st.rstd, nmr), g.y, be.y));
-          o.z = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 2] + b.z, st.rstd, nmr), g.z, be.z));
-          o.w = tc_act<ACT_O>(fmaf(fmaf(v[g4 * 4 + 3] + b.w, st.rstd, nmr), g.w, be.w));
-          *reinterpret_cast<float4*>(region + (size_t)row * (L * 4) + (((c >> 2) ^ (row & 7)) << 4)) = o;
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float xh[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = cb + g8 * 8 + 4 * h;
+            const float4 b = *reinterpret_cast<const float4*>(s_b2 + c);
+            const float4 g = *reinterpret_cast<const float4*>(s_g2 + c);
+            const float4 be = *reinterpret_cast<const float4*>(s_be2 + c);
+            xh[4 * h + 0] = fmaf(v[g8 * 8 + 4 * h + 0] + b.x, st.rstd, nmr);
+            xh[4 * h + 1] = fmaf(v[g8 * 8 + 4 * h + 1] + b.y, st.rstd, nmr);
+            xh[4 * h + 2] = fmaf(v[g8 * 8 + 4 * h + 2] + b.z, st.rstd, nmr);
+            xh[4 * h + 3] = fmaf(v[g8 * 8 + 4 * h + 3] + b.w, st.rstd, nmr);
+            float4 o;
+            o.x = tc_act<ACT_O>(fmaf(xh[4 * h + 0], g.x, be.x));
+            o.y = tc_act<ACT_O>(fmaf(xh[4 * h + 1], g.y, be.y));
+            o.z = tc_act<ACT_O>(fmaf(xh[4 * h + 2], g.z, be.z));
+            o.w = tc_act<ACT_O>(fmaf(xh[4 * h + 3], g.w, be.w));
+            *reinterpret_cast<float4*>(region + (size_t)row * (L * 4) + (((c >> 2) ^ (row & 7)) << 4)) = o;
+          }
+          if (xh2_t)
+            xh2_t[(size_t)((cb + g8 * 8) >> 3) * TILE_M + row] =
+                make_uint4(pack_bf16(xh[0], xh[1]), pack_bf16(xh[2], xh[3]), pack_bf16(xh[4], xh[5]), pack_bf16(xh[6], xh[7]));
         }
       }
     }
@@ -302,6 +334,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     MARK(6);
   }
 
+  if (tid == 0 && g_img) bulk_wait0();  // outstanding image stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
@@ -432,26 +465,30 @@ extern "C" int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t 
 }
 
 static void* g_fwd_phase_clk = nullptr;
+static int fwd_stagger() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("HGNN_FWD_STAGGER"); v = e ? atoi(e) : 0; }
+  return v;
+}
 // debug hook (not part of the stable ABI): device buffer of 16 uint64 that CTA 0 of the forward kernel fills with per-phase cycles
 extern "C" void hgnn_tc_debug_set_fwd_phase_clock(void* dev_u64x16) { g_fwd_phase_clk = dev_u64x16; }
 
 extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t) { return 256; }
-extern "C" size_t hgnn_tc_edge_a0_image_bytes(int64_t n_edges, int64_t latent) {
-  int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
-  return (size_t)tiles * (3 * latent / KBLK) * A_BLK_BYTES;
+extern "C" size_t hgnn_tc_edge_stash_bytes(int64_t n_edges, int64_t latent) {
+  return edge_stash_layout(n_edges > 0 ? n_edges : 1, (int)latent).total;
 }
 
 template <int L>
 static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src, const int32_t* dst,
                            const int32_t* perm, int64_t n_edges, float* e_out, const int32_t* rowptr, int64_t n_nodes, float* agg,
-                           uint8_t* a0_img, cudaStream_t st) {
+                           uint8_t* stash, cudaStream_t st) {
   size_t smem = Cfg<L>::SMEM;
   auto kern = k_tc_edge_fwd<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
   HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
-  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg, a0_img,
-                                        (unsigned long long*)g_fwd_phase_clk);
+  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg, stash, edge_stash_layout(n_edges, L),
+                                        (unsigned long long*)g_fwd_phase_clk, fwd_stagger());
   if (agg) {
     int64_t threads = n_nodes * (L / 4);
     k_agg_fixup<L><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(e_out, perm, rowptr, n_nodes, agg);
@@ -461,7 +498,7 @@ static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const f
 
 extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
                                     const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges,
-                                    int64_t n_nodes, float* e_out, float* agg, void* a0_img, void* ws, size_t ws_bytes,
+                                    int64_t n_nodes, float* e_out, float* agg, void* stash, void* ws, size_t ws_bytes,
                                     void* stream) {
   (void)ws; (void)ws_bytes;
   HGNN_REQUIRE(agg == nullptr || (rowptr != nullptr && n_nodes > 0),
@@ -480,6 +517,6 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
                 "tc_edge_forward: latent %d / hidden %d / activations (%d, %d) not built (need latent in {64,128}, hidden = 2*latent, GELU/Tanh)",
                 p->latent, p->hidden, p->act_hidden, p->act_out);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)a0_img, st);
-  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)a0_img, st);
+  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)stash, st);
+  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)stash, st);
 }

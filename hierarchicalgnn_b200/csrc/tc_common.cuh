@@ -244,10 +244,12 @@ __device__ __forceinline__ void ln_partial(uint32_t taddr, const float* __restri
 
 // act(LayerNorm(accumulator + bias)) -> bf16, written as the K-major swizzled A-operand image of the next GEMM.
 // sb / sg / sbe are the full per-column parameter arrays; c0 = first column owned by this thread.
+// xh_out (optional): the normalised pre-affine values xhat = (h - mean) * rstd are also stashed in HBM as bf16, 8 per
+// uint4, in [column chunk][row] order (a warp's 32 rows of one chunk are 512 contiguous bytes) for the backward pass.
 template <int ACT, int NCH>
 __device__ __forceinline__ void ln_act_to_image(uint32_t taddr, const float* __restrict__ sb, const float* __restrict__ sg,
                                                 const float* __restrict__ sbe, int c0, float mean, float rstd,
-                                                uint8_t* __restrict__ img, int row) {
+                                                uint8_t* __restrict__ img, int row, uint4* __restrict__ xh_out = nullptr) {
   float v[32];
   const float nmr = -mean * rstd;
 #pragma unroll 1
@@ -257,23 +259,52 @@ __device__ __forceinline__ void ln_act_to_image(uint32_t taddr, const float* __r
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
       const int c = cb + g8 * 8;
-      float o[8];
+      float o[8], xh[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 b = *reinterpret_cast<const float4*>(sb + c + 4 * h);
         const float4 g = *reinterpret_cast<const float4*>(sg + c + 4 * h);
         const float4 be = *reinterpret_cast<const float4*>(sbe + c + 4 * h);
-        o[4 * h + 0] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 0] + b.x, rstd, nmr), g.x, be.x));
-        o[4 * h + 1] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 1] + b.y, rstd, nmr), g.y, be.y));
-        o[4 * h + 2] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 2] + b.z, rstd, nmr), g.z, be.z));
-        o[4 * h + 3] = tc_act<ACT>(fmaf(fmaf(v[g8 * 8 + 4 * h + 3] + b.w, rstd, nmr), g.w, be.w));
+        xh[4 * h + 0] = fmaf(v[g8 * 8 + 4 * h + 0] + b.x, rstd, nmr);
+        xh[4 * h + 1] = fmaf(v[g8 * 8 + 4 * h + 1] + b.y, rstd, nmr);
+        xh[4 * h + 2] = fmaf(v[g8 * 8 + 4 * h + 2] + b.z, rstd, nmr);
+        xh[4 * h + 3] = fmaf(v[g8 * 8 + 4 * h + 3] + b.w, rstd, nmr);
+        o[4 * h + 0] = tc_act<ACT>(fmaf(xh[4 * h + 0], g.x, be.x));
+        o[4 * h + 1] = tc_act<ACT>(fmaf(xh[4 * h + 1], g.y, be.y));
+        o[4 * h + 2] = tc_act<ACT>(fmaf(xh[4 * h + 2], g.z, be.z));
+        o[4 * h + 3] = tc_act<ACT>(fmaf(xh[4 * h + 3], g.w, be.w));
       }
       *reinterpret_cast<uint4*>(img + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
           make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      if (xh_out)
+        xh_out[(size_t)(c >> 3) * TILE_M + row] =
+            make_uint4(pack_bf16(xh[0], xh[1]), pack_bf16(xh[2], xh[3]), pack_bf16(xh[4], xh[5]), pack_bf16(xh[6], xh[7]));
     }
   }
 }
 
+// What the forward edge step leaves in HBM for its backward (one caller-owned buffer, hgnn_tc_edge_stash_bytes):
+//   a0  [tiles][3L/64][16 KB]  bf16 tile image of the gathered input [x[src] | x[dst] | e]   (weight-gradient operand)
+//   g   [tiles][2L/64][16 KB]  bf16 tile image of act(LN1(h1))                                (weight-gradient operand)
+//   xh1 [tiles][2L/8][128]     uint4 = 8 bf16 of xhat1 = (h1 - mean1) rstd1                   (LN1 / activation adjoint)
+//   xh2 [tiles][L/8][128]      uint4 = 8 bf16 of xhat2                                        (LN2 / activation adjoint)
+//   rstd [tiles][2][128]       fp32 rstd1, rstd2 per row
+struct EdgeStash {
+  size_t a0, g, xh1, xh2, rstd, total;
+  int64_t tiles;
+};
+__host__ __device__ inline EdgeStash edge_stash_layout(int64_t n_edges, int L) {
+  EdgeStash S{};
+  S.tiles = (n_edges + TILE_M - 1) / TILE_M;
+  size_t off = 0;
+  S.a0 = off;   off += (size_t)S.tiles * (3 * L / KBLK) * A_BLK_BYTES;
+  S.g = off;    off += (size_t)S.tiles * (2 * L / KBLK) * A_BLK_BYTES;
+  S.xh1 = off;  off += (size_t)S.tiles * (2 * L / 8) * TILE_M * 16;
+  S.xh2 = off;  off += (size_t)S.tiles * (L / 8) * TILE_M * 16;
+  S.rstd = off; off += (size_t)S.tiles * 2 * TILE_M * 4;
+  S.total = off;
+  return S;
+}
 
 // ---- pieces shared by the fused edge kernels and the per-layer row kernels ----
 // (gathers assume 256-thread CTAs: 16 threads per 256 B row piece, 16 rows per pass)

@@ -570,8 +570,8 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[
     if agg is not None:
         perm, rowptr = (None if plan_d.is_identity() else plan_d.perm), plan_d.rowptr
     a0 = None
-    if save_image:  # bf16 tile image of [x[src] | x[dst] | e] for the backward pass (768 B/edge at L = 128)
-        a0 = torch.empty(_lib.lib().hgnn_tc_edge_a0_image_bytes(n_edges, e.shape[1]), dtype=torch.uint8, device=e.device)
+    if save_image:  # the forward's stash for the backward pass: operand images + bf16 xhat's + rstd (2 KB/edge at L = 128)
+        a0 = torch.empty(_lib.lib().hgnn_tc_edge_stash_bytes(n_edges, e.shape[1]), dtype=torch.uint8, device=e.device)
     with _timed("tc_edge_forward"):
         check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), _ptr(perm),
                                               _ptr(rowptr), n_edges, x.shape[0], _ptr(out), _ptr(agg), _ptr(a0), None, 0,

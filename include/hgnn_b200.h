@@ -226,24 +226,26 @@ int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca
  * each finished tile in shared memory (no atomics); this needs perm/rowptr = the by-destination plan of
  * hgnn_csr_build (perm may be NULL when the edges are already stored destination-sorted: rows then stream in place). Segments crossing a row-group boundary (hub nodes) and empty segments are completed by a small
  * second kernel inside the same call.
- * a0_img (optional, hgnn_tc_edge_a0_image_bytes): the bf16 tile image of the gathered input [x[src] | x[dst] | e]
- * that the kernel builds anyway is also left in HBM; the backward pass and the weight-gradient GEMM consume it with
- * bulk copies instead of gathering again (pass it when a backward will follow). */
+ * stash (optional, hgnn_tc_edge_stash_bytes): pass it when a backward will follow. The kernel then also leaves in HBM,
+ * per 128-edge tile, the bf16 tile images of its two MMA operands ([x[src] | x[dst] | e] and the hidden activation),
+ * the normalised pre-affine activations of both LayerNorms as bf16 and the row rstd's (2 KB per edge at latent 128):
+ * everything hgnn_tc_edge_backward and the weight-gradient GEMM need, so the backward recomputes nothing and
+ * never gathers again. */
 size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges);
-size_t hgnn_tc_edge_a0_image_bytes(int64_t n_edges, int64_t latent);
+size_t hgnn_tc_edge_stash_bytes(int64_t n_edges, int64_t latent);
 int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
                          const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges, int64_t n_nodes,
-                         float* e_out, float* agg, void* a0_img, void* ws, size_t ws_bytes, void* stream);
+                         float* e_out, float* agg, void* stash, void* ws, size_t ws_bytes, void* stream);
 
-/* Backward of the tensor-core edge step (latent 128): in-kernel recompute (no saved activations),
+/* Backward of the tensor-core edge step (latent 128) from the forward's stash (no recompute, no gathers):
  * data gradients as per-edge rows (d_e final; d_xsrc_rows / d_xdst_rows are reduced by the caller
  * with hgnn_segment_reduce over the by-source / by-destination plans), weight gradients by the
  * tcgen05 split-K kernel, bias/LayerNorm gradients dvec{1,2} = [3, width] (d bias, d gamma, d beta).
- * a0_img / perm must be the image and row order of the matching hgnn_tc_edge_forward call.
+ * stash / perm must be the buffer and row order of the matching hgnn_tc_edge_forward call.
  * grad_agg (optional, [n_nodes, L]) is the cotangent of agg = scatter_add(e_out, dst): the kernel uses
  * grad_eout[i] + grad_agg[dst_i]. w1t/w2t_packed are hgnn_tc_pack_weights images of W1^T / W2^T. */
 size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges);
-int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const void* a0_img,
+int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const void* stash,
                           const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_edges, const float* grad_eout,
                           const float* grad_agg, float* d_e, float* d_xsrc_rows, float* d_xdst_rows, float* dW1, float* dW2,
                           float* dvec1, float* dvec2, void* ws, size_t ws_bytes, void* stream);

@@ -22,16 +22,12 @@ _lib.lib().hgnn_tc_debug_set_phase_clock(clk.data_ptr())
 step(); torch.cuda.synchronize()
 _lib.lib().hgnn_tc_debug_set_phase_clock(None)
 c = clk.cpu().tolist()
-names = ["setup+G", "GEMM1(gather)", "EPI-A", "GEMM2", "EPI-B", "GEMM3", "EPI-C", "GEMM4", "EPI-D"]
+names = ["setup", "LOAD(gout)", "EPI-B", "GEMM3", "EPI-C", "GEMM4", "EPI-D"]
 tiles = (E + 127) // 128 // 148 + 1
-tot = sum(c[:9])
-for nm, v in zip(names, c[:9]):
+tot = sum(c[:7])
+for nm, v in zip(names, c[:7]):
     print(f"{nm:14s} {v / tiles:9.0f} cyc/tile  {100 * v / tot:5.1f}%")
 print(f"total {tot / tiles:.0f} cycles/tile over ~{tiles} tiles")
-sub = ["gout loads issued", "kb0-1 issued", "wait A_REST", "wait W_KB2 + kb2", "kb3-5", "drain: ACC + barrier"]
-for nm, v in zip(sub, c[9:15]):
-    print(f"   GEMM1 / {nm:24s} {v / tiles:9.0f} cyc/tile")
-
 # forward kernel
 clk.zero_()
 _lib.lib().hgnn_tc_debug_set_fwd_phase_clock(clk.data_ptr())
