@@ -274,8 +274,10 @@ def run_gpu(args):
         fwd_b, bwd_b = alg_bytes_per_edge(L, N / E)
         # dominant kernel of the step by measured time
         top = max(prof, key=prof.get) if prof else None
+        # algorithmic FLOPs per edge: forward 16 L^2; the fp32 path recomputes the forward in its backward
+        # (32 L^2 data + 16 L^2 weights), the tensor-core path stashes activations instead (16 L^2 data + 16 L^2 weights)
         flops_edge = {"mlp_forward": 16 * L * L, "mlp_backward_data": 32 * L * L, "mlp_backward_weights": 16 * L * L,
-                      "tc_edge_forward": 16 * L * L, "tc_edge_backward": 48 * L * L}
+                      "tc_edge_forward": 16 * L * L, "tc_edge_backward": 32 * L * L}
         if top in flops_edge:
             ach = flops_edge[top] * E / (prof[top] * 1e-3) / 1e12
             peak = pk["bf16_tflops_sustained"]
@@ -288,7 +290,19 @@ def run_gpu(args):
         if roof is not None:
             roof["kernel_ms"] = {k: round(v, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])}
             roof["step_hbm_frac"] = (fwd_b + bwd_b) * E / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"]
-            roof["step_tensor_frac"] = 64 * L * L * E / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]
+            step_flops = (48 if "tc_edge_backward" in prof else 64) * L * L  # 64 L^2 only where the backward recomputes
+            roof["step_tensor_frac"] = step_flops * E / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]
+            roof["step_flops_per_edge"] = step_flops
+            # measured DRAM traffic of the dominant call from the committed ncu capture of this same workload
+            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if os.path.exists(tpath):
+                try:
+                    t = json.load(open(tpath)).get(top)
+                    if t and t.get("edges") == E and t.get("latent") == L:
+                        roof["traffic"] = t["dram_bytes_per_launch"]
+                        roof["traffic_source"] = t.get("source")
+                except Exception:  # noqa: BLE001
+                    pass
 
     # ---- end to end through the public module API with HOST buffers ----
     e2e = None
