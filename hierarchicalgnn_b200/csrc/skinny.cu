@@ -46,6 +46,31 @@ __device__ __forceinline__ void lane_source(const NarrowInArgs& A, int lane, int
   col = c;
 }
 
+// Sums 8 per-lane values across the warp with 9 shuffles instead of 40: each step folds half of the remaining values
+// onto the partner lane (log-step transpose-reduce); on return lane l holds the warp total of value (l & 7) in v[0].
+__device__ __forceinline__ float warp_sum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 8);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+  return v[0];
+}
+
 // shared: Wt[K][N] | bias[N] | gamma[N] | beta[N]
 template <int NJ>
 __device__ __forceinline__ void stage_params(const NarrowInArgs& A, float* sm) {
@@ -104,7 +129,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_narrow_in_fwd(NarrowInArgs A, fl
 
 // partial layout per CTA: [K + 3][N] = dW^T rows (k-major) | d bias | d gamma | d beta
 template <int NJ>
-__global__ void __launch_bounds__(SK_THREADS) k_narrow_in_bwd(NarrowInArgs A, const float* __restrict__ gout, float* __restrict__ d_in,
+__global__ void __launch_bounds__(SK_THREADS, 2) k_narrow_in_bwd(NarrowInArgs A, const float* __restrict__ gout, float* __restrict__ d_in,
                                                               float* __restrict__ partial) {
   extern __shared__ float sm[];
   const int N = A.N;
@@ -185,14 +210,9 @@ __global__ void __launch_bounds__(SK_THREADS) k_narrow_in_bwd(NarrowInArgs A, co
       }
     }
     if (d_in) {
-      float mine = 0.f;
-#pragma unroll
-      for (int k = 0; k < NI_MAX_K; ++k) {
-        if (k < A.K) {
-          const float s = warp_sum(da[k]);
-          if (lane == k) mine = s;
-        }
-      }
+      // after the transpose-reduce lane l holds column ((l & 4) | (l & 2) | (l & 1)) bit-reversed pairing: value index
+      // = 4 * bit2(l) + 2 * bit1(l) + bit0(l) = l & 7
+      const float mine = warp_sum8(da, lane);
       if (lane < A.K) d_in[(size_t)r * A.K + lane] = mine;
     }
   }
