@@ -50,6 +50,11 @@ inline int num_sms() {
   return sms;
 }
 
+// graph_ops.cu: ordered segmented row sums; skip_short = only the hub segments (> 512 rows; one CTA each), for callers
+// whose own kernel already produced the short ones
+int launch_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight, const int32_t* perm,
+                          const int32_t* rowptr, int64_t n_segments, int mean, float* out, bool skip_short, cudaStream_t st);
+
 // simple bump allocator over the caller-provided workspace
 struct Workspace {
   char* base;

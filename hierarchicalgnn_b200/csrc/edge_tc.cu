@@ -352,8 +352,17 @@ __global__ void __launch_bounds__(256) k_agg_fixup(const float* __restrict__ e_o
   if (s >= n_nodes) return;
   const int beg = rowptr[s], end = rowptr[s + 1];
   if (end > beg && beg / G == (end - 1) / G) return;  // finished inside the edge kernel
+  if (end - beg > 512) return;                        // hub segment: summed by the per-CTA long-segment kernel
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = beg; j < end; ++j) {
+  int j = beg;
+  for (; j + 16 <= end; j += 16) {  // hub nodes: 16 row loads in flight, summed in row order
+    float4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = *(reinterpret_cast<const float4*>(e_out + (size_t)(perm ? perm[j + u] : j + u) * L) + c);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+  for (; j < end; ++j) {
     const float4 v = *(reinterpret_cast<const float4*>(e_out + (size_t)(perm ? perm[j] : j) * L) + c);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
@@ -492,6 +501,8 @@ static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const f
   if (agg) {
     int64_t threads = n_nodes * (L / 4);
     k_agg_fixup<L><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(e_out, perm, rowptr, n_nodes, agg);
+    int rc = launch_segment_reduce(e_out, L, nullptr, nullptr, perm, rowptr, n_nodes, 0, agg, /*skip_short=*/true, st);
+    if (rc) return rc;
   }
   return check_launch("tc_edge_forward");
 }

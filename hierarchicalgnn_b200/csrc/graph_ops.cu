@@ -5,6 +5,8 @@
 // deterministic sequential sum per segment (no float atomics).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace hgnn;
@@ -125,7 +127,8 @@ template <> __device__ __forceinline__ float zero_v<float>() { return 0.f; }
 template <int VEC>
 __global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict__ src, int chunks, const int32_t* __restrict__ gather,
                                  const float* __restrict__ weight, const int32_t* __restrict__ perm,
-                                 const int32_t* __restrict__ rowptr, int64_t n_seg, int mean, float* __restrict__ out) {
+                                 const int32_t* __restrict__ rowptr, int64_t n_seg, int mean, float* __restrict__ out,
+                                 int long_threshold) {
   using V = typename VecT<VEC>::type;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t s = t / chunks;
@@ -133,8 +136,23 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict_
   if (s >= n_seg) return;
   const V* __restrict__ rows = reinterpret_cast<const V*>(src);
   int beg = rowptr[s], end = rowptr[s + 1];
+  if (long_threshold > 0 && end - beg > long_threshold) return;  // hub segment: k_segment_reduce_long owns it
   V acc = zero_v<V>();
   int j = beg;
+  // long segments (hub nodes): 16 independent row loads in flight per step, summed in the same row order
+  for (; j + 16 <= end; j += 16) {
+    V v[16];
+    float w[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = perm ? perm[j + u] : j + u;
+      const int64_t r = gather ? gather[i] : i;
+      w[u] = weight ? weight[i] : 1.f;
+      v[u] = rows[r * chunks + c];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) fma_acc(acc, w[u], v[u]);
+  }
   for (; j + 4 <= end; j += 4) {
     int i0 = perm ? perm[j] : j, i1 = perm ? perm[j + 1] : j + 1, i2 = perm ? perm[j + 2] : j + 2, i3 = perm ? perm[j + 3] : j + 3;
     int64_t r0 = gather ? gather[i0] : i0, r1 = gather ? gather[i1] : i1, r2 = gather ? gather[i2] : i2, r3 = gather ? gather[i3] : i3;
@@ -150,6 +168,72 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict_
   }
   if (mean) scale_v(acc, 1.0f / (float)max(end - beg, 1));
   reinterpret_cast<V*>(out)[s * chunks + c] = acc;
+}
+
+// Hub segments (more than `long_threshold` rows): one CTA per segment, the rows split into blockDim / chunks contiguous
+// parts that are summed in parallel (each part in row order, 16 loads in flight) and then combined in part order —
+// a fixed association for a given segment length, so still bit-reproducible.
+constexpr int LONG_THREADS = 1024;
+template <int VEC>
+__global__ void __launch_bounds__(LONG_THREADS) k_segment_reduce_long(const float* __restrict__ src, int chunks,
+                                                                      const int32_t* __restrict__ gather, const float* __restrict__ weight,
+                                                                      const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
+                                                                      int64_t n_seg, int mean, float* __restrict__ out, int long_threshold) {
+  using V = typename VecT<VEC>::type;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  V* part_sum = reinterpret_cast<V*>(sm_raw);
+  const V* __restrict__ rows = reinterpret_cast<const V*>(src);
+  const int nparts = blockDim.x / chunks;
+  const int part = threadIdx.x / chunks, c = threadIdx.x % chunks;
+  // this CTA owns segment ids {b, b + grid, b + 2 grid, ...} (consecutive ids — where power-law hubs cluster — land on
+  // different CTAs): one parallel look at rowptr finds the (rare) hub segments among them
+  __shared__ int s_queue[LONG_THREADS];
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  {
+    const int64_t s = (int64_t)threadIdx.x * gridDim.x + blockIdx.x;
+    if (s < n_seg && rowptr[s + 1] - rowptr[s] > long_threshold) s_queue[atomicAdd(&s_count, 1)] = (int)s;
+  }
+  __syncthreads();
+  const int n_long = s_count;  // queue order varies run to run; each segment's sum does not depend on it
+  for (int qi = 0; qi < n_long; ++qi) {
+    const int64_t s = s_queue[qi];
+    const int beg = rowptr[s], end = rowptr[s + 1];
+    const int per = (end - beg + nparts - 1) / nparts;
+    if (part < nparts) {
+      const int b0 = min(end, beg + part * per), b1 = min(end, b0 + per);
+      V acc = zero_v<V>();
+      int j = b0;
+      for (; j + 16 <= b1; j += 16) {
+        V v[16];
+        float w[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int i = perm ? perm[j + u] : j + u;
+          const int64_t r = gather ? gather[i] : i;
+          w[u] = weight ? weight[i] : 1.f;
+          v[u] = rows[r * chunks + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) fma_acc(acc, w[u], v[u]);
+      }
+      for (; j < b1; ++j) {
+        const int i = perm ? perm[j] : j;
+        const int64_t r = gather ? gather[i] : i;
+        fma_acc(acc, weight ? weight[i] : 1.f, rows[r * chunks + c]);
+      }
+      part_sum[part * chunks + c] = acc;
+    }
+    __syncthreads();
+    if (part == 0) {
+      V acc = part_sum[c];
+      for (int p = 1; p < nparts; ++p) fma_acc(acc, 1.f, part_sum[p * chunks + c]);
+      if (mean) scale_v(acc, 1.0f / (float)(end - beg));
+      reinterpret_cast<V*>(out)[s * chunks + c] = acc;
+    }
+    __syncthreads();
+  }
 }
 
 template <int VEC>
@@ -193,20 +277,36 @@ __global__ void __launch_bounds__(256) k_edge_dot(const float* __restrict__ a, c
 
 }  // namespace
 
+namespace hgnn {
+// launches the per-thread kernel for ordinary segments and the per-CTA kernel for hub segments (> 512 rows)
+int launch_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight, const int32_t* perm,
+                          const int32_t* rowptr, int64_t n_segments, int mean, float* out, bool skip_short, cudaStream_t st) {
+  bool vec = (width % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
+  int chunks = vec ? (int)(width / 4) : (int)width;
+  const int long_threshold = chunks <= 256 ? 512 : 0;  // hub path needs >= 4 row parts per 1024-thread CTA
+  if (!skip_short) {
+    int64_t threads = n_segments * chunks;
+    unsigned grid = (unsigned)((threads + 255) / 256);
+    if (vec) k_segment_reduce<4><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
+    else k_segment_reduce<1><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
+  }
+  if (long_threshold > 0) {
+    unsigned grid = (unsigned)((n_segments + LONG_THREADS - 1) / LONG_THREADS);  // one segment id per thread to inspect
+    size_t smem = (size_t)LONG_THREADS * (vec ? 16 : 4);
+    if (vec) k_segment_reduce_long<4><<<grid, LONG_THREADS, smem, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
+    else k_segment_reduce_long<1><<<grid, LONG_THREADS, smem, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
+  }
+  return check_launch("segment_reduce");
+}
+}  // namespace hgnn
+
 extern "C" int hgnn_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight,
                                    const int32_t* perm, const int32_t* rowptr, int64_t n_segments, int mean, float* out,
                                    void* stream) {
   if (n_segments <= 0 || width <= 0) return HGNN_OK;
   HGNN_REQUIRE(src && rowptr && out, "segment_reduce: NULL pointer");
   HGNN_REQUIRE(width <= 65536, "segment_reduce: width too large");
-  cudaStream_t st = (cudaStream_t)stream;
-  bool vec = (width % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
-  int chunks = vec ? (int)(width / 4) : (int)width;
-  int64_t threads = n_segments * chunks;
-  unsigned grid = (unsigned)((threads + 255) / 256);
-  if (vec) k_segment_reduce<4><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out);
-  else k_segment_reduce<1><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out);
-  return check_launch("segment_reduce");
+  return hgnn::launch_segment_reduce(src, width, gather, weight, perm, rowptr, n_segments, mean, out, false, (cudaStream_t)stream);
 }
 
 extern "C" int hgnn_gather_rows(const float* src, int64_t width, const int32_t* idx, const float* weight, int64_t n_items,

@@ -189,7 +189,7 @@ def segment_reduce_raw(src: Tensor, plan: SegmentPlan, gather32: Optional[Tensor
             check(_lib.lib().hgnn_segment_reduce(_ptr(src), width, _ptr(gather32), _ptr(weight), _ptr(plan.perm),
                                                  _ptr(plan.rowptr), plan.n_segments, int(mean), _ptr(out), _stream()),
                   "segment_reduce")
-        _count()
+        _count(2)  # per-thread kernel for ordinary segments + per-CTA kernel for hub segments
     return out
 
 
@@ -576,7 +576,7 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[
         check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), _ptr(perm),
                                               _ptr(rowptr), n_edges, x.shape[0], _ptr(out), _ptr(agg), _ptr(a0), None, 0,
                                               _stream()), "tc_edge_forward")
-    _count(1 if agg is None else 2)
+    _count(1 if agg is None else 3)  # edge kernel (+ aggregate fix-up and hub-segment kernels)
     TC_CALLS["count"] += 1
     return a0
 

@@ -264,3 +264,31 @@ def test_bad_arguments_surface_last_error(ops):
         ops.knn_radius(torch.randn(4, 40, device=DEV), torch.randn(4, 40, device=DEV), 3, 1.0)
     with pytest.raises(HgnnError, match="k must be"):
         ops.knn_radius(torch.randn(4, 8, device=DEV), torch.randn(4, 8, device=DEV), 64, 1.0)
+
+
+@pytest.mark.parametrize("width", [128, 3, 64])
+def test_scatter_add_hub_segments(ops, width):
+    """Power-law degrees: segments longer than 512 rows take the per-CTA long-segment kernel (rows split into parts summed
+    in parallel, combined in part order). Same fp64 tolerance as ordinary segments, bit-identical run to run, means too."""
+    g = torch.Generator().manual_seed(7)
+    n_items, n_seg = 40_000, 300
+    u = torch.rand(n_items, generator=g)
+    idx = (n_seg * u.pow(4.0)).long().clamp_(max=n_seg - 1)      # segment 0 holds ~ n_items * 300^-0.25 = 9.6k rows
+    deg = torch.bincount(idx, minlength=n_seg)
+    assert int(deg.max()) > 5000 and int((deg > 512).sum()) >= 3 and int((deg == 0).sum()) >= 0
+    src = torch.randn(n_items, width, generator=g)
+    want = torch.zeros(n_seg, width, dtype=torch.float64).index_add_(0, idx, src.double())
+    a = ops.scatter_add(src.to(DEV), idx.to(DEV), dim_size=n_seg)
+    b = ops.scatter_add(src.to(DEV), idx.to(DEV), dim_size=n_seg)
+    assert torch.equal(a, b)
+    assert float((a.cpu().double() - want).abs().max()) < 2e-5 * float(deg.max()) ** 0.5
+    m = ops.scatter_mean(src.to(DEV), idx.to(DEV), dim_size=n_seg)
+    assert float((m.cpu().double() - want / deg.clamp(min=1).unsqueeze(1)).abs().max()) < 1e-5
+    # weighted gather + reduce through the same kernels, gradient = transposed plan
+    w = torch.rand(n_items, 1, generator=g)
+    table = torch.randn(500, width, generator=g)
+    gi = torch.randint(0, 500, (n_items,), generator=g)
+    td = table.to(DEV).requires_grad_(True)
+    out = ops.gather_scatter(td, w.to(DEV), ops.plan_for(gi.to(DEV), 500), ops.plan_for(idx.to(DEV), n_seg))
+    want2 = torch.zeros(n_seg, width, dtype=torch.float64).index_add_(0, idx, (w.double() * table.double()[gi]))
+    assert float((out.detach().cpu().double() - want2).abs().max()) < 2e-5 * float(deg.max()) ** 0.5
