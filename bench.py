@@ -72,6 +72,14 @@ def peaks():
     return p
 
 
+def workload_config(L, E, N, world):
+    """The bench line's `config`, shared by both arms (the reference arm times a bounded sample of this workload)."""
+    return {"workload": f"edge_step_fwd_bwd L={L} E={E} N=E/10 (BASELINE config 2)", "latent": L,
+            "edges_per_gpu": E, "nodes_per_gpu": N, "l2_policy": "inputs (edge latents %d MB) larger than L2" % (E * L * 4 >> 20),
+            "parallelism": f"dp{world}" if world > 1 else "single",
+            "edge_order": "destination-sorted once per event (outside the step)"}
+
+
 def alg_bytes_per_edge(L, n_over_e):
     """fwd 2*L*4 + 8 + 2*(N/E)*L*4 ; bwd 3*L*4 + 8 + 3*(N/E)*L*4."""
     fwd = 8 * L + 8 + 8 * L * n_over_e
@@ -121,8 +129,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1e3 * t / len(timed), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"edge_step_fwd_bwd L={args.latent} E={args.edges} N=E/10 (config 2)",
-                   "latent": args.latent, "edges_per_gpu": args.edges},
+        "config": workload_config(args.latent, args.edges, max(2, int(round(args.edges * 0.1))), args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"oracle/hgnn_oracle.py edge step fwd+bwd on E={n} edges (N=E/10), L={args.latent}, "
                                    f"{len(timed)} timed passes, torch CPU fp32"},
@@ -378,9 +385,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ops.compute_dtype(net), "data": "synthetic",
-            "config": {"workload": f"edge_step_fwd_bwd L={L} E={E} N=E/10 (BASELINE config 2)", "latent": L,
-                       "edges_per_gpu": E, "nodes_per_gpu": N, "l2_policy": "inputs (edge latents %d MB) larger than L2" % (E * L * 4 >> 20),
-                       "parallelism": f"dp{world}" if world > 1 else "single", "edge_order": "destination-sorted once per event (outside the step)"},
+            "config": workload_config(L, E, N, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
