@@ -124,6 +124,15 @@ SIGNATURES = {
     "hgnn_narrow_out_forward": (C.c_int, [vp, i64, i64, vp, vp, i64, vp, vp]),
     "hgnn_narrow_out_backward_workspace_bytes": (sz, [i64, i64]),
     "hgnn_narrow_out_backward": (C.c_int, [vp, i64, i64, vp, i64, vp, vp, vp, vp, vp, sz, vp]),
+    "hgnn_tc_gemm_supported": (C.c_int, [C.POINTER(TcRowLayer)]),
+    "hgnn_tc_gemm": (C.c_int, [C.POINTER(TcRowLayer), i64, vp, i64, i64, vp, vp]),
+    "hgnn_ln_act_supported": (C.c_int, [i64]),
+    "hgnn_ln_act_forward": (C.c_int, [vp, i64, i64, vp, vp, f32, C.c_int, vp, vp, vp]),
+    "hgnn_ln_act_backward_workspace_bytes": (sz, [i64]),
+    "hgnn_ln_act_backward": (C.c_int, [vp, vp, i64, i64, vp, vp, f32, C.c_int, vp, vp, vp, sz, vp]),
+    "hgnn_tc_wgrad_supported": (C.c_int, [i64, i64]),
+    "hgnn_tc_wgrad_workspace_bytes": (sz, [i64, i64, i64]),
+    "hgnn_tc_wgrad": (C.c_int, [vp, i64, vp, i64, i64, vp, vp, sz, vp]),
     "hgnn_tc_row_supported": (C.c_int, [C.POINTER(TcRowLayer)]),
     "hgnn_tc_row_image_bytes": (sz, [i64, i64]),
     "hgnn_tc_row_forward": (C.c_int, [C.POINTER(TcRowLayer), i64, vp, vp, vp]),

@@ -37,6 +37,8 @@ struct RowFwdArgs {
   float eps;
   const float* skip;  // [rows, N] rows added after the activation (NULL: none)
   float* out;
+  int64_t ld_out;     // row stride of out (floats); the N output columns start at col0 (plain-GEMM mode writes a column block)
+  int col0;
   uint8_t* a_img;     // optional [tiles][nkb][16 KB]
   int64_t rows;
 };
@@ -46,14 +48,16 @@ struct RowCfg {
   static constexpr int W_BLK = N * ROW_BYTES;
   static constexpr int STAGE = A_BLK_BYTES + W_BLK;
   static constexpr int RING = 2 * STAGE;
-  static constexpr int SW = 128;                         // columns staged per output pass
+  static constexpr int PC = N / 2 < 64 ? N / 2 : 64;     // columns a thread stages per output pass
+  static constexpr int SW = 2 * PC;                      // columns staged per output pass (both column halves)
   static constexpr int STAGING = TILE_M * SW * 4;
   static constexpr int REGION = RING > STAGING ? RING : STAGING;
   // region | bias, gamma, beta | row ids (3 x 128) | LN exchange (128 x 4) | 8 barriers | tmem slot
   static constexpr int SMEM = REGION + 3 * N * 4 + MAX_SEG * TILE_M * 4 + TILE_M * 4 * 4 + 8 * 8 + 16;
 };
 
-template <int N, int ACT>
+// RAW = plain GEMM: out[:, col0 : col0 + N] = [segments] . W^T (+ bias), no LayerNorm / activation / residual
+template <int N, int ACT, bool RAW>
 __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
   using C = RowCfg<N>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -78,7 +82,11 @@ __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(s_tmem), N);
-  for (int i = tid; i < N; i += RF_THREADS) { s_b[i] = A.bias[i]; s_g[i] = A.gamma[i]; s_be[i] = A.beta[i]; }
+  for (int i = tid; i < N; i += RF_THREADS) {
+    s_b[i] = A.bias ? A.bias[i] : 0.f;
+    s_g[i] = RAW ? 1.f : A.gamma[i];
+    s_be[i] = RAW ? 0.f : A.beta[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,9 +108,10 @@ __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     if (tid < TILE_M) {
-      int64_t j = (int64_t)tile * TILE_M + tid;
-      if (j >= A.rows) j = A.rows - 1;  // padding rows repeat the last row; never stored
-      for (int s = 0; s < A.n_seg; ++s) s_ids[s * TILE_M + tid] = A.seg_idx[s] ? A.seg_idx[s][j] : (int)j;
+      const int64_t j = (int64_t)tile * TILE_M + tid;
+      // padding rows of the last tile gather zeros (id -1): never stored, and zero in the saved image so that the
+      // weight-gradient GEMM over the images sees no phantom rows
+      for (int s = 0; s < A.n_seg; ++s) s_ids[s * TILE_M + tid] = j < A.rows ? (A.seg_idx[s] ? A.seg_idx[s][j] : (int)j) : -1;
     }
     __syncthreads();
 
@@ -146,16 +155,20 @@ __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
     // ---- epilogue: bias + LayerNorm + activation from TMEM, staged 128 columns at a time ----
     {
       constexpr int NC = N / 2;           // columns per thread
-      constexpr int PC = 64;              // columns a thread stages per pass
+      constexpr int PC = C::PC;           // columns a thread stages per pass
       constexpr int PASSES = NC / PC;
       const int c0 = hsel * NC;
-      float mloc, m2;
-      ln_partial<NC / 32>(t_lane + c0, s_b + c0, mloc, m2);
-      s_red[row * 4 + hsel * 2] = mloc;
-      s_red[row * 4 + hsel * 2 + 1] = m2;
-      __syncthreads();
-      const LnStat st = combine_halves(s_red, row, NC, A.eps);
-      const float nmr = -st.mean * st.rstd;
+      float rstd = 1.f, nmr = 0.f;
+      if constexpr (!RAW) {
+        float mloc, m2;
+        ln_partial<NC / 32>(t_lane + c0, s_b + c0, mloc, m2);
+        s_red[row * 4 + hsel * 2] = mloc;
+        s_red[row * 4 + hsel * 2 + 1] = m2;
+        __syncthreads();
+        const LnStat st = combine_halves(s_red, row, NC, A.eps);
+        rstd = st.rstd;
+        nmr = -st.mean * st.rstd;
+      }
       float v[32];
 #pragma unroll 1
       for (int p = 0; p < PASSES; ++p) {
@@ -171,16 +184,20 @@ __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
             const float4 g = *reinterpret_cast<const float4*>(s_g + c);
             const float4 be = *reinterpret_cast<const float4*>(s_be + c);
             float4 o;
-            o.x = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 0] + b.x, st.rstd, nmr), g.x, be.x));
-            o.y = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 1] + b.y, st.rstd, nmr), g.y, be.y));
-            o.z = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 2] + b.z, st.rstd, nmr), g.z, be.z));
-            o.w = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 3] + b.w, st.rstd, nmr), g.w, be.w));
+            if constexpr (RAW) {
+              o = make_float4(v[g4 * 4 + 0] + b.x, v[g4 * 4 + 1] + b.y, v[g4 * 4 + 2] + b.z, v[g4 * 4 + 3] + b.w);
+            } else {
+              o.x = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 0] + b.x, rstd, nmr), g.x, be.x));
+              o.y = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 1] + b.y, rstd, nmr), g.y, be.y));
+              o.z = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 2] + b.z, rstd, nmr), g.z, be.z));
+              o.w = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 3] + b.w, rstd, nmr), g.w, be.w));
+            }
             *reinterpret_cast<float4*>(region + (size_t)row * (C::SW * 4) + (((sc4 + g4) ^ (row & 7)) << 4)) = o;
           }
         }
         __syncthreads();
         {
-          constexpr int CPR = C::SW / 4;                       // 32 float4 chunks per staged row
+          constexpr int CPR = C::SW / 4;                       // float4 chunks per staged row
           constexpr int ROWS_PER_WARP = TILE_M / (RF_THREADS / 32);
 #pragma unroll 4
           for (int idx = lane; idx < ROWS_PER_WARP * CPR; idx += 32) {
@@ -189,8 +206,8 @@ __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
             if (j < A.rows) {
               float4 y = *reinterpret_cast<const float4*>(region + (size_t)r * (C::SW * 4) + ((c4 ^ (r & 7)) << 4));
               const int sc = c4 * 4;
-              const size_t g = (size_t)j * N + (sc / PC) * NC + p * PC + (sc % PC);
-              if (A.skip) {
+              const size_t g = (size_t)j * A.ld_out + A.col0 + (sc / PC) * NC + p * PC + (sc % PC);
+              if (!RAW && A.skip) {
                 const float4 sk = __ldg(reinterpret_cast<const float4*>(A.skip + g));
                 y.x += sk.x; y.y += sk.y; y.z += sk.z; y.w += sk.w;
               }
@@ -557,9 +574,9 @@ BwdLayout bwd_layout(int64_t rows, int K, int N) {
   return Y;
 }
 
-template <int N, int ACT>
+template <int N, int ACT, bool RAW = false>
 int launch_fwd(const RowFwdArgs& a, cudaStream_t st) {
-  auto kern = k_tc_row_fwd<N, ACT>;
+  auto kern = k_tc_row_fwd<N, ACT, RAW>;
   size_t smem = RowCfg<N>::SMEM;
   HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (a.rows + TILE_M - 1) / TILE_M;
@@ -633,9 +650,44 @@ extern "C" int hgnn_tc_row_forward(const hgnn_tc_row_layer* d, int64_t rows, flo
   a.w_packed = (const uint8_t*)d->w_packed;
   a.bias = d->bias; a.gamma = d->gamma; a.beta = d->beta; a.eps = d->ln_eps;
   a.skip = d->skip;
-  a.out = out; a.a_img = (uint8_t*)a_img; a.rows = rows;
+  a.out = out; a.ld_out = d->n_out; a.col0 = 0; a.a_img = (uint8_t*)a_img; a.rows = rows;
   cudaStream_t st = (cudaStream_t)stream;
   return ROW_DISPATCH(launch_fwd, d->n_out, d->act, a, st);
+}
+
+extern "C" int hgnn_tc_gemm_supported(const hgnn_tc_row_layer* d) {
+  if (!d || d->n_seg < 1 || d->n_seg > MAX_SEG) return 0;
+  int k = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    if (d->seg_width[s] <= 0 || d->seg_width[s] % KBLK != 0) return 0;
+    k += d->seg_width[s];
+  }
+  return k <= 768 && (d->n_out == 64 || d->n_out == 128 || d->n_out == 256);
+}
+
+extern "C" int hgnn_tc_gemm(const hgnn_tc_row_layer* d, int64_t rows, float* out, int64_t ld_out, int64_t col0, void* a_img,
+                            void* stream) {
+  HGNN_REQUIRE(d != nullptr, "tc_gemm: descriptor is NULL");
+  if (!hgnn_tc_gemm_supported(d))
+    return fail(HGNN_ERR_UNSUPPORTED, "tc_gemm: needs 1..3 segments of width %% 64 == 0, fan-in <= 768, n_out in {64, 128, 256}");
+  if (rows <= 0) return HGNN_OK;
+  HGNN_REQUIRE(out && d->w_packed, "tc_gemm: NULL pointer");
+  HGNN_REQUIRE(rows < INT32_MAX && ld_out >= col0 + d->n_out && col0 >= 0 && col0 % 4 == 0 && ld_out % 4 == 0,
+               "tc_gemm: bad output geometry (ld_out %lld, col0 %lld)", (long long)ld_out, (long long)col0);
+  RowFwdArgs a{};
+  a.n_seg = d->n_seg;
+  for (int s = 0; s < d->n_seg; ++s) {
+    HGNN_REQUIRE(d->seg_ptr[s] != nullptr, "tc_gemm: segment %d is NULL", s);
+    a.seg_ptr[s] = d->seg_ptr[s]; a.seg_idx[s] = d->seg_idx[s]; a.seg_width[s] = d->seg_width[s];
+  }
+  a.nkb = layer_k(d) / KBLK;
+  a.w_packed = (const uint8_t*)d->w_packed;
+  a.bias = d->bias; a.gamma = nullptr; a.beta = nullptr; a.eps = 0.f; a.skip = nullptr;
+  a.out = out; a.ld_out = ld_out; a.col0 = (int)col0; a.a_img = (uint8_t*)a_img; a.rows = rows;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->n_out == 64) return launch_fwd<64, HGNN_ACT_NONE, true>(a, st);
+  if (d->n_out == 128) return launch_fwd<128, HGNN_ACT_NONE, true>(a, st);
+  return launch_fwd<256, HGNN_ACT_NONE, true>(a, st);
 }
 
 extern "C" size_t hgnn_tc_row_backward_workspace_bytes(int64_t rows, int64_t k, int64_t n_out) {

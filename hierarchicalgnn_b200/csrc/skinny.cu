@@ -362,6 +362,113 @@ __global__ void k_narrow_out_reduce(const float* __restrict__ partial, int n_par
   if (i < n_w) dW[i] = s; else db[i - n_w] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-wise LayerNorm + activation (+ residual) on an already computed pre-activation h[rows, N] (bias included), and its
+// adjoint. The companions of hgnn_tc_gemm for layers too wide to normalise inside the GEMM kernel (fan-out 512 at latent
+// 256) or too narrow for it (fan-out 64): one warp per row, lane l owns columns l, l + 32, ...
+template <int NJ>
+__global__ void __launch_bounds__(SK_THREADS) k_ln_act_fwd(const float* __restrict__ h, int64_t rows, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps, int act,
+                                                           const float* __restrict__ skip, float* __restrict__ out) {
+  constexpr int N = 32 * NJ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[NJ], b[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { g[j] = gamma[lane + 32 * j]; b[j] = beta[lane + 32 * j]; }
+  const float invN = 1.0f / N;
+  for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < rows; r += (int64_t)gridDim.x * SK_WARPS) {
+    float v[NJ];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { v[j] = __ldg(h + (size_t)r * N + lane + 32 * j); sum += v[j]; }
+    const float mean = warp_sum(sum) * invN;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) * invN + eps);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float y = act_fwd(act, fmaf((v[j] - mean) * rstd, g[j], b[j]));
+      if (skip) y += __ldg(skip + (size_t)r * N + lane + 32 * j);
+      out[(size_t)r * N + lane + 32 * j] = y;
+    }
+  }
+}
+
+// delta = LayerNorm/activation adjoint of grad_out at h; partial per CTA: [3][N] = sum delta | sum d xhat | sum d
+template <int NJ>
+__global__ void __launch_bounds__(SK_THREADS) k_ln_act_bwd(const float* __restrict__ h, const float* __restrict__ gout, int64_t rows,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                           int act, float* __restrict__ delta, float* __restrict__ partial) {
+  constexpr int N = 32 * NJ;
+  extern __shared__ float s_acc[];  // [3][N]
+  for (int i = threadIdx.x; i < 3 * N; i += SK_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[NJ], b[NJ], ab[NJ], ag[NJ], abe[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { g[j] = gamma[lane + 32 * j]; b[j] = beta[lane + 32 * j]; ab[j] = ag[j] = abe[j] = 0.f; }
+  const float invN = 1.0f / N;
+  for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < rows; r += (int64_t)gridDim.x * SK_WARPS) {
+    float v[NJ], go[NJ];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      v[j] = __ldg(h + (size_t)r * N + lane + 32 * j);
+      go[j] = __ldg(gout + (size_t)r * N + lane + 32 * j);
+      sum += v[j];
+    }
+    const float mean = warp_sum(sum) * invN;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) * invN + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float xh = (v[j] - mean) * rstd;
+      const float d = go[j] * act_bwd(act, fmaf(xh, g[j], b[j]));
+      ag[j] = fmaf(d, xh, ag[j]);
+      abe[j] += d;
+      const float gd = g[j] * d;
+      v[j] = xh;
+      go[j] = gd;
+      s1 += gd;
+      s2 = fmaf(gd, xh, s2);
+    }
+    s1 = warp_sum(s1) * invN;
+    s2 = warp_sum(s2) * invN;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float dl = rstd * (go[j] - s1 - v[j] * s2);
+      ab[j] += dl;
+      delta[(size_t)r * N + lane + 32 * j] = dl;
+    }
+  }
+  for (int w = 0; w < SK_WARPS; ++w) {  // ordered accumulation over the warps
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int c = lane + 32 * j;
+        s_acc[c] += ab[j];
+        s_acc[N + c] += ag[j];
+        s_acc[2 * N + c] += abe[j];
+      }
+    }
+    __syncthreads();
+  }
+  float* o = partial + (size_t)blockIdx.x * 3 * N;
+  for (int i = threadIdx.x; i < 3 * N; i += SK_THREADS) o[i] = s_acc[i];
+}
+
+__global__ void k_partial_reduce(const float* __restrict__ partial, int n_part, int width, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) s += partial[(size_t)p * width + i];
+  out[i] = s;
+}
+
 int narrow_in_args(const hgnn_mlp_desc* d, int64_t rows, NarrowInArgs& a, const char* who) {
   HGNN_REQUIRE(d != nullptr, "%s: desc is NULL", who);
   if (!hgnn_narrow_in_supported(d))
@@ -511,4 +618,53 @@ extern "C" int hgnn_narrow_out_backward(const float* a, int64_t rows, int64_t k,
   const int total = NO * K + NO;
   k_narrow_out_reduce<<<(total + 255) / 256, 256, 0, st>>>(partial, grid, stride, NO * K, NO, dW, db);
   return check_launch("narrow_out_backward (reduce)");
+}
+
+extern "C" int hgnn_ln_act_supported(int64_t n) { return n == 64 || n == 128 || n == 256 || n == 512; }
+
+extern "C" int hgnn_ln_act_forward(const float* h, int64_t rows, int64_t n, const float* gamma, const float* beta, float eps, int act,
+                                   const float* skip, float* out, void* stream) {
+  if (!hgnn_ln_act_supported(n)) return fail(HGNN_ERR_UNSUPPORTED, "ln_act_forward: width must be 64, 128, 256 or 512 (got %lld)", (long long)n);
+  if (rows <= 0) return HGNN_OK;
+  HGNN_REQUIRE(h && gamma && beta && out, "ln_act_forward: NULL pointer");
+  HGNN_REQUIRE(act >= HGNN_ACT_NONE && act <= HGNN_ACT_SIGMOID, "ln_act_forward: unknown activation %d", act);
+  const int grid = skinny_grid(rows, SK_WARPS * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n / 32) {
+    case 2: k_ln_act_fwd<2><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out); break;
+    case 4: k_ln_act_fwd<4><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out); break;
+    case 8: k_ln_act_fwd<8><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out); break;
+    default: k_ln_act_fwd<16><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out); break;
+  }
+  return check_launch("ln_act_forward");
+}
+
+extern "C" size_t hgnn_ln_act_backward_workspace_bytes(int64_t n) { return (size_t)2 * num_sms() * 3 * n * 4 + 256; }
+
+extern "C" int hgnn_ln_act_backward(const float* h, const float* grad_out, int64_t rows, int64_t n, const float* gamma,
+                                    const float* beta, float eps, int act, float* delta, float* dvec, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  if (!hgnn_ln_act_supported(n)) return fail(HGNN_ERR_UNSUPPORTED, "ln_act_backward: width must be 64, 128, 256 or 512 (got %lld)", (long long)n);
+  HGNN_REQUIRE(dvec != nullptr, "ln_act_backward: dvec is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(dvec, 0, (size_t)3 * n * 4, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(h && grad_out && gamma && beta && delta && ws, "ln_act_backward: NULL pointer");
+  HGNN_REQUIRE(act >= HGNN_ACT_NONE && act <= HGNN_ACT_SIGMOID, "ln_act_backward: unknown activation %d", act);
+  const int grid = skinny_grid(rows, SK_WARPS * 8);
+  HGNN_REQUIRE(ws_bytes >= (size_t)grid * 3 * n * 4, "ln_act_backward: workspace too small");
+  float* partial = (float*)ws;
+  const size_t smem = (size_t)3 * n * 4;
+  switch (n / 32) {
+    case 2: k_ln_act_bwd<2><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial); break;
+    case 4: k_ln_act_bwd<4><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial); break;
+    case 8: k_ln_act_bwd<8><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial); break;
+    default: k_ln_act_bwd<16><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial); break;
+  }
+  int rc = check_launch("ln_act_backward");
+  if (rc) return rc;
+  k_partial_reduce<<<(int)((3 * n + 255) / 256), 256, 0, st>>>(partial, grid, (int)(3 * n), dvec);
+  return check_launch("ln_act_backward (reduce)");
 }

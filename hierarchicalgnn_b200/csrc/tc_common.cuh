@@ -313,7 +313,10 @@ __host__ __device__ inline EdgeStash edge_stash_layout(int64_t n_edges, int L) {
 __device__ __forceinline__ void gather_load(float4 (&v)[8], const float* __restrict__ base, int ld, const int* __restrict__ rowid, int col0) {
   const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) v[p] = __ldg(reinterpret_cast<const float4*>(base + (size_t)rowid[p * 16 + rr] * ld + col0) + sub);
+  for (int p = 0; p < 8; ++p) {  // a negative row id marks a padding row of the last tile: zeros (also in the saved image)
+    const int rid = rowid[p * 16 + rr];
+    v[p] = rid >= 0 ? __ldg(reinterpret_cast<const float4*>(base + (size_t)rid * ld + col0) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 // gimg (optional): the same swizzled bf16 block is also left in HBM — the backward pass and the weight-gradient GEMM
 // read these tile images back with bulk copies instead of re-gathering

@@ -234,3 +234,79 @@ extern "C" int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows,
   hgnn::tc::WgradProblem p{img_a, (int)ca, 0, (int)ca, img_b, (int)cb, 0, (int)cb, out, (int)cb, 0, 0, 0};
   return hgnn::tc::launch_wgrad(&p, 1, (int)tiles, rest, ws_bytes - (size_t)(rest - (char*)ws), st);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dW[n_out, fan_in] = delta^T A from two tile images (the A-operand images hgnn_tc_gemm leaves behind): tiled into
+// <= 256 x 128 / 128 x 256 problems of the split-K kernel above, four per launch.
+namespace {
+int build_wgrad_problems(const uint8_t* d_img, int n_out, const uint8_t* a_img, int fan_in, float* dW, hgnn::tc::WgradProblem* pr,
+                         int max_pr) {
+  int n = 0;
+  if (n_out % 128 == 0) {  // delta supplies the M side (M = 128 per half)
+    for (int ca0 = 0; ca0 < n_out; ca0 += 256) {
+      const int ca = std::min(256, n_out - ca0);
+      const int cb_max = ca == 256 ? 128 : 256;  // keeps a double-buffered stage inside shared memory
+      for (int cb0 = 0; cb0 < fan_in; cb0 += cb_max) {
+        const int cb = std::min(cb_max, fan_in - cb0);
+        if (n == max_pr) return -1;
+        pr[n++] = hgnn::tc::WgradProblem{d_img, n_out, ca0, ca, a_img, fan_in, cb0, cb, dW, fan_in, ca0, cb0, 0};
+      }
+    }
+  } else if (fan_in % 128 == 0) {  // narrow fan-out (64): the input image supplies the M side, result stored transposed
+    for (int ca0 = 0; ca0 < fan_in; ca0 += 256) {
+      const int ca = std::min(256, fan_in - ca0);
+      const int cb_max = ca == 256 ? 128 : 256;
+      for (int cb0 = 0; cb0 < n_out; cb0 += cb_max) {
+        const int cb = std::min(cb_max, n_out - cb0);
+        if (n == max_pr) return -1;
+        pr[n++] = hgnn::tc::WgradProblem{a_img, fan_in, ca0, ca, d_img, n_out, cb0, cb, dW, fan_in, cb0, ca0, 1};
+      }
+    }
+  } else {
+    return -2;
+  }
+  return n;
+}
+constexpr int WG_MAX_PROBLEMS = 32;
+}  // namespace
+
+extern "C" int hgnn_tc_wgrad_supported(int64_t n_out, int64_t fan_in) {
+  return n_out > 0 && fan_in > 0 && n_out % 64 == 0 && fan_in % 64 == 0 && n_out <= 512 && fan_in <= 768 &&
+         (n_out % 128 == 0 || fan_in % 128 == 0);
+}
+
+extern "C" size_t hgnn_tc_wgrad_workspace_bytes(int64_t rows, int64_t n_out, int64_t fan_in) {
+  (void)n_out; (void)fan_in;
+  int64_t tiles = (rows + TILE_M - 1) / TILE_M;
+  int splits = hgnn::tc::wgrad_splits(WG_MAX_ROLES, (int)std::max<int64_t>(tiles, 1));
+  int splits1 = hgnn::tc::wgrad_splits(1, (int)std::max<int64_t>(tiles, 1));
+  // four problems of at most 256 x 128 floats per split, or a single one with all the SMs' splits
+  size_t a = (size_t)WG_MAX_ROLES * align_up((size_t)splits * 256 * 128 * 4, 256);
+  size_t b = align_up((size_t)splits1 * 256 * 128 * 4, 256);
+  return std::max(a, b) + 1024;
+}
+
+extern "C" int hgnn_tc_wgrad(const void* delta_img, int64_t n_out, const void* a_img, int64_t fan_in, int64_t rows, float* dW,
+                             void* ws, size_t ws_bytes, void* stream) {
+  if (!hgnn_tc_wgrad_supported(n_out, fan_in))
+    return fail(HGNN_ERR_UNSUPPORTED, "tc_wgrad: need n_out, fan_in multiples of 64 (one of them of 128), n_out <= 512, fan_in <= 768");
+  HGNN_REQUIRE(dW != nullptr, "tc_wgrad: dW is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0) {
+    HGNN_CUDA_TRY(cudaMemsetAsync(dW, 0, (size_t)n_out * fan_in * 4, st));
+    return HGNN_OK;
+  }
+  HGNN_REQUIRE(delta_img && a_img && ws, "tc_wgrad: NULL pointer");
+  hgnn::tc::WgradProblem pr[WG_MAX_PROBLEMS];
+  int n = build_wgrad_problems((const uint8_t*)delta_img, (int)n_out, (const uint8_t*)a_img, (int)fan_in, dW, pr, WG_MAX_PROBLEMS);
+  HGNN_REQUIRE(n > 0, "tc_wgrad: could not tile the problem");
+  const int tiles = (int)((rows + TILE_M - 1) / TILE_M);
+  uintptr_t base = align_up((uintptr_t)ws, 256);
+  size_t avail = ws_bytes - (size_t)(base - (uintptr_t)ws);
+  for (int i = 0; i < n; i += WG_MAX_ROLES) {
+    const int cnt = std::min(WG_MAX_ROLES, n - i);
+    int rc = hgnn::tc::launch_wgrad(pr + i, cnt, tiles, (void*)base, avail, st);  // stream order serialises workspace reuse
+    if (rc) return rc;
+  }
+  return HGNN_OK;
+}

@@ -872,6 +872,140 @@ def tc_row_layer(meta: RowLayerMeta, segs: Sequence[Tensor], skip: Optional[Tens
     return _TcRowLayer.apply(meta, len(segs), *segs, *extra, W, b, gamma, beta)
 
 
+# ---------------------------------------------------------------------------
+# generic tensor-core layer: plain tcgen05 GEMM(s) + row-wise LayerNorm/activation kernels (latent 64 / 256 shapes)
+# ---------------------------------------------------------------------------
+def _width_chunks(n: int):
+    """[(offset, width)] with widths in {256, 128, 64} covering n (a multiple of 64)."""
+    out, off = [], 0
+    while off < n:
+        rest = n - off
+        w = 256 if rest >= 256 else (128 if rest >= 128 else 64)
+        out.append((off, w))
+        off += w
+    return out
+
+
+@functools.lru_cache(maxsize=256)
+def tc_split_supported(seg_widths, n_out: int, act: Optional[str]) -> bool:
+    k = sum(seg_widths)
+    return (1 <= len(seg_widths) <= MAX_SEGS and all(w > 0 and w % 64 == 0 for w in seg_widths) and k <= 768
+            and n_out in (64, 128, 256, 512) and act in ACT_CODES and (n_out % 128 == 0 or k % 128 == 0))
+
+
+def tc_pack_split(W: Tensor):
+    """Weight images of one Linear for the generic layer: W row chunks (forward GEMMs, one per <= 256 output columns) and
+    W^T row chunks (data-gradient GEMMs, one per <= 256 input columns): ([(col0, n, image)], [(col0, n, image)])."""
+    Wd = W.detach()
+    fwd = [(c0, n, tc_pack_weight(Wd[c0:c0 + n].contiguous())) for c0, n in _width_chunks(Wd.shape[0])]
+    Wt = Wd.t().contiguous()
+    bwd = [(c0, n, tc_pack_weight(Wt[c0:c0 + n].contiguous())) for c0, n in _width_chunks(Wt.shape[0])]
+    return fwd, bwd
+
+
+def _gemm_desc(seg_tensors, seg_plans, n_out, w_packed, bias_ptr):
+    d = _lib.TcRowLayer()
+    d.n_seg, d.n_out, d.act, d.ln_eps = len(seg_tensors), n_out, 0, 0.0
+    for s, t in enumerate(seg_tensors):
+        d.seg_ptr[s] = t.data_ptr()
+        d.seg_width[s] = t.shape[1]
+        d.seg_idx[s] = seg_plans[s].keys32.data_ptr() if seg_plans[s] is not None else None
+    d.w_packed = _ptr(w_packed)
+    d.bias = bias_ptr
+    return d
+
+
+class _TcSplitLayer(torch.autograd.Function):
+    """out = act(LayerNorm(W . concat(gathered segments) + b)) (+ skip) as tcgen05 GEMM(s) + a row-wise LayerNorm kernel:
+    the layer shapes of latent 64 / 256 (fan-out 64 or 512, fan-in up to 768) that the fused kernels do not cover.
+    Keeps the pre-activation h (fp32) and the bf16 image of the gathered input for the backward."""
+
+    @staticmethod
+    def forward(ctx, meta: RowLayerMeta, n_seg: int, *tensors):
+        _need_cuda(*tensors)
+        segs = [_f32(t) for t in tensors[:n_seg]]
+        skip = _f32(tensors[n_seg]) if meta.has_skip else None
+        W, b, g, be = [_f32(t) for t in tensors[n_seg + int(meta.has_skip):]]
+        N, K = W.shape
+        rows = meta.seg_plans[0].n_items if meta.seg_plans[0] is not None else segs[0].shape[0]
+        dev = W.device
+        fwd_chunks, _ = meta.pack()
+        L_ = _lib.lib()
+        h = torch.empty((rows, N), dtype=torch.float32, device=dev)
+        out = torch.empty((rows, N), dtype=torch.float32, device=dev)
+        if skip is not None and tuple(skip.shape) != (rows, N):
+            raise _lib.HgnnError(f"generic layer: residual has shape {tuple(skip.shape)}, output {(rows, N)}")
+        need_bwd = any(ctx.needs_input_grad[2:])
+        a_img = torch.empty(L_.hgnn_tc_row_image_bytes(rows, K), dtype=torch.uint8, device=dev) if (need_bwd and rows) else None
+        if rows:
+            with _timed("tc_split_forward"):
+                for i, (c0, n, img) in enumerate(fwd_chunks):
+                    d = _gemm_desc(segs, meta.seg_plans, n, img, b.data_ptr() + 4 * c0)
+                    check(L_.hgnn_tc_gemm(C.byref(d), rows, _ptr(h), N, c0, _ptr(a_img) if i == 0 else None, _stream()), "tc_gemm")
+                check(L_.hgnn_ln_act_forward(_ptr(h), rows, N, _ptr(g), _ptr(be), meta.eps, meta.act, _ptr(skip), _ptr(out), _stream()),
+                      "ln_act_forward")
+            _count(len(fwd_chunks) + 1)
+            TC_ROW_CALLS["count"] += 1
+        ctx.meta, ctx.n_seg, ctx.rows, ctx.a_img = meta, n_seg, rows, a_img
+        ctx.widths = [t.shape[1] for t in segs]
+        ctx.seg_rows = [t.shape[0] for t in segs]
+        ctx.save_for_backward(W, g, be, h)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        meta, n_seg, rows = ctx.meta, ctx.n_seg, ctx.rows
+        W, g, be, h = ctx.saved_tensors
+        gout = _f32(gout)
+        dev = W.device
+        N, K = W.shape
+        L_ = _lib.lib()
+        dW = torch.empty_like(W)
+        dvec = torch.empty((3, N), dtype=torch.float32, device=dev)
+        d_in = torch.empty((rows, K), dtype=torch.float32, device=dev)
+        if rows:
+            _, bwd_chunks = meta.pack()
+            delta = torch.empty((rows, N), dtype=torch.float32, device=dev)
+            d_img = torch.empty(L_.hgnn_tc_row_image_bytes(rows, N), dtype=torch.uint8, device=dev)
+            ws = _workspace(max(L_.hgnn_ln_act_backward_workspace_bytes(N), L_.hgnn_tc_wgrad_workspace_bytes(rows, N, K)), dev)
+            with _timed("tc_split_backward"):
+                check(L_.hgnn_ln_act_backward(_ptr(h), _ptr(gout), rows, N, _ptr(g), _ptr(be), meta.eps, meta.act, _ptr(delta),
+                                              _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "ln_act_backward")
+                for i, (c0, n, img) in enumerate(bwd_chunks):  # d_in[:, c0 : c0 + n] = delta . W[:, c0 : c0 + n]
+                    d = _gemm_desc([delta], [None], n, img, None)
+                    check(L_.hgnn_tc_gemm(C.byref(d), rows, _ptr(d_in), K, c0, _ptr(d_img) if i == 0 else None, _stream()), "tc_gemm")
+                check(L_.hgnn_tc_wgrad(_ptr(d_img), N, _ptr(ctx.a_img), K, rows, _ptr(dW), _ptr(ws), ws.numel(), _stream()), "tc_wgrad")
+            _count(2 + len(bwd_chunks) + 2 * ((N // 128 or 1) * (K // 128 or 1) // 4 + 1))
+            TC_ROW_CALLS["count"] += 1
+        else:
+            dW.zero_()
+            dvec.zero_()
+        grads: List[Optional[Tensor]] = [None, None]
+        need = ctx.needs_input_grad[2:]
+        off = 0
+        for s in range(n_seg):
+            w = ctx.widths[s]
+            gs = None
+            if need[s]:
+                gs = d_in if n_seg == 1 else d_in[:, off:off + w]
+                plan = meta.seg_plans[s]
+                if plan is not None:
+                    if plan.n_segments != ctx.seg_rows[s]:
+                        raise _lib.HgnnError("generic layer: gather plan does not cover the gathered tensor")
+                    gs = segment_reduce_raw(gs.contiguous(), plan)
+            grads.append(gs)
+            off += w
+        if meta.has_skip:
+            grads.append(gout if need[n_seg] else None)
+        grads += [dW, dvec[0], dvec[1], dvec[2]]
+        return tuple(grads)
+
+
+def tc_split_layer(meta: RowLayerMeta, segs: Sequence[Tensor], skip: Optional[Tensor], W, b, gamma, beta) -> Tensor:
+    extra = [skip] if meta.has_skip else []
+    return _TcSplitLayer.apply(meta, len(segs), *segs, *extra, W, b, gamma, beta)
+
+
 def fused_mlp(meta: MlpMeta, segs: Sequence[Tensor], params: Sequence[Tensor]) -> Tensor:
     """Row-wise MLP on the concatenation of (optionally gathered) segments, with
     LayerNorm/activation per layer and an optional skip connection — one kernel

@@ -64,16 +64,20 @@ class FusedMLP(nn.Sequential):
             plans = [None] * len(segs)
         ps, acts, lns, eps = self._params()
         packer = self._tc_packer(segs, plans, skip, lns)
+        if packer is not None and self._layers()[1][0].out_features != 128 and torch.is_grad_enabled() and (
+                any(t.requires_grad for t in segs) or any(p.requires_grad for p in ps)):
+            packer = None  # the fused edge kernel has a tensor-core backward at latent 128 only: train layer by layer
         if packer is None:
             groups = self._row_groups(segs, plans, skip)
             if groups is not None:
                 return self._run_groups(groups, list(segs), list(plans), skip)
+            packer = self._tc_packer(segs, plans, skip, lns)
         meta = ops.MlpMeta(plans, acts, lns, skip, eps, tc_pack=packer)
         return ops.fused_mlp(meta, list(segs), ps)
 
     # ---- layer-wise execution: tensor-core row layers where a kernel exists, fp32 SIMT groups elsewhere ----
     def _row_groups(self, segs, plans, skip):
-        """[("tc", l) | ("nin", l) | ("nout", l) | ("simt", l0, l1)] covering the layers in order, or None when no layer
+        """[("tc", l) | ("tcs", l) | ("nin", l) | ("nout", l) | ("simt", l0, l1)] covering the layers in order, or None when no layer
         has a specialised kernel (precision fp32, CPU tensors, odd shapes): the whole stack then runs as one fp32 kernel.
         tc = tensor-core row layer, nin / nout = skinny fan-in / fan-out layers, simt = generic fused fp32 group."""
         if ops.get_precision() == "fp32" or not all(t.is_cuda for t in segs):
@@ -90,6 +94,8 @@ class FusedMLP(nn.Sequential):
             kind = None
             if ln is not None and ops.tc_row_supported(w_in, lin.out_features, act):
                 kind = "tc"
+            elif ln is not None and ops.tc_split_supported(w_in, lin.out_features, act):
+                kind = "tcs"  # plain tcgen05 GEMM(s) + row-wise LayerNorm kernel (latent 64 / 256 shapes)
             elif l == 0 and not has_res and ops.narrow_in_supported(w_in, lin.out_features):
                 kind = "nin"
             elif (not has_res and ln is None and act is None and len(w_in) == 1 and (l > 0 or plans[0] is None)
@@ -106,6 +112,20 @@ class FusedMLP(nn.Sequential):
         if cur is not None:
             groups.append(("simt", cur, len(layers)))
         return groups if special else None
+
+    def _split_pack(self, l):
+        lin = self._layers()[l][0]
+
+        def pack():
+            w = lin.weight
+            key = (w.data_ptr(), w._version)
+            cache = self.__dict__.setdefault("_split_cache", {})
+            hit = cache.get(l)
+            if hit is None or hit[0] != key:
+                hit = (key,) + ops.tc_pack_split(w)
+                cache[l] = hit
+            return hit[1], hit[2]
+        return pack
 
     def _row_pack(self, l):
         lin = self._layers()[l][0]
@@ -133,6 +153,12 @@ class FusedMLP(nn.Sequential):
                 res = residual if l == last else None
                 meta = ops.RowLayerMeta(cur_plans, act, ln.eps, res is not None, self._row_pack(l))
                 y = ops.tc_row_layer(meta, cur_segs, res, lin.weight, lin.bias, ln.weight, ln.bias)
+            elif grp[0] == "tcs":
+                l = grp[1]
+                lin, ln, act = layers[l]
+                res = residual if l == last else None
+                meta = ops.RowLayerMeta(cur_plans, act, ln.eps, res is not None, self._split_pack(l))
+                y = ops.tc_split_layer(meta, cur_segs, res, lin.weight, lin.bias, ln.weight, ln.bias)
             elif grp[0] == "nin":
                 lin, ln, act = layers[grp[1]]
                 ps = [lin.weight, lin.bias] + ([ln.weight, ln.bias] if ln is not None else [])

@@ -312,6 +312,31 @@ size_t hgnn_narrow_out_backward_workspace_bytes(int64_t fan_in, int64_t n_out);
 int hgnn_narrow_out_backward(const float* a, int64_t rows, int64_t fan_in, const float* W, int64_t n_out, const float* grad_out,
                              float* d_a, float* dW, float* db, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Generic tensor-core layer pieces for the shapes the fused kernels above do not cover (latent 64 / 256: fan-out 64 or
+ * 512, fan-in up to 768) — a make_mlp layer then runs as  hgnn_tc_gemm (one call per <= 256 output columns)  ->
+ * hgnn_ln_act_forward;  its backward as  hgnn_ln_act_backward -> hgnn_tc_gemm on W^T (data gradient)  ->
+ * hgnn_tc_wgrad over the two A-operand images the GEMM calls leave behind.
+ *  hgnn_tc_gemm: out[r, col0 : col0 + n_out] = [seg0[i0(r)] | seg1[i1(r)] | seg2[i2(r)]] . W^T (+ bias); the descriptor's
+ *    act / gamma / beta / skip are ignored; n_out in {64, 128, 256}, segment widths % 64 == 0, fan-in <= 768;
+ *    a_img (optional) receives the bf16 tile image of the gathered input.
+ *  hgnn_ln_act_forward / backward: row-wise LayerNorm + activation (+ residual) on h[rows, n] (bias included), n in
+ *    {64, 128, 256, 512}; backward gives delta[rows, n] and dvec[3, n] = (d bias, d gamma, d beta), ordered sums.
+ *  hgnn_tc_wgrad: dW[n_out, fan_in] = delta^T A from the two images (split-K over rows, ordered reduce).
+ * ------------------------------------------------------------------------ */
+int hgnn_tc_gemm_supported(const hgnn_tc_row_layer* d);
+int hgnn_tc_gemm(const hgnn_tc_row_layer* d, int64_t rows, float* out, int64_t ld_out, int64_t col0, void* a_img, void* stream);
+int hgnn_ln_act_supported(int64_t n);
+int hgnn_ln_act_forward(const float* h, int64_t rows, int64_t n, const float* gamma, const float* beta, float eps, int act,
+                        const float* skip, float* out, void* stream);
+size_t hgnn_ln_act_backward_workspace_bytes(int64_t n);
+int hgnn_ln_act_backward(const float* h, const float* grad_out, int64_t rows, int64_t n, const float* gamma, const float* beta,
+                         float eps, int act, float* delta, float* dvec, void* ws, size_t ws_bytes, void* stream);
+int hgnn_tc_wgrad_supported(int64_t n_out, int64_t fan_in);
+size_t hgnn_tc_wgrad_workspace_bytes(int64_t rows, int64_t n_out, int64_t fan_in);
+int hgnn_tc_wgrad(const void* delta_img, int64_t n_out, const void* a_img, int64_t fan_in, int64_t rows, float* dW, void* ws,
+                  size_t ws_bytes, void* stream);
+
 /* Profiling hook: when set (device buffer of 16 uint64), CTA 0 of hgnn_tc_edge_backward accumulates the cycles it
  * spends in each phase of the tile loop (GEMM1, EPI-A, GEMM2, EPI-B, GEMM3, EPI-C, GEMM4, EPI-D). NULL disables. */
 void hgnn_tc_debug_set_phase_clock(void* dev_u64x16);

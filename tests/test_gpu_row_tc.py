@@ -157,3 +157,100 @@ def test_node_network_routes_through_row_layers_and_matches_fp32_path():
     assert float((res["auto"][0] - res["fp32"][0]).abs().max()) < 3e-2
     for a, b in zip(res["auto"][1:], res["fp32"][1:]):
         assert rel(a, b) < 2e-2
+
+
+SPLIT_CASES = [
+    # widths, n_out, rows, n_src, gathered, act, skip     (latent 256 / 64 layer shapes)
+    ([256, 256, 256], 512, 700, 60, [True, True, False], "GELU", False),   # edge network layer 1 at latent 256
+    ([512], 256, 1000, 0, [False], "Tanh", True),                          # edge network layer 2 at latent 256 (+ residual)
+    ([256, 256], 512, 300, 0, [False, False], "GELU", False),              # node network layer 1 at latent 256
+    ([64, 64, 64], 128, 900, 80, [True, True, False], "GELU", False),      # edge network layer 1 at latent 64
+    ([128], 64, 515, 0, [False], "Tanh", True),                            # edge network layer 2 at latent 64 (+ residual)
+    ([128], 64, 3, 0, [False], "GELU", False),
+    ([256, 256, 256], 512, 128 * 150 + 7, 0, [False, False, False], "GELU", False),  # more tiles than SMs
+]
+
+
+@pytest.mark.parametrize("widths,n_out,rows,n_src,gathered,act,skip", SPLIT_CASES)
+def test_tc_split_layer_forward_and_backward(widths, n_out, rows, n_src, gathered, act, skip):
+    """Generic tensor-core layer (plain tcgen05 GEMMs + row-wise LayerNorm kernels) for the latent 64 / 256 shapes."""
+    from hierarchicalgnn_b200 import ops
+    assert ops.tc_split_supported(tuple(widths), n_out, act) and not ops.tc_row_supported(widths, n_out, act)
+    W, b, gamma, beta, segs, idx = _layer_case(widths, n_out, rows, n_src, seed=rows + n_out + 1, gathered=gathered)
+    g = torch.Generator().manual_seed(98)
+    res = torch.randn(rows, n_out, generator=g) if skip else None
+    cot = torch.randn(rows, n_out, generator=g)
+    leaves = [t.clone().double().requires_grad_(True) for t in segs]
+    Wr, br, gr, ber = [t.clone().double().requires_grad_(True) for t in (W, b, gamma, beta)]
+    resr = None if res is None else res.clone().double().requires_grad_(True)
+    want = _reference(Wr, br, gr, ber, leaves, idx, act, resr, emulate=False)
+    (want * cot.double()).sum().backward()
+    want_emul = _reference(W, b, gamma, beta, segs, idx, act, res, emulate=True)
+
+    Wd, bd, gd, bed = [t.to(DEV).requires_grad_(True) for t in (W, b, gamma, beta)]
+    segs_d = [t.to(DEV).requires_grad_(True) for t in segs]
+    res_d = None if res is None else res.to(DEV).requires_grad_(True)
+    plans = [None if i is None else ops.plan_for(i.to(DEV), n_src) for i in idx]
+    packed = ops.tc_pack_split(Wd)
+    meta = ops.RowLayerMeta(plans, act, 1e-5, res is not None, lambda: packed)
+    outs = []
+    for _ in range(2):
+        for t in segs_d + [Wd, bd, gd, bed] + ([res_d] if res_d is not None else []):
+            t.grad = None
+        got = ops.tc_split_layer(meta, segs_d, res_d, Wd, bd, gd, bed)
+        (got * cot.to(DEV)).sum().backward()
+        outs.append([got.detach().clone(), Wd.grad.clone(), bd.grad.clone(), gd.grad.clone(), bed.grad.clone()] + [t.grad.clone() for t in segs_d])
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)  # bit-identical run to run
+    out = outs[0][0].cpu().double()
+    assert float((out - want_emul).abs().max()) < 4e-3
+    assert float((out - want_emul).abs().mean()) < 2e-4
+    assert float((out - want.detach()).abs().max()) < 3e-2
+
+    def rel(x, y):
+        return float((x.detach().cpu().double() - y).norm() / y.norm().clamp_min(1e-30))
+    for t_d, t_r in zip(segs_d, leaves):
+        assert rel(t_d.grad, t_r.grad) < 1.5e-2
+    assert rel(Wd.grad, Wr.grad) < 1.5e-2
+    assert rel(bd.grad, br.grad) < 1.5e-2 and rel(gd.grad, gr.grad) < 1.5e-2 and rel(bed.grad, ber.grad) < 1.5e-2
+    if res is not None:
+        assert torch.equal(res_d.grad.cpu(), cot)
+
+
+@pytest.mark.parametrize("L", [64, 256])
+def test_interaction_cell_other_latents_route_through_tensor_cores(L):
+    """InteractionGNNCell at latent 64 / 256 (the BC config's default latent is 256): every layer of both networks runs
+    on tensor cores on the default path (row layers where they apply, generic GEMM + LayerNorm layers elsewhere) and the
+    cell agrees with the fp32 path within the bf16 tolerance, outputs and gradients."""
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.gnn_utils import InteractionGNNCell
+    from hierarchicalgnn_b200.synth import synth_edge_problem
+    from hierarchicalgnn_b200.training_utils import kaiming_init
+    hp = dict(latent=L, hidden=2 * L, nb_edge_layer=2, nb_node_layer=3, layernorm=True, hidden_activation="GELU")
+    torch.manual_seed(0)
+    cell = InteractionGNNCell(hp)
+    kaiming_init(cell)
+    cell.to(DEV)
+    nodes, edges, graph = synth_edge_problem(3000, L, seed=3)
+    g = torch.Generator().manual_seed(2)
+    cn, ce = torch.randn(nodes.shape, generator=g).to(DEV), torch.randn(edges.shape, generator=g).to(DEV)
+    res = {}
+    for mode in ("fp32", "auto"):
+        old = ops.set_precision(mode)
+        try:
+            cell.zero_grad(set_to_none=True)
+            nd, ed = nodes.to(DEV).requires_grad_(True), edges.to(DEV).requires_grad_(True)
+            l0 = ops.TC_ROW_CALLS["count"]
+            a, b = cell(nd, ed, graph.to(DEV))
+            ((a * cn).sum() + (b * ce).sum()).backward()
+            used = ops.TC_ROW_CALLS["count"] - l0
+            res[mode] = [a.detach(), b.detach(), nd.grad, ed.grad] + [p.grad.clone() for p in cell.parameters()]
+        finally:
+            ops.set_precision(old)
+        assert used == (10 if mode == "auto" else 0)  # 5 layers, forward + backward each
+
+    def rel(x, y):
+        return float((x - y).norm() / y.norm().clamp_min(1e-30))
+    assert float((res["auto"][0] - res["fp32"][0]).abs().max()) < 3e-2 and float((res["auto"][1] - res["fp32"][1]).abs().max()) < 3e-2
+    for x, y in zip(res["auto"][2:], res["fp32"][2:]):
+        assert rel(x, y) < 3e-2

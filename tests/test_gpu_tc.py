@@ -99,8 +99,9 @@ def test_tc_edge_forward_vs_emulated_and_fp32_oracle(L, E, N):
     try:
         n0 = ops.TC_CALLS["count"]
         gd = graph.to(DEV)
-        got = net.fused([x.to(DEV), x.to(DEV)][0:1] * 2 + [e.to(DEV)],
-                        [ops.plan_for(gd[0], N), ops.plan_for(gd[1], N), None], skip=2).cpu()
+        with torch.no_grad():  # inference: the fused kernel at both latents (training at latent 64 goes layer by layer)
+            got = net.fused([x.to(DEV), x.to(DEV)][0:1] * 2 + [e.to(DEV)],
+                            [ops.plan_for(gd[0], N), ops.plan_for(gd[1], N), None], skip=2).cpu()
         assert ops.TC_CALLS["count"] == n0 + 1, "tensor-core kernel was not used"
     finally:
         ops.set_precision(old)
@@ -109,11 +110,11 @@ def test_tc_edge_forward_vs_emulated_and_fp32_oracle(L, E, N):
     assert float((got - want_fp32).abs().max()) < 2e-2  # bf16 tolerance on latents
 
 
-def test_tc_edge_forward_backward_gradients_close_to_fp32_L64():
-    """Forward on tensor cores, backward through the fp32 recompute kernels: gradients must
-    stay within bf16 tolerance of the all-fp32 oracle."""
+def test_tc_edge_step_training_at_latent_64_gradients_close_to_fp32():
+    """Latent 64 with gradients: the edge network runs layer by layer on tensor cores (plain tcgen05 GEMMs + row-wise
+    LayerNorm kernels, forward and backward); gradients stay within the bf16 tolerance of the all-fp32 oracle."""
     from hierarchicalgnn_b200 import ops
-    L, E, N = 64, 600, 40  # latent 64: tensor-core forward, fp32 SIMT backward
+    L, E, N = 64, 600, 40
     net, x, e, graph = _edge_case(L, E, N, seed=5)
     sd = {"m." + k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
     hp = dict(nb_edge_layer=2, hidden_activation="GELU", layernorm=True)
@@ -125,13 +126,18 @@ def test_tc_edge_forward_backward_gradients_close_to_fp32_L64():
     xd, ed, gd = x.to(DEV).requires_grad_(True), e.to(DEV).requires_grad_(True), graph.to(DEV)
     old = ops.set_precision("bf16")
     try:
+        n0 = ops.TC_ROW_CALLS["count"]
         out = net.fused([xd, xd, ed], [ops.plan_for(gd[0], N), ops.plan_for(gd[1], N), None], skip=2)
+        (out * cot.to(DEV)).sum().backward()
+        assert ops.TC_ROW_CALLS["count"] - n0 == 4  # two layers, forward + backward
     finally:
         ops.set_precision(old)
-    (out * cot.to(DEV)).sum().backward()
-    torch.testing.assert_close(ed.grad.cpu(), er.grad, rtol=1e-3, atol=1e-4)
-    torch.testing.assert_close(xd.grad.cpu(), xr.grad, rtol=1e-3, atol=1e-3)
-    torch.testing.assert_close(net[0].weight.grad.cpu(), sd["m.0.weight"].grad, rtol=1e-3, atol=1e-3)
+
+    def rel(a, b):
+        return float((a.cpu() - b).norm() / b.norm())
+    assert rel(ed.grad, er.grad) < 1.5e-2 and rel(xd.grad, xr.grad) < 1.5e-2
+    assert rel(net[0].weight.grad, sd["m.0.weight"].grad) < 1.5e-2 and rel(net[3].weight.grad, sd["m.3.weight"].grad) < 1.5e-2
+    assert rel(net[1].weight.grad, sd["m.1.weight"].grad) < 1.5e-2 and rel(net[4].bias.grad, sd["m.4.bias"].grad) < 1.5e-2
 
 
 def _emulated_grads(net, x, e, graph, cot, L):
