@@ -77,15 +77,16 @@ for L, E, pl in [(128, 100_000, False), (128, 1_000_000, False), (128, 4_000_000
     gp = GraphPlans(gph, N, N, dst_sorted=True); gp.by_src; gp.by_dst
     ce, ca = torch.randn_like(e), torch.randn(N, L, device=DEV)
     params = list(cell.edge_network.parameters())
-    c0, r0 = ops.TC_CALLS["count"], ops.LAUNCHES["count"]
+    c0, r0 = ops.TC_CALLS["count"], ops.TC_ROW_CALLS["count"]
     def step():
         e2, agg = cell.edge_network.edge_step(n, e, gp.by_src, gp.by_dst)
         if agg is None:
             agg = ops.scatter_add(e2, gph[1], dim_size=N, plan=gp.by_dst)
         torch.autograd.grad([e2, agg], [n, e] + params, [ce, ca])
     t = timeit(step, n=5)
-    used = ops.TC_CALLS["count"] - c0
-    path = {0: "fp32 SIMT", 8: "tcgen05 fwd + fp32 bwd"}.get(used, "tcgen05 fwd + bwd") if used != 16 else "tcgen05 fwd + bwd"
+    used, used_rows = ops.TC_CALLS["count"] - c0, ops.TC_ROW_CALLS["count"] - r0
+    path = ("fused tcgen05 edge kernels (fwd + bwd)" if used else
+            ("layer-wise tcgen05 GEMMs + LayerNorm kernels (fwd + bwd)" if used_rows else "fp32 SIMT"))
     print(f"| {L} | {E:,} | {'power-law (hubs)' if pl else 'uniform'} | {path} | {t:.3f} | {E / t / 1e3:.1f} |")
     del cell, n, e, gph, gp
 
