@@ -20,6 +20,9 @@
 //   EPI2   bias + LayerNorm + Tanh to a swizzled fp32 staging tile, then a
 //          coalesced pass adds the fp32 skip row and stores e' as full 512 B rows.
 // Weights are never resident in full: smem per CTA is ~105 KB at L = 128.
+// Training (stash != NULL) also leaves in HBM what the backward needs, so that it recomputes nothing: the two MMA
+// operand images (A0 written while gathering, g by one bulk copy), the normalised pre-affine activations of both
+// LayerNorms as bf16 and the row rstd's (tc_common.cuh: EdgeStash, 2 KB per edge at L = 128).
 #include <algorithm>
 #include <cstdlib>
 
