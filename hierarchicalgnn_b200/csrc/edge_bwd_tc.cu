@@ -4,14 +4,21 @@
 // The forward kernel (edge_tc.cu) stashes, per 128-edge tile, what the adjoint needs in bf16 — the normalised
 // pre-affine activations xhat1 / xhat2, the row rstd's, and the two MMA operand images A0 and g — so nothing is
 // recomputed here (the reference recomputes the whole cell under torch.utils.checkpoint, gnn_utils.py:14-15; on a
-// 180 GB part 2 KB per edge-step is the cheaper side of that trade). Per tile:
+// 180 GB part 1.5 KB per edge-step is the cheaper side of that trade). Per tile:
 //
 //   LOAD   gout = grad_eout[i] + grad_agg[dst_i] -> bf16 image in shared memory; xhat2 / rstd rows into registers
 //   EPI-B  d(y2) = gout * tanh'(gamma2 xhat2 + beta2), LayerNorm-2 adjoint -> delta2 (bf16 image, in place over gout)
 //   GEMM3  dG = delta2 W2           (W2^T image, two N = 128 halves of the hidden width, accumulators in TMEM)
 //   EPI-C  d(y1) = dG * gelu'(gamma1 xhat1 + beta1) (parked in TMEM), LayerNorm-1 adjoint -> delta1 (bf16 image)
-//   GEMM4  dA0 = delta1 W1          (W1^T image streamed in twelve 16 KB (segment, K-block) pieces through 6 slots)
-//   EPI-D  per-edge rows d(x[src]), d(x[dst]) and d(e) = dA0_e + gout, as coalesced full rows
+//   GEMM4  d(e)_mlp = delta1 W1c    (the edge-latent columns of W1 only: four 16 KB W1c^T pieces through the slots)
+//   EPI-D  d(e) = d(e)_mlp + gout, as coalesced full rows
+//
+// The node part of the first layer's adjoint is NOT done per edge. W1 acts linearly on [x[src] | x[dst] | e], so
+//   d(x)[n]  = (sum_{src_i = n} delta1_i) W1a + (sum_{dst_i = n} delta1_i) W1b,   dW1a = R_src^T X,  dW1b = R_dst^T X
+// with R_src / R_dst the per-node sums of delta1: after this kernel a segmented reduce over the delta1 image builds
+// R = [R_src | R_dst] ([nodes, 2H]), one node-level GEMM gives d(x) and one node-level weight-gradient GEMM dW1a / dW1b
+// (10x fewer rows than edges). Two thirds of GEMM4 / EPI-D, both per-edge d(x) row tensors (1 KB per edge written and
+// read back) and two thirds of the per-edge dW1 GEMM disappear.
 //
 // gout folds the adjoint of the scatter_add that follows the edge step. The delta1 / delta2 images go to HBM with
 // bulk copies; with the forward's A0 / g images they are the operands of the weight-gradient kernel (wgrad_tc.cu).
@@ -47,8 +54,8 @@ constexpr int RED_OFF = IDS_OFF + 2 * TILE_M * 4;      // [128 rows][4 splits][2
 constexpr int BAR_OFF = RED_OFF + TILE_M * 8 * 4;
 constexpr int NBAR = NSLOT + NSLOT + 1;
 constexpr int SMEM_BYTES = BAR_OFF + NBAR * 8 + 16;
-constexpr int NPIECE = 3 * NKB2;                        // 12 W1^T pieces, segment-major; piece b lives in slot (b + 4) % 6
-constexpr uint32_t TM_DG = 0, TM_DA0 = 0;               // dG / d(y1): hidden unit c at column c; dA0: segment s at column s * L
+constexpr int NPIECE = NKB2;                            // 4 W1c^T pieces (K-blocks over the hidden width); piece b lives in slot (b + 4) % 6
+constexpr uint32_t TM_DG = 0, TM_DA0 = 0;               // dG / d(y1): hidden unit c at column c; d(e)_mlp re-uses columns [0, L) afterwards
 
 struct BwdArgs {
   hgnn_tc_edge_params P;
@@ -56,7 +63,7 @@ struct BwdArgs {
   const uint8_t* w2t;   // W2^T image: [H rows, L cols]
   const int32_t* dst; const int32_t* perm;  // perm: tile row j -> edge id (NULL = identity)
   const float* g_e; const float* g_agg;   // upstream: d/d e_out [E, L], d/d agg [N, L] (may be NULL)
-  float* d_e; float* d_xs; float* d_xd;   // [E, L] each
+  float* d_e;                              // [E, L]
   const uint4* xh1; const uint4* xh2; const float* rstd;  // forward stash (EdgeStash in tc_common.cuh)
   uint8_t* d1_img; uint8_t* d2_img;
   float* colpart;                          // [grid][4][PAR_FLOATS]
@@ -126,9 +133,8 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     mbar_expect_tx(BAR(B_FULL + slot), bytes);
     bulk_g2s(sm_u + slot * SEG_BLK, src, bytes, BAR(B_FULL + slot));
   };
-  auto piece_src = [&](int b) {  // piece b = (segment sg, K-block kb over the hidden width)
-    const int sg = b / NKB2, kb = b % NKB2;
-    return A.w1t + (size_t)kb * W1T_BLK + (size_t)sg * SEG_BLK;
+  auto piece_src = [&](int kb) {  // piece kb = rows [2L, 3L) (the edge-latent inputs) of K-block kb of the W1^T image
+    return A.w1t + (size_t)kb * W1T_BLK + (size_t)2 * SEG_BLK;
   };
   // first blocks of a tile: W2^T K-blocks 0 / 1 (32 KB each, slots 0+1 / 2+3) and W1^T pieces 0 / 1 (slots 4 / 5)
   auto head_fill = [&]() {  // thread 32
@@ -288,13 +294,10 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     uint4 xq1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) xq1[j] = __ldg(A.xh1 + ((size_t)tile * (H / 8) + cs * 8 + j) * TILE_M + row);
-    if (tid == 32) {  // W1^T pieces 2..5 replace W2^T as its MMAs retire
+    if (tid == 32) {  // W1c^T pieces 2 / 3 replace W2^T K-block 0 as its MMAs retire
       free_wait(0);
       fill(0, piece_src(2), SEG_BLK);
       fill(1, piece_src(3), SEG_BLK);
-      free_wait(2);
-      fill(2, piece_src(4), SEG_BLK);
-      fill(3, piece_src(5), SEG_BLK);
     }
     if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
     __syncthreads();
@@ -378,28 +381,20 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     __syncthreads();
 
     MARK(4);
-    // ================= GEMM4: dA0 = delta1 W1, one N = 128 accumulator per input segment =================
+    // ================= GEMM4: d(e)_mlp = delta1 W1c, one N = 128 accumulator =================
     if (tid == 0) {
       bulk_s2g(A.d1_img + (size_t)tile * A2_BYTES, sm_u + A2_OFF, A2_BYTES);
       bulk_commit();
       tc_fence_after();
 #pragma unroll
-      for (int b = 0; b < NPIECE; ++b) {
-        const int slot = (b + 4) % NSLOT, sg = b / NKB2, kb = b % NKB2;
+      for (int kb = 0; kb < NPIECE; ++kb) {
+        const int slot = (kb + 4) % NSLOT;
         full_wait(slot);
-        umma_kblock(tmem + TM_DA0 + sg * L, sm_u + A2_OFF + kb * A_BLK_BYTES, sm_u + slot * SEG_BLK, idesc_l, kb == 0);
+        umma_kblock(tmem + TM_DA0, sm_u + A2_OFF + kb * A_BLK_BYTES, sm_u + slot * SEG_BLK, idesc_l, kb == 0);
         umma_commit(BAR(B_FREE + slot));
       }
       umma_commit(BAR(ACC));
       bulk_wait_read0();  // delta1 / delta2 images have left shared memory before their regions are reused
-    }
-    if (tid == 32) {  // pieces 6..11 follow pieces 0..5 through the same slots
-#pragma unroll
-      for (int b = 6; b < NPIECE; ++b) {
-        const int slot = (b + 4) % NSLOT;
-        free_wait(slot);
-        fill(slot, piece_src(b), SEG_BLK);
-      }
     }
     float4 skipg[8];  // fp32 upstream gradient of this lane's 8 output chunks (skip path of d(e)), in flight under GEMM4
 #pragma unroll
@@ -418,41 +413,33 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
     acc_par ^= 1;
     tc_fence_after();
     // every MMA has retired: request the next tile's first weight blocks under EPI-D
-    if (tid == 32) {
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s) free_wait(s);  // pieces 8..11 (slots 0..3), 6 / 7 (slots 4 / 5): all complete
+    if (tid == 32) {  // consume the remaining retirements: W2^T K-block 1 (slot 2), pieces 0 / 1 (slots 4 / 5), 2 / 3 (slots 0 / 1)
+      free_wait(2); free_wait(4); free_wait(5); free_wait(0); free_wait(1);
       if (has_next) head_fill();
     }
 
     MARK(5);
-    // ================= EPI-D: rows of d(x[src]), d(x[dst]), d(e) through a swizzled fp32 staging tile =================
-#pragma unroll 1
-    for (int sg = 0; sg < 3; ++sg) {
-      {
-        float v[32];
-        tmem_ld32(t_lane + TM_DA0 + sg * L + cs * 32, v);
+    // ================= EPI-D: rows of d(e) through a swizzled fp32 staging tile =================
+    {
+      float v[32];
+      tmem_ld32(t_lane + TM_DA0 + cs * 32, v);
 #pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          const int c4 = cs * 8 + g4;
-          *reinterpret_cast<float4*>(sm + A2_OFF + (size_t)row * (L * 4) + ((c4 ^ (row & 7)) << 4)) =
-              make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
-        }
+      for (int g4 = 0; g4 < 8; ++g4) {
+        const int c4 = cs * 8 + g4;
+        *reinterpret_cast<float4*>(sm + A2_OFF + (size_t)row * (L * 4) + ((c4 ^ (row & 7)) << 4)) =
+            make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
       }
-      __syncthreads();
-      float* outp = sg == 0 ? A.d_xs : (sg == 1 ? A.d_xd : A.d_e);
+    }
+    __syncthreads();
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {  // 8 rows per warp, one float4 chunk per lane
-        const int r = warp * 8 + k, c4 = lane;
-        const int64_t j = (int64_t)tile * TILE_M + r;
-        if (j < A.n_edges) {
-          float4 y = *reinterpret_cast<const float4*>(sm + A2_OFF + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
-          if (sg == 2) {  // skip connection: d(e) += gout (fp32)
-            y.x += skipg[k].x; y.y += skipg[k].y; y.z += skipg[k].z; y.w += skipg[k].w;
-          }
-          *reinterpret_cast<float4*>(outp + (size_t)s_eid[r] * L + c4 * 4) = y;
-        }
+    for (int k = 0; k < 8; ++k) {  // 8 rows per warp, one float4 chunk per lane; skip connection: d(e) += gout (fp32)
+      const int r = warp * 8 + k, c4 = lane;
+      const int64_t j = (int64_t)tile * TILE_M + r;
+      if (j < A.n_edges) {
+        float4 y = *reinterpret_cast<const float4*>(sm + A2_OFF + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
+        y.x += skipg[k].x; y.y += skipg[k].y; y.z += skipg[k].z; y.w += skipg[k].w;
+        *reinterpret_cast<float4*>(A.d_e + (size_t)s_eid[r] * L + c4 * 4) = y;
       }
-      __syncthreads();
     }
     fence_proxy_async();  // staging (generic proxy) precedes the next tile's bulk store from / writes into these bytes
     tc_fence_before();
@@ -491,25 +478,125 @@ __global__ void k_colpart_reduce(const float* __restrict__ part, int n_part, flo
   if (i < 3 * H) dvec1[i] = s; else dvec2[i - 3 * H] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// R[side][n, c] = sum over the tile rows p of segment n (side 0: rows with src = n, side 1: rows with dst = n) of
+// delta1[p, c], read straight from the bf16 delta1 tile image the kernel above left in HBM, summed in fp32 in plan order
+// (ordered: bit-reproducible). One warp per segment, lane = one 16-byte chunk (8 of the 256 hidden columns): a row is
+// four full 128 B lines. Hub segments (> IMG_LONG rows) are left to k_img_segment_reduce_long.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int IMG_LONG = 1024;
+struct ImgPlan { const int32_t* rows; const int32_t* rowptr; };  // rows == NULL: tile rows are already segment-sorted
+
+__device__ __forceinline__ void img_row_add(float (&acc)[8], const uint8_t* __restrict__ img, int p, int kb, int c16) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)(p >> 7) * NKB2 + kb) * A_BLK_BYTES + sw128_off(p & 127, c16)));
+  float f[8];
+  unpack8(q, f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] += f[i];
+}
+
+// rows [b0, b1) of one plan, summed in order into acc (whole warp; lane = chunk)
+__device__ __forceinline__ void img_rows_sum(float (&acc)[8], const uint8_t* __restrict__ img, const int32_t* __restrict__ rows,
+                                             int b0, int b1, int lane) {
+  const int kb = lane >> 3, c16 = lane & 7;
+  for (int j0 = b0; j0 < b1; j0 += 32) {
+    const int n = min(32, b1 - j0);
+    const int mine = (lane < n) ? (rows ? __ldg(rows + j0 + lane) : j0 + lane) : 0;  // one coalesced look at the row list
+    int u = 0;
+    for (; u + 8 <= n; u += 8) {  // 8 independent 16-byte loads in flight per lane
+      uint4 q[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int p = __shfl_sync(0xffffffffu, mine, u + k);
+        q[k] = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)(p >> 7) * NKB2 + kb) * A_BLK_BYTES + sw128_off(p & 127, c16)));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float f[8];
+        unpack8(q[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    }
+    for (; u < n; ++u) img_row_add(acc, img, __shfl_sync(0xffffffffu, mine, u), kb, c16);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_img_segment_reduce(const uint8_t* __restrict__ img, ImgPlan ps, ImgPlan pd, int64_t n_seg,
+                                                            float* __restrict__ R) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * 8 + warp;
+  if (s >= n_seg) return;
+  const ImgPlan P = blockIdx.y == 0 ? ps : pd;
+  const int beg = P.rowptr[s], end = P.rowptr[s + 1];
+  if (end - beg > IMG_LONG) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  img_rows_sum(acc, img, P.rows, beg, end, lane);
+  float4* o = reinterpret_cast<float4*>(R + ((size_t)blockIdx.y * n_seg + s) * H + lane * 8);
+  o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// hub segments: a CTA per segment, its 8 warps sum 8 contiguous parts in parallel, combined in part order
+__global__ void __launch_bounds__(256) k_img_segment_reduce_long(const uint8_t* __restrict__ img, ImgPlan ps, ImgPlan pd, int64_t n_seg,
+                                                                 float* __restrict__ R) {
+  __shared__ int s_queue[256];
+  __shared__ int s_count;
+  __shared__ float s_part[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ImgPlan P = blockIdx.y == 0 ? ps : pd;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  {  // this CTA inspects segment ids {b, b + grid, ...}: neighbouring ids (where hubs cluster) land on different CTAs
+    const int64_t s = (int64_t)threadIdx.x * gridDim.x + blockIdx.x;
+    if (s < n_seg && P.rowptr[s + 1] - P.rowptr[s] > IMG_LONG) s_queue[atomicAdd(&s_count, 1)] = (int)s;
+  }
+  __syncthreads();
+  const int n_long = s_count;
+  for (int qi = 0; qi < n_long; ++qi) {
+    const int64_t s = s_queue[qi];
+    const int beg = P.rowptr[s], end = P.rowptr[s + 1];
+    const int per = (end - beg + 7) / 8;
+    const int b0 = min(end, beg + warp * per), b1 = min(end, b0 + per);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    img_rows_sum(acc, img, P.rows, b0, b1, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[warp][lane * 8 + i] = acc[i];
+    __syncthreads();
+    {
+      const int c = threadIdx.x;
+      float t = s_part[0][c];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += s_part[w][c];
+      R[((size_t)blockIdx.y * n_seg + s) * H + c] = t;
+    }
+    __syncthreads();
+  }
+}
+
 struct Layout {
-  size_t d1, d2, colpart, wgrad, total;
-  int grid, tiles;
+  size_t d1, d2, colpart, wgrad, r, r_img, x_img, total;
+  int grid, tiles, node_tiles;
   size_t wgrad_bytes;
 };
 
-Layout make_layout(int64_t n_edges) {
+Layout make_layout(int64_t n_edges, int64_t n_nodes) {
   Layout Y{};
   Y.tiles = (int)((n_edges + TILE_M - 1) / TILE_M);
+  Y.node_tiles = (int)((n_nodes + TILE_M - 1) / TILE_M);
   Y.grid = std::max(1, std::min(Y.tiles, num_sms()));
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = align_up(off, 1024); off = o + b; return o; };
   Y.d1 = take((size_t)Y.tiles * NKB2 * A_BLK_BYTES);
   Y.d2 = take((size_t)Y.tiles * NKBL * A_BLK_BYTES);
   Y.colpart = take((size_t)Y.grid * 4 * PAR_FLOATS * 4);
-  // wgrad partials: 3 roles of [256 x 128] + 1 role of [128 x 256]
-  int splits = hgnn::tc::wgrad_splits(4, Y.tiles);
-  Y.wgrad_bytes = (size_t)4 * align_up((size_t)splits * 256 * 128 * 4, 256) + 256;
+  // wgrad partials: two launches of two [256 x 128] problems each (edge level: dW1c, dW2; node level: dW1a, dW1b)
+  int splits = std::max(hgnn::tc::wgrad_splits(2, Y.tiles), hgnn::tc::wgrad_splits(2, std::max(1, Y.node_tiles)));
+  Y.wgrad_bytes = (size_t)2 * align_up((size_t)splits * 256 * 128 * 4, 256) + 256;
   Y.wgrad = take(Y.wgrad_bytes);
+  Y.r = take((size_t)n_nodes * 2 * H * 4);                                // R_src [n, H] then R_dst [n, H], fp32
+  Y.r_img = take((size_t)Y.node_tiles * (2 * H / KBLK) * A_BLK_BYTES);    // its bf16 tile image (left by the d(x) GEMM)
+  Y.x_img = take((size_t)Y.node_tiles * (L / KBLK) * A_BLK_BYTES);        // bf16 tile image of x
   Y.total = align_up(off, 1024);
   return Y;
 }
@@ -520,31 +607,34 @@ static void* g_phase_clk = nullptr;
 // debug hook (not part of the stable ABI): device buffer of 16 uint64 that CTA 0 fills with per-phase cycle counts
 extern "C" void hgnn_tc_debug_set_phase_clock(void* dev_u64x16) { g_phase_clk = dev_u64x16; }
 
-extern "C" size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges) {
-  return make_layout(n_edges > 0 ? n_edges : 1).total + 1024;
+extern "C" size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges, int64_t n_nodes) {
+  return make_layout(n_edges > 0 ? n_edges : 1, n_nodes > 0 ? n_nodes : 1).total + 1024;
 }
 
 extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed,
-                                     const void* stash, const int32_t* src, const int32_t* dst, const int32_t* perm,
-                                     int64_t n_edges, const float* grad_eout, const float* grad_agg, float* d_e, float* d_xsrc_rows,
-                                     float* d_xdst_rows, float* dW1, float* dW2, float* dvec1, float* dvec2, void* ws,
-                                     size_t ws_bytes, void* stream) {
+                                     const void* wx_packed, const void* stash, const float* x, int64_t n_nodes,
+                                     const int32_t* dst, const int32_t* perm, const int32_t* src_rows, const int32_t* src_rowptr,
+                                     const int32_t* dst_rows, const int32_t* dst_rowptr, int64_t n_edges, const float* grad_eout,
+                                     const float* grad_agg, float* d_e, float* d_x, float* dW1, float* dW2, float* dvec1,
+                                     float* dvec2, void* ws, size_t ws_bytes, void* stream) {
   HGNN_REQUIRE(p != nullptr, "tc_edge_backward: params is NULL");
   HGNN_REQUIRE(p->latent == 128 && p->hidden == 256, "tc_edge_backward: only latent 128 / hidden 256 is built (got %d / %d)",
                p->latent, p->hidden);
+  HGNN_REQUIRE(n_nodes > 0 && n_nodes < INT32_MAX, "tc_edge_backward: bad n_nodes");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_edges <= 0) {
     if (dW1) HGNN_CUDA_TRY(cudaMemsetAsync(dW1, 0, (size_t)H * K1 * 4, st));
     if (dW2) HGNN_CUDA_TRY(cudaMemsetAsync(dW2, 0, (size_t)L * H * 4, st));
     if (dvec1) HGNN_CUDA_TRY(cudaMemsetAsync(dvec1, 0, (size_t)3 * H * 4, st));
     if (dvec2) HGNN_CUDA_TRY(cudaMemsetAsync(dvec2, 0, (size_t)3 * L * 4, st));
+    if (d_x) HGNN_CUDA_TRY(cudaMemsetAsync(d_x, 0, (size_t)n_nodes * L * 4, st));
     return HGNN_OK;
   }
-  HGNN_REQUIRE(w1t_packed && w2t_packed && stash && src && dst && grad_eout && d_e && d_xsrc_rows && d_xdst_rows && dW1 && dW2 &&
-               dvec1 && dvec2 && ws, "tc_edge_backward: NULL pointer");
+  HGNN_REQUIRE(w1t_packed && w2t_packed && wx_packed && stash && x && dst && src_rows && src_rowptr && dst_rowptr && grad_eout &&
+               d_e && d_x && dW1 && dW2 && dvec1 && dvec2 && ws, "tc_edge_backward: NULL pointer");
   HGNN_REQUIRE(n_edges < INT32_MAX, "tc_edge_backward: too many edges");
   HGNN_REQUIRE(p->gamma1 && p->beta1 && p->gamma2 && p->beta2 && p->b1 && p->b2, "tc_edge_backward: NULL parameter pointer");
-  Layout Y = make_layout(n_edges);
+  Layout Y = make_layout(n_edges, n_nodes);
   uintptr_t base = align_up((uintptr_t)ws, 1024);
   if (ws_bytes < (base - (uintptr_t)ws) + Y.total) return fail(HGNN_ERR_WORKSPACE, "tc_edge_backward: workspace too small");
   uint8_t* w = (uint8_t*)base;
@@ -554,9 +644,9 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   A.P = *p;
   A.w1t = (const uint8_t*)w1t_packed;
   A.w2t = (const uint8_t*)w2t_packed;
-  A.dst = dst; A.perm = perm;  // src only matters to the caller's by-source reduction of d_xsrc_rows
+  A.dst = dst; A.perm = perm;
   A.g_e = grad_eout; A.g_agg = grad_agg;
-  A.d_e = d_e; A.d_xs = d_xsrc_rows; A.d_xd = d_xdst_rows;
+  A.d_e = d_e;
   A.xh1 = (const uint4*)(sb + SL.xh1); A.xh2 = (const uint4*)(sb + SL.xh2); A.rstd = (const float*)(sb + SL.rstd);
   A.d1_img = w + Y.d1; A.d2_img = w + Y.d2;
   A.colpart = (float*)(w + Y.colpart);
@@ -575,12 +665,35 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   int rc = check_launch("tc_edge_backward");
   if (rc) return rc;
   k_colpart_reduce<<<(PAR_FLOATS + 255) / 256, 256, 0, st>>>(A.colpart, Y.grid * 4, dvec1, dvec2);
-  // weight gradients: dW1[:, seg] = delta1^T A0[:, seg] (3 problems), dW2 = delta2^T g
+
+  // ---- node level: R = per-node sums of delta1 by source / by destination ----
+  float* R = (float*)(w + Y.r);
+  const ImgPlan ps{src_rows, src_rowptr}, pd{dst_rows, dst_rowptr};
+  k_img_segment_reduce<<<dim3((unsigned)((n_nodes + 7) / 8), 2), 256, 0, st>>>(A.d1_img, ps, pd, n_nodes, R);
+  k_img_segment_reduce_long<<<dim3((unsigned)((n_nodes + 255) / 256), 2), 256, 0, st>>>(A.d1_img, ps, pd, n_nodes, R);
+  rc = check_launch("tc_edge_backward (delta1 node sums)");
+  if (rc) return rc;
+  // d(x) = [R_src | R_dst] . [W1a ; W1b]  (wx_packed = image of [W1a^T | W1b^T] as an [L, 2H] Linear weight); the GEMM
+  // leaves the bf16 tile image of [R_src | R_dst] behind for the weight-gradient GEMM
+  hgnn_tc_row_layer g{};
+  g.n_seg = 2; g.n_out = L; g.act = HGNN_ACT_NONE;
+  g.seg_ptr[0] = R; g.seg_ptr[1] = R + (size_t)n_nodes * H;
+  g.seg_width[0] = H; g.seg_width[1] = H;
+  g.w_packed = wx_packed;
+  rc = hgnn_tc_gemm(&g, n_nodes, d_x, L, 0, w + Y.r_img, st);
+  if (rc) return rc;
+  rc = hgnn::tc::launch_make_image(x, n_nodes, L, w + Y.x_img, st);
+  if (rc) return rc;
+  // weight gradients. Edge level: dW1[:, 2L:3L] = delta1^T A0[:, e columns], dW2 = delta2^T g.
+  // Node level: dW1[:, 0:L] = R_src^T X, dW1[:, L:2L] = R_dst^T X.
   const uint8_t* a0_img = sb + SL.a0;
   const uint8_t* g_img = sb + SL.g;
-  hgnn::tc::WgradProblem pr[4];
-  for (int s = 0; s < 3; ++s)
-    pr[s] = hgnn::tc::WgradProblem{A.d1_img, H, 0, H, a0_img, K1, s * L, L, dW1, K1, 0, s * L, 0};
-  pr[3] = hgnn::tc::WgradProblem{A.d2_img, L, 0, L, g_img, H, 0, H, dW2, H, 0, 0, 0};
-  return hgnn::tc::launch_wgrad(pr, 4, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, st);
+  hgnn::tc::WgradProblem pe[2], pn[2];
+  pe[0] = hgnn::tc::WgradProblem{A.d1_img, H, 0, H, a0_img, L, 0, L, dW1, K1, 0, 2 * L, 0};
+  pe[1] = hgnn::tc::WgradProblem{A.d2_img, L, 0, L, g_img, H, 0, H, dW2, H, 0, 0, 0};
+  rc = hgnn::tc::launch_wgrad(pe, 2, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, st);
+  if (rc) return rc;
+  for (int sd = 0; sd < 2; ++sd)
+    pn[sd] = hgnn::tc::WgradProblem{w + Y.r_img, 2 * H, sd * H, H, w + Y.x_img, L, 0, L, dW1, K1, 0, sd * L, 0};
+  return hgnn::tc::launch_wgrad(pn, 2, Y.node_tiles, w + Y.wgrad, Y.wgrad_bytes, st);  // stream order serialises the workspace reuse
 }

@@ -21,8 +21,8 @@
 //          coalesced pass adds the fp32 skip row and stores e' as full 512 B rows.
 // Weights are never resident in full: smem per CTA is ~105 KB at L = 128.
 // Training (stash != NULL) also leaves in HBM what the backward needs, so that it recomputes nothing: the two MMA
-// operand images (A0 written while gathering, g by one bulk copy), the normalised pre-affine activations of both
-// LayerNorms as bf16 and the row rstd's (tc_common.cuh: EdgeStash, 2 KB per edge at L = 128).
+// operand images (the e columns of A0 written while gathering, g by one bulk copy), the normalised pre-affine activations of both
+// LayerNorms as bf16 and the row rstd's (tc_common.cuh: EdgeStash, 1.5 KB per edge at L = 128).
 #include <algorithm>
 #include <cstdlib>
 
@@ -163,7 +163,9 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
         mbar_expect_tx(BAR(W_FULL + s), C::W1_BLK);
         bulk_g2s(region_u + s * C::STAGE + A_BLK_BYTES, w1p + (size_t)kb * C::W1_BLK, C::W1_BLK, BAR(W_FULL + s));
       }
-      gather_store(stage, pre, a0_img ? a0_img + ((size_t)tile * C::NKB1 + kb) * A_BLK_BYTES : nullptr);
+      // the edge-latent K-blocks are also left in HBM as the weight-gradient operand (x columns: handled per node)
+      constexpr int KB_E = 2 * L / KBLK;
+      gather_store(stage, pre, (a0_img && kb >= KB_E) ? a0_img + ((size_t)tile * (L / KBLK) + (kb - KB_E)) * A_BLK_BYTES : nullptr);
       if (kb + 1 < C::NKB1) gather_load(pre, seg_base(kb + 1), L, seg_rows(kb + 1), ((kb + 1) * KBLK) % L);  // next block in flight
       fence_proxy_async();
       __syncthreads();

@@ -284,7 +284,8 @@ __device__ __forceinline__ void ln_act_to_image(uint32_t taddr, const float* __r
 }
 
 // What the forward edge step leaves in HBM for its backward (one caller-owned buffer, hgnn_tc_edge_stash_bytes):
-//   a0  [tiles][3L/64][16 KB]  bf16 tile image of the gathered input [x[src] | x[dst] | e]   (weight-gradient operand)
+//   a0  [tiles][L/64][16 KB]   bf16 tile image of the edge-latent columns e of the gathered input (weight-gradient operand;
+//                              the x[src] / x[dst] columns are not kept: their weight gradient is formed per node)
 //   g   [tiles][2L/64][16 KB]  bf16 tile image of act(LN1(h1))                                (weight-gradient operand)
 //   xh1 [tiles][2L/8][128]     uint4 = 8 bf16 of xhat1 = (h1 - mean1) rstd1                   (LN1 / activation adjoint)
 //   xh2 [tiles][L/8][128]      uint4 = 8 bf16 of xhat2                                        (LN2 / activation adjoint)
@@ -297,7 +298,7 @@ __host__ __device__ inline EdgeStash edge_stash_layout(int64_t n_edges, int L) {
   EdgeStash S{};
   S.tiles = (n_edges + TILE_M - 1) / TILE_M;
   size_t off = 0;
-  S.a0 = off;   off += (size_t)S.tiles * (3 * L / KBLK) * A_BLK_BYTES;
+  S.a0 = off;   off += (size_t)S.tiles * (L / KBLK) * A_BLK_BYTES;
   S.g = off;    off += (size_t)S.tiles * (2 * L / KBLK) * A_BLK_BYTES;
   S.xh1 = off;  off += (size_t)S.tiles * (2 * L / 8) * TILE_M * 16;
   S.xh2 = off;  off += (size_t)S.tiles * (L / 8) * TILE_M * 16;
@@ -426,6 +427,8 @@ struct WgradProblem {
 size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits);
 int wgrad_splits(int n_roles, int n_tiles);
 int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st);
+// fp32 [rows, cols] (cols % 64 == 0) -> bf16 tile image, padding rows of the last tile zeroed
+int launch_make_image(const float* src, int64_t rows, int cols, uint8_t* img, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace hgnn

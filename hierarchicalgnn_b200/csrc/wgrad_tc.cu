@@ -167,6 +167,13 @@ size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits) {
   return tot + 256;
 }
 
+int launch_make_image(const float* src, int64_t rows, int cols, uint8_t* img, cudaStream_t st) {
+  HGNN_REQUIRE(src && img && rows > 0 && cols % KBLK == 0, "make_image: bad argument");
+  const int64_t tiles = (rows + TILE_M - 1) / TILE_M, t = tiles * TILE_M * (cols / 8);
+  k_make_image<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(src, rows, cols, img);
+  return check_launch("make_image");
+}
+
 int wgrad_splits(int n_roles, int n_tiles) {
   int s = std::max(1, num_sms() / std::max(1, n_roles));
   return std::max(1, std::min(s, n_tiles));

@@ -406,11 +406,10 @@ class _FusedMLP(torch.autograd.Function):
         dev = segs[0].device
         gout = _f32(gout)
         if rows and tc_backward_available(meta, layers) and ctx.a0 is not None:
-            d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, gout, ctx.a0)
+            d_x, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, gout, ctx.a0)
             need = ctx.needs_input_grad[2:]
-            gx_s = segment_reduce_raw(d_xs, meta.seg_plans[0]) if need[0] else None
-            gx_d = segment_reduce_raw(d_xd, meta.seg_plans[1]) if need[1] else None
-            return (None, None, gx_s, gx_d, d_e if need[2] else None,
+            # segments 0 and 1 are the same tensor (tc path precondition): its whole gradient goes out through segment 0
+            return (None, None, d_x if need[0] else None, None, d_e if need[2] else None,
                     dW1, dv1[0], dv1[1], dv1[2], dW2, dv2[0], dv2[1], dv2[2])
         L = _lib.lib()
         need = ctx.needs_input_grad[2:]
@@ -530,32 +529,57 @@ def tc_backward_available(meta: MlpMeta, layers) -> bool:
     return meta.tc_pack is not None and layers[1][0].shape[0] == 128 and layers[0][0].shape[0] == 256
 
 
-def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, a0_img: Tensor, perm: Optional[Tensor] = None,
-                         grad_agg: Optional[Tensor] = None):
-    """Backward of the tensor-core edge step from the forward's saved A0 image (same row order ``perm``).
-    Returns (d_xsrc_rows, d_xdst_rows, d_e, dW1, dW2, dvec1, dvec2)."""
+def _tile_row_plans(plan_s: SegmentPlan, plan_d: SegmentPlan, dst_sorted: bool):
+    """CSR over the forward kernel's TILE ROWS grouped by source / by destination node, for the per-node sums of delta1
+    in the backward: (src_rows, src_rowptr, dst_rows | None, dst_rowptr). Tile row j holds edge plan_d.perm[j] when the
+    forward ran destination-sorted (the fused-aggregate path), edge j otherwise. Cached on the source plan."""
+    key = (id(plan_d), bool(dst_sorted))
+    cache = plan_s.__dict__.setdefault("_tile_rows", {})
+    hit = cache.get(key)
+    if hit is None:
+        if not dst_sorted:
+            hit = (plan_s.perm, plan_s.rowptr, plan_d.perm, plan_d.rowptr, plan_d)
+        elif plan_d.is_identity():
+            hit = (plan_s.perm, plan_s.rowptr, None, plan_d.rowptr, plan_d)
+        else:
+            pos = torch.empty_like(plan_d.perm)  # edge id -> tile row
+            pos[plan_d.perm.long()] = torch.arange(plan_d.n_items, dtype=torch.int32, device=pos.device)
+            hit = (pos[plan_s.perm.long()].contiguous(), plan_s.rowptr, None, plan_d.rowptr, plan_d)
+        cache.clear()  # one entry: the plans of one graph are used together
+        cache[key] = hit
+    return hit[:4]
+
+
+def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, stash: Tensor, perm: Optional[Tensor] = None,
+                         grad_agg: Optional[Tensor] = None, dst_sorted: bool = False):
+    """Backward of the tensor-core edge step from the forward's stash (same row order ``perm``; ``dst_sorted`` says that
+    order is the by-destination plan's). Returns (d_x, d_e, dW1, dW2, dvec1, dvec2): d_x is the complete node gradient
+    (both gathers), computed per node from the segment sums of delta1."""
     x, e = segs[0], segs[2]
     plan_s, plan_d = meta.seg_plans[0], meta.seg_plans[1]
-    w1p, w2p, w1tp, w2tp = meta.tc_pack()
+    w1p, w2p, w1tp, w2tp, wxp = meta.tc_pack()
     p = _tc_params(meta, layers, w1p, w2p)
     E, Lw = e.shape
+    N = x.shape[0]
     dev = e.device
     d_e = torch.empty_like(e)
-    d_xs = torch.empty((E, Lw), dtype=torch.float32, device=dev)
-    d_xd = torch.empty((E, Lw), dtype=torch.float32, device=dev)
+    d_x = torch.empty((N, Lw), dtype=torch.float32, device=dev)
     dW1, dW2 = torch.empty_like(layers[0][0]), torch.empty_like(layers[1][0])
     dv1 = torch.empty((3, layers[0][0].shape[0]), dtype=torch.float32, device=dev)
     dv2 = torch.empty((3, layers[1][0].shape[0]), dtype=torch.float32, device=dev)
+    src_rows, src_rowptr, dst_rows, dst_rowptr = _tile_row_plans(plan_s, plan_d, dst_sorted)
     L_ = _lib.lib()
-    ws = _workspace(L_.hgnn_tc_edge_backward_workspace_bytes(E), dev)
+    ws = _workspace(L_.hgnn_tc_edge_backward_workspace_bytes(E, N), dev)
     with _timed("tc_edge_backward"):
-        check(L_.hgnn_tc_edge_backward(C.byref(p), _ptr(w1tp), _ptr(w2tp), _ptr(a0_img), _ptr(plan_s.keys32),
-                                       _ptr(plan_d.keys32), _ptr(perm), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_xs), _ptr(d_xd),
+        check(L_.hgnn_tc_edge_backward(C.byref(p), _ptr(w1tp), _ptr(w2tp), _ptr(wxp), _ptr(stash), _ptr(x), N,
+                                       _ptr(plan_d.keys32), _ptr(perm), _ptr(src_rows), _ptr(src_rowptr), _ptr(dst_rows),
+                                       _ptr(dst_rowptr), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_x),
                                        _ptr(dW1), _ptr(dW2), _ptr(dv1), _ptr(dv2), _ptr(ws), ws.numel(), _stream()),
               "tc_edge_backward")
-    _count(4)  # data-gradient kernel, column-sum reduce, weight-gradient GEMM, its ordered reduce
+    # data-gradient kernel, column-sum reduce, delta1 node sums (2), d(x) GEMM, x image, 2 x (weight-gradient GEMM + ordered reduce)
+    _count(10)
     TC_CALLS["count"] += 1
-    return d_xs, d_xd, d_e, dW1, dW2, dv1, dv2
+    return d_x, d_e, dW1, dW2, dv1, dv2
 
 
 def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[Tensor] = None, save_image: bool = False):
@@ -570,7 +594,7 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[
     if agg is not None:
         perm, rowptr = (None if plan_d.is_identity() else plan_d.perm), plan_d.rowptr
     a0 = None
-    if save_image:  # the forward's stash for the backward pass: operand images + bf16 xhat's + rstd (2 KB/edge at L = 128)
+    if save_image:  # the forward's stash for the backward pass: operand images + bf16 xhat's + rstd (1.5 KB/edge at L = 128)
         a0 = torch.empty(_lib.lib().hgnn_tc_edge_stash_bytes(n_edges, e.shape[1]), dtype=torch.uint8, device=e.device)
     with _timed("tc_edge_forward"):
         check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), _ptr(perm),
@@ -612,11 +636,10 @@ class _TcEdgeStepAgg(torch.autograd.Function):
         d, rows, layers = _build_desc(meta, segs, ps)
         g_out = torch.zeros_like(e) if g_out is None else _f32(g_out)
         g_agg = None if g_agg is None else _f32(g_agg)
-        d_xs, d_xd, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, ctx.a0, None if meta.seg_plans[1].is_identity() else meta.seg_plans[1].perm, g_agg)
-        gx = None
-        if ctx.needs_input_grad[1]:
-            gx = segment_reduce_raw(d_xs, meta.seg_plans[0])
-            gx.add_(segment_reduce_raw(d_xd, meta.seg_plans[1]))
+        plan_d = meta.seg_plans[1]
+        d_x, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, ctx.a0,
+                                                            None if plan_d.is_identity() else plan_d.perm, g_agg, dst_sorted=True)
+        gx = d_x if ctx.needs_input_grad[1] else None
         return (None, gx, d_e if ctx.needs_input_grad[2] else None, dW1, dv1[0], dv1[1], dv1[2], dW2, dv2[0], dv2[1], dv2[2])
 
 

@@ -222,8 +222,11 @@ class FusedMLP(nn.Sequential):
             cached = getattr(self, "_tc_cache", None)
             if cached is None or cached[0] != key:
                 # bf16 shadow copies, rebuilt lazily when the fp32 parameters change; never registered
+                w1d = w1.detach()
+                # [W1[:, 0:L]^T | W1[:, L:2L]^T] as an [L, 2H] Linear weight: the node-level d(x) GEMM of the backward
+                wx = torch.cat([w1d[:, :L].t(), w1d[:, L:2 * L].t()], dim=1).contiguous()
                 cached = (key, ops.tc_pack_weight(w1), ops.tc_pack_weight(w2),
-                          ops.tc_pack_weight_t(w1), ops.tc_pack_weight_t(w2))
+                          ops.tc_pack_weight_t(w1), ops.tc_pack_weight_t(w2), ops.tc_pack_weight(wx))
                 object.__setattr__(self, "_tc_cache", cached)
             return cached[1:]
         return pack

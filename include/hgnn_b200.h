@@ -227,8 +227,8 @@ int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca
  * hgnn_csr_build (perm may be NULL when the edges are already stored destination-sorted: rows then stream in place). Segments crossing a row-group boundary (hub nodes) and empty segments are completed by a small
  * second kernel inside the same call.
  * stash (optional, hgnn_tc_edge_stash_bytes): pass it when a backward will follow. The kernel then also leaves in HBM,
- * per 128-edge tile, the bf16 tile images of its two MMA operands ([x[src] | x[dst] | e] and the hidden activation),
- * the normalised pre-affine activations of both LayerNorms as bf16 and the row rstd's (2 KB per edge at latent 128):
+ * per 128-edge tile, the bf16 tile images of the edge-latent columns of its first MMA operand and of the hidden activation,
+ * the normalised pre-affine activations of both LayerNorms as bf16 and the row rstd's (1.5 KB per edge at latent 128):
  * everything hgnn_tc_edge_backward and the weight-gradient GEMM need, so the backward recomputes nothing and
  * never gathers again. */
 size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges);
@@ -237,18 +237,27 @@ int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const flo
                          const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges, int64_t n_nodes,
                          float* e_out, float* agg, void* stash, void* ws, size_t ws_bytes, void* stream);
 
-/* Backward of the tensor-core edge step (latent 128) from the forward's stash (no recompute, no gathers):
- * data gradients as per-edge rows (d_e final; d_xsrc_rows / d_xdst_rows are reduced by the caller
- * with hgnn_segment_reduce over the by-source / by-destination plans), weight gradients by the
- * tcgen05 split-K kernel, bias/LayerNorm gradients dvec{1,2} = [3, width] (d bias, d gamma, d beta).
- * stash / perm must be the buffer and row order of the matching hgnn_tc_edge_forward call.
+/* Backward of the tensor-core edge step (latent 128) from the forward's stash (no recompute, no gathers).
+ * Per edge it back-propagates through Tanh/LN/Linear/GELU/LN and the edge-latent columns of the first Linear only
+ * (d_e, final). The node part of the first layer is linear in x, so it is done per NODE: a segmented reduce over the
+ * delta1 tile image gives R_src[n] / R_dst[n] = sum of delta1 over the edges leaving / entering n, then
+ *   d_x = R_src W1[:, 0:L] + R_dst W1[:, L:2L]   (one node-level tcgen05 GEMM, d_x is [n_nodes, L], complete)
+ *   dW1[:, 0:L] = R_src^T x,  dW1[:, L:2L] = R_dst^T x   (node-level weight-gradient GEMM)
+ * (the adjoint of nodes[graph[0]] / nodes[graph[1]] in gnn_utils.py:61, which autograd does as two index_add's over
+ * [E, L] rows). dW1[:, 2L:3L], dW2 come from the per-edge tcgen05 split-K kernel; dvec{1,2} = [3, width] (d bias,
+ * d gamma, d beta). stash / perm must be the buffer and row order of the matching hgnn_tc_edge_forward call.
+ * {src,dst}_rows / {src,dst}_rowptr: CSR over the forward's TILE ROWS (position j of the row order, not edge ids) grouped
+ * by source / destination node; dst_rows may be NULL when the row order is already destination-sorted.
  * grad_agg (optional, [n_nodes, L]) is the cotangent of agg = scatter_add(e_out, dst): the kernel uses
- * grad_eout[i] + grad_agg[dst_i]. w1t/w2t_packed are hgnn_tc_pack_weights images of W1^T / W2^T. */
-size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges);
-int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const void* stash,
-                          const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_edges, const float* grad_eout,
-                          const float* grad_agg, float* d_e, float* d_xsrc_rows, float* d_xdst_rows, float* dW1, float* dW2,
-                          float* dvec1, float* dvec2, void* ws, size_t ws_bytes, void* stream);
+ * grad_eout[i] + grad_agg[dst_i]. w1t/w2t_packed are hgnn_tc_pack_weights images of W1^T / W2^T; wx_packed is the image
+ * of the [L, 2H] matrix [W1[:, 0:L]^T | W1[:, L:2L]^T]. */
+size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges, int64_t n_nodes);
+int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const void* wx_packed,
+                          const void* stash, const float* x, int64_t n_nodes, const int32_t* dst, const int32_t* perm,
+                          const int32_t* src_rows, const int32_t* src_rowptr, const int32_t* dst_rows,
+                          const int32_t* dst_rowptr, int64_t n_edges, const float* grad_eout, const float* grad_agg, float* d_e,
+                          float* d_x, float* dW1, float* dW2, float* dvec1, float* dvec2, void* ws, size_t ws_bytes,
+                          void* stream);
 
 /* ------------------------------------------------------------------------
  * Tensor-core row layer: ONE make_mlp layer (utils.py:183-196) on a gathered concatenation,
