@@ -110,7 +110,7 @@ SIGNATURES = {
     "hgnn_tc_debug_gemm": (C.c_int, [vp, vp, i64, i64, i64, vp, vp]),
     "hgnn_tc_debug_wgrad_workspace_bytes": (sz, [i64, i64, i64]),
     "hgnn_tc_debug_wgrad": (C.c_int, [vp, vp, i64, i64, i64, vp, vp, sz, vp]),
-    "hgnn_tc_edge_forward_workspace_bytes": (sz, [i64]),
+    "hgnn_tc_edge_forward_workspace_bytes": (sz, [i64, i64, i64]),
     "hgnn_tc_edge_backward_workspace_bytes": (sz, [i64, i64]),
     # (p, w1t, w2t, wx, stash, x, n_nodes, dst, perm, src_rows, src_rowptr, dst_rows, dst_rowptr, n_edges, g_e, g_agg, d_e, d_x,
     #  dW1, dW2, dv1, dv2, ws, ws_bytes, stream)

@@ -59,7 +59,7 @@ struct Cfg {
 
 template <int L, int ACT_H, int ACT_O>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* __restrict__ e, const int32_t* __restrict__ src,
+k_tc_edge_fwd(hgnn_tc_edge_params P, const uint16_t* __restrict__ xb16, const float* __restrict__ e, const int32_t* __restrict__ src,
               const int32_t* __restrict__ dst, const int32_t* __restrict__ perm, int64_t n_edges, float* __restrict__ e_out,
               const int32_t* __restrict__ rowptr, float* __restrict__ agg, uint8_t* __restrict__ stash, EdgeStash SL,
               unsigned long long* __restrict__ phase_clk, int stagger_cycles) {
@@ -149,32 +149,42 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     __syncthreads();
     MARK(0);
 
-    // ---- GEMM1: D1[128, H] = [x[src] | x[dst] | e] . W1^T ----
-    auto seg_base = [&](int kb) { return (kb * KBLK) / L == 2 ? e : x; };
-    auto seg_rows = [&](int kb) { const int sg = (kb * KBLK) / L; return sg == 0 ? s_src : (sg == 1 ? s_dst : s_eid); };
+    // ---- GEMM1: D1[128, H] = [x[src] | x[dst] | e] . W1^T, K-blocks visited e first (its fp32 rows come from HBM: their
+    // loads are issued at tile start), then x[src], x[dst] from the bf16 shadow copy of the node rows, two blocks in flight ----
+    constexpr int KPS = L / KBLK;  // K-blocks per segment
+    auto blk_seg = [&](int i) { return i < KPS ? 2 : (i < 2 * KPS ? 0 : 1); };
+    auto blk_kb = [&](int i) { return blk_seg(i) * KPS + i % KPS; };  // K-block index in the concatenation / W1 image order
+    auto blk_rows = [&](int i) { return blk_seg(i) == 0 ? s_src : s_dst; };
     float4 pre[8];
-    gather_load(pre, seg_base(0), L, seg_rows(0), 0);
-    for (int kb = 0; kb < C::NKB1; ++kb, ++it1) {
+    uint4 xv[2][4];
+    gather_load(pre, e, L, s_eid, 0);
+    if constexpr (KPS == 1) gather_load_bf16(xv[0], xb16, L, blk_rows(KPS), 0);
+#pragma unroll
+    for (int i = 0; i < C::NKB1; ++i, ++it1) {
       const int s = it1 % C::NSTAGE;
       const uint32_t ph = (it1 / C::NSTAGE) & 1;
       uint8_t* stage = region + s * C::STAGE;
       mbar_wait(BAR(ST_FREE + s), ph ^ 1);  // MMAs that last read this stage are done
       if (tid == 0) {
         mbar_expect_tx(BAR(W_FULL + s), C::W1_BLK);
-        bulk_g2s(region_u + s * C::STAGE + A_BLK_BYTES, w1p + (size_t)kb * C::W1_BLK, C::W1_BLK, BAR(W_FULL + s));
+        bulk_g2s(region_u + s * C::STAGE + A_BLK_BYTES, w1p + (size_t)blk_kb(i) * C::W1_BLK, C::W1_BLK, BAR(W_FULL + s));
       }
-      // the edge-latent K-blocks are also left in HBM as the weight-gradient operand (x columns: handled per node)
-      constexpr int KB_E = 2 * L / KBLK;
-      gather_store(stage, pre, (a0_img && kb >= KB_E) ? a0_img + ((size_t)tile * (L / KBLK) + (kb - KB_E)) * A_BLK_BYTES : nullptr);
-      if (kb + 1 < C::NKB1) gather_load(pre, seg_base(kb + 1), L, seg_rows(kb + 1), ((kb + 1) * KBLK) % L);  // next block in flight
+      if (i < KPS) {  // the edge-latent K-blocks are also left in HBM as the weight-gradient operand (x columns: handled per node)
+        gather_store(stage, pre, a0_img ? a0_img + ((size_t)tile * KPS + i) * A_BLK_BYTES : nullptr);
+        if (i + 1 < KPS) gather_load(pre, e, L, s_eid, (i + 1) * KBLK);
+      } else {
+        gather_store_bf16(stage, xv[(i - KPS) & 1]);
+      }
+      if (i + 2 >= KPS && i + 2 < C::NKB1)  // node rows two blocks ahead
+        gather_load_bf16(xv[(i + 2 - KPS) & 1], xb16, L, blk_rows(i + 2), ((i + 2) % KPS) * KBLK);
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
         mbar_wait(BAR(W_FULL + s), ph);
         tc_fence_after();
-        umma_kblock(tmem, region_u + s * C::STAGE, region_u + s * C::STAGE + A_BLK_BYTES, idesc1, kb == 0);
+        umma_kblock(tmem, region_u + s * C::STAGE, region_u + s * C::STAGE + A_BLK_BYTES, idesc1, i == 0);
         umma_commit(BAR(ST_FREE + s));
-        if (kb == C::NKB1 - 1) umma_commit(BAR(ACC_FULL));
+        if (i == C::NKB1 - 1) umma_commit(BAR(ACC_FULL));
       }
     }
     if (warp == 0) mbar_wait(BAR(ACC_FULL), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
@@ -289,21 +299,34 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
     tc_fence_before();
     __syncthreads();
     MARK(4);
-    // ---- coalesced pass: + fp32 skip row, full-row stores ----
+    // ---- coalesced pass: + fp32 skip row, full-row stores. The skip rows are fetched eight at a time into registers
+    // before anything depends on them (one L2 round trip per batch instead of one per row) ----
     {
       constexpr int CPR = L / 4;                       // float4 chunks per row
       constexpr int ROWS_PER_WARP = TILE_M / (TC_THREADS / 32);
-#pragma unroll 8
-      for (int idx = lane; idx < ROWS_PER_WARP * CPR; idx += 32) {
-        const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
-        const int64_t j = (int64_t)tile * TILE_M + r;
-        if (j < n_edges) {
-          const float4 y = *reinterpret_cast<const float4*>(region + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
-          const size_t g = (size_t)s_eid[r] * L + c4 * 4;
-          const float4 sk = __ldg(reinterpret_cast<const float4*>(e + g));
-          const float4 o = make_float4(y.x + sk.x, y.y + sk.y, y.z + sk.z, y.w + sk.w);
-          *reinterpret_cast<float4*>(e_out + g) = o;
-          if (agg) *reinterpret_cast<float4*>(region + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4)) = o;
+      constexpr int ITERS = ROWS_PER_WARP * CPR / 32;
+      constexpr int BATCH = 8;
+      static_assert(ITERS % BATCH == 0, "store pass batches");
+#pragma unroll 1
+      for (int b0 = 0; b0 < ITERS; b0 += BATCH) {
+        float4 sk[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {  // padding rows carry the (valid) id of the last edge: load unconditionally
+          const int idx = lane + (b0 + u) * 32;
+          const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
+          sk[u] = __ldg(reinterpret_cast<const float4*>(e + (size_t)s_eid[r] * L + c4 * 4));
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+          const int idx = lane + (b0 + u) * 32;
+          const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
+          float4* sp = reinterpret_cast<float4*>(region + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
+          const float4 y = *sp;
+          const float4 o = make_float4(y.x + sk[u].x, y.y + sk[u].y, y.z + sk[u].z, y.w + sk[u].w);
+          if ((int64_t)tile * TILE_M + r < n_edges) {
+            *reinterpret_cast<float4*>(e_out + (size_t)s_eid[r] * L + c4 * 4) = o;
+            if (agg) *sp = o;
+          }
         }
       }
     }
@@ -343,6 +366,14 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const float* __restrict__ x, const float* _
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// bf16 shadow copy of the node rows (each row is gathered ~2 E/N times per step: convert once, gather half the bytes)
+__global__ void __launch_bounds__(256) k_rows_to_bf16(const float* __restrict__ x, int64_t n8, uint4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+  out[i] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
 }
 
 // segments the fused reduce did not finish: empty (-> zeros) or spanning a row-group boundary (-> ordered sum of e_out rows)
@@ -487,7 +518,10 @@ static int fwd_stagger() {
 // debug hook (not part of the stable ABI): device buffer of 16 uint64 that CTA 0 of the forward kernel fills with per-phase cycles
 extern "C" void hgnn_tc_debug_set_fwd_phase_clock(void* dev_u64x16) { g_fwd_phase_clk = dev_u64x16; }
 
-extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t) { return 256; }
+extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges, int64_t n_nodes, int64_t latent) {
+  (void)n_edges;
+  return align_up((size_t)(n_nodes > 0 ? n_nodes : 1) * (size_t)latent * 2, 256) + 256;  // bf16 shadow copy of x
+}
 extern "C" size_t hgnn_tc_edge_stash_bytes(int64_t n_edges, int64_t latent) {
   return edge_stash_layout(n_edges > 0 ? n_edges : 1, (int)latent).total;
 }
@@ -495,13 +529,20 @@ extern "C" size_t hgnn_tc_edge_stash_bytes(int64_t n_edges, int64_t latent) {
 template <int L>
 static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src, const int32_t* dst,
                            const int32_t* perm, int64_t n_edges, float* e_out, const int32_t* rowptr, int64_t n_nodes, float* agg,
-                           uint8_t* stash, cudaStream_t st) {
+                           uint8_t* stash, void* ws, size_t ws_bytes, cudaStream_t st) {
+  uint16_t* xb16 = (uint16_t*)align_up((uintptr_t)ws, 256);
+  if (ws == nullptr || ws_bytes < ((uintptr_t)xb16 - (uintptr_t)ws) + (size_t)n_nodes * L * 2)
+    return fail(HGNN_ERR_WORKSPACE, "tc_edge_forward: workspace too small (hgnn_tc_edge_forward_workspace_bytes)");
+  {
+    const int64_t n8 = n_nodes * L / 8;
+    k_rows_to_bf16<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(x, n8, reinterpret_cast<uint4*>(xb16));
+  }
   size_t smem = Cfg<L>::SMEM;
   auto kern = k_tc_edge_fwd<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
   HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
   unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
-  kern<<<grid, TC_THREADS, smem, st>>>(*p, x, e, src, dst, perm, n_edges, e_out, rowptr, agg, stash, edge_stash_layout(n_edges, L),
+  kern<<<grid, TC_THREADS, smem, st>>>(*p, xb16, e, src, dst, perm, n_edges, e_out, rowptr, agg, stash, edge_stash_layout(n_edges, L),
                                         (unsigned long long*)g_fwd_phase_clk, fwd_stagger());
   if (agg) {
     int64_t threads = n_nodes * (L / 4);
@@ -516,7 +557,6 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
                                     const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges,
                                     int64_t n_nodes, float* e_out, float* agg, void* stash, void* ws, size_t ws_bytes,
                                     void* stream) {
-  (void)ws; (void)ws_bytes;
   HGNN_REQUIRE(agg == nullptr || (rowptr != nullptr && n_nodes > 0),
                "tc_edge_forward: the fused aggregate needs the destination-sorted plan (rowptr; perm unless the edges are stored sorted) and n_nodes");
   if (n_edges <= 0 && agg != nullptr) {
@@ -525,6 +565,7 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
   HGNN_REQUIRE(p != nullptr, "tc_edge_forward: params is NULL");
   if (n_edges <= 0) return HGNN_OK;
   HGNN_REQUIRE(x && e && src && dst && e_out, "tc_edge_forward: NULL pointer");
+  HGNN_REQUIRE(n_nodes > 0 && n_nodes < INT32_MAX, "tc_edge_forward: n_nodes (rows of x) is required");
   HGNN_REQUIRE(p->w1_packed && p->w2_packed && p->b1 && p->gamma1 && p->beta1 && p->b2 && p->gamma2 && p->beta2,
                "tc_edge_forward: NULL parameter pointer");
   HGNN_REQUIRE(n_edges < INT32_MAX, "tc_edge_forward: too many edges");
@@ -533,6 +574,6 @@ extern "C" int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x
                 "tc_edge_forward: latent %d / hidden %d / activations (%d, %d) not built (need latent in {64,128}, hidden = 2*latent, GELU/Tanh)",
                 p->latent, p->hidden, p->act_hidden, p->act_out);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)stash, st);
-  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)stash, st);
+  if (p->latent == 128) return launch_edge_fwd<128>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)stash, ws, ws_bytes, st);
+  return launch_edge_fwd<64>(p, x, e, src, dst, perm, n_edges, e_out, rowptr, n_nodes, agg, (uint8_t*)stash, ws, ws_bytes, st);
 }

@@ -199,19 +199,34 @@ __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
         {
           constexpr int CPR = C::SW / 4;                       // float4 chunks per staged row
           constexpr int ROWS_PER_WARP = TILE_M / (RF_THREADS / 32);
-#pragma unroll 4
-          for (int idx = lane; idx < ROWS_PER_WARP * CPR; idx += 32) {
-            const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
-            const int64_t j = (int64_t)tile * TILE_M + r;
-            if (j < A.rows) {
-              float4 y = *reinterpret_cast<const float4*>(region + (size_t)r * (C::SW * 4) + ((c4 ^ (r & 7)) << 4));
+          constexpr int ITERS = ROWS_PER_WARP * CPR / 32;
+          constexpr int BATCH = ITERS % 8 == 0 ? 8 : 4;
+          static_assert(ITERS % BATCH == 0, "store pass batches");
+          const bool has_skip = !RAW && A.skip != nullptr;
+#pragma unroll 1
+          for (int b0 = 0; b0 < ITERS; b0 += BATCH) {
+            float4 sk[BATCH];  // residual rows of the whole batch in flight before anything depends on them
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+              const int idx = lane + (b0 + u) * 32;
+              const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
+              const int64_t j = (int64_t)tile * TILE_M + r;
               const int sc = c4 * 4;
               const size_t g = (size_t)j * A.ld_out + A.col0 + (sc / PC) * NC + p * PC + (sc % PC);
-              if (!RAW && A.skip) {
-                const float4 sk = __ldg(reinterpret_cast<const float4*>(A.skip + g));
-                y.x += sk.x; y.y += sk.y; y.z += sk.z; y.w += sk.w;
+              sk[u] = (has_skip && j < A.rows) ? __ldg(reinterpret_cast<const float4*>(A.skip + g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+              const int idx = lane + (b0 + u) * 32;
+              const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
+              const int64_t j = (int64_t)tile * TILE_M + r;
+              if (j < A.rows) {
+                float4 y = *reinterpret_cast<const float4*>(region + (size_t)r * (C::SW * 4) + ((c4 ^ (r & 7)) << 4));
+                const int sc = c4 * 4;
+                const size_t g = (size_t)j * A.ld_out + A.col0 + (sc / PC) * NC + p * PC + (sc % PC);
+                y.x += sk[u].x; y.y += sk[u].y; y.z += sk[u].z; y.w += sk[u].w;
+                *reinterpret_cast<float4*>(A.out + g) = y;
               }
-              *reinterpret_cast<float4*>(A.out + g) = y;
             }
           }
         }

@@ -339,6 +339,23 @@ __device__ __forceinline__ void gather_a_block(uint8_t* __restrict__ blk, const 
   gather_store(blk, v);
 }
 
+// gather one K-block (64 bf16 columns starting at col0) of rows rowid[r] of a bf16 [rows, ld] matrix: 8 threads per 128 B row
+// piece, 32 rows per pass, 16 registers per thread — two K-blocks fit in flight where one fp32 block did. The chunks land in
+// the swizzled operand block as they are (no conversion).
+__device__ __forceinline__ void gather_load_bf16(uint4 (&v)[4], const uint16_t* __restrict__ base, int ld, const int* __restrict__ rowid, int col0) {
+  const int c16 = threadIdx.x & 7, rr = threadIdx.x >> 3;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int rid = rowid[p * 32 + rr];
+    v[p] = rid >= 0 ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)rid * ld + col0) + c16) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void gather_store_bf16(uint8_t* __restrict__ blk, const uint4 (&v)[4]) {
+  const int c16 = threadIdx.x & 7, rr = threadIdx.x >> 3;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) *reinterpret_cast<uint4*>(blk + sw128_off(p * 32 + rr, c16)) = v[p];
+}
+
 struct LnStat { float mean, rstd; };
 
 // Chan-combine the two half-row partials (n each): returns mean / rstd of the full row

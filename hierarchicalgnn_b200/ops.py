@@ -596,11 +596,12 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[
     a0 = None
     if save_image:  # the forward's stash for the backward pass: operand images + bf16 xhat's + rstd (1.5 KB/edge at L = 128)
         a0 = torch.empty(_lib.lib().hgnn_tc_edge_stash_bytes(n_edges, e.shape[1]), dtype=torch.uint8, device=e.device)
+    ws = _workspace(_lib.lib().hgnn_tc_edge_forward_workspace_bytes(n_edges, x.shape[0], e.shape[1]), e.device)
     with _timed("tc_edge_forward"):
         check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), _ptr(perm),
-                                              _ptr(rowptr), n_edges, x.shape[0], _ptr(out), _ptr(agg), _ptr(a0), None, 0,
+                                              _ptr(rowptr), n_edges, x.shape[0], _ptr(out), _ptr(agg), _ptr(a0), _ptr(ws), ws.numel(),
                                               _stream()), "tc_edge_forward")
-    _count(1 if agg is None else 3)  # edge kernel (+ aggregate fix-up and hub-segment kernels)
+    _count(2 if agg is None else 4)  # bf16 node-row copy, edge kernel (+ aggregate fix-up and hub-segment kernels)
     TC_CALLS["count"] += 1
     return a0
 

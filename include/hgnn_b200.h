@@ -231,7 +231,9 @@ int hgnn_tc_debug_wgrad(const float* A, const float* B, int64_t rows, int64_t ca
  * the normalised pre-affine activations of both LayerNorms as bf16 and the row rstd's (1.5 KB per edge at latent 128):
  * everything hgnn_tc_edge_backward and the weight-gradient GEMM need, so the backward recomputes nothing and
  * never gathers again. */
-size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges);
+/* ws (hgnn_tc_edge_forward_workspace_bytes) holds the bf16 shadow copy of x the call makes first: every node row is gathered
+ * ~2 E / N times, so it is converted once and gathered as 256 B rows (n_nodes = rows of x, always required). */
+size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges, int64_t n_nodes, int64_t latent);
 size_t hgnn_tc_edge_stash_bytes(int64_t n_edges, int64_t latent);
 int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const float* e, const int32_t* src,
                          const int32_t* dst, const int32_t* perm, const int32_t* rowptr, int64_t n_edges, int64_t n_nodes,
