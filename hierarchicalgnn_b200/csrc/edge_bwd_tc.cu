@@ -469,6 +469,8 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+#include "edge_bwd2_tc.cuh"
+
 // dvec1[3, H] = (db1, dgamma1, dbeta1), dvec2[3, L]: ordered sum over [grid * 4] partial vectors
 __global__ void k_colpart_reduce(const float* __restrict__ part, int n_part, float* __restrict__ dvec1, float* __restrict__ dvec2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -574,8 +576,29 @@ __global__ void __launch_bounds__(256) k_img_segment_reduce_long(const uint8_t* 
   }
 }
 
+// d bias1 = sum over edges of delta1 = sum over nodes of R_dst (every edge has exactly one destination): two-stage ordered
+// column sum of the fp32 [n, H] matrix (used with the two-CTA kernel, which does not accumulate d bias1 itself)
+__global__ void __launch_bounds__(H) k_rows_colsum_partial(const float* __restrict__ R, int64_t n_rows, float* __restrict__ part) {
+  const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = min(n_rows, (int64_t)blockIdx.x * per), r1 = min(n_rows, r0 + per);
+  const int c = threadIdx.x;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int64_t r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    s0 += R[r * H + c]; s1 += R[(r + 1) * H + c]; s2 += R[(r + 2) * H + c]; s3 += R[(r + 3) * H + c];
+  }
+  for (; r < r1; ++r) s0 += R[r * H + c];
+  part[(size_t)blockIdx.x * H + c] = (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(H) k_rows_colsum_final(const float* __restrict__ part, int n_part, float* __restrict__ out) {
+  float s = 0.f;
+  for (int p = 0; p < n_part; ++p) s += part[(size_t)p * H + threadIdx.x];
+  out[threadIdx.x] = s;
+}
+
 struct Layout {
-  size_t d1, d2, colpart, wgrad, r, r_img, x_img, total;
+  size_t d1, d2, colpart, wgrad, r, r_img, x_img, rsum, total;
+  int rsum_parts;
   int grid, tiles, node_tiles;
   size_t wgrad_bytes;
 };
@@ -584,7 +607,7 @@ Layout make_layout(int64_t n_edges, int64_t n_nodes) {
   Layout Y{};
   Y.tiles = (int)((n_edges + TILE_M - 1) / TILE_M);
   Y.node_tiles = (int)((n_nodes + TILE_M - 1) / TILE_M);
-  Y.grid = std::max(1, std::min(Y.tiles, num_sms()));
+  Y.grid = std::max(1, std::min(Y.tiles, 2 * num_sms()));  // sized for the two-CTA kernel; the one-CTA kernel uses half
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = align_up(off, 1024); off = o + b; return o; };
   Y.d1 = take((size_t)Y.tiles * NKB2 * A_BLK_BYTES);
@@ -597,6 +620,8 @@ Layout make_layout(int64_t n_edges, int64_t n_nodes) {
   Y.r = take((size_t)n_nodes * 2 * H * 4);                                // R_src [n, H] then R_dst [n, H], fp32
   Y.r_img = take((size_t)Y.node_tiles * (2 * H / KBLK) * A_BLK_BYTES);    // its bf16 tile image (left by the d(x) GEMM)
   Y.x_img = take((size_t)Y.node_tiles * (L / KBLK) * A_BLK_BYTES);        // bf16 tile image of x
+  Y.rsum_parts = 2 * num_sms();
+  Y.rsum = take((size_t)Y.rsum_parts * H * 4);
   Y.total = align_up(off, 1024);
   return Y;
 }
@@ -658,19 +683,32 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
     A.stagger_cycles = stagger;
   }
   HGNN_REQUIRE(p->act_hidden == HGNN_ACT_GELU && p->act_out == HGNN_ACT_TANH, "tc_edge_backward: only GELU / Tanh is built");
-  size_t smem = SMEM_BYTES;
-  auto kern = k_tc_edge_bwd<HGNN_ACT_GELU, HGNN_ACT_TANH>;
-  HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<Y.grid, NT, smem, st>>>(A);
+  static int two_cta = -1;  // HGNN_BWD_V2=0 selects the one-CTA-per-SM kernel (A/B comparisons)
+  if (two_cta < 0) { const char* e = getenv("HGNN_BWD_V2"); two_cta = e ? atoi(e) : 1; }
+  int grid = Y.grid;
+  if (two_cta) {
+    auto kern = v2::k_tc_edge_bwd2<HGNN_ACT_GELU, HGNN_ACT_TANH>;
+    HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::SMEM_BYTES2));
+    kern<<<grid, v2::NT2, v2::SMEM_BYTES2, st>>>(A);
+  } else {
+    grid = std::max(1, std::min(Y.tiles, num_sms()));
+    auto kern = k_tc_edge_bwd<HGNN_ACT_GELU, HGNN_ACT_TANH>;
+    HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    kern<<<grid, NT, SMEM_BYTES, st>>>(A);
+  }
   int rc = check_launch("tc_edge_backward");
   if (rc) return rc;
-  k_colpart_reduce<<<(PAR_FLOATS + 255) / 256, 256, 0, st>>>(A.colpart, Y.grid * 4, dvec1, dvec2);
+  k_colpart_reduce<<<(PAR_FLOATS + 255) / 256, 256, 0, st>>>(A.colpart, grid * 4, dvec1, dvec2);
 
   // ---- node level: R = per-node sums of delta1 by source / by destination ----
   float* R = (float*)(w + Y.r);
   const ImgPlan ps{src_rows, src_rowptr}, pd{dst_rows, dst_rowptr};
   k_img_segment_reduce<<<dim3((unsigned)((n_nodes + 7) / 8), 2), 256, 0, st>>>(A.d1_img, ps, pd, n_nodes, R);
   k_img_segment_reduce_long<<<dim3((unsigned)((n_nodes + 255) / 256), 2), 256, 0, st>>>(A.d1_img, ps, pd, n_nodes, R);
+  if (two_cta) {  // d bias1 = column sums of R_dst (written after k_colpart_reduce left zeros there)
+    k_rows_colsum_partial<<<Y.rsum_parts, H, 0, st>>>(R + (size_t)n_nodes * H, n_nodes, (float*)(w + Y.rsum));
+    k_rows_colsum_final<<<1, H, 0, st>>>((const float*)(w + Y.rsum), Y.rsum_parts, dvec1);
+  }
   rc = check_launch("tc_edge_backward (delta1 node sums)");
   if (rc) return rc;
   // d(x) = [R_src | R_dst] . [W1a ; W1b]  (wx_packed = image of [W1a^T | W1b^T] as an [L, 2H] Linear weight); the GEMM
