@@ -471,13 +471,33 @@ __global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
 
 #include "edge_bwd2_tc.cuh"
 
-// dvec1[3, H] = (db1, dgamma1, dbeta1), dvec2[3, L]: ordered sum over [grid * 4] partial vectors
-__global__ void k_colpart_reduce(const float* __restrict__ part, int n_part, float* __restrict__ dvec1, float* __restrict__ dvec2) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= PAR_FLOATS) return;
+// out[i] = sum_p part[p][i] for i < width, in a fixed order: a block owns 32 columns, its 8 warps sum 8 contiguous ranges of
+// the partial vectors in parallel, the 8 range sums are combined in range order. Columns >= split go to out1[i - split].
+__global__ void __launch_bounds__(256) k_ordered_colsum(const float* __restrict__ part, int n_part, int width, float* __restrict__ out0,
+                                                        int split, float* __restrict__ out1) {
+  __shared__ float s_sum[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int per = (n_part + 7) / 8, p0 = min(n_part, grp * per), p1 = min(n_part, p0 + per);
   float s = 0.f;
-  for (int p = 0; p < n_part; ++p) s += part[(size_t)p * PAR_FLOATS + i];
-  if (i < 3 * H) dvec1[i] = s; else dvec2[i - 3 * H] = s;
+  if (i < width) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // eight loads in flight; fixed association
+    int p = p0;
+    for (; p + 8 <= p1; p += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += part[(size_t)(p + k) * width + i];
+    }
+    for (; p < p1; ++p) a[0] += part[(size_t)p * width + i];
+    s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
+  s_sum[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && i < width) {
+    float t = s_sum[0][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) t += s_sum[g][lane];
+    if (i < split) out0[i] = t; else out1[i - split] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -489,38 +509,31 @@ __global__ void k_colpart_reduce(const float* __restrict__ part, int n_part, flo
 constexpr int IMG_LONG = 1024;
 struct ImgPlan { const int32_t* rows; const int32_t* rowptr; };  // rows == NULL: tile rows are already segment-sorted
 
-__device__ __forceinline__ void img_row_add(float (&acc)[8], const uint8_t* __restrict__ img, int p, int kb, int c16) {
-  const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)(p >> 7) * NKB2 + kb) * A_BLK_BYTES + sw128_off(p & 127, c16)));
-  float f[8];
-  unpack8(q, f);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] += f[i];
-}
-
-// rows [b0, b1) of one plan, summed in order into acc (whole warp; lane = chunk)
+// rows [b0, b1) of one plan, summed in order into acc (whole warp; lane = chunk): loads go out in batches of 8 (the last
+// one predicated, so a tail of a few rows costs one round trip, not one per row), the adds follow in row order
 __device__ __forceinline__ void img_rows_sum(float (&acc)[8], const uint8_t* __restrict__ img, const int32_t* __restrict__ rows,
                                              int b0, int b1, int lane) {
   const int kb = lane >> 3, c16 = lane & 7;
   for (int j0 = b0; j0 < b1; j0 += 32) {
     const int n = min(32, b1 - j0);
     const int mine = (lane < n) ? (rows ? __ldg(rows + j0 + lane) : j0 + lane) : 0;  // one coalesced look at the row list
-    int u = 0;
-    for (; u + 8 <= n; u += 8) {  // 8 independent 16-byte loads in flight per lane
+#pragma unroll 1
+    for (int u = 0; u < n; u += 8) {
       uint4 q[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int p = __shfl_sync(0xffffffffu, mine, u + k);
-        q[k] = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)(p >> 7) * NKB2 + kb) * A_BLK_BYTES + sw128_off(p & 127, c16)));
+        const int p = __shfl_sync(0xffffffffu, mine, (u + k) & 31);
+        q[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (u + k < n) q[k] = __ldg(reinterpret_cast<const uint4*>(img + ((size_t)(p >> 7) * NKB2 + kb) * A_BLK_BYTES + sw128_off(p & 127, c16)));
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float f[8];
         unpack8(q[k], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];  // + 0.0f for the predicated-off tail: exact
       }
     }
-    for (; u < n; ++u) img_row_add(acc, img, __shfl_sync(0xffffffffu, mine, u), kb, c16);
   }
 }
 
@@ -590,12 +603,6 @@ __global__ void __launch_bounds__(H) k_rows_colsum_partial(const float* __restri
   for (; r < r1; ++r) s0 += R[r * H + c];
   part[(size_t)blockIdx.x * H + c] = (s0 + s1) + (s2 + s3);
 }
-__global__ void __launch_bounds__(H) k_rows_colsum_final(const float* __restrict__ part, int n_part, float* __restrict__ out) {
-  float s = 0.f;
-  for (int p = 0; p < n_part; ++p) s += part[(size_t)p * H + threadIdx.x];
-  out[threadIdx.x] = s;
-}
-
 struct Layout {
   size_t d1, d2, colpart, wgrad, r, r_img, x_img, rsum, total;
   int rsum_parts;
@@ -698,7 +705,8 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   }
   int rc = check_launch("tc_edge_backward");
   if (rc) return rc;
-  k_colpart_reduce<<<(PAR_FLOATS + 255) / 256, 256, 0, st>>>(A.colpart, grid * 4, dvec1, dvec2);
+  // dvec1[3, H] = (db1, dgamma1, dbeta1), dvec2[3, L]: ordered sum over the [grid * 4] partial vectors of the kernel
+  k_ordered_colsum<<<(PAR_FLOATS + 31) / 32, 256, 0, st>>>(A.colpart, grid * 4, PAR_FLOATS, dvec1, 3 * H, dvec2);
 
   // ---- node level: R = per-node sums of delta1 by source / by destination ----
   float* R = (float*)(w + Y.r);
@@ -707,7 +715,7 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   k_img_segment_reduce_long<<<dim3((unsigned)((n_nodes + 255) / 256), 2), 256, 0, st>>>(A.d1_img, ps, pd, n_nodes, R);
   if (two_cta) {  // d bias1 = column sums of R_dst (written after k_colpart_reduce left zeros there)
     k_rows_colsum_partial<<<Y.rsum_parts, H, 0, st>>>(R + (size_t)n_nodes * H, n_nodes, (float*)(w + Y.rsum));
-    k_rows_colsum_final<<<1, H, 0, st>>>((const float*)(w + Y.rsum), Y.rsum_parts, dvec1);
+    k_ordered_colsum<<<H / 32, 256, 0, st>>>((const float*)(w + Y.rsum), Y.rsum_parts, H, dvec1, H, nullptr);
   }
   rc = check_launch("tc_edge_backward (delta1 node sums)");
   if (rc) return rc;
