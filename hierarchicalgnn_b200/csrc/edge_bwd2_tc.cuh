@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
   const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
   const uint32_t idesc_l = make_idesc(TILE_M, L);
 
+  // the fp32 upstream-gradient rows are read twice per tile (bf16 image, then the skip path of d(e)): keep / release in L2
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
   uint32_t acc_par = 0;
   int nx_eid = 0, nx_dst = 0;
   // every completion of a barrier is awaited exactly once, in order: thread 0 consumes B_FULL, thread 32 consumes B_FREE
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         for (int p = 0; p < 8; ++p) {
           const int r = (p0 + p) * 8 + g_rr;
           const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-          gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gv[p] = live ? ldg_f4_hint(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub, pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
           ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + g_sub)
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
     for (int k = 0; k < 8; ++k) {
       const int r = warp * 16 + k;
       const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-      float4 go = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 go = live ? ldg_f4_hint(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane, pol_drop) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (live && A.g_agg) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + lane);
         go.x += a.x; go.y += a.y; go.z += a.z; go.w += a.w;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         for (int k = 0; k < 8; ++k) {
           const int r = warp * 16 + 8 + k;
           const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-          float4 go = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 go = live ? ldg_f4_hint(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane, pol_drop) : make_float4(0.f, 0.f, 0.f, 0.f);
           if (live && A.g_agg) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + lane);
             go.x += a.x; go.y += a.y; go.z += a.z; go.w += a.w;

@@ -107,6 +107,9 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const uint16_t* __restrict__ xb16, const fl
   uint4* const xh2_st = stash ? reinterpret_cast<uint4*>(stash + SL.xh2) : nullptr;
   float* const rstd_st = stash ? reinterpret_cast<float*>(stash + SL.rstd) : nullptr;
 
+  // the fp32 edge rows are read twice per tile (GEMM1 operand, then the skip connection) with the tile's whole stash
+  // streaming out in between: keep them in L2 after the first read, release them on the second
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
   uint32_t it1 = 0, it2 = 0, acc_par = 0;
   const int q = warp & 3, hsel = warp >> 2;
   const int row = q * 32 + lane;
@@ -157,7 +160,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const uint16_t* __restrict__ xb16, const fl
     auto blk_rows = [&](int i) { return blk_seg(i) == 0 ? s_src : s_dst; };
     float4 pre[8];
     uint4 xv[2][4];
-    gather_load(pre, e, L, s_eid, 0);
+    gather_load_hint(pre, e, L, s_eid, 0, pol_keep);
     if constexpr (KPS == 1) gather_load_bf16(xv[0], xb16, L, blk_rows(KPS), 0);
 #pragma unroll
     for (int i = 0; i < C::NKB1; ++i, ++it1) {
@@ -171,7 +174,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const uint16_t* __restrict__ xb16, const fl
       }
       if (i < KPS) {  // the edge-latent K-blocks are also left in HBM as the weight-gradient operand (x columns: handled per node)
         gather_store(stage, pre, a0_img ? a0_img + ((size_t)tile * KPS + i) * A_BLK_BYTES : nullptr);
-        if (i + 1 < KPS) gather_load(pre, e, L, s_eid, (i + 1) * KBLK);
+        if (i + 1 < KPS) gather_load_hint(pre, e, L, s_eid, (i + 1) * KBLK, pol_keep);
       } else {
         gather_store_bf16(stage, xv[(i - KPS) & 1]);
       }
@@ -314,7 +317,7 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const uint16_t* __restrict__ xb16, const fl
         for (int u = 0; u < BATCH; ++u) {  // padding rows carry the (valid) id of the last edge: load unconditionally
           const int idx = lane + (b0 + u) * 32;
           const int r = warp * ROWS_PER_WARP + idx / CPR, c4 = idx % CPR;
-          sk[u] = __ldg(reinterpret_cast<const float4*>(e + (size_t)s_eid[r] * L + c4 * 4));
+          sk[u] = ldg_f4_hint(reinterpret_cast<const float4*>(e + (size_t)s_eid[r] * L + c4 * 4), pol_drop);
         }
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {

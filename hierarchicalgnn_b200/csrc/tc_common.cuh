@@ -55,6 +55,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// L2 residency hints for rows that are read twice per tile with ~100 MB of streaming traffic in between (the fp32 skip
+// rows): first read evict_last (stay), second read evict_first (done with it)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+  return v;
+}
 // generic-proxy smem writes -> visible to the async proxy (tensor core / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -317,6 +331,16 @@ __device__ __forceinline__ void gather_load(float4 (&v)[8], const float* __restr
   for (int p = 0; p < 8; ++p) {  // a negative row id marks a padding row of the last tile: zeros (also in the saved image)
     const int rid = rowid[p * 16 + rr];
     v[p] = rid >= 0 ? __ldg(reinterpret_cast<const float4*>(base + (size_t)rid * ld + col0) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// same, with an L2 cache-policy hint on the loads
+__device__ __forceinline__ void gather_load_hint(float4 (&v)[8], const float* __restrict__ base, int ld, const int* __restrict__ rowid, int col0,
+                                                 uint64_t pol) {
+  const int sub = threadIdx.x & 15, rr = threadIdx.x >> 4;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int rid = rowid[p * 16 + rr];
+    v[p] = rid >= 0 ? ldg_f4_hint(reinterpret_cast<const float4*>(base + (size_t)rid * ld + col0) + sub, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 // gimg (optional): the same swizzled bf16 block is also left in HBM — the backward pass and the weight-gradient GEMM

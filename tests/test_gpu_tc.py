@@ -194,6 +194,58 @@ def test_tc_edge_backward_vs_oracle(E, N):
     torch.testing.assert_close(ed.grad.cpu(), ge, rtol=5e-2, atol=5e-3)
 
 
+@pytest.mark.parametrize("path", ["rows_in_edge_order", "rows_destination_sorted"])
+def test_tc_edge_backward_node_level_adjoint_with_hubs(path):
+    """The node part of the first layer's adjoint is formed per node from segment sums of the delta1 tile image
+    (hgnn_tc_edge_backward): hub nodes on BOTH sides (> 1024 rows: the per-CTA long-segment kernel), nodes without edges,
+    an unsorted duplicate-containing graph, through both row orders of the forward (edge-id order for .fused(),
+    the by-destination plan's order for .edge_step()). Gradients within the bf16 tolerance of the fp64 oracle."""
+    from hierarchicalgnn_b200 import ops
+    L, E, N = 128, 6000, 60
+    net, x, e, graph = _edge_case(L, E, N, seed=77)
+    graph[0, 100:2700] = 3        # source hub: 2600 rows
+    graph[1, 2000:4600] = 7       # destination hub: 2600 rows (overlapping the source hub's rows)
+    graph[:, 5000:5100] = graph[:, 4900:5000]  # duplicates
+    graph[graph == 11] = 12       # node 11 has no edges at all
+    g = torch.Generator().manual_seed(4)
+    cot = torch.randn(E, L, generator=g)
+    cot_a = torch.randn(N, L, generator=g) if path == "rows_destination_sorted" else None
+    # oracle: d(sum(e' * cot) + sum(scatter_add(e', dst) * cot_a)) = backward of e' with cotangent cot + cot_a[dst]
+    cot_eff = cot if cot_a is None else cot + cot_a[graph[1]]
+    gx, ge, gp = _emulated_grads(net, x, e, graph, cot_eff, L)
+    net.to(DEV)
+    xd, ed, gd = x.to(DEV).requires_grad_(True), e.to(DEV).requires_grad_(True), graph.to(DEV)
+    old = ops.set_precision("bf16")
+    try:
+        n0 = ops.TC_CALLS["count"]
+        ps, pd = ops.plan_for(gd[0], N), ops.plan_for(gd[1], N)
+        assert not pd.is_identity()
+        if cot_a is None:
+            out = net.fused([xd, xd, ed], [ps, pd, None], skip=2)
+            (out * cot.to(DEV)).sum().backward()
+        else:
+            out, agg = net.edge_step(xd, ed, ps, pd)
+            assert agg is not None
+            ((out * cot.to(DEV)).sum() + (agg * cot_a.to(DEV)).sum()).backward()
+        assert ops.TC_CALLS["count"] == n0 + 2
+    finally:
+        ops.set_precision(old)
+
+    def rel(a, b):
+        return float((a - b).norm() / b.norm().clamp(min=1e-12))
+    assert rel(xd.grad.cpu(), gx) < 1.5e-2
+    assert rel(xd.grad.cpu()[[3, 7]], gx[[3, 7]]) < 1.5e-2          # the hubs themselves
+    assert float(xd.grad[11].abs().max()) == 0.0                    # isolated node: exact zero
+    assert rel(ed.grad.cpu(), ge) < 1.5e-2
+    for k, prm in {"0.weight": net[0].weight, "0.bias": net[0].bias, "1.weight": net[1].weight, "1.bias": net[1].bias,
+                   "3.weight": net[3].weight, "4.bias": net[4].bias}.items():
+        assert rel(prm.grad.cpu(), gp[k]) < 1.5e-2, k
+    # the three column blocks of dW1 come from different kernels (node level: x[src], x[dst]; edge level: e)
+    for blk in range(3):
+        sl = slice(blk * L, (blk + 1) * L)
+        assert rel(net[0].weight.grad.cpu()[:, sl], gp["0.weight"][:, sl]) < 1.5e-2, blk
+
+
 def test_tc_edge_backward_is_deterministic():
     from hierarchicalgnn_b200 import ops
     L, E, N = 128, 3000, 100
