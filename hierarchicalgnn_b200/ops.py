@@ -85,7 +85,14 @@ def compute_dtype(module=None) -> str:
     return "bf16" if (TC_CALLS["count"] or TC_ROW_CALLS["count"]) else "f32"
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (every launch goes there). The raw getter avoids
+    building a torch.cuda.Stream object per call (18 us -> <1 us: ~1300 calls per BC-HGNN step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -576,8 +583,9 @@ def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, stash: Tenso
                                        _ptr(dst_rowptr), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_x),
                                        _ptr(dW1), _ptr(dW2), _ptr(dv1), _ptr(dv2), _ptr(ws), ws.numel(), _stream()),
               "tc_edge_backward")
-    # data-gradient kernel, column-sum reduce, delta1 node sums (2), d(x) GEMM, x image, 2 x (weight-gradient GEMM + ordered reduce)
-    _count(10)
+    # data-gradient kernel, column-sum reduce, delta1 node sums (2) + their column sum (2), d(x) GEMM, x image,
+    # 2 x (weight-gradient GEMM + ordered reduce)
+    _count(12)
     TC_CALLS["count"] += 1
     return d_x, d_e, dW1, dW2, dv1, dv2
 
