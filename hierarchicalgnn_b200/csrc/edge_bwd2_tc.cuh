@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
       free_wait(0); fill(6);
       free_wait(1); fill(7);
     }
-    float4 skipg[8];  // fp32 upstream gradient (skip path of d(e)) of this lane's first 8 output rows, in flight under GEMM4
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    float4 skipg[16];  // fp32 upstream gradient (skip path of d(e)) of this lane's 16 output rows, in flight under GEMM4
+#pragma unroll         // (the adjoint passes' registers are dead here: 64 registers of loads cost nothing)
+    for (int k = 0; k < 16; ++k) {
       const int r = warp * 16 + k;
       const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
       float4 go = live ? ldg_f4_hint(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane, pol_drop) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -381,28 +381,12 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
     tc_fence_before();
     __syncthreads();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {  // 16 rows per warp, one float4 chunk per lane; skip connection: d(e) += gout (fp32)
-      if (half == 1) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int r = warp * 16 + 8 + k;
-          const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-          float4 go = live ? ldg_f4_hint(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane, pol_drop) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live && A.g_agg) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + lane);
-            go.x += a.x; go.y += a.y; go.z += a.z; go.w += a.w;
-          }
-          skipg[k] = go;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int r = warp * 16 + half * 8 + k, c4 = lane;
-        if ((int64_t)tile * TILE_M + r < A.n_edges) {
-          float4 y = *reinterpret_cast<const float4*>(sm + A2_OFF2 + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
-          y.x += skipg[k].x; y.y += skipg[k].y; y.z += skipg[k].z; y.w += skipg[k].w;
-          *reinterpret_cast<float4*>(A.d_e + (size_t)s_eid[r] * L + c4 * 4) = y;
-        }
+    for (int k = 0; k < 16; ++k) {  // 16 rows per warp, one float4 chunk per lane; skip connection: d(e) += gout (fp32)
+      const int r = warp * 16 + k, c4 = lane;
+      if ((int64_t)tile * TILE_M + r < A.n_edges) {
+        float4 y = *reinterpret_cast<const float4*>(sm + A2_OFF2 + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
+        y.x += skipg[k].x; y.y += skipg[k].y; y.z += skipg[k].z; y.w += skipg[k].w;
+        *reinterpret_cast<float4*>(A.d_e + (size_t)s_eid[r] * L + c4 * 4) = y;
       }
     }
     fence_proxy_async();  // staging (generic proxy) precedes the next tile's bulk store from these bytes
