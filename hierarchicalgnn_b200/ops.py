@@ -603,7 +603,7 @@ def tc_edge_forward_raw(meta: MlpMeta, segs, layers, out: Tensor, agg: Optional[
         perm, rowptr = (None if plan_d.is_identity() else plan_d.perm), plan_d.rowptr
     a0 = None
     if save_image:  # the forward's stash for the backward pass: operand images + bf16 xhat's + rstd (1.5 KB/edge at L = 128)
-        a0 = torch.empty(_lib.lib().hgnn_tc_edge_stash_bytes(n_edges, e.shape[1]), dtype=torch.uint8, device=e.device)
+        a0 = _workspace(_lib.lib().hgnn_tc_edge_stash_bytes(n_edges, e.shape[1]), e.device)
     ws = _workspace(_lib.lib().hgnn_tc_edge_forward_workspace_bytes(n_edges, x.shape[0], e.shape[1]), e.device)
     with _timed("tc_edge_forward"):
         check(_lib.lib().hgnn_tc_edge_forward(C.byref(p), _ptr(x), _ptr(e), _ptr(plan_s.keys32), _ptr(plan_d.keys32), _ptr(perm),

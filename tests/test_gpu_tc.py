@@ -246,6 +246,40 @@ def test_tc_edge_backward_node_level_adjoint_with_hubs(path):
         assert rel(net[0].weight.grad.cpu()[:, sl], gp["0.weight"][:, sl]) < 1.5e-2, blk
 
 
+@pytest.mark.parametrize("E,N", [(1000, 90), (129, 5), (4097, 700)])
+def test_tc_edge_step_stays_inside_its_workspaces(monkeypatch, E, N):
+    """Every caller-owned scratch buffer of the tensor-core edge step (forward workspace, stash, backward workspace) is
+    handed out with 4 KB guard bands on both sides; the kernels must leave the guards untouched (ragged last tiles, node
+    counts that are not multiples of 128)."""
+    from hierarchicalgnn_b200 import ops
+    L = 128
+    net, x, e, graph = _edge_case(L, E, N, seed=E + 1)
+    net.to(DEV)
+    parents = []
+    G = 4096
+
+    def guarded(nbytes, device):
+        n = max(int(nbytes), 256)
+        parent = torch.full((n + 2 * G,), 0xA5, dtype=torch.uint8, device=device)
+        parents.append((parent, n))
+        return parent[G:G + n]
+    monkeypatch.setattr(ops, "_workspace", guarded)
+    xd, ed, gd = x.to(DEV).requires_grad_(True), e.to(DEV).requires_grad_(True), graph.to(DEV)
+    old = ops.set_precision("bf16")
+    try:
+        ps, pd = ops.plan_for(gd[0], N), ops.plan_for(gd[1], N)
+        out, agg = net.edge_step(xd, ed, ps, pd)
+        (out.sum() + agg.sum()).backward()
+        out2 = net.fused([xd, xd, ed], [ps, pd, None], skip=2)
+        out2.square().sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_precision(old)
+    assert len(parents) >= 6  # forward workspace + stash + backward workspace, twice
+    for parent, n in parents:
+        assert bool((parent[:G] == 0xA5).all()) and bool((parent[G + n:] == 0xA5).all()), f"guard band of a {n}-byte buffer was written"
+
+
 def test_tc_edge_backward_is_deterministic():
     from hierarchicalgnn_b200 import ops
     L, E, N = 128, 3000, 100
