@@ -102,7 +102,7 @@ for name, npart, fpt in [("1 GeV", 1200, 4.0), ("full pile-up", 12000, 11.5)]:
     def fb():
         ec.zero_grad(set_to_none=True)
         torch.nn.functional.binary_cross_entropy(ec(x.clone(), gph), y).backward()
-    t = timeit(fb, n=3, warm=2)
+    t = timeit(fb, n=5, warm=4)
     print(f"| EC-IN (14 cells, latent 128) | {name}: N={x.shape[0]:,} E_d={Ed:,} | {t:.2f} | {Ed * 14 / t / 1e3:.1f} |")
     del ec
     bc = model_selector("4", dict(latent=128)); kaiming_init(bc); bc.to(DEV).train()
@@ -111,7 +111,7 @@ for name, npart, fpt in [("1 GeV", 1200, 4.0), ("full pile-up", 12000, 11.5)]:
         bc.zero_grad(set_to_none=True)
         bg, sc, emb = bc(x.clone(), gph, clusters=clusters)
         (sc.sum() + emb.sum()).backward()
-    t = timeit(fb2, n=3, warm=2)
+    t = timeit(fb2, n=5, warm=4)
     print(f"| BC-HGNN-GMM (6+6 cells, latent 128, S={npart:,}) | {name}: N={x.shape[0]:,} E_d={Ed:,} | {t:.2f} | {Ed * 12 / t / 1e3:.1f} |")
     del bc
     torch.cuda.empty_cache()
