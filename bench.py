@@ -343,7 +343,9 @@ def run_gpu(args):
             e_d = e_b.detach().requires_grad_(True)
             plans = GraphPlans(g_d, N, N)  # a new graph arrives with every event: plan build is inside the step
             e2, agg, grads = step(n_d, e_d, plans)
-            metric = torch.stack([e2.sum() + agg.sum(), grads[1].abs().sum()])
+            # detached: out_host lives across steps, and an in-place copy of a tensor with history would chain every step's
+            # autograd graph (and what its nodes hold) behind it
+            metric = torch.stack([e2.detach().sum() + agg.detach().sum(), grads[1].abs().sum()])
             out_host.copy_(metric, non_blocking=True)
 
         if args.e2e_mode == "serial":

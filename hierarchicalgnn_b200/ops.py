@@ -112,6 +112,25 @@ def _ptr(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def _save_with_scratch(ctx, tensors, scratch: Optional[Tensor]):
+    """save_for_backward(*tensors [, scratch]). Kernel scratch a backward needs (the edge-step stash, tile images) goes
+    through autograd's saved-tensor mechanism rather than a ctx attribute, so it is released with the graph's buffers
+    right after the backward has run even when something — a logged loss, an in-place copy of a metric — keeps the
+    graph NODES alive (1.5 KB per edge per cell otherwise stays pinned for as long as those references live)."""
+    ctx.has_scratch = scratch is not None
+    if scratch is not None:
+        ctx.save_for_backward(*tensors, scratch)
+    else:
+        ctx.save_for_backward(*tensors)
+
+
+def _saved_and_scratch(ctx):
+    saved = ctx.saved_tensors
+    if ctx.has_scratch:
+        return saved[:-1], saved[-1]
+    return saved, None
+
+
 def _workspace(nbytes: int, device) -> Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -392,28 +411,28 @@ class _FusedMLP(torch.autograd.Function):
         params = [_f32(t) for t in tensors[n_seg:]]
         d, rows, layers = _build_desc(meta, segs, params)
         out = torch.empty((rows, layers[-1][0].shape[0]), dtype=torch.float32, device=segs[0].device)
-        ctx.a0 = None
+        stash = None
         if rows and meta.tc_pack is not None:
-            ctx.a0 = tc_edge_forward_raw(meta, segs, layers, out,
-                                         save_image=any(ctx.needs_input_grad[2:]) and tc_backward_available(meta, layers))
+            stash = tc_edge_forward_raw(meta, segs, layers, out,
+                                        save_image=any(ctx.needs_input_grad[2:]) and tc_backward_available(meta, layers))
         elif rows:
             with _timed("mlp_forward"):
                 check(_lib.lib().hgnn_mlp_forward(C.byref(d), rows, _ptr(out), _stream()), "mlp_forward")
             _count()
         ctx.meta, ctx.n_seg = meta, n_seg
-        ctx.save_for_backward(*segs, *params)
+        _save_with_scratch(ctx, [*segs, *params], stash)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         meta, n_seg = ctx.meta, ctx.n_seg
-        saved = ctx.saved_tensors
+        saved, stash = _saved_and_scratch(ctx)
         segs, params = list(saved[:n_seg]), list(saved[n_seg:])
         d, rows, layers = _build_desc(meta, segs, params)
         dev = segs[0].device
         gout = _f32(gout)
-        if rows and tc_backward_available(meta, layers) and ctx.a0 is not None:
-            d_x, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, gout, ctx.a0)
+        if rows and tc_backward_available(meta, layers) and stash is not None:
+            d_x, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, gout, stash)
             need = ctx.needs_input_grad[2:]
             # segments 0 and 1 are the same tensor (tc path precondition): its whole gradient goes out through segment 0
             return (None, None, d_x if need[0] else None, None, d_e if need[2] else None,
@@ -632,21 +651,20 @@ class _TcEdgeStepAgg(torch.autograd.Function):
         # one launch: edge MLP + skip + destination-sorted reduce (+ the bf16 input image the backward will stream)
         a0 = tc_edge_forward_raw(meta, segs, layers, out, agg, save_image=need_bwd)
         ctx.meta = meta
-        ctx.a0 = a0
-        ctx.save_for_backward(segs[0], segs[2], *ps)
+        _save_with_scratch(ctx, [segs[0], segs[2], *ps], a0)
         return out, agg
 
     @staticmethod
     def backward(ctx, g_out, g_agg):
         meta = ctx.meta
-        saved = ctx.saved_tensors
+        saved, stash = _saved_and_scratch(ctx)
         x, e, ps = saved[0], saved[1], list(saved[2:])
         segs = [x, x, e]
         d, rows, layers = _build_desc(meta, segs, ps)
         g_out = torch.zeros_like(e) if g_out is None else _f32(g_out)
         g_agg = None if g_agg is None else _f32(g_agg)
         plan_d = meta.seg_plans[1]
-        d_x, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, ctx.a0,
+        d_x, d_e, dW1, dW2, dv1, dv2 = tc_edge_backward_raw(meta, segs, layers, g_out, stash,
                                                             None if plan_d.is_identity() else plan_d.perm, g_agg, dst_sorted=True)
         gx = d_x if ctx.needs_input_grad[1] else None
         return (None, gx, d_e if ctx.needs_input_grad[2] else None, dW1, dv1[0], dv1[1], dv1[2], dW2, dv2[0], dv2[1], dv2[2])
@@ -847,16 +865,16 @@ class _TcRowLayer(torch.autograd.Function):
                 check(_lib.lib().hgnn_tc_row_forward(C.byref(d), rows, _ptr(out), _ptr(a_img), _stream()), "tc_row_forward")
             _count()
             TC_ROW_CALLS["count"] += 1
-        ctx.meta, ctx.n_seg, ctx.rows, ctx.a_img = meta, n_seg, rows, a_img
+        ctx.meta, ctx.n_seg, ctx.rows = meta, n_seg, rows
         ctx.widths = [t.shape[1] for t in segs]
         ctx.seg_rows = [t.shape[0] for t in segs]
-        ctx.save_for_backward(W, b, g, be)
+        _save_with_scratch(ctx, [W, b, g, be], a_img)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         meta, n_seg, rows = ctx.meta, ctx.n_seg, ctx.rows
-        W, b, g, be = ctx.saved_tensors
+        (W, b, g, be), a_img = _saved_and_scratch(ctx)
         gout = _f32(gout)
         dev = W.device
         N, K = W.shape
@@ -871,7 +889,7 @@ class _TcRowLayer(torch.autograd.Function):
         if rows:
             ws = _workspace(L_.hgnn_tc_row_backward_workspace_bytes(rows, K, N), dev)
             with _timed("tc_row_backward"):
-                check(L_.hgnn_tc_row_backward(C.byref(d), _ptr(wt_packed), _ptr(ctx.a_img), rows, _ptr(gout), _ptr(d_in), _ptr(dW),
+                check(L_.hgnn_tc_row_backward(C.byref(d), _ptr(wt_packed), _ptr(a_img), rows, _ptr(gout), _ptr(d_in), _ptr(dW),
                                               _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "tc_row_backward")
             _count(4)  # data-gradient kernel, column-sum reduce, weight-gradient GEMM, its ordered reduce
             TC_ROW_CALLS["count"] += 1
@@ -978,16 +996,16 @@ class _TcSplitLayer(torch.autograd.Function):
                       "ln_act_forward")
             _count(len(fwd_chunks) + 1)
             TC_ROW_CALLS["count"] += 1
-        ctx.meta, ctx.n_seg, ctx.rows, ctx.a_img = meta, n_seg, rows, a_img
+        ctx.meta, ctx.n_seg, ctx.rows = meta, n_seg, rows
         ctx.widths = [t.shape[1] for t in segs]
         ctx.seg_rows = [t.shape[0] for t in segs]
-        ctx.save_for_backward(W, g, be, h)
+        _save_with_scratch(ctx, [W, g, be, h], a_img)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         meta, n_seg, rows = ctx.meta, ctx.n_seg, ctx.rows
-        W, g, be, h = ctx.saved_tensors
+        (W, g, be, h), a_img = _saved_and_scratch(ctx)
         gout = _f32(gout)
         dev = W.device
         N, K = W.shape
@@ -1006,7 +1024,7 @@ class _TcSplitLayer(torch.autograd.Function):
                 for i, (c0, n, img) in enumerate(bwd_chunks):  # d_in[:, c0 : c0 + n] = delta . W[:, c0 : c0 + n]
                     d = _gemm_desc([delta], [None], n, img, None)
                     check(L_.hgnn_tc_gemm(C.byref(d), rows, _ptr(d_in), K, c0, _ptr(d_img) if i == 0 else None, _stream()), "tc_gemm")
-                check(L_.hgnn_tc_wgrad(_ptr(d_img), N, _ptr(ctx.a_img), K, rows, _ptr(dW), _ptr(ws), ws.numel(), _stream()), "tc_wgrad")
+                check(L_.hgnn_tc_wgrad(_ptr(d_img), N, _ptr(a_img), K, rows, _ptr(dW), _ptr(ws), ws.numel(), _stream()), "tc_wgrad")
             _count(2 + len(bwd_chunks) + 2 * ((N // 128 or 1) * (K // 128 or 1) // 4 + 1))
             TC_ROW_CALLS["count"] += 1
         else:

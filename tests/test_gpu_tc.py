@@ -280,6 +280,32 @@ def test_tc_edge_step_stays_inside_its_workspaces(monkeypatch, E, N):
         assert bool((parent[:G] == 0xA5).all()) and bool((parent[G + n:] == 0xA5).all()), f"guard band of a {n}-byte buffer was written"
 
 
+def test_tc_edge_step_stash_is_released_by_the_backward_not_by_the_graph():
+    """The forward's stash (1.5 KB per edge) is an autograd saved tensor: it is freed when the backward has consumed it, even
+    while the outputs — and with them the graph nodes — are still referenced (a logged loss, a metric copied in place)."""
+    from hierarchicalgnn_b200 import ops, _lib
+    L, E, N = 128, 200_000, 20_000
+    net, x, e, graph = _edge_case(L, E, N, seed=3)
+    net.to(DEV)
+    xd, ed, gd = x.to(DEV).requires_grad_(True), e.to(DEV).requires_grad_(True), graph.to(DEV)
+    stash_bytes = _lib.lib().hgnn_tc_edge_stash_bytes(E, L)
+    old = ops.set_precision("bf16")
+    try:
+        ps, pd = ops.plan_for(gd[0], N), ops.plan_for(gd[1], N)
+        out, agg = net.edge_step(xd, ed, ps, pd)
+        loss = out.sum() + agg.sum()
+        torch.cuda.synchronize()
+        before = torch.cuda.memory_allocated()
+        grads = torch.autograd.grad(loss, [xd, ed])
+        del grads
+        torch.cuda.synchronize()
+        after = torch.cuda.memory_allocated()
+    finally:
+        ops.set_precision(old)
+    assert loss.grad_fn is not None and out.grad_fn is not None  # the graph nodes are still alive
+    assert before - after >= 0.9 * stash_bytes, (before, after, stash_bytes)
+
+
 def test_tc_edge_backward_is_deterministic():
     from hierarchicalgnn_b200 import ops
     L, E, N = 128, 3000, 100
