@@ -136,20 +136,27 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
     }
     const float rstd1 = __ldg(A.rstd + (size_t)tile * 2 * TILE_M + row);
     const float rstd2 = __ldg(A.rstd + (size_t)tile * 2 * TILE_M + TILE_M + row);
+    const uint4* xh2 = A.xh2 + ((size_t)tile * (L / 8) + hs * 8) * TILE_M + row;  // this thread's 8 x 8 bf16 of xhat2
+    uint4 xq2_nx[4];  // first chunk in flight across the barrier
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xq2_nx[j] = __ldg(xh2 + (size_t)j * TILE_M);
     __syncthreads();
     if (tid < TILE_M && has_next) nx_dst = A.dst[nx_eid];
     MARK(1);
 
     // ================= EPI-B: d(y2) = gout * act'(y2) (parked in TMEM), LayerNorm-2 adjoint -> delta2 (in place over gout) =====
     {
-      const uint4* xh2 = A.xh2 + ((size_t)tile * (L / 8) + hs * 8) * TILE_M + row;  // this thread's 8 x 8 bf16 of xhat2
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         const int cb = hs * 64 + ch * 32;
         uint4 xq[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) xq[j] = __ldg(xh2 + (size_t)(ch * 4 + j) * TILE_M);
+        for (int j = 0; j < 4; ++j) xq[j] = xq2_nx[j];
+        if (ch == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xq2_nx[j] = __ldg(xh2 + (size_t)(4 + j) * TILE_M);
+        }
         float u[32], tmp[32];
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -240,6 +247,11 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
       free_wait(0); fill(4);
       free_wait(1); fill(5);
     }
+    // stashed xhat1 of this thread's first 32 hidden columns: in flight under GEMM3
+    const uint4* xh1 = A.xh1 + ((size_t)tile * (H / 8) + hs * 16) * TILE_M + row;  // this thread's 16 x 8 bf16 of xhat1
+    uint4 xq_nx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xq_nx[j] = __ldg(xh1 + (size_t)j * TILE_M);
     if (warp == 0) mbar_wait(BAR(ACC), acc_par);
     __syncthreads();
     acc_par ^= 1;
@@ -248,7 +260,6 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
 
     // ================= EPI-C: d(y1) = dG * act'(y1) (parked in place), LayerNorm-1 adjoint -> delta1 image =================
     {
-      const uint4* xh1 = A.xh1 + ((size_t)tile * (H / 8) + hs * 16) * TILE_M + row;  // this thread's 16 x 8 bf16 of xhat1
       const uint32_t t_dg = t_lane + hs * 128;
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -256,7 +267,11 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         const int cb = hs * 128 + ch * 32;
         uint4 xq[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) xq[j] = __ldg(xh1 + (size_t)(ch * 4 + j) * TILE_M);
+        for (int j = 0; j < 4; ++j) xq[j] = xq_nx[j];
+        if (ch + 1 < 4) {  // next chunk's xhat1 while this one is processed
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xq_nx[j] = __ldg(xh1 + (size_t)((ch + 1) * 4 + j) * TILE_M);
+        }
         float u[32], tmp[32];
         tmem_ld32(t_dg + ch * 32, u);
 #pragma unroll
