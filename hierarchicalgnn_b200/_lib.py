@@ -113,9 +113,9 @@ SIGNATURES = {
     "hgnn_tc_edge_forward_workspace_bytes": (sz, [i64, i64, i64]),
     "hgnn_tc_edge_backward_workspace_bytes": (sz, [i64, i64]),
     # (p, w1t, w2t, wx, stash, x, n_nodes, dst, perm, src_rows, src_rowptr, dst_rows, dst_rowptr, n_edges, g_e, g_agg, d_e, d_x,
-    #  dW1, dW2, dv1, dv2, ws, ws_bytes, stream)
+    #  dW1, dW2, dv1, dv2, ws, ws_bytes, stream, aux_stream)
     "hgnn_tc_edge_backward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp,
-                                        vp, vp, vp, vp, vp, sz, vp]),
+                                        vp, vp, vp, vp, vp, sz, vp, vp]),
     "hgnn_tc_debug_set_phase_clock": (None, [vp]),
     "hgnn_tc_debug_set_fwd_phase_clock": (None, [vp]),
     "hgnn_narrow_in_supported": (C.c_int, [C.POINTER(MlpDesc)]),

@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(H) k_rows_colsum_partial(const float* __restri
   part[(size_t)blockIdx.x * H + c] = (s0 + s1) + (s2 + s3);
 }
 struct Layout {
-  size_t d1, d2, colpart, wgrad, r, r_img, x_img, rsum, total;
+  size_t d1, d2, colpart, wgrad, wgrad_node, r, r_img, x_img, rsum, total;
   int rsum_parts;
   int grid, tiles, node_tiles;
   size_t wgrad_bytes;
@@ -624,6 +624,7 @@ Layout make_layout(int64_t n_edges, int64_t n_nodes) {
   int splits = std::max(hgnn::tc::wgrad_splits(2, Y.tiles), hgnn::tc::wgrad_splits(2, std::max(1, Y.node_tiles)));
   Y.wgrad_bytes = (size_t)2 * align_up((size_t)splits * 256 * 128 * 4, 256) + 256;
   Y.wgrad = take(Y.wgrad_bytes);
+  Y.wgrad_node = take(Y.wgrad_bytes);  // the node-level launch may run concurrently with the edge-level one (aux stream)
   Y.r = take((size_t)n_nodes * 2 * H * 4);                                // R_src [n, H] then R_dst [n, H], fp32
   Y.r_img = take((size_t)Y.node_tiles * (2 * H / KBLK) * A_BLK_BYTES);    // its bf16 tile image (left by the d(x) GEMM)
   Y.x_img = take((size_t)Y.node_tiles * (L / KBLK) * A_BLK_BYTES);        // bf16 tile image of x
@@ -648,7 +649,7 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
                                      const int32_t* dst, const int32_t* perm, const int32_t* src_rows, const int32_t* src_rowptr,
                                      const int32_t* dst_rows, const int32_t* dst_rowptr, int64_t n_edges, const float* grad_eout,
                                      const float* grad_agg, float* d_e, float* d_x, float* dW1, float* dW2, float* dvec1,
-                                     float* dvec2, void* ws, size_t ws_bytes, void* stream) {
+                                     float* dvec2, void* ws, size_t ws_bytes, void* stream, void* aux_stream) {
   HGNN_REQUIRE(p != nullptr, "tc_edge_backward: params is NULL");
   HGNN_REQUIRE(p->latent == 128 && p->hidden == 256, "tc_edge_backward: only latent 128 / hidden 256 is built (got %d / %d)",
                p->latent, p->hidden);
@@ -706,6 +707,28 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   int rc = check_launch("tc_edge_backward");
   if (rc) return rc;
   // dvec1[3, H] = (db1, dgamma1, dbeta1), dvec2[3, L]: ordered sum over the [grid * 4] partial vectors of the kernel
+  // Per-edge weight gradients: dW1[:, 2L:3L] = delta1^T A0[:, e columns], dW2 = delta2^T g. They depend only on the kernel above
+  // and stream 1.5 KB per edge at the HBM roof, while the node-level chain below is a string of short latency-bound launches:
+  // with an auxiliary stream the two run side by side (fork / join with two events created for this call).
+  const uint8_t* a0_img = sb + SL.a0;
+  const uint8_t* g_img = sb + SL.g;
+  hgnn::tc::WgradProblem pe[2], pn[2];
+  pe[0] = hgnn::tc::WgradProblem{A.d1_img, H, 0, H, a0_img, L, 0, L, dW1, K1, 0, 2 * L, 0};
+  pe[1] = hgnn::tc::WgradProblem{A.d2_img, L, 0, L, g_img, H, 0, H, dW2, H, 0, 0, 0};
+  cudaStream_t aux = (cudaStream_t)aux_stream;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (aux != nullptr && aux != st) {
+    HGNN_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    HGNN_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    HGNN_CUDA_TRY(cudaEventRecord(ev_fork, st));
+    HGNN_CUDA_TRY(cudaStreamWaitEvent(aux, ev_fork, 0));
+    rc = hgnn::tc::launch_wgrad(pe, 2, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, aux);
+    HGNN_CUDA_TRY(cudaEventRecord(ev_join, aux));
+    if (rc) { cudaStreamWaitEvent(st, ev_join, 0); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); return rc; }
+  }
+  auto join = [&]() {  // the caller's stream owns every buffer again once it has waited for the auxiliary stream
+    if (ev_join) { cudaStreamWaitEvent(st, ev_join, 0); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); ev_join = nullptr; }
+  };
   k_ordered_colsum<<<(PAR_FLOATS + 31) / 32, 256, 0, st>>>(A.colpart, grid * 4, PAR_FLOATS, dvec1, 3 * H, dvec2);
 
   // ---- node level: R = per-node sums of delta1 by source / by destination ----
@@ -718,7 +741,7 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
     k_ordered_colsum<<<H / 32, 256, 0, st>>>((const float*)(w + Y.rsum), Y.rsum_parts, H, dvec1, H, nullptr);
   }
   rc = check_launch("tc_edge_backward (delta1 node sums)");
-  if (rc) return rc;
+  if (rc) { join(); return rc; }
   // d(x) = [R_src | R_dst] . [W1a ; W1b]  (wx_packed = image of [W1a^T | W1b^T] as an [L, 2H] Linear weight); the GEMM
   // leaves the bf16 tile image of [R_src | R_dst] behind for the weight-gradient GEMM
   hgnn_tc_row_layer g{};
@@ -727,19 +750,15 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   g.seg_width[0] = H; g.seg_width[1] = H;
   g.w_packed = wx_packed;
   rc = hgnn_tc_gemm(&g, n_nodes, d_x, L, 0, w + Y.r_img, st);
-  if (rc) return rc;
+  if (rc) { join(); return rc; }
   rc = hgnn::tc::launch_make_image(x, n_nodes, L, w + Y.x_img, st);
-  if (rc) return rc;
-  // weight gradients. Edge level: dW1[:, 2L:3L] = delta1^T A0[:, e columns], dW2 = delta2^T g.
-  // Node level: dW1[:, 0:L] = R_src^T X, dW1[:, L:2L] = R_dst^T X.
-  const uint8_t* a0_img = sb + SL.a0;
-  const uint8_t* g_img = sb + SL.g;
-  hgnn::tc::WgradProblem pe[2], pn[2];
-  pe[0] = hgnn::tc::WgradProblem{A.d1_img, H, 0, H, a0_img, L, 0, L, dW1, K1, 0, 2 * L, 0};
-  pe[1] = hgnn::tc::WgradProblem{A.d2_img, L, 0, L, g_img, H, 0, H, dW2, H, 0, 0, 0};
-  rc = hgnn::tc::launch_wgrad(pe, 2, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, st);
-  if (rc) return rc;
+  if (rc) { join(); return rc; }
+  // node-level weight gradients: dW1[:, 0:L] = R_src^T X, dW1[:, L:2L] = R_dst^T X
   for (int sd = 0; sd < 2; ++sd)
     pn[sd] = hgnn::tc::WgradProblem{w + Y.r_img, 2 * H, sd * H, H, w + Y.x_img, L, 0, L, dW1, K1, 0, sd * L, 0};
-  return hgnn::tc::launch_wgrad(pn, 2, Y.node_tiles, w + Y.wgrad, Y.wgrad_bytes, st);  // stream order serialises the workspace reuse
+  rc = hgnn::tc::launch_wgrad(pn, 2, Y.node_tiles, w + Y.wgrad_node, Y.wgrad_bytes, st);
+  if (rc) { join(); return rc; }
+  if (ev_join) join();
+  else rc = hgnn::tc::launch_wgrad(pe, 2, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, st);  // no auxiliary stream: in line
+  return rc;
 }

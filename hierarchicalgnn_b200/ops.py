@@ -96,6 +96,22 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_AUX_STREAMS = {}
+
+
+def _aux_stream(device) -> Optional[int]:
+    """A second stream per device for the calls that can run two independent launch chains side by side (the backward of the
+    edge step: per-edge weight-gradient GEMM beside the node-level chain). The C call forks and joins by itself; HGNN_AUX_STREAM=0
+    disables it."""
+    if os.environ.get("HGNN_AUX_STREAM", "1") == "0":
+        return None
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _AUX_STREAMS.get(idx)
+    if st is None:
+        st = _AUX_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st.cuda_stream
+
+
 def _need_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -600,7 +616,7 @@ def tc_edge_backward_raw(meta: MlpMeta, segs, layers, gout: Tensor, stash: Tenso
         check(L_.hgnn_tc_edge_backward(C.byref(p), _ptr(w1tp), _ptr(w2tp), _ptr(wxp), _ptr(stash), _ptr(x), N,
                                        _ptr(plan_d.keys32), _ptr(perm), _ptr(src_rows), _ptr(src_rowptr), _ptr(dst_rows),
                                        _ptr(dst_rowptr), E, _ptr(gout), _ptr(grad_agg), _ptr(d_e), _ptr(d_x),
-                                       _ptr(dW1), _ptr(dW2), _ptr(dv1), _ptr(dv2), _ptr(ws), ws.numel(), _stream()),
+                                       _ptr(dW1), _ptr(dW2), _ptr(dv1), _ptr(dv2), _ptr(ws), ws.numel(), _stream(), _aux_stream(dev)),
               "tc_edge_backward")
     # data-gradient kernel, column-sum reduce, delta1 node sums (2) + their column sum (2), d(x) GEMM, x image,
     # 2 x (weight-gradient GEMM + ordered reduce)

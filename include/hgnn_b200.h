@@ -252,14 +252,17 @@ int hgnn_tc_edge_forward(const hgnn_tc_edge_params* p, const float* x, const flo
  * by source / destination node; dst_rows may be NULL when the row order is already destination-sorted.
  * grad_agg (optional, [n_nodes, L]) is the cotangent of agg = scatter_add(e_out, dst): the kernel uses
  * grad_eout[i] + grad_agg[dst_i]. w1t/w2t_packed are hgnn_tc_pack_weights images of W1^T / W2^T; wx_packed is the image
- * of the [L, 2H] matrix [W1[:, 0:L]^T | W1[:, L:2L]^T]. */
+ * of the [L, 2H] matrix [W1[:, 0:L]^T | W1[:, L:2L]^T].
+ * aux_stream (optional, NULL = none): a second stream of the same device. The per-edge weight-gradient GEMM then runs on it,
+ * beside the node-level chain on `stream` (fork after the data kernel, join before returning: when the call returns, `stream`
+ * is ordered after everything the call enqueued on either stream, so the caller needs no extra synchronisation). */
 size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges, int64_t n_nodes);
 int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w1t_packed, const void* w2t_packed, const void* wx_packed,
                           const void* stash, const float* x, int64_t n_nodes, const int32_t* dst, const int32_t* perm,
                           const int32_t* src_rows, const int32_t* src_rowptr, const int32_t* dst_rows,
                           const int32_t* dst_rowptr, int64_t n_edges, const float* grad_eout, const float* grad_agg, float* d_e,
                           float* d_x, float* dW1, float* dW2, float* dvec1, float* dvec2, void* ws, size_t ws_bytes,
-                          void* stream);
+                          void* stream, void* aux_stream);
 
 /* ------------------------------------------------------------------------
  * Tensor-core row layer: ONE make_mlp layer (utils.py:183-196) on a gathered concatenation,
