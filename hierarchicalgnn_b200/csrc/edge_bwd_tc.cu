@@ -2,7 +2,7 @@
 // Tanh/LayerNorm/Linear/GELU/LayerNorm/Linear of InteractionGNNCell.edge_update (gnn_utils.py:56-64).
 //
 // The forward kernel (edge_tc.cu) stashes, per 128-edge tile, what the adjoint needs in bf16 — the normalised
-// pre-affine activations xhat1 / xhat2, the row rstd's, and the two MMA operand images A0 and g — so nothing is
+// pre-affine activations xhat1 / xhat2, the row rstd's, and the MMA operand images A0[:, e columns] and g — so nothing is
 // recomputed here (the reference recomputes the whole cell under torch.utils.checkpoint, gnn_utils.py:14-15; on a
 // 180 GB part 1.5 KB per edge-step is the cheaper side of that trade). Per tile:
 //
@@ -25,7 +25,12 @@
 // Bias / LayerNorm-affine gradients are reduced across rows with a register transpose-reduce, summed in fixed order.
 // Weight traffic is decoupled from the tile loop: a producer thread (thread 32) refills the six weight slots as the
 // MMAs retire and already requests the next tile's first blocks under EPI-D; the MMA thread (thread 0) never waits
-// for a retirement. One CTA per SM, 16 warps, ~200 KB of shared memory, 384 TMEM columns in use.
+// for a retirement.
+//
+// Two kernels implement this tile program. k_tc_edge_bwd2 (edge_bwd2_tc.cuh) is the one hgnn_tc_edge_backward launches: two
+// 256-thread CTAs per SM, 104 KB of shared memory and 256 TMEM columns each. k_tc_edge_bwd below is its predecessor — one
+// 512-thread CTA per SM, ~200 KB of shared memory, six weight slots — kept behind HGNN_BWD_V2=0 as the A/B baseline
+// (tests/test_gpu_tc.py::test_two_cta_backward_kernel_agrees_with_the_one_cta_kernel).
 #include <algorithm>
 #include <cstdlib>
 
