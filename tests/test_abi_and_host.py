@@ -146,3 +146,41 @@ def test_lightning_compat_surface():
     assert isinstance(opt, torch.optim.AdamW) and opt.defaults["amsgrad"] and sched["interval"] == "epoch"
     for hook in ("training_step", "validation_step", "test_step", "optimizer_step", "configure_optimizers"):
         assert callable(getattr(m, hook))
+
+
+def test_kernel_scratch_is_an_autograd_saved_tensor_released_by_backward():
+    """ops._save_with_scratch / _saved_and_scratch (host logic, CPU tensors): scratch a backward needs travels as a saved
+    tensor, so it is dropped when the backward has run even while the outputs keep the graph nodes alive; without scratch
+    the helpers degrade to plain save_for_backward."""
+    import gc
+    import weakref
+    from hierarchicalgnn_b200 import ops
+
+    refs = {}
+
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, with_scratch):
+            scratch = torch.full((1024,), 3.0) if with_scratch else None
+            if scratch is not None:
+                refs["scratch"] = weakref.ref(scratch)
+            ops._save_with_scratch(ctx, [x], scratch)
+            return x * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            (x,), scratch = ops._saved_and_scratch(ctx)
+            refs["seen"] = None if scratch is None else float(scratch[0])
+            return g * 2, None
+
+    x = torch.ones(4, requires_grad=True)
+    y = F.apply(x, True)
+    loss = y.sum()
+    assert refs["scratch"]() is not None            # alive while the backward is still to come
+    loss.backward()
+    gc.collect()
+    assert refs["seen"] == 3.0
+    assert y.grad_fn is not None and refs["scratch"]() is None   # graph node still referenced, scratch gone
+    y2 = F.apply(x, False)
+    y2.sum().backward()
+    assert refs["seen"] is None
