@@ -184,3 +184,42 @@ def test_kernel_scratch_is_an_autograd_saved_tensor_released_by_backward():
     y2 = F.apply(x, False)
     y2.sum().backward()
     assert refs["seen"] is None
+
+
+def test_tile_row_plans_group_the_forward_rows_by_source_and_destination():
+    """ops._tile_row_plans (host logic of the node-level adjoint, CPU tensors through duck-typed plans): the CSR handed to
+    hgnn_tc_edge_backward must list, per node, exactly the forward's TILE ROWS whose edge leaves / enters that node — for
+    rows in edge-id order (.fused), for rows in the by-destination plan's order (.edge_step), and for edges stored sorted."""
+    from hierarchicalgnn_b200 import ops
+
+    class Plan:  # what SegmentPlan exposes: items ordered by (key, item id)
+        def __init__(self, keys, n):
+            self.n_items, self.n_segments = keys.numel(), n
+            self.perm = torch.argsort(keys, stable=True).to(torch.int32)
+            self.rowptr = torch.zeros(n + 1, dtype=torch.int32)
+            self.rowptr[1:] = torch.cumsum(torch.bincount(keys, minlength=n), 0)
+            self.keys32 = keys.to(torch.int32)
+
+        def is_identity(self):
+            return bool((self.keys32[1:] >= self.keys32[:-1]).all())
+
+    g = torch.Generator().manual_seed(5)
+    N, E = 13, 200
+    for presorted in (False, True):
+        graph = torch.randint(0, N, (2, E), generator=g)
+        if presorted:
+            graph = graph[:, torch.argsort(graph[1], stable=True)]
+        ps, pd = Plan(graph[0], N), Plan(graph[1], N)
+        for dst_sorted in (False, True):
+            src_rows, src_ptr, dst_rows, dst_ptr = ops._tile_row_plans(ps, pd, dst_sorted)
+            # tile row j holds edge row_edge[j]
+            row_edge = pd.perm.long() if (dst_sorted and not pd.is_identity()) else torch.arange(E)
+            if dst_rows is None:
+                dst_rows = torch.arange(E, dtype=torch.int32)
+            for rows, ptr, key in ((src_rows, src_ptr, graph[0]), (dst_rows, dst_ptr, graph[1])):
+                assert sorted(rows.tolist()) == list(range(E))            # every tile row exactly once
+                for n in range(N):
+                    mine = rows[int(ptr[n]):int(ptr[n + 1])].long()
+                    assert bool((key[row_edge[mine]] == n).all())          # ... in the segment of its node
+                    assert int(ptr[n + 1] - ptr[n]) == int((key == n).sum())
+            ps.__dict__.pop("_tile_rows", None)
