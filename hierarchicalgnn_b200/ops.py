@@ -113,9 +113,20 @@ def _aux_stream(device) -> Optional[int]:
 
 
 def _need_cuda(*tensors):
+    """Every launch goes to the CURRENT device's current stream and workspaces are allocated beside the tensors, so all
+    tensor arguments must live on the current device (one process per GPU; use torch.cuda.set_device / torch.cuda.device)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.HgnnError("hierarchicalgnn_b200 ops need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.HgnnError("tensor on %s but the current CUDA device is cuda:%d: kernels launch on the current device's "
+                                 "stream (call torch.cuda.set_device(%d) or wrap the call in torch.cuda.device)"
+                                 % (t.device, cur, t.device.index))
 
 
 def _f32(t: Tensor) -> Tensor:

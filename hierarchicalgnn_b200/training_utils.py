@@ -67,16 +67,31 @@ def model_selector(model_name, sweep_configs=None, yaml_path=None):
 
 def kaiming_init(model):
     """Name-keyed normal init (training_utils.py:48-58): biases 0; ``*0.weight`` (first layer of
-    each MLP) ~ N(0, 1/fan_in); other matrices ~ N(0, 2/fan_in); 1-D weights untouched."""
-    for name, p in model.named_parameters():
-        if name.endswith(".bias"):
-            p.data.zero_()
-        elif p.dim() < 2:
-            continue
-        elif name.endswith("0.weight"):
-            p.data.normal_(0, 1 / math.sqrt(p.shape[1]))
-        else:
-            p.data.normal_(0, math.sqrt(2) / math.sqrt(p.shape[1]))
+    each MLP) ~ N(0, 1/fan_in); other matrices ~ N(0, 2/fan_in); 1-D weights untouched.
+    Written through the tensors themselves under no_grad (not through ``.data``), so the parameters' version counters
+    move and the packed bf16 weight images of the tensor-core kernels are rebuilt on the next forward."""
+    import torch
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith(".bias"):
+                p.zero_()
+            elif p.dim() < 2:
+                continue
+            elif name.endswith("0.weight"):
+                p.normal_(0, 1 / math.sqrt(p.shape[1]))
+            else:
+                p.normal_(0, math.sqrt(2) / math.sqrt(p.shape[1]))
+    invalidate_packed_weights(model)
+
+
+def invalidate_packed_weights(model):
+    """Drop every cached bf16 weight image below ``model``. Needed only after writes that bypass autograd's version
+    counter (``p.data.copy_(...)``, ``p.data.normal_()``, raw pointer updates): in-place ops on the parameter itself and
+    optimizer steps bump the counter and are picked up automatically."""
+    for m in model.modules():
+        drop = getattr(m, "_drop_packed", None)
+        if drop is not None:
+            drop()
 
 
 def load_from_pretrained(model, path=None, ckpt=None):

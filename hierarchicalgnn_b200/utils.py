@@ -45,6 +45,15 @@ class FusedMLP(nn.Sequential):
         object.__setattr__(self, "_layer_cache", out)
         return out
 
+    def _drop_packed(self):
+        for k in ("_tc_cache", "_row_cache", "_split_cache"):
+            self.__dict__.pop(k, None)
+
+    def invalidate_packed_weights(self):
+        """Forget the packed bf16 weight images (they are keyed on (data_ptr, version counter) of the fp32 weights; a write
+        through ``weight.data`` does not move the counter — call this after such a write)."""
+        self._drop_packed()
+
     def _params(self):
         ps, acts, lns = [], [], []
         eps = 1e-5

@@ -14,6 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import reference_harness as rh  # noqa: E402
+from oracle.seeded_state import seeded_init  # noqa: E402
 from hierarchicalgnn_b200.synth import synth_event  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -182,9 +183,108 @@ def golden_mlp_layout(C):
     torch.save(out, os.path.join(OUT, "make_mlp.pt"))
 
 
+def bf16_grads(model):
+    """Parameter gradients stored as bf16 (2^-9 relative; the tensor-core tests state 1.5e-2 rel-Frobenius)."""
+    return {k: (p.grad.to(torch.bfloat16) if p.grad is not None else None) for k, p in model.named_parameters()}
+
+
+def golden_latent128(C):
+    """Latent-128 fixtures for the DEFAULT (tensor-core) path: the shapes the tcgen05 kernels accept. State dicts are
+    not stored: both sides call oracle.seeded_state.seeded_init(module, seed) and compare checksums."""
+    BIG = dict(latent=128, hidden="ratio", hidden_ratio=2)
+    g = torch.Generator().manual_seed(17)
+    out = {}
+    # --- InteractionGNNCell (gnn_utils.py:18-71)
+    hp = rh.load_yaml_hparams("EC", **BIG)
+    cell = C["gnn_utils"].InteractionGNNCell(hp)
+    ck = seeded_init(cell, 101)
+    N, E, L = 211, 1500, 128
+    graph = rand_graph(N - 6, N - 6, E, g)      # last 6 nodes isolated
+    graph[:, :7] = graph[:, 7:14]               # duplicate edges
+    graph[1, 20:180] = 5                        # a hub spanning more than one 128-row tile
+    nodes = torch.randn(N, L, generator=g).requires_grad_(True)
+    edges = torch.randn(E, L, generator=g).requires_grad_(True)
+    n2, e2 = cell(nodes, edges, graph)
+    wn, we = torch.randn(N, L, generator=g), torch.randn(E, L, generator=g)
+    ((n2 * wn).sum() + (e2 * we).sum()).backward()
+    out["cell"] = dict(hparams=hp, seed=101, checksum=ck, nodes=nodes.detach(), edges=edges.detach(), graph=graph,
+                       out_nodes=n2.detach(), out_edges=e2.detach(), w_nodes=wn, w_edges=we,
+                       grad_nodes=nodes.grad.clone(), grad_edges=edges.grad.clone(), grad_params=bf16_grads(cell))
+    # --- HierarchicalGNNCell (gnn_utils.py:74-169)
+    hp = rh.load_yaml_hparams("BC", **BIG)
+    cell = C["gnn_utils"].HierarchicalGNNCell(hp)
+    ck = seeded_init(cell, 102)
+    N, E, S = 300, 1300, 24
+    graph = rand_graph(N, N, E, g)
+    bg = torch.stack([torch.arange(N).repeat_interleave(3), torch.randint(0, S, (3 * N,), generator=g)], 0)
+    sg = torch.unique(rand_graph(S, S, 150, g), dim=1)
+    t = lambda *s: torch.randn(*s, generator=g).requires_grad_(True)
+    nodes, edges, sn, se = t(N, L), t(E, L), t(S, L), t(sg.shape[1], L)
+    bw = torch.rand(bg.shape[1], 1, generator=g).requires_grad_(True)
+    sw = torch.rand(sg.shape[1], 1, generator=g).requires_grad_(True)
+    outs = cell(nodes, edges, sn, se, graph, bg, bw, sg, sw)
+    ws = [torch.randn(o.shape, generator=g) for o in outs]
+    sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+    out["hcell"] = dict(hparams=hp, seed=102, checksum=ck, nodes=nodes.detach(), edges=edges.detach(),
+                        supernodes=sn.detach(), superedges=se.detach(), graph=graph, bipartite_graph=bg,
+                        bipartite_weights=bw.detach(), super_graph=sg, super_weights=sw.detach(),
+                        outs=[o.detach() for o in outs], ws=ws,
+                        grads=dict(nodes=nodes.grad, edges=edges.grad, supernodes=sn.grad, superedges=se.grad,
+                                   bipartite_weights=bw.grad, super_weights=sw.grad), grad_params=bf16_grads(cell))
+    # --- EC_InteractionGNN, 2 cells (EC/Models/IN.py:118-128): model-level gradients
+    hp = rh.load_yaml_hparams("EC", **BIG, n_interaction_graph_iters=2)
+    m = C["EC_InteractionGNN"](hp)
+    ck = seeded_init(m, 103)
+    ev = synth_event(60, 8, 0.05, 3.0, seed=1003)
+    x = ev.x.clone()
+    scores = m(x, ev.edge_index)
+    loss = torch.nn.functional.binary_cross_entropy(scores, ev.y_pid.float())
+    loss.backward()
+    out["ec"] = dict(hparams=hp, seed=103, checksum=ck, x=ev.x, graph=ev.edge_index, y=ev.y_pid, scores=scores.detach(),
+                     loss=loss.detach(), grad_x=x.grad.clone(), grad_params=bf16_grads(m))
+    # --- BC_HierarchicalGNN_GMM, 1 + 2 cells (BC/Models/HGNN_GMM.py:323-346), clusters recorded for injection
+    hp = rh.load_yaml_hparams("BC", **BIG, n_interaction_graph_iters=1, n_hierarchical_graph_iters=2)
+    m = C["BC_HierarchicalGNN_GMM"](hp)
+    ck = seeded_init(m, 104)
+    m.hgnn_block.GMM_model.set_params(random_state=0)
+    ev = synth_event(60, 8, 0.05, 2.0, seed=1004)
+    rec = {}
+    orig = m.hgnn_block.clustering
+
+    def spy(x, emb, graph):
+        c = orig(x, emb, graph)
+        rec["clusters"] = c.clone()
+        return c
+    m.hgnn_block.clustering = spy
+    sgc = m.hgnn_block.super_graph_construction
+    sgc_fwd = sgc.forward
+
+    def spy_sg(*a, **k):
+        r = sgc_fwd(*a, **k)
+        rec["super_graph"] = r[0].clone()
+        return r
+    sgc.forward = spy_sg
+    m.train()
+    before = {k: v.detach().clone() for k, v in m.state_dict().items() if "running_" in k or "knn_radius" in k}
+    x = ev.x.clone()
+    bgr, scores, emb = m(x, ev.edge_index)
+    gg = torch.Generator().manual_seed(5)
+    wsc, wem = torch.randn(scores.shape, generator=gg), torch.randn(emb.shape, generator=gg)
+    ((scores * wsc).sum() + (emb * wem).sum()).backward()
+    out["bc"] = dict(hparams=hp, seed=104, checksum=ck, x=ev.x, graph=ev.edge_index, clusters=rec["clusters"],
+                     super_graph=rec["super_graph"], bipartite_graph=bgr, scores=scores.detach(), embeddings=emb.detach(),
+                     ws=wsc, we=wem, grad_x=x.grad.clone(), grad_params=bf16_grads(m))
+    torch.save(out, os.path.join(OUT, "latent128.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     C = rh.reference_classes()
+    if "--only-latent128" in sys.argv:
+        golden_latent128(C)
+        print("latent128.pt", os.path.getsize(os.path.join(OUT, "latent128.pt")))
+        return
+    golden_latent128(C)
     golden_mlp_layout(C)
     golden_cells(C)
     golden_dgc(C)

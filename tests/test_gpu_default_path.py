@@ -1,0 +1,212 @@
+"""Parity of the DEFAULT (tensor-core, precision "auto") path — the one bench.py measures — against
+  * fixtures recorded from the UNMODIFIED reference at latent 128 (tests/golden/latent128.pt, oracle/make_golden.py), and
+  * the fp64 oracle at BASELINE config 3 (BC_HierarchicalGNN_GMM, latent 128, 6 + 6 cells, one synthetic 1 GeV event).
+Stated tolerances (bf16 MMA operands, fp32 accumulate / LayerNorm / storage): O(1) latents 2e-2 max-abs,
+sigmoid scores 1e-2, gradients relative-Frobenius 1.5e-2 per cell and 3e-2 through a whole model (several cells compound),
+unit-norm embeddings 1e-2."""
+import pytest
+import torch
+
+from oracle import hgnn_oracle as O
+from oracle.seeded_state import seeded_init
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LAT = 2e-2
+GRAD_CELL = 1.5e-2
+GRAD_MODEL = 3e-2
+
+
+@pytest.fixture(autouse=True)
+def default_precision():
+    from hierarchicalgnn_b200 import ops
+    old = ops.set_precision("auto")
+    yield
+    ops.set_precision(old)
+
+
+def _rel(a, b, floor=1e-3):
+    return float((a.double().cpu() - b.double().cpu()).norm() / (b.double().cpu().norm() + floor))
+
+
+def _module(cls, r):
+    m = cls(r["hparams"])
+    assert seeded_init(m, r["seed"]) == pytest.approx(r["checksum"], rel=1e-12), "seeded state differs from the reference's"
+    return m.to(DEV)
+
+
+def _check_param_grads(module, want, tol):
+    worst = ("", 0.0)
+    for k, p in module.named_parameters():
+        w = want[k]
+        if w is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        e = _rel(p.grad, w.float())
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < tol, worst
+
+
+def test_interaction_cell_latent128_default_path_vs_reference(golden):
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.gnn_utils import InteractionGNNCell
+    r = golden("latent128.pt")["cell"]
+    cell = _module(InteractionGNNCell, r)
+    nodes, edges = r["nodes"].to(DEV).requires_grad_(True), r["edges"].to(DEV).requires_grad_(True)
+    t0, r0 = ops.TC_CALLS["count"], ops.TC_ROW_CALLS["count"]
+    n2, e2 = cell(nodes, edges, r["graph"].to(DEV))
+    assert ops.TC_CALLS["count"] - t0 == 1 and ops.TC_ROW_CALLS["count"] - r0 == 3  # fused edge step + 3 node-network layers
+    assert float((n2.detach().cpu() - r["out_nodes"]).abs().max()) < LAT
+    assert float((e2.detach().cpu() - r["out_edges"]).abs().max()) < LAT
+    ((n2 * r["w_nodes"].to(DEV)).sum() + (e2 * r["w_edges"].to(DEV)).sum()).backward()
+    assert ops.TC_CALLS["count"] - t0 == 2  # ... and its tensor-core backward
+    assert _rel(nodes.grad, r["grad_nodes"]) < GRAD_CELL
+    assert _rel(edges.grad, r["grad_edges"]) < GRAD_CELL
+    _check_param_grads(cell, r["grad_params"], GRAD_CELL)
+
+
+def test_hierarchical_cell_latent128_default_path_vs_reference(golden):
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.gnn_utils import HierarchicalGNNCell
+    r = golden("latent128.pt")["hcell"]
+    cell = _module(HierarchicalGNNCell, r)
+    names = ["nodes", "edges", "supernodes", "superedges", "bipartite_weights", "super_weights"]
+    t = {k: r[k].to(DEV).requires_grad_(True) for k in names}
+    t0, r0 = ops.TC_CALLS["count"], ops.TC_ROW_CALLS["count"]
+    outs = cell(t["nodes"], t["edges"], t["supernodes"], t["superedges"], r["graph"].to(DEV),
+                r["bipartite_graph"].to(DEV), t["bipartite_weights"], r["super_graph"].to(DEV), t["super_weights"])
+    assert ops.TC_CALLS["count"] - t0 == 2 and ops.TC_ROW_CALLS["count"] - r0 == 6  # edge + superedge steps, 2 x 3 row layers
+    for o, w in zip(outs, r["outs"]):
+        assert float((o.detach().cpu() - w).abs().max()) < LAT
+    sum((o * w.to(DEV)).sum() for o, w in zip(outs, r["ws"])).backward()
+    for k in names:
+        assert _rel(t[k].grad, r["grads"][k]) < GRAD_CELL, k
+    _check_param_grads(cell, r["grad_params"], GRAD_CELL)
+
+
+def test_ec_model_latent128_default_path_gradients_vs_reference(golden):
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.EdgeClassifier.Models.IN import EC_InteractionGNN
+    r = golden("latent128.pt")["ec"]
+    model = _module(EC_InteractionGNN, r)
+    x = r["x"].to(DEV)
+    t0 = ops.TC_CALLS["count"]
+    scores = model(x, r["graph"].to(DEV))
+    assert ops.TC_CALLS["count"] - t0 == 2
+    assert float((scores.detach().cpu() - r["scores"]).abs().max()) < 1e-2
+    loss = torch.nn.functional.binary_cross_entropy(scores, r["y"].float().to(DEV))
+    assert abs(float(loss) - float(r["loss"])) < 5e-3
+    loss.backward()
+    assert ops.TC_CALLS["count"] - t0 == 4
+    assert _rel(x.grad, r["grad_x"], floor=1e-6) < GRAD_MODEL
+    _check_param_grads(model, r["grad_params"], GRAD_MODEL)
+    assert abs(O.roc_auc(r["scores"], r["y"]) - O.roc_auc(scores.detach().cpu(), r["y"])) <= 1e-3
+
+
+def test_bc_model_latent128_default_path_vs_reference(golden):
+    """Small BC_HierarchicalGNN_GMM (1 + 2 cells) with the reference's own clusters and supergraph / bipartite graph
+    injected (kNN on bf16-perturbed embeddings may legitimately flip near-tie neighbours; the kNN kernel has its own
+    bit-exactness tests)."""
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.BipartiteClassification.Models.HGNN_GMM import BC_HierarchicalGNN_GMM
+    r = golden("latent128.pt")["bc"]
+    model = _module(BC_HierarchicalGNN_GMM, r).train()
+    _inject_graphs(model, r["super_graph"].to(DEV), r["bipartite_graph"].to(DEV))
+    x = r["x"].to(DEV)
+    t0 = ops.TC_CALLS["count"]
+    bg, scores, emb = model(x, r["graph"].to(DEV), clusters=r["clusters"].to(DEV))
+    # 1 IN cell + first HGNN cell's edge and superedge steps (the last cell's are dead and skipped)
+    assert ops.TC_CALLS["count"] - t0 == 3
+    assert torch.equal(bg.cpu(), r["bipartite_graph"])
+    assert float((emb.detach().cpu() - r["embeddings"]).abs().max()) < 1e-2
+    assert float((scores.detach().cpu() - r["scores"]).abs().max()) < 1e-2
+    ((scores * r["ws"].to(DEV)).sum() + (emb * r["we"].to(DEV)).sum()).backward()
+    assert _rel(x.grad, r["grad_x"], floor=1e-6) < GRAD_MODEL
+    _check_param_grads(model, r["grad_params"], GRAD_MODEL)
+
+
+def _inject_graphs(model, super_graph, bipartite_graph):
+    """Make both DynamicGraphConstruction modules use a given edge list (their differentiable half still runs)."""
+    for mod, g in ((model.hgnn_block.super_graph_construction, super_graph),
+                   (model.hgnn_block.bipartite_graph_construction, bipartite_graph)):
+        orig = mod.forward
+
+        def fwd(*a, _orig=orig, _g=g, **k):
+            k["graph"] = _g
+            return _orig(*a, **k)
+        mod.forward = fwd
+
+
+def test_bc_config3_default_path_forward_backward_vs_fp64_oracle():
+    """BASELINE config 3: BC_HierarchicalGNN_GMM, latent 128, 6 + 6 cells, one synthetic 1 GeV event (12 000 hits, ~108 k
+    directed edges), forward + backward on the default path, against the oracle evaluated in fp64 (on the GPU: the oracle
+    is plain functional torch; only the device differs from its CPU use). Supernodes = particles (clusters injected,
+    SURVEY §8d); the oracle gets the graphs the model built, and separately its own kNN graphs must agree with them on
+    all but near-tie neighbours."""
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.synth import synth_event
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    torch.manual_seed(0)
+    model = model_selector("BC-HGNN-GMM", dict(latent=128))
+    kaiming_init(model)
+    hp = dict(model.hparams)
+    assert hp["n_interaction_graph_iters"] == 6 and hp["n_hierarchical_graph_iters"] == 6 and hp["hidden"] == 256
+    ev = synth_event(1200, 10, 0.0, 4.0, seed=1000)
+    clusters = (ev.pid - 1).to(DEV)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.to(DEV).train()
+    seen = {}
+    sgc = model.hgnn_block.super_graph_construction
+    orig = sgc.forward
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        seen["super_graph"] = out[0]
+        return out
+    sgc.forward = spy
+    x = ev.x.to(DEV)
+    t0, r0 = ops.TC_CALLS["count"], ops.TC_ROW_CALLS["count"]
+    bg, scores, emb = model(x, ev.edge_index.to(DEV), clusters=clusters)
+    n_tc_fwd, n_row_fwd = ops.TC_CALLS["count"] - t0, ops.TC_ROW_CALLS["count"] - r0
+    assert n_tc_fwd == 6 + 2 * 5        # 6 IN cells; 5 live HGNN cells x (edge + superedge); the last cell's are dead
+    assert n_row_fwd >= 6 * 3 + 6 * 6   # node networks of 6 IN cells, node + supernode networks of 6 HGNN cells
+    g = torch.Generator().manual_seed(5)
+    ws, we = torch.randn(scores.shape, generator=g).to(DEV), torch.randn(emb.shape, generator=g).to(DEV)
+    ((scores * ws).sum() + (emb * we).sum()).backward()
+    assert ops.TC_CALLS["count"] - t0 == 2 * n_tc_fwd  # every fused edge step had its tensor-core backward
+
+    # ---- fp64 oracle on the same graphs ----
+    sd64 = O.leaf_state({k: v.to(DEV) for k, v in O.cast_state(sd, torch.float64).items()})
+    x64 = ev.x.double().to(DEV).requires_grad_(True)
+    bg_o, scores_o, emb_o = O.bc_forward(sd64, hp, x64, ev.edge_index.to(DEV), clusters=clusters, training=True,
+                                         super_graph=seen["super_graph"], bipartite_graph=bg)
+    assert torch.equal(bg_o, bg)
+    assert float((emb.detach().double() - emb_o.detach()).abs().max()) < 1e-2
+    assert float((scores.detach().double() - scores_o.detach()).abs().max()) < 1e-2
+    assert float((scores.detach().double() - scores_o.detach()).abs().mean()) < 2e-3
+    loss_o = (scores_o * ws.double()).sum() + (emb_o * we.double()).sum()
+    names = [k for k, v in sd64.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss_o, [x64] + [sd64[k] for k in names], allow_unused=True)
+    assert _rel(x.grad, grads[0], floor=1e-6) < 5e-2
+    got = dict(model.named_parameters())
+    worst = ("", 0.0)
+    for k, go in zip(names, grads[1:]):
+        if go is None or float(go.abs().max()) == 0.0:  # dead parameters (last cell's edge / superedge networks)
+            assert got[k].grad is None or float(got[k].grad.abs().max()) == 0.0, k
+            continue
+        e = _rel(got[k].grad, go)
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < 5e-2, worst  # 12 cells of bf16-operand GEMMs compound; per cell the bound is 1.5e-2
+
+    # ---- the graphs themselves: the oracle's kNN on ITS embeddings vs the model's on the bf16-path embeddings ----
+    with torch.no_grad():
+        means_o = torch.nn.functional.normalize(O.scatter_mean(emb_o.detach(), clusters, int(clusters.max()) + 1))
+        idx_o = O.knn_radius(emb_o.detach().cpu(), means_o.cpu(), hp["bipartitegraph_sparsity"], 1.0)
+    rows = torch.arange(idx_o.shape[0]).unsqueeze(1).expand_as(idx_o)
+    ok = idx_o >= 0
+    want = set(zip(rows[ok].tolist(), idx_o[ok].tolist()))
+    have = set(zip(bg[0].tolist(), bg[1].tolist()))
+    assert len(want & have) >= 0.97 * len(want)  # only near-tie neighbours may differ between bf16 and fp64 embeddings

@@ -77,3 +77,90 @@ def test_edge_step_at_baseline_size_properties():
     deg = torch.bincount(gd[1], minlength=N)
     assert float((agg.double() - ref).abs().max()) < 1e-5 * float(deg.max()) ** 0.5 + 1e-5
     assert bool((agg[deg == 0] == 0).all())
+
+
+def test_edge_step_at_baseline_size_all_gradients_vs_fp64_reference():
+    """E = 1e6, L = 128: e', the fused aggregate and EVERY gradient (d_x through the node-level adjoint, d_e, dW1 / dW2 from
+    the split-K over 7 813 tiles, biases, LayerNorm affine) against the oracle evaluated in fp64 on the GPU. Tolerance:
+    relative Frobenius 1.5e-2 (bf16 MMA operands), max-abs 2e-2 on the O(1) outputs."""
+    from hierarchicalgnn_b200 import ops
+    from hierarchicalgnn_b200.gnn_utils import GraphPlans
+    L, E = 128, 1_000_000
+    hp, cell, nodes, edges, graph = _problem(E, L, seed=43)
+    N = nodes.shape[0]
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():  # non-trivial biases / LayerNorm affine so that their gradients carry signal
+        for k, p in cell.edge_network.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+    sd = {"edge_network." + k: v.detach().clone() for k, v in cell.edge_network.state_dict().items()}
+    cell.to(DEV)
+    net = cell.edge_network
+    names = [k for k, _ in net.named_parameters()]
+    params = [p for _, p in net.named_parameters()]
+    nd, ed, gd = nodes.to(DEV).requires_grad_(True), edges.to(DEV).requires_grad_(True), graph.to(DEV)
+    gp = GraphPlans(gd, N, N, dst_sorted=True)
+    cot_e, cot_a = torch.randn(E, L, generator=g).to(DEV), torch.randn(N, L, generator=g).to(DEV)
+    old = ops.set_precision("auto")
+    try:
+        e2, agg = net.edge_step(nd, ed, gp.by_src, gp.by_dst)
+        assert agg is not None
+        got = torch.autograd.grad([e2, agg], [nd, ed] + params, [cot_e, cot_a])
+    finally:
+        ops.set_precision(old)
+    sd64 = {k: v.double().to(DEV).requires_grad_(True) for k, v in sd.items()}
+    n64, e64 = nodes.double().to(DEV).requires_grad_(True), edges.double().to(DEV).requires_grad_(True)
+    e2_o = O.edge_step(sd64, "edge_network", hp, n64, e64, gd)
+    agg_o = O.scatter_add(e2_o, gd[1], N)
+    want = torch.autograd.grad([e2_o, agg_o], [n64, e64] + [sd64["edge_network." + k] for k in names],
+                               [cot_e.double(), cot_a.double()])
+    assert float((e2.detach().double() - e2_o.detach()).abs().max()) < 2e-2
+    deg = float(torch.bincount(gd[1], minlength=N).max())
+    assert float((agg.detach().double() - agg_o.detach()).abs().max()) < 2e-2 * deg ** 0.5 + 1e-3
+
+    def rel(a, b):
+        return float((a.double() - b).norm() / b.norm())
+    errs = {"d_nodes": rel(got[0], want[0]), "d_edges": rel(got[1], want[1])}
+    for k, a, b in zip(names, got[2:], want[2:]):
+        errs[k] = rel(a, b)
+    bad = {k: v for k, v in errs.items() if not v < 1.5e-2}
+    assert not bad, errs
+
+
+@pytest.mark.parametrize("P1,P2,k,sym", [(120_000, 12_000, 5, False), (12_000, 12_000, 10, True)])
+def test_knn_bit_exact_at_full_pileup_sizes(P1, P2, k, sym):
+    """The two kNN shapes of a full pile-up event (bipartite: 120 000 hits x 12 000 supernodes, k = 5; supergraph:
+    12 000^2, k = 10, self matches kept) against an fp64 brute force evaluated on the GPU in query chunks: identical
+    neighbour table (ties -> smaller index) wherever the fp64 distances have no fp32-level near-tie at the decision
+    boundaries; the seed is required to have (almost) none."""
+    from hierarchicalgnn_b200 import ops
+    g = torch.Generator().manual_seed(P1 + k)
+    centres = torch.nn.functional.normalize(torch.randn(P2, 8, generator=g))
+    if sym:
+        q = centres.clone()
+    else:
+        q = torch.nn.functional.normalize(centres[torch.randint(0, P2, (P1,), generator=g)] + 0.3 * torch.randn(P1, 8, generator=g))
+    radius = 0.9
+    qd, rd = q.to(DEV), centres.to(DEV)
+    got = ops.knn_radius(qd, rd, k, radius)
+    assert got.shape == (P1, k)
+    q64, r64 = qd.double(), rd.double()
+    r2 = radius * radius
+    n_bad = n_amb = 0
+    for s in range(0, P1, 4096):
+        qc = q64[s:s + 4096]
+        d2 = (qc[:, None, :] - r64[None, :, :]).square().sum(-1)                    # direct sum of squared differences
+        srt = torch.sort(d2, dim=1, stable=True)                                    # ties -> smaller index
+        top, idx = srt.values[:, :k + 1], srt.indices[:, :k]
+        want = torch.where(top[:, :k] < r2, idx, torch.full_like(idx, -1))
+        # rows whose answer could flip under fp32 rounding of the distances: a relative gap < 2e-6 (3x the fp32 error bound of an 8-term sum of squares) between consecutive
+        # ranks (up to rank k+1) or between a kept distance and the radius
+        gaps = (top[:, 1:] - top[:, :-1]) / top[:, 1:].clamp(min=1e-30)
+        amb = (gaps < 2e-6).any(1) | (((top[:, :k] - r2).abs() / r2) < 2e-6).any(1)
+        if sym:  # the self match at distance exactly 0 is rank 0 by construction: its gap to rank 1 is never a tie
+            amb = (gaps[:, 1:] < 2e-6).any(1) | (((top[:, :k] - r2).abs() / r2) < 2e-6).any(1)
+        neq = (got[s:s + 4096] != want).any(1)
+        n_bad += int((neq & ~amb).sum())
+        n_amb += int(amb.sum())
+    assert n_bad == 0
+    assert n_amb <= P1 // 100  # the certificate covers >= 99 % of the queries

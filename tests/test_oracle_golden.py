@@ -197,3 +197,85 @@ def test_scatter_and_knn_primitives_tiny():
     lab = O.connected_component_labels(torch.tensor([[0, 3], [1, 4]]), 6)
     assert lab.tolist() == [0, 0, -1, 3, 3, -1]
     assert O.cluster_labels_from_components(torch.tensor([0, 0, -1, 3, 3, 3]), 3).tolist() == [-1, -1, -1, 0, 0, 0]
+
+
+# ---- latent-128 fixtures (the shapes the tensor-core kernels accept); states are seed-reproduced, checksum-verified ----
+
+def _seeded_sd(cls, r, prefix=""):
+    """Construct the drop-in module on CPU (construction only: no compute), give it the fixture's seeded state."""
+    from oracle.seeded_state import seeded_init
+    m = cls(r["hparams"])
+    assert seeded_init(m, r["seed"]) == pytest.approx(r["checksum"], rel=1e-12), "seeded state differs from the reference's"
+    return {prefix + k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def _rel(a, b, floor=1e-3):
+    """relative Frobenius distance; `floor` absorbs gradients that are analytically zero (e.g. the BatchNorm bias in front of
+    an exp weighting that is then divided by its mean) and hold only rounding noise on both sides"""
+    return float((a.double() - b.double()).norm() / (b.double().norm() + floor))
+
+
+def test_latent128_interaction_cell(golden):
+    from hierarchicalgnn_b200.gnn_utils import InteractionGNNCell
+    r = golden("latent128.pt")["cell"]
+    sd = O.leaf_state(_seeded_sd(InteractionGNNCell, r, "c."))
+    nodes, edges = r["nodes"].clone().requires_grad_(True), r["edges"].clone().requires_grad_(True)
+    n2, e2 = O.interaction_cell(sd, "c", r["hparams"], nodes, edges, r["graph"])
+    torch.testing.assert_close(n2, r["out_nodes"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(e2, r["out_edges"], rtol=1e-4, atol=2e-5)
+    loss = (n2 * r["w_nodes"]).sum() + (e2 * r["w_edges"]).sum()
+    gn, ge = torch.autograd.grad(loss, [nodes, edges], retain_graph=True)
+    assert _rel(gn, r["grad_nodes"]) < 1e-4 and _rel(ge, r["grad_edges"]) < 1e-4
+    for k, g in _grads(loss, sd).items():
+        assert _rel(g, r["grad_params"][k[2:]].float()) < 6e-3, k  # fixture gradients are stored as bf16
+
+
+def test_latent128_hierarchical_cell(golden):
+    from hierarchicalgnn_b200.gnn_utils import HierarchicalGNNCell
+    r = golden("latent128.pt")["hcell"]
+    sd = O.leaf_state(_seeded_sd(HierarchicalGNNCell, r, "c."))
+    names = ["nodes", "edges", "supernodes", "superedges", "bipartite_weights", "super_weights"]
+    t = {k: r[k].clone().requires_grad_(True) for k in names}
+    outs = O.hierarchical_cell(sd, "c", r["hparams"], t["nodes"], t["edges"], t["supernodes"], t["superedges"], r["graph"],
+                               r["bipartite_graph"], t["bipartite_weights"], r["super_graph"], t["super_weights"])
+    for o, w in zip(outs, r["outs"]):
+        torch.testing.assert_close(o, w, rtol=1e-4, atol=3e-5)
+    loss = sum((o * w).sum() for o, w in zip(outs, r["ws"]))
+    gs = torch.autograd.grad(loss, [t[k] for k in names], retain_graph=True)
+    for k, g in zip(names, gs):
+        assert _rel(g, r["grads"][k]) < 1e-4, k
+    for k, g in _grads(loss, sd).items():
+        assert _rel(g, r["grad_params"][k[2:]].float()) < 6e-3, k
+
+
+def test_latent128_ec_and_bc_models(golden):
+    from hierarchicalgnn_b200.BipartiteClassification.Models.HGNN_GMM import BC_HierarchicalGNN_GMM
+    from hierarchicalgnn_b200.EdgeClassifier.Models.IN import EC_InteractionGNN
+    G = golden("latent128.pt")
+    r = G["ec"]
+    sd = O.leaf_state(_seeded_sd(EC_InteractionGNN, r))
+    x = r["x"].clone().requires_grad_(True)
+    scores = O.ec_forward(sd, r["hparams"], x, r["graph"])
+    torch.testing.assert_close(scores, r["scores"], rtol=1e-4, atol=5e-6)
+    loss = torch.nn.functional.binary_cross_entropy(scores, r["y"].float())
+    assert _rel(torch.autograd.grad(loss, x, retain_graph=True)[0], r["grad_x"]) < 1e-3
+    for k, g in _grads(loss, sd).items():
+        assert _rel(g, r["grad_params"][k].float()) < 6e-3, k
+    r = G["bc"]
+    sd = O.leaf_state(_seeded_sd(BC_HierarchicalGNN_GMM, r))
+    x = r["x"].clone().requires_grad_(True)
+    bg, scores, emb = O.bc_forward(sd, r["hparams"], x, r["graph"], clusters=r["clusters"], training=True)
+    po, pr = O.canonical_edge_order(bg), O.canonical_edge_order(r["bipartite_graph"])
+    assert torch.equal(bg[:, po], r["bipartite_graph"][:, pr])
+    torch.testing.assert_close(emb, r["embeddings"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(scores[po], r["scores"][pr], rtol=1e-3, atol=1e-4)
+    inv = torch.empty_like(po)
+    inv[po] = torch.arange(len(po))
+    loss = (scores * r["ws"][pr][inv]).sum() + (emb * r["we"]).sum()
+    assert _rel(torch.autograd.grad(loss, x, retain_graph=True)[0], r["grad_x"]) < 5e-3
+    for k, g in _grads(loss, sd).items():
+        w = r["grad_params"][k]
+        if w is None:
+            assert g is None or float(g.abs().max()) == 0.0, k
+        else:
+            assert _rel(g, w.float()) < 8e-3, k
