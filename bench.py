@@ -11,8 +11,18 @@ fwd+bwd pass over all E edges; value = E * steps / time, summed over ranks
 (each rank owns an independent batch of edges = data-parallel events; weight
 gradients are all-reduced over NCCL, the only exchange the DP path has).
 
+Besides `value` (device-timed, inputs resident) the line carries
+  e2e            BASELINE config 3 through the public model API from HOST buffers: BC_HierarchicalGNN_GMM (latent 128,
+                 6 + 6 cells) forward + backward on synthetic 1 GeV events, x[N,3] / edge_index / cluster labels uploaded
+                 from pinned memory every step, the loss read back; same metric (edge-steps/s = E_d * 12 cells / time)
+  models         device-timed and end-to-end times of BASELINE configs 1 (EC-IN forward) and 3 (BC fwd+bwd) on 1 GeV events
+  dp_training    (N > 1) BASELINE config 4: BC training steps (loss, backward with the bucketed all-reduce overlapped,
+                 clip 0.5, AdamW) on per-rank 1 GeV events
+  partition      (N > 1) BASELINE config 5: one full-pile-up shaped event, destination-partitioned (strong scaling)
+  roofline, cpu_baseline   as the contract asks.
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--latent L] [--edges E]
-  python bench.py --impl reference      # CPU arm: the oracle port on host cores
+  python bench.py --impl reference      # CPU arm: the reference's own InteractionGNNCell code on the host cores
 """
 from __future__ import annotations
 
@@ -44,9 +54,11 @@ def parse():
     ap.add_argument("--edges", type=int, default=1_000_000)
     ap.add_argument("--impl", default="hgnn_b200", choices=["hgnn_b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("HGNN_PRECISION", "auto"))
-    ap.add_argument("--cpu-edges", type=int, default=40_000, help="bounded CPU-baseline sample size")
+    ap.add_argument("--cpu-edges", type=int, default=250_000, help="bounded sample size of the cpu_baseline leg of the GPU arm")
+    ap.add_argument("--ref-edges", type=int, default=0, help="edges per step of --impl reference (0 = the full --edges workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-models", action="store_true", help="skip the config 1 / 3 / 4 / 5 sub-benchmarks")
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "serial"],
                     help="pipelined: step i+1's H2D upload runs on a copy stream under step i's kernels; serial: same stream")
     ap.add_argument("--mode", default="dp", choices=["dp", "partition"],
@@ -88,51 +100,118 @@ def alg_bytes_per_edge(L, n_over_e):
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference edge step on the host cores
+# CPU arm. Nothing here imports the product package: inputs come from oracle/inputs.py, the timed code is the
+# reference's own InteractionGNNCell (vendored by oracle/make_ref.py into oracle/_ref, kind "reference") or, where that
+# copy is absent, the oracle restatement (kind "port").
 # ---------------------------------------------------------------------------
-def cpu_edge_step_rate(L, n_edges, reps, seed=42):
-    from hierarchicalgnn_b200.synth import synth_edge_problem
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def have_vendored_reference():
+    return os.path.exists(os.path.join(REF_DIR, "Modules", "gnn_utils.py"))
+
+
+def _reference_classes():
+    os.environ["HGNN_REFERENCE_ROOT"] = REF_DIR
+    import importlib
+    from oracle import reference_harness as rh
+    importlib.reload(rh)  # picks the vendored root up even if the harness was imported earlier
+    return rh, rh.reference_classes()
+
+
+def cpu_edge_step_rate(L, n_edges, reps, kind, seed=42, warm=1):
+    """Edge step + the scatter_add that feeds the next node update, forward + backward, fp32 on all host threads.
+    kind "reference": gnn_utils.InteractionGNNCell.edge_update (checkpointed, as the reference runs it) + torch_scatter
+    semantics from oracle/stubs; kind "port": oracle/hgnn_oracle.py. Returns (edge-steps/s from the median, cores, times)."""
     from oracle import hgnn_oracle as O
-    from oracle.reference_harness import kaiming_init
+    from oracle.inputs import synth_edge_problem
+    from oracle.seeded_state import seeded_init
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     hp = hparams(L)
-    torch.manual_seed(0)
-    from hierarchicalgnn_b200.utils import make_mlp
-    net = make_mlp(3 * L, 2 * L, L, 2, layer_norm=True, output_activation="Tanh", hidden_activation="GELU")
-    kaiming_init(net)
-    sd = O.leaf_state({"edge_network." + k: v for k, v in net.state_dict().items()})
     nodes, edges, graph = synth_edge_problem(n_edges, L, seed=seed)
+    N = nodes.shape[0]
+    g = torch.Generator().manual_seed(7)
+    cot_e, cot_a = torch.randn(n_edges, L, generator=g), torch.randn(N, L, generator=g)
+    if kind == "reference":
+        rh, C = _reference_classes()
+        from torch_scatter import scatter_add  # oracle/stubs restatement (put on sys.path by the harness)
+        cell = C["gnn_utils"].InteractionGNNCell(hp)
+        seeded_init(cell, 0)
+
+        def one():
+            cell.zero_grad(set_to_none=True)
+            n_, e_ = nodes.clone().requires_grad_(True), edges.clone().requires_grad_(True)
+            e2 = cell.edge_update(n_, e_, graph)
+            agg = scatter_add(e2, graph[1], dim=0, dim_size=N)
+            ((e2 * cot_e).sum() + (agg * cot_a).sum()).backward()
+    else:
+        net = torch.nn.Sequential()  # parameter container with make_mlp's key layout (0,1,3,4)
+        net.add_module("0", torch.nn.Linear(3 * L, 2 * L)); net.add_module("1", torch.nn.LayerNorm(2 * L))
+        net.add_module("3", torch.nn.Linear(2 * L, L)); net.add_module("4", torch.nn.LayerNorm(L))
+        seeded_init(net, 0)
+        sd = O.leaf_state({"edge_network." + k: v for k, v in net.state_dict().items()})
+
+        def one():
+            for v in sd.values():
+                v.grad = None
+            n_, e_ = nodes.clone().requires_grad_(True), edges.clone().requires_grad_(True)
+            e2 = O.edge_step(sd, "edge_network", hp, n_, e_, graph)
+            agg = O.scatter_add(e2, graph[1], N)
+            ((e2 * cot_e).sum() + (agg * cot_a).sum()).backward()
     times = []
-    for i in range(reps + 1):
-        for v in sd.values():
-            v.grad = None
+    for i in range(warm + reps):
         t0 = time.perf_counter()
-        O.edge_step_cell_fwd_bwd(sd, "edge_network", hp, nodes, edges, graph)
+        one()
         times.append(time.perf_counter() - t0)
-    times = times[1:]  # first call warms the allocator / MKL
+    times = times[warm:]
     return n_edges / statistics.median(times), cores, times
+
+
+def cpu_ec_forward_seconds(reps=2):
+    """BASELINE config 1: the reference's EC_InteractionGNN.forward (latent 128, 14 cells) on one synthetic 1 GeV event,
+    fp32, torch CPU with all host threads. Returns (best seconds, edge-steps per forward, cores) or None without oracle/_ref."""
+    if not have_vendored_reference():
+        return None
+    from oracle.inputs import synth_event
+    from oracle.seeded_state import seeded_init
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rh, C = _reference_classes()
+    hp = rh.load_yaml_hparams("EC")
+    model = C["EC_InteractionGNN"](hp)
+    seeded_init(model, 0)
+    model.eval()
+    ev = synth_event(1200, 10, 0.0, 4.0, seed=1000)
+    best = None
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            model(ev.x.clone(), ev.edge_index)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best, 2 * ev.edge_index.shape[1] * hp["n_interaction_graph_iters"], cores
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_edges
-    per_step = []
-    from hierarchicalgnn_b200.synth import synth_edge_problem  # noqa: F401
-    rate, cores, times = cpu_edge_step_rate(args.latent, n, args.warmup + args.steps - 1)
-    timed = times[-args.steps:] if len(times) >= args.steps else times
-    t = sum(timed)
-    value = n * len(timed) / t
+    n = args.ref_edges or args.edges
+    kind = "reference" if have_vendored_reference() else "port"
+    rate, cores, times = cpu_edge_step_rate(args.latent, n, args.steps, kind, warm=max(1, min(args.warmup, 2)))
+    t = sum(times)
+    value = n * len(times) / t
+    cfg = workload_config(args.latent, n, max(2, int(round(n * 0.1))), 1)
+    cfg["parallelism"] = "host threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1e3 * t / len(timed), "higher_is_better": True,
+        "steps": len(times), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * t / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.latent, args.edges, max(2, int(round(args.edges * 0.1))), args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"oracle/hgnn_oracle.py edge step fwd+bwd on E={n} edges (N=E/10), L={args.latent}, "
-                                   f"{len(timed)} timed passes, torch CPU fp32"},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": (f"{'reference gnn_utils.InteractionGNNCell.edge_update (checkpointed) + scatter_add' if kind == 'reference' else 'oracle/hgnn_oracle.py edge step + scatter_add'}"
+                                    f", forward + backward, E={n} edges (N=E/10), L={args.latent}, {len(times)} timed passes, torch CPU fp32, {cores} threads")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,6 +266,176 @@ class ClockSampler:
         except OSError:
             pass
         return out
+
+
+def _event_pool(n_events, seed0, n_particles=1200):
+    """Pinned host copies of `n_events` synthetic 1 GeV events: x, edge_index, cluster labels (= particle)."""
+    from hierarchicalgnn_b200.synth import synth_event
+    pool = []
+    for i in range(n_events):
+        ev = synth_event(n_particles, 10, 0.0, 4.0, seed=seed0 + i)
+        pool.append(dict(x=ev.x.pin_memory(), graph=ev.edge_index.pin_memory(), clusters=(ev.pid - 1).pin_memory(),
+                         y=ev.y_pid.float().pin_memory(), pid=ev.pid.pin_memory(), pt=ev.pt.pin_memory(),
+                         e_directed=2 * ev.edge_index.shape[1]))
+    return pool
+
+
+def _timed(fn, k, barrier, world, dev):
+    """k calls of fn(i) between two CUDA events on the current stream, barrier + synchronize on both sides; max over ranks."""
+    import torch.distributed as dist
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(k):
+        fn(i)
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / k
+
+
+def model_benchmarks(args, dev, world, rank, barrier):
+    """BASELINE configs 1 and 3 on synthetic 1 GeV events (12 000 hits, ~108 k directed edges), each timed twice:
+    device-timed with the event resident in HBM, and end to end from pinned HOST buffers with the result read back."""
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    out = {}
+    pool = _event_pool(4, 1000 + 16 * rank)
+    k = max(3, min(args.steps, 10))
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    # ---- config 3: BC_HierarchicalGNN_GMM, latent 128, forward + backward (supernodes = particles, SURVEY §8d) ----
+    torch.manual_seed(0)
+    bc = model_selector("BC-HGNN-GMM", dict(latent=128))
+    kaiming_init(bc)
+    bc.to(dev).train()
+    n_cells = bc.hparams["n_interaction_graph_iters"] + bc.hparams["n_hierarchical_graph_iters"]
+    bc_params = [p for p in bc.parameters()]
+
+    def bc_step(x, graph, clusters):
+        for p in bc_params:
+            p.grad = None
+        bg, scores, emb = bc(x, graph, clusters=clusters)
+        loss = scores.mean() + emb.square().mean()
+        loss.backward()
+        return loss.detach()
+
+    resident = [tuple(ev[k_].to(dev) for k_ in ("x", "graph", "clusters")) for ev in pool]
+
+    def bc_device(i):
+        x, g, c = resident[i % len(resident)]
+        bc_step(x.clone(), g, c)
+
+    def bc_e2e(i):
+        ev = pool[i % len(pool)]
+        x, g, c = (ev[k_].to(dev, non_blocking=True) for k_ in ("x", "graph", "clusters"))
+        loss_host.copy_(bc_step(x, g, c).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the loss before the next event
+
+    for i in range(3):
+        bc_device(i)
+        bc_e2e(i)
+    dms = _timed(bc_device, k, barrier, world, dev)
+    ems = _timed(bc_e2e, k, barrier, world, dev)
+    es = sum(pool[i % len(pool)]["e_directed"] for i in range(k)) / k * n_cells
+    h2d = sum(sum(pool[i % len(pool)][k_].numel() * pool[i % len(pool)][k_].element_size() for k_ in ("x", "graph", "clusters"))
+              for i in range(k)) // k
+    out["config3_bc_fwd_bwd_1gev"] = {
+        "workload": f"BC_HierarchicalGNN_GMM latent 128, {n_cells} cells, forward + backward, synthetic 1 GeV events "
+                    f"(12 000 hits, ~{int(es / n_cells)} directed edges; supernodes = particles), {world} GPU(s) x 1 event per step",
+        "device_ms_per_step": dms, "e2e_ms_per_step": ems, "steps": k, "edge_steps_per_event": es,
+        "device_edge_steps_per_s": world * es / (dms * 1e-3), "e2e_edge_steps_per_s": world * es / (ems * 1e-3),
+        "events_per_s_e2e": world / (ems * 1e-3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
+    del bc, bc_params, resident
+
+    # ---- config 1: EC_InteractionGNN forward (inference), latent 128, 14 cells ----
+    if not args.no_models:
+        torch.manual_seed(0)
+        ec = model_selector("EC-IN")
+        kaiming_init(ec)
+        ec.to(dev).eval()
+        n_cells = ec.hparams["n_interaction_graph_iters"]
+        resident = [tuple(ev[k_].to(dev) for k_ in ("x", "graph")) for ev in pool]
+        score_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def ec_device(i):
+            x, g = resident[i % len(resident)]
+            with torch.no_grad():
+                ec(x, g)
+
+        def ec_e2e(i):
+            ev = pool[i % len(pool)]
+            x, g = ev["x"].to(dev, non_blocking=True), ev["graph"].to(dev, non_blocking=True)
+            with torch.no_grad():
+                score_host.copy_(ec(x, g).mean().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for i in range(3):
+            ec_device(i)
+            ec_e2e(i)
+        dms = _timed(ec_device, k, barrier, world, dev)
+        ems = _timed(ec_e2e, k, barrier, world, dev)
+        es = sum(pool[i % len(pool)]["e_directed"] for i in range(k)) / k * n_cells
+        out["config1_ec_forward_1gev"] = {
+            "workload": f"EC_InteractionGNN latent 128, {n_cells} cells, forward only, synthetic 1 GeV events",
+            "device_ms_per_step": dms, "e2e_ms_per_step": ems, "steps": k, "edge_steps_per_event": es,
+            "device_edge_steps_per_s": world * es / (dms * 1e-3), "e2e_edge_steps_per_s": world * es / (ems * 1e-3)}
+    return out
+
+
+def dp_training_benchmark(args, dev, world, rank, barrier):
+    """BASELINE config 4: HGNN_GMM (latent 128) TRAINING on per-rank synthetic 1 GeV events, data-parallel: training_step
+    (hinge embedding loss + assignment BCE with the scipy matching on the host, as the reference), backward with the
+    bucketed gradient all-reduce launched from hooks, global-norm clip 0.5 (Notebooks/script.py:35), AdamW step, buffer
+    broadcast. Supernodes = particles (clustering injected)."""
+    from types import SimpleNamespace
+    from hierarchicalgnn_b200.parallel import DataParallelTrainer
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    torch.manual_seed(0)
+    model = model_selector("BC-HGNN-GMM", dict(latent=128, loss_schedule=0.5))
+    kaiming_init(model)
+    model.to(dev).train()
+    opt = model.configure_optimizers()[0][0]
+    trainer = DataParallelTrainer(model, opt, clip=0.5, bucket_bytes=4 << 20)
+    pool = _event_pool(4, 3000 + 16 * rank)
+    dev_pool = []
+    for ev in pool:
+        dev_pool.append(SimpleNamespace(x=ev["x"].to(dev), edge_index=ev["graph"].to(dev), pid=ev["pid"].to(dev),
+                                        pt=ev["pt"].to(dev), clusters=ev["clusters"].to(dev)))
+    cur = {}
+    model.hgnn_block.clustering = lambda x, emb, graph: cur["clusters"]  # supernodes = particles
+
+    def step(i):
+        b = dev_pool[i % len(dev_pool)]
+        cur["clusters"] = b.clusters
+        b.x = b.x.detach().clone()
+        trainer.step(b)
+
+    for i in range(3):
+        step(i)
+    k = max(3, min(args.steps, 10))
+    ms = _timed(step, k, barrier, world, dev)
+    n_cells = model.hparams["n_interaction_graph_iters"] + model.hparams["n_hierarchical_graph_iters"]
+    es = sum(pool[i % len(pool)]["e_directed"] for i in range(k)) / k * n_cells
+    grad_bytes = sum(b["flat"].numel() for b in trainer.buckets.buckets) * 4
+    res = {"workload": f"BC_HierarchicalGNN_GMM latent 128 training step (loss + backward + overlapped all-reduce + clip 0.5 + AdamW), "
+                       f"1 synthetic 1 GeV event per GPU per step, {world} GPUs",
+           "ms_per_step": ms, "steps": k, "events_per_s": world / (ms * 1e-3), "edge_steps_per_s": world * es / (ms * 1e-3),
+           "gradient_bytes": grad_bytes, "buckets": len(trainer.buckets.buckets),
+           "timing": "wall of the training loop on the device clock (CUDA events, max over ranks); includes the host-side scipy matching"}
+    trainer.buckets.remove()
+    return res
+
+
+def partition_benchmark(args, dev, world, rank, barrier):
+    """BASELINE config 5 inside the default line: one full-pile-up shaped event (E = 3 M directed edges, N = 120 k), one
+    interaction cell forward + backward, destination-partitioned over the ranks; the one-GPU time of the same event is
+    measured in the same run (every rank runs it redundantly) so that the speed-up is self-contained."""
+    res = run_partition(args, dev=dev, world=world, rank=rank, barrier=barrier, emit=False, steps=max(3, min(args.steps, 10)))
+    return res
 
 
 def run_gpu(args):
@@ -301,7 +550,9 @@ def run_gpu(args):
             roof["step_tensor_frac"] = step_flops * E / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]
             roof["step_flops_per_edge"] = step_flops
             # measured DRAM traffic of the dominant call from the committed ncu capture of this same workload
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+            if not os.path.exists(tpath):
+                tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
             if os.path.exists(tpath):
                 try:
                     t = json.load(open(tpath)).get(top)
@@ -311,82 +562,36 @@ def run_gpu(args):
                 except Exception:  # noqa: BLE001
                     pass
 
-    # ---- end to end through the public module API with HOST buffers ----
-    e2e = None
+    # ---- end to end through the public MODEL API with HOST buffers: BASELINE config 3 (and config 1) on 1 GeV events ----
+    e2e, models = None, None
     if not args.no_e2e:
-        pin = lambda t: t.pin_memory()
-        nodes_p, edges_p, graph_p, ce_p, ca_p = map(pin, (nodes_h, edges_h, graph_h, cot_e_h, cot_a_h))
-        h2d = sum(t.numel() * t.element_size() for t in (nodes_p, edges_p, graph_p))
-        out_host = torch.empty(2, dtype=torch.float32).pin_memory()
-
-        copy_stream = torch.cuda.Stream(device=dev)
-        # two preallocated device input sets (double buffer): uploads never allocate, so the step time does not depend on
-        # what the caching allocator happens to hold
-        slots = [tuple(torch.empty_like(t, device=dev) for t in (nodes_p, edges_p, graph_p)) for _ in range(2)]
-
-        def upload(i):
-            """H2D copy of step i's inputs from pinned host memory into device slot i % 2, on the copy stream (step i+1's
-            upload runs under step i's kernels; every step's copy is inside the timed region). The slot's previous user,
-            step i-2, has been synchronised by the host before this is issued."""
-            bufs = slots[i % 2]
-            with torch.cuda.stream(copy_stream):
-                for dst_t, src_t in zip(bufs, (nodes_p, edges_p, graph_p)):
-                    dst_t.copy_(src_t, non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(copy_stream)
-            return bufs, done
-
-        def e2e_step(cur):
-            (n_b, e_b, g_d), done = cur
-            torch.cuda.current_stream().wait_event(done)
-            n_d = n_b.detach().requires_grad_(True)
-            e_d = e_b.detach().requires_grad_(True)
-            plans = GraphPlans(g_d, N, N)  # a new graph arrives with every event: plan build is inside the step
-            e2, agg, grads = step(n_d, e_d, plans)
-            # detached: out_host lives across steps, and an in-place copy of a tensor with history would chain every step's
-            # autograd graph (and what its nodes hold) behind it
-            metric = torch.stack([e2.detach().sum() + agg.detach().sum(), grads[1].abs().sum()])
-            out_host.copy_(metric, non_blocking=True)
-
-        if args.e2e_mode == "serial":
-            copy_stream = torch.cuda.current_stream()
-
-        def e2e_run(k):
-            cur = upload(0)
-            for i in range(k):
-                nxt = upload(i + 1) if (i + 1 < k and args.e2e_mode == "pipelined") else None
-                if args.e2e_mode == "serial" and i > 0:
-                    cur = upload(i)
-                e2e_step(cur)
-                torch.cuda.current_stream().synchronize()  # the host reads the step's result before the next step
-                cur = nxt
-            return out_host
-
-        e2e_run(3)
-        barrier()
-        k = max(3, min(args.steps, 10))
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        e2e_run(k)
-        t1.record()
-        barrier()
-        ems = t0.elapsed_time(t1)
-        if world > 1:
-            t = torch.tensor([ems], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        e2e = {"value": world * E / (ems / k * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-               "ms_per_step": ems / k, "steps": k,
-               "pipeline": ("double-buffered H2D on a copy stream into preallocated device slots" if args.e2e_mode == "pipelined" else "H2D on the compute stream")
-                           + ", host sync + 8 B D2H per step"}
+        models = model_benchmarks(args, dev, world, rank, barrier)
+        m3 = models["config3_bc_fwd_bwd_1gev"]
+        e2e = {"value": m3["e2e_edge_steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": m3["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": m3["d2h_bytes_per_step"], "ms_per_step": m3["e2e_ms_per_step"], "steps": m3["steps"],
+               "device_ms_per_step": m3["device_ms_per_step"],
+               "workload": m3["workload"],
+               "pipeline": "per step: x[N,3] f32 + edge_index[2,E] i64 + cluster labels[N] i64 copied from pinned host memory on the "
+                           "compute stream, model forward + backward, 4 B loss read back (host sync)"}
+    extra = {}
+    if world > 1 and not args.no_models:
+        extra["dp_training"] = dp_training_benchmark(args, dev, world, rank, barrier)
+        extra["partition"] = partition_benchmark(args, dev, world, rank, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cores, times = cpu_edge_step_rate(L, args.cpu_edges, 3)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle/hgnn_oracle.py edge step fwd+bwd, E={args.cpu_edges} edges (N=E/10), L={L}, median of 3, "
-                         f"torch CPU fp32, {cores} threads"}
+        kind = "reference" if have_vendored_reference() else "port"
+        rate, cores, times = cpu_edge_step_rate(L, args.cpu_edges, 5, kind)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{'reference gnn_utils.InteractionGNNCell.edge_update (checkpointed) + scatter_add' if kind == 'reference' else 'oracle port'}"
+                         f", forward + backward, E={args.cpu_edges} edges (N=E/10), L={L}, 1 warm-up + median of 5, torch CPU fp32, {cores} threads"}
+        if kind == "reference":  # the restatement timed beside the reference's own code: validates the port's speed
+            prate, _, _ = cpu_edge_step_rate(L, args.cpu_edges, 3, "port")
+            cpu["port_value"] = prate
+        ec = cpu_ec_forward_seconds(2) if not args.no_models else None
+        if ec is not None:
+            cpu["config1_ec_forward_1gev"] = {"seconds": ec[0], "edge_steps_per_s": ec[1] / ec[0], "cores": ec[2],
+                                              "what": "reference EC_InteractionGNN.forward (latent 128, 14 cells), one synthetic 1 GeV event, fp32, best of 2"}
 
     if rank == 0:
         line = {
@@ -395,95 +600,112 @@ def run_gpu(args):
             "dtype": ops.compute_dtype(net), "data": "synthetic",
             "config": workload_config(L, E, N, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "models": models,
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_partition(args):
+def run_partition(args, dev=None, world=None, rank=None, barrier=None, emit=True, steps=None):
     """BASELINE config 5: one full-pile-up shaped event (N = 0.04 E), one InteractionGNNCell fwd+bwd, destination-
     partitioned over the ranks: all-gather of node rows forward, reduce-scatter of node gradients backward,
-    all-reduce of weight gradients. Strong scaling: value = E_total / time."""
+    all-reduce of weight gradients. Strong scaling: value = E_total / time. The same event is also run un-partitioned on
+    one GPU (every rank, redundantly, in a group of its own) so that the record carries its own 1-GPU denominator."""
     import torch.distributed as dist
     from hierarchicalgnn_b200 import ops
     from hierarchicalgnn_b200.gnn_utils import InteractionGNNCell
-    from hierarchicalgnn_b200.parallel import (allreduce_gradients, cuda_cell_callables, pad_rows, partition_by_destination,
+    from hierarchicalgnn_b200.parallel import (cuda_cell_callables, pad_rows, partition_by_destination,
                                                partitioned_interaction_cell)
     from hierarchicalgnn_b200.synth import synth_edge_problem
     from hierarchicalgnn_b200.training_utils import kaiming_init
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    own_pg = dev is None
+    if own_pg:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+    steps = steps or args.steps
     L = args.latent
-    E = args.edges if args.edges != 1_000_000 else 3_000_000
+    E = args.edges if (own_pg and args.edges != 1_000_000) else 3_000_000
     torch.manual_seed(0)
     cell = InteractionGNNCell(hparams(L))
     kaiming_init(cell)
     cell.to(dev)
     nodes_h, edges_h, graph_h = synth_edge_problem(E, L, seed=2000, nodes_per_edge=0.04)
     N = nodes_h.shape[0]
-    part = partition_by_destination(graph_h, N, world, rank)
     g = torch.Generator().manual_seed(11)
     cot_n, cot_e = torch.randn(N, L, generator=g), torch.randn(E, L, generator=g)
-    own = slice(part.node_lo, part.node_hi)
-    cot_n_d, cot_e_d = cot_n[own].to(dev), cot_e[part.edge_ids].to(dev)
-    nodes = pad_rows(nodes_h, world * part.block).to(dev).requires_grad_(True)
-    e_loc = edges_h[part.edge_ids].to(dev).requires_grad_(True)
-    part.graph, part.dst_local, part.edge_ids = part.graph.to(dev), part.dst_local.to(dev), part.edge_ids.to(dev)
     node_fn, edge_fn, seg = cuda_cell_callables(cell)
     params = list(cell.parameters())
+    solo = None
+    if world > 1:
+        groups = [dist.new_group([r]) for r in range(world)]  # every rank creates every group (collective call)
+        solo = groups[rank]
 
-    def step():
-        n2, e2 = partitioned_interaction_cell(part, nodes, e_loc, node_fn, edge_fn, seg)
-        grads = torch.autograd.grad([n2[own], e2], [nodes, e_loc] + params, [cot_n_d, cot_e_d])
-        if world > 1:
-            flat = torch.cat([x.reshape(-1) for x in grads[2:]])
-            dist.all_reduce(flat)
-            # replicated input nodes: each rank holds the gradient of its own block only (the other rows are zero),
-            # so the sum over ranks is an all-gather of the owned blocks
-            gfull = torch.empty_like(grads[0])
-            dist.all_gather_into_tensor(gfull, grads[0][part.node_lo:part.node_lo + part.block].contiguous())
-        return n2, e2
+    def make_step(w, r, group):
+        part = partition_by_destination(graph_h, N, w, r)
+        own = slice(part.node_lo, part.node_hi)
+        cot_n_d, cot_e_d = cot_n[own].to(dev), cot_e[part.edge_ids].to(dev)
+        nodes = pad_rows(nodes_h, w * part.block).to(dev).requires_grad_(True)
+        e_loc = edges_h[part.edge_ids].to(dev).requires_grad_(True)
+        part.graph, part.dst_local, part.edge_ids = part.graph.to(dev), part.dst_local.to(dev), part.edge_ids.to(dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        def step(_i=0):
+            n2, e2 = partitioned_interaction_cell(part, nodes, e_loc, node_fn, edge_fn, seg, group=group)
+            grads = torch.autograd.grad([n2[own], e2], [nodes, e_loc] + params, [cot_n_d, cot_e_d])
+            if w > 1:
+                flat = torch.cat([x.reshape(-1) for x in grads[2:]])
+                dist.all_reduce(flat, group=group)
+                # replicated input nodes: each rank holds the gradient of its own block only (the other rows are zero),
+                # so the sum over ranks is an all-gather of the owned blocks
+                gfull = torch.empty_like(grads[0])
+                dist.all_gather_into_tensor(gfull, grads[0][part.node_lo:part.node_lo + part.block].contiguous(), group=group)
+            return n2, e2
+        return step, part
 
+    one_gpu_ms = None
+    if world > 1:  # the 1-GPU denominator, measured here and now with the same kernels
+        step1, _ = make_step(1, 0, solo)
+        for _ in range(3):
+            step1()
+        one_gpu_ms = _timed(step1, steps, barrier, world, dev)
+        del step1
+        torch.cuda.empty_cache()
+    step, part = make_step(world, rank, None)
     for _ in range(max(args.warmup, 3)):
         step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(dev.index) if (rank == 0 and own_pg) else None
     l0 = ops.LAUNCHES["count"]
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        step()
-    b.record()
-    barrier()
-    ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = _timed(step, steps, barrier, world, dev)
+    launches = ops.LAUNCHES["count"] - l0
     clocks = sampler.stop() if sampler else None
-    if rank == 0:
+    res = {"workload": f"InteractionGNNCell fwd+bwd on one full-pile-up shaped event, L={L} E={E} N={N}, destination-partitioned "
+                       f"x{world} (BASELINE config 5)", "ms_per_step": ms, "steps": steps, "edge_steps_per_s": E / (ms * 1e-3),
+           "one_gpu_ms_per_step": one_gpu_ms, "speedup_vs_1gpu": (one_gpu_ms / ms) if one_gpu_ms else None,
+           "edges_rank0": int(part.edge_ids.numel()), "scaling": "strong"}
+    if emit and rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": E / (ms / args.steps * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "metric": METRIC, "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": ops.compute_dtype(), "data": "synthetic",
-            "config": {"workload": f"InteractionGNNCell fwd+bwd on one full-pile-up shaped event, L={L} E={E} N={N}, "
-                                   f"destination-partitioned (BASELINE config 5)", "latent": L, "edges_total": E,
+            "config": {"workload": res["workload"], "latent": L, "edges_total": E,
                        "nodes_total": N, "parallelism": f"dst-partition x{world}", "l2_policy": "inputs larger than L2",
-                       "edges_rank0": int(part.edge_ids.numel())},
-            "clocks": clocks, "e2e": None, "gpu_launches": ops.LAUNCHES["count"] - l0, "roofline": None, "cpu_baseline": None}))
-    if world > 1:
+                       "edges_rank0": res["edges_rank0"]},
+            "clocks": clocks, "e2e": None, "gpu_launches": launches, "roofline": None, "cpu_baseline": None,
+            "partition": res}))
+    if own_pg and world > 1:
         dist.destroy_process_group()
+    return res
 
 
 def main():

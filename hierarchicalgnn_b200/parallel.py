@@ -41,14 +41,21 @@ Tensor = torch.Tensor
 def allreduce_gradients(params: Sequence[Tensor], world_size: Optional[int] = None, average: bool = True,
                         bucket_bytes: int = 64 << 20, group=None) -> None:
     """In-place all-reduce of ``p.grad`` over the group in flat fp32 buckets (NVSwitch: size buckets for launch
-    latency, not for link count). Parameters without a gradient contribute zeros so every rank reduces the same
-    layout (the last HGNN cell's dead edge networks)."""
+    latency, not for link count). A parameter without a gradient on this rank contributes zeros so every rank reduces
+    the same layout; one that has a gradient on NO rank (the last HGNN cell's dead edge networks) keeps
+    ``grad = None``, so the optimizer skips it exactly as on one GPU."""
     if not dist.is_initialized():
         return
     world = world_size or dist.get_world_size(group)
     if world == 1:
         return
     params = [p for p in params if p.requires_grad]
+    if not params:
+        return
+    has = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=params[0].device)
+    dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
+    has = has.cpu()
+    params = [p for p, h in zip(params, has) if h > 0]
     bucket: List[Tensor] = []
     size = 0
 
@@ -91,9 +98,145 @@ def clip_grad_norm_(params: Sequence[Tensor], max_norm: float) -> Tensor:
     return total
 
 
+class GradientBuckets:
+    """Bucketed gradient all-reduce OVERLAPPED with the backward pass.
+
+    Parameters are packed, in reverse registration order (the order the backward produces them), into flat fp32
+    buckets of ~``bucket_bytes``; every parameter's ``.grad`` is a view into its bucket, so autograd accumulates
+    straight into the buffer that travels. A post-accumulate hook counts arrivals; when a bucket is complete its
+    all-reduce is issued asynchronously (NCCL's own stream) while the backward keeps producing the earlier layers'
+    gradients. ``finish()`` reduces what is left (buckets holding parameters that received no gradient on this rank),
+    waits, averages, and restores ``.grad = None`` for parameters that received a gradient on NO rank (the last HGNN
+    cell's dead edge / superedge networks: the optimizer must skip them exactly as on one GPU)."""
+
+    def __init__(self, params: Sequence[Tensor], bucket_bytes: int = 4 << 20, group=None, average: bool = True):
+        self.group, self.average = group, average
+        self.params = [p for p in params if p.requires_grad]
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets: List[dict] = []
+        cur, size = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self._close(cur)
+                cur, size = [], 0
+        if cur:
+            self._close(cur)
+        self._where = {}
+        for bi, b in enumerate(self.buckets):
+            for p in b["params"]:
+                self._where[id(p)] = bi
+        self._hooks = [p.register_post_accumulate_grad_hook(self._arrived) for p in self.params]
+        self._fired = [0.0] * len(self.params)
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._dead = None  # indices of parameters that get a gradient on no rank (structural: decided on the first step)
+
+    def _close(self, plist):
+        n = sum(p.numel() for p in plist)
+        flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)
+        views, off = [], 0
+        for p in plist:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.buckets.append(dict(params=plist, flat=flat, views=views, pending=len(plist), work=None))
+
+    def prepare(self):
+        """Before the backward: zero the buckets and point every .grad at its view."""
+        self._fired = [0.0] * len(self.params)
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"] = len(b["params"])
+            b["work"] = None
+            for p, v in zip(b["params"], b["views"]):
+                p.grad = v
+
+    def _arrived(self, p):
+        b = self.buckets[self._where[id(p)]]
+        self._fired[self._index[id(p)]] = 1.0
+        b["pending"] -= 1
+        if b["pending"] == 0 and self.world > 1:
+            b["work"] = dist.all_reduce(b["flat"], group=self.group, async_op=True)
+
+    def finish(self):
+        """After the backward: reduce the incomplete buckets, wait for all, average; un-set dead gradients."""
+        if self.world > 1:
+            for b in self.buckets:
+                if b["work"] is None:
+                    b["work"] = dist.all_reduce(b["flat"], group=self.group, async_op=True)
+            fired = None
+            if self._dead is None:  # one small MAX all-reduce + host read, first step only
+                fired = torch.tensor(self._fired, device=self.buckets[0]["flat"].device)
+                dist.all_reduce(fired, op=dist.ReduceOp.MAX, group=self.group)
+            for b in self.buckets:
+                b["work"].wait()
+                if self.average:
+                    b["flat"].div_(self.world)
+            if fired is not None:
+                self._dead = [i for i, f in enumerate(fired.cpu().tolist()) if f == 0]
+        else:
+            self._dead = [i for i, f in enumerate(self._fired) if f == 0]
+        for i in self._dead:
+            self.params[i].grad = None
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def sync_buffers(model, src: int = 0, group=None) -> None:
+    """Broadcast the floating-point module buffers (BatchNorm running statistics, ``knn_radius``, ``score_cut``) from one
+    rank, so that replicas keep building the same graphs and a checkpoint does not depend on the rank that wrote it."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    bufs = [b for b in model.buffers() if b.is_floating_point() and b.numel() > 0]
+    if not bufs:
+        return
+    flat = torch.cat([b.reshape(-1).float() for b in bufs])
+    dist.broadcast(flat, src=src, group=group)
+    off = 0
+    for b in bufs:
+        b.copy_(flat[off:off + b.numel()].view_as(b))
+        off += b.numel()
+
+
+class DataParallelTrainer:
+    """Drives ``training_step`` / ``optimizer_step`` of a LightningModule-style model data-parallel over events (the
+    reference trains with batch_size = 1 on one GPU, edge_classifier_base.py:41; Notebooks/script.py:35 clips at 0.5).
+    Per step: local forward + backward with the bucketed all-reduce overlapped, global-norm clip on the reduced
+    gradients, optimizer step, buffer broadcast. The step counter lives here, not in ``model.trainer``."""
+
+    def __init__(self, model, optimizer, clip: Optional[float] = 0.5, bucket_bytes: int = 4 << 20, group=None,
+                 sync_buffers_every: int = 1):
+        self.model, self.optimizer, self.clip, self.group = model, optimizer, clip, group
+        self.buckets = GradientBuckets(list(model.parameters()), bucket_bytes, group)
+        self.global_step = 0
+        self.sync_every = sync_buffers_every
+
+    def step(self, batch) -> Tensor:
+        self.buckets.prepare()
+        loss = self.model.training_step(batch, 0)
+        loss.backward()
+        self.buckets.finish()
+        params = self.buckets.params
+        if self.clip is not None:
+            clip_grad_norm_(params, self.clip)
+        if hasattr(self.model, "trainer") and hasattr(self.model.trainer, "global_step"):
+            try:
+                self.model.trainer.global_step = self.global_step  # the warm-up schedule of optimizer_step reads it
+            except AttributeError:
+                pass  # a real pytorch_lightning Trainer owns its counter
+        self.model.optimizer_step(optimizer=self.optimizer)
+        self.global_step += 1
+        if self.sync_every and self.global_step % self.sync_every == 0:
+            sync_buffers(self.model, 0, self.group)
+        return loss.detach()
+
+
 def data_parallel_step(model, batch, optimizer, clip: Optional[float] = 0.5, group=None) -> Tensor:
-    """One DP training step of a LightningModule-style model: local ``training_step`` on this rank's event,
-    gradient all-reduce (mean), clip, ``optimizer_step`` hook."""
+    """One DP training step without persistent state: local ``training_step``, gradient all-reduce (mean) after the
+    backward, clip, ``optimizer_step`` hook. ``DataParallelTrainer`` is the overlapped version."""
     optimizer.zero_grad(set_to_none=True)
     loss = model.training_step(batch, 0)
     loss.backward()
@@ -102,7 +245,6 @@ def data_parallel_step(model, batch, optimizer, clip: Optional[float] = 0.5, gro
     if clip is not None:
         clip_grad_norm_(params, clip)
     model.optimizer_step(optimizer=optimizer)
-    model.trainer.global_step += 1
     return loss.detach()
 
 

@@ -223,3 +223,44 @@ def test_tile_row_plans_group_the_forward_rows_by_source_and_destination():
                     assert bool((key[row_edge[mine]] == n).all())          # ... in the segment of its node
                     assert int(ptr[n + 1] - ptr[n]) == int((key == n).sum())
             ps.__dict__.pop("_tile_rows", None)
+
+
+def test_oracle_side_input_generators_equal_the_package_generators():
+    """bench.py's CPU arms build their inputs from oracle/inputs.py (no product import); same seeds -> same tensors."""
+    from hierarchicalgnn_b200 import synth as S
+    from oracle import inputs as I
+    a, b = I.synth_edge_problem(3000, 32, seed=5), S.synth_edge_problem(3000, 32, seed=5)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    a, b = I.synth_edge_problem(2000, 16, seed=6, nodes_per_edge=0.04, power_law=True), S.synth_edge_problem(2000, 16, seed=6, nodes_per_edge=0.04, power_law=True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    ea, eb = I.synth_event(50, 7, 0.1, 3.0, seed=9), S.synth_event(50, 7, 0.1, 3.0, seed=9)
+    for k in ("x", "pid", "pt", "edge_index", "y_pid"):
+        assert torch.equal(getattr(ea, k), getattr(eb, k)), k
+
+
+def test_ops_refuse_tensors_of_another_device_than_the_current_one():
+    """Launches go to the current device's stream: a tensor living elsewhere must raise, not fault."""
+    from hierarchicalgnn_b200 import ops, _lib
+
+    class Fake:
+        is_cuda = True
+        device = torch.device("cuda", 1)
+    import unittest.mock as mock
+    with mock.patch.object(torch.cuda, "current_device", return_value=0):
+        with pytest.raises(_lib.HgnnError, match="current CUDA device"):
+            ops._need_cuda(Fake())
+
+
+def test_kaiming_init_moves_the_version_counter_and_drops_packed_images():
+    from hierarchicalgnn_b200.training_utils import invalidate_packed_weights, kaiming_init
+    from hierarchicalgnn_b200.utils import make_mlp
+    net = make_mlp(12, 8, 4, 2, layer_norm=True, output_activation="Tanh")
+    v0 = net[0].weight._version
+    object.__setattr__(net, "_tc_cache", ("stale",))
+    net.__dict__["_row_cache"] = {0: "stale"}
+    kaiming_init(net)
+    assert net[0].weight._version > v0
+    assert "_tc_cache" not in net.__dict__ and "_row_cache" not in net.__dict__
+    net.__dict__["_split_cache"] = {0: "stale"}
+    invalidate_packed_weights(net)
+    assert "_split_cache" not in net.__dict__

@@ -61,10 +61,66 @@ def _dp_case(rank, world):
     for p, q in zip(net.parameters(), ref.parameters()):
         torch.testing.assert_close(p.grad, q.grad, rtol=1e-5, atol=1e-6)
     for p in dead.parameters():
-        assert float(p.grad.abs().max()) == 0.0
+        assert p.grad is None  # no gradient on any rank: stays None, the optimizer skips it as on one GPU
     total = clip_grad_norm_(list(net.parameters()), 1e-3)
     after = torch.sqrt(sum(p.grad.square().sum() for p in net.parameters()))
     assert float(after) <= 1e-3 * 1.001 and float(total) > 0
+
+
+class _ToyTask(torch.nn.Module):
+    """LightningModule-shaped toy: training_step / optimizer_step, a dead sub-network, a BatchNorm buffer."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                                       torch.nn.Linear(32, 1))
+        self.dead = torch.nn.Linear(3, 3)
+        self.bn = torch.nn.BatchNorm1d(6)
+
+    def training_step(self, batch, batch_idx=0):
+        return self.net(self.bn(batch)).square().mean()
+
+    def optimizer_step(self, optimizer=None, **kw):
+        optimizer.step()
+        optimizer.zero_grad()
+
+
+def _dp_trainer_case(rank, world):
+    """DataParallelTrainer (bucketed all-reduce launched from backward hooks, clip, buffer broadcast) == one process that
+    averages the two ranks' gradients by hand, for three optimizer steps."""
+    from hierarchicalgnn_b200.parallel import DataParallelTrainer, clip_grad_norm_
+    torch.manual_seed(0)
+    model = _ToyTask()
+    ref = _ToyTask()
+    ref.load_state_dict(model.state_dict())
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
+    opt_ref = torch.optim.AdamW(ref.parameters(), lr=1e-2)
+    tr = DataParallelTrainer(model, opt, clip=0.05, bucket_bytes=256)  # several buckets
+    assert len(tr.buckets.buckets) >= 3
+    data = torch.randn(3, world, 9, 6, generator=torch.Generator().manual_seed(1))
+    for step in range(3):
+        loss = tr.step(data[step, rank])
+        # reference: mean of the per-rank losses; BatchNorm statistics as rank 0 sees them (buffers are broadcast from rank 0)
+        import copy
+        opt_ref.zero_grad(set_to_none=True)
+        live = [p for k, p in ref.named_parameters() if not k.startswith("dead.")]
+        for r in range(world):
+            m = copy.deepcopy(ref)
+            gs = torch.autograd.grad(m.training_step(data[step, r]), [p for k, p in m.named_parameters() if not k.startswith("dead.")])
+            for p, g in zip(live, gs):
+                p.grad = g / world if p.grad is None else p.grad + g / world
+            if r == 0:
+                ref.bn.load_state_dict(m.bn.state_dict())
+        clip_grad_norm_(list(ref.parameters()), 0.05)
+        opt_ref.step()
+        for (k, p), q in zip(model.named_parameters(), ref.parameters()):
+            torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6, msg=lambda m: f"step {step} {k}: {m}")
+        for (k, b), c in zip(model.named_buffers(), ref.buffers()):
+            if b.is_floating_point():
+                torch.testing.assert_close(b, c, rtol=1e-5, atol=1e-6, msg=lambda m: f"step {step} buffer {k}: {m}")
+    assert all(p.grad is None for p in model.dead.parameters())
+    assert tr.global_step == 3
+    tr.buckets.remove()
 
 
 def _partition_case(rank, world):
@@ -124,6 +180,10 @@ def _partition_case(rank, world):
 
 def test_data_parallel_gradient_allreduce_world2():
     _run(_dp_case)
+
+
+def test_data_parallel_trainer_overlapped_buckets_world2():
+    _run(_dp_trainer_case)
 
 
 def test_destination_partitioned_cells_match_single_process_world2():
