@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
 
     // ================= EPI-B: d(y2) = gout * act'(y2) (parked in TMEM), LayerNorm-2 adjoint -> delta2 (in place over gout) =====
     {
-      float s1 = 0.f, s2 = 0.f;
+      float2 s1v = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         const int cb = hs * 64 + ch * 32;
@@ -162,24 +162,24 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         for (int g8 = 0; g8 < 4; ++g8) {
           const int c = cb + g8 * 8;
           const uint4 pk = *reinterpret_cast<const uint4*>(sm + A2_OFF2 + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3));
-          float go[8], xh[8];
-          unpack8(pk, go);
-          unpack8(xq[g8], xh);
+          float2 go[4], xh[4];
+          unpack8_2(pk, go);
+          unpack8_2(xq[g8], xh);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 g = *reinterpret_cast<const float4*>(s_g2 + c + 4 * h);
             const float4 be = *reinterpret_cast<const float4*>(s_be2 + c + 4 * h);
-            const float gg[4] = {g.x, g.y, g.z, g.w}, ee[4] = {be.x, be.y, be.z, be.w};
+            const float2 gg[2] = {make_float2(g.x, g.y), make_float2(g.z, g.w)}, ee[2] = {make_float2(be.x, be.y), make_float2(be.z, be.w)};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int i = g8 * 8 + 4 * h + k;
-              const float x = xh[4 * h + k];
-              const float d = go[4 * h + k] * tc_act_bwd<ACT_O>(fmaf(x, gg[k], ee[k]));
-              const float gd = gg[k] * d;
-              u[i] = d;
-              tmp[i] = d * x;
-              s1 += gd;
-              s2 = fmaf(gd, x, s2);
+            for (int k = 0; k < 2; ++k) {
+              const int i = g8 * 8 + 4 * h + 2 * k;
+              const float2 x = xh[2 * h + k];
+              const float2 d = mul2(go[2 * h + k], tc_act_bwd2<ACT_O>(fma2(x, gg[k], ee[k])));
+              const float2 gd = mul2(gg[k], d), dx = mul2(d, x);
+              u[i] = d.x; u[i + 1] = d.y;
+              tmp[i] = dx.x; tmp[i + 1] = dx.y;
+              s1v = add2(s1v, gd);
+              s2v = fma2(gd, x, s2v);
             }
           }
         }
@@ -187,11 +187,12 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         acc_dg2[ch] += warp_colsum32(tmp, lane);
         acc_dbe2[ch] += warp_colsum32(u, lane);
       }
-      s_red[row * 4 + hs * 2] = s1;
-      s_red[row * 4 + hs * 2 + 1] = s2;
+      s_red[row * 4 + hs * 2] = s1v.x + s1v.y;
+      s_red[row * 4 + hs * 2 + 1] = s2v.x + s2v.y;
       __syncthreads();
       const float t1 = (s_red[row * 4] + s_red[row * 4 + 2]) * (1.0f / L);
       const float t2 = (s_red[row * 4 + 1] + s_red[row * 4 + 3]) * (1.0f / L);
+      const float2 rs = splat2(rstd2), nt1r = splat2(-t1 * rstd2), nt2r = splat2(-t2 * rstd2);
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         const int cb = hs * 64 + ch * 32;
@@ -203,16 +204,17 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           const int c = cb + g8 * 8;
-          float xh[8];
-          unpack8(xq[g8], xh);
+          float2 xh[4];
+          unpack8_2(xq[g8], xh);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 g = *reinterpret_cast<const float4*>(s_g2 + c + 4 * h);
-            const float gg[4] = {g.x, g.y, g.z, g.w};
+            const float2 gg[2] = {make_float2(g.x, g.y), make_float2(g.z, g.w)};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int i = g8 * 8 + 4 * h + k;
-              u[i] = rstd2 * (gg[k] * u[i] - t1 - xh[4 * h + k] * t2);
+            for (int k = 0; k < 2; ++k) {  // delta = rstd (gamma d - t1 - xhat t2)
+              const int i = g8 * 8 + 4 * h + 2 * k;
+              const float2 w = fma2(xh[2 * h + k], nt2r, fma2(gg[k], mul2(make_float2(u[i], u[i + 1]), rs), nt1r));
+              u[i] = w.x; u[i + 1] = w.y;
             }
           }
           *reinterpret_cast<uint4*>(sm + A2_OFF2 + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
     // ================= EPI-C: d(y1) = dG * act'(y1) (parked in place), LayerNorm-1 adjoint -> delta1 image =================
     {
       const uint32_t t_dg = t_lane + hs * 128;
-      float s1 = 0.f, s2 = 0.f;
+      float2 s1v = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int cb = hs * 128 + ch * 32;
@@ -276,23 +278,23 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         tmem_ld32(t_dg + ch * 32, u);
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          float xh[8];
-          unpack8(xq[g8], xh);
+          float2 xh[4];
+          unpack8_2(xq[g8], xh);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 g = *reinterpret_cast<const float4*>(s_g1 + cb + g8 * 8 + 4 * h);
             const float4 be = *reinterpret_cast<const float4*>(s_be1 + cb + g8 * 8 + 4 * h);
-            const float gg[4] = {g.x, g.y, g.z, g.w}, ee[4] = {be.x, be.y, be.z, be.w};
+            const float2 gg[2] = {make_float2(g.x, g.y), make_float2(g.z, g.w)}, ee[2] = {make_float2(be.x, be.y), make_float2(be.z, be.w)};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int i = g8 * 8 + 4 * h + k;
-              const float x = xh[4 * h + k];
-              const float d = u[i] * tc_act_bwd<ACT_H>(fmaf(x, gg[k], ee[k]));
-              const float gd = gg[k] * d;
-              u[i] = d;
-              tmp[i] = d * x;
-              s1 += gd;
-              s2 = fmaf(gd, x, s2);
+            for (int k = 0; k < 2; ++k) {
+              const int i = g8 * 8 + 4 * h + 2 * k;
+              const float2 x = xh[2 * h + k];
+              const float2 d = mul2(make_float2(u[i], u[i + 1]), tc_act_bwd2<ACT_H>(fma2(x, gg[k], ee[k])));
+              const float2 gd = mul2(gg[k], d), dx = mul2(d, x);
+              u[i] = d.x; u[i + 1] = d.y;
+              tmp[i] = dx.x; tmp[i + 1] = dx.y;
+              s1v = add2(s1v, gd);
+              s2v = fma2(gd, x, s2v);
             }
           }
         }
@@ -301,11 +303,12 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         acc_dbe1[ch] += warp_colsum32(u, lane);
       }
       if (tid == 0) bulk_wait_read0();  // the delta2 image has left shared memory: pass 2 overwrites its bytes with delta1
-      s_red[row * 4 + hs * 2] = s1;     // (EPI-B's readers of s_red passed the barriers of GEMM3)
-      s_red[row * 4 + hs * 2 + 1] = s2;
+      s_red[row * 4 + hs * 2] = s1v.x + s1v.y;     // (EPI-B's readers of s_red passed the barriers of GEMM3)
+      s_red[row * 4 + hs * 2 + 1] = s2v.x + s2v.y;
       __syncthreads();
       const float t1 = (s_red[row * 4] + s_red[row * 4 + 2]) * (1.0f / H);
       const float t2 = (s_red[row * 4 + 1] + s_red[row * 4 + 3]) * (1.0f / H);
+      const float2 rs = splat2(rstd1), nt1r = splat2(-t1 * rstd1), nt2r = splat2(-t2 * rstd1);
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         const int cb = hs * 128 + ch * 32;
@@ -316,16 +319,17 @@ __global__ void __launch_bounds__(NT2, 2) k_tc_edge_bwd2(BwdArgs A) {
         tmem_ld32(t_dg + ch * 32, u);
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          float xh[8];
-          unpack8(xq[g8], xh);
+          float2 xh[4];
+          unpack8_2(xq[g8], xh);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 g = *reinterpret_cast<const float4*>(s_g1 + cb + g8 * 8 + 4 * h);
-            const float gg[4] = {g.x, g.y, g.z, g.w};
+            const float2 gg[2] = {make_float2(g.x, g.y), make_float2(g.z, g.w)};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int i = g8 * 8 + 4 * h + k;
-              u[i] = rstd1 * (gg[k] * u[i] - t1 - xh[4 * h + k] * t2);
+            for (int k = 0; k < 2; ++k) {
+              const int i = g8 * 8 + 4 * h + 2 * k;
+              const float2 w = fma2(xh[2 * h + k], nt2r, fma2(gg[k], mul2(make_float2(u[i], u[i + 1]), rs), nt1r));
+              u[i] = w.x; u[i + 1] = w.y;
             }
           }
           const int c = cb + g8 * 8;

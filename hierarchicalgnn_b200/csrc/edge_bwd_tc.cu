@@ -27,10 +27,8 @@
 // MMAs retire and already requests the next tile's first blocks under EPI-D; the MMA thread (thread 0) never waits
 // for a retirement.
 //
-// Two kernels implement this tile program. k_tc_edge_bwd2 (edge_bwd2_tc.cuh) is the one hgnn_tc_edge_backward launches: two
-// 256-thread CTAs per SM, 104 KB of shared memory and 256 TMEM columns each. k_tc_edge_bwd below is its predecessor — one
-// 512-thread CTA per SM, ~200 KB of shared memory, six weight slots — kept behind HGNN_BWD_V2=0 as the A/B baseline
-// (tests/test_gpu_tc.py::test_two_cta_backward_kernel_agrees_with_the_one_cta_kernel).
+// k_tc_edge_bwd2 (edge_bwd2_tc.cuh) implements this tile program: two 256-thread CTAs per SM, 104 KB of shared memory and
+// 256 TMEM columns each (its one-CTA predecessor, 1.27 ms against 1.06 ms per million edges, was removed in round 2).
 #include <algorithm>
 #include <cstdlib>
 
@@ -85,393 +83,6 @@ __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
     f[2 * i] = __uint_as_float(w[i] << 16);
     f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
-}
-
-template <int ACT_H, int ACT_O>
-__global__ void __launch_bounds__(NT, 1) k_tc_edge_bwd(BwdArgs A) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* const sm = smem_raw;
-  float* s_par = reinterpret_cast<float*>(sm + PAR_OFF);
-  float *s_b1 = s_par, *s_g1 = s_par + H, *s_be1 = s_par + 2 * H, *s_b2 = s_par + 3 * H, *s_g2 = s_par + 3 * H + L,
-        *s_be2 = s_par + 3 * H + 2 * L;
-  int* s_eid = reinterpret_cast<int*>(sm + IDS_OFF);
-  int* s_dst = s_eid + TILE_M;
-  float* s_red = reinterpret_cast<float*>(sm + RED_OFF);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + BAR_OFF + NBAR * 8);
-  const uint32_t sm_u = smem_u32(sm), bar0 = sm_u + BAR_OFF;
-  if ((sm_u & 1023u) != 0) __trap();
-  enum { B_FULL = 0, B_FREE = NSLOT, ACC = 2 * NSLOT };
-  auto BAR = [&](int i) { return bar0 + 8u * i; };
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, cs = warp >> 2;  // TMEM lane quarter, column split
-  const int row = q * 32 + lane;
-  const hgnn_tc_edge_params& P = A.P;
-
-  if (tid == 0) {
-    for (int i = 0; i < NBAR; ++i) mbar_init(BAR(i), 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(s_tmem), 512);
-  for (int i = tid; i < H; i += NT) { s_b1[i] = P.b1[i]; s_g1[i] = P.gamma1[i]; s_be1[i] = P.beta1[i]; }
-  for (int i = tid; i < L; i += NT) { s_b2[i] = P.b2[i]; s_g2[i] = P.gamma2[i]; s_be2[i] = P.beta2[i]; }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-  const uint32_t idesc_l = make_idesc(TILE_M, L);
-
-  uint32_t acc_par = 0;
-  int nx_eid = 0, nx_dst = 0;  // row ids of the next tile, prefetched
-  // mbarrier phase bookkeeping. Every completion of a barrier is awaited exactly once, in order, by one thread:
-  //   thread 0  consumes B_FULL[slot]  (nf = completions consumed so far -> next wait parity nf & 1)
-  //   thread 32 consumes B_FREE[slot]  (nr likewise)
-  uint32_t nf[NSLOT] = {0, 0, 0, 0, 0, 0}, nr[NSLOT] = {0, 0, 0, 0, 0, 0};
-  // per-lane column-sum accumulators: lane c of warp (q, cs) owns columns cs*64 + {c, 32 + c} of H and cs*32 + c of L
-  float acc_db1[2] = {0.f, 0.f}, acc_dg1[2] = {0.f, 0.f}, acc_dbe1[2] = {0.f, 0.f};
-  float acc_db2 = 0.f, acc_dg2 = 0.f, acc_dbe2 = 0.f;
-
-  auto full_wait = [&](int slot) { mbar_wait(BAR(B_FULL + slot), nf[slot] & 1); nf[slot]++; tc_fence_after(); };  // thread 0
-  auto free_wait = [&](int slot) { mbar_wait(BAR(B_FREE + slot), nr[slot] & 1); nr[slot]++; };                    // thread 32
-  auto fill = [&](int slot, const void* src, uint32_t bytes) {                                                    // thread 32
-    mbar_expect_tx(BAR(B_FULL + slot), bytes);
-    bulk_g2s(sm_u + slot * SEG_BLK, src, bytes, BAR(B_FULL + slot));
-  };
-  auto piece_src = [&](int kb) {  // piece kb = rows [2L, 3L) (the edge-latent inputs) of K-block kb of the W1^T image
-    return A.w1t + (size_t)kb * W1T_BLK + (size_t)2 * SEG_BLK;
-  };
-  // first blocks of a tile: W2^T K-blocks 0 / 1 (32 KB each, slots 0+1 / 2+3) and W1^T pieces 0 / 1 (slots 4 / 5)
-  auto head_fill = [&]() {  // thread 32
-    fill(0, A.w2t, W2T_BLK);
-    fill(2, A.w2t + W2T_BLK, W2T_BLK);
-    fill(4, piece_src(0), SEG_BLK);
-    fill(5, piece_src(1), SEG_BLK);
-  };
-
-  long long t_prev = clock64();
-  auto MARK = [&](int ph) {
-    if (A.phase_clk && tid == 0 && blockIdx.x == 0) { long long t = clock64(); atomicAdd(A.phase_clk + ph, (unsigned long long)(t - t_prev)); t_prev = t; }
-  };
-  const int n_tiles = (int)((A.n_edges + TILE_M - 1) / TILE_M);
-  // All CTAs start together and every tile costs the same, so without this the SMs stay in lock-step and their
-  // HBM-heavy phases (gradient rows in, gradient rows out) coincide: stagger the start by a fraction of a tile so the
-  // memory system sees a steady demand instead of bursts.
-  if (A.stagger_cycles > 0 && n_tiles > (int)gridDim.x) {
-    const long long t0 = clock64(), wait = (long long)(blockIdx.x % 4) * A.stagger_cycles;
-    while (clock64() - t0 < wait) {}
-  }
-  if (tid == 32 && (int)blockIdx.x < n_tiles) head_fill();
-
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ================= tile setup: row ids (fetched one tile ahead into registers; see below) =================
-    if (tid < TILE_M) {
-      if (tile == (int)blockIdx.x) {
-        int64_t j = (int64_t)tile * TILE_M + tid;
-        if (j >= A.n_edges) j = A.n_edges - 1;
-        nx_eid = A.perm ? A.perm[j] : (int)j;
-        nx_dst = A.dst[nx_eid];
-      }
-      s_eid[tid] = nx_eid;
-      s_dst[tid] = nx_dst;
-    }
-    __syncthreads();
-    const bool has_next = tile + (int)gridDim.x < n_tiles;
-    if (tid < TILE_M && has_next) {  // first link of the dependent chain perm -> src/dst for the next tile
-      int64_t j = (int64_t)(tile + gridDim.x) * TILE_M + tid;
-      if (j >= A.n_edges) j = A.n_edges - 1;
-      nx_eid = A.perm ? A.perm[j] : (int)j;
-    }
-    MARK(0);
-    // ================= LOAD: upstream gradient tile -> bf16 image; stashed xhat2 / rstd of this thread's row ==========
-    const float rstd1 = __ldg(A.rstd + (size_t)tile * 2 * TILE_M + row);
-    const float rstd2 = __ldg(A.rstd + (size_t)tile * 2 * TILE_M + TILE_M + row);
-    uint4 xq2[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) xq2[j] = __ldg(A.xh2 + ((size_t)tile * (L / 8) + cs * 4 + j) * TILE_M + row);
-    {
-      const int g_sub = tid & 31, g_rr = tid >> 5;  // 32 threads per row, 16 rows per pass
-      float4 gv[TILE_M / 16], ga[TILE_M / 16];
-#pragma unroll
-      for (int p = 0; p < TILE_M / 16; ++p) {
-        const int r = p * 16 + g_rr;
-        const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-        gv[p] = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + g_sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ga[p] = (live && A.g_agg) ? __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + g_sub)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int p = 0; p < TILE_M / 16; ++p) {  // zero rows for padding: their delta's vanish
-        const int r = p * 16 + g_rr;
-        const int c = g_sub * 4;
-        *reinterpret_cast<uint2*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(r, (c % KBLK) >> 3) + ((c >> 2) & 1) * 8) =
-            make_uint2(pack_bf16(gv[p].x + ga[p].x, gv[p].y + ga[p].y), pack_bf16(gv[p].z + ga[p].z, gv[p].w + ga[p].w));
-      }
-    }
-    __syncthreads();
-    if (tid < TILE_M && has_next) nx_dst = A.dst[nx_eid];  // second link, consumed next tile
-
-    MARK(1);
-    // ================= EPI-B: d(y2) = gout * act'(y2), LayerNorm-2 adjoint -> delta2 (in place over gout) =============
-    {
-      const int c0 = cs * 32;
-      float v[32], dy[32];
-      const float4* g4 = reinterpret_cast<const float4*>(s_g2 + c0);
-      const float4* e4 = reinterpret_cast<const float4*>(s_be2 + c0);
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
-        const int c = c0 + g8 * 8;
-        const uint4 pk = *reinterpret_cast<const uint4*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3));
-        float go[8], xh[8];
-        unpack8(pk, go);
-        unpack8(xq2[g8], xh);
-        const float4 ga = g4[2 * g8], gb = g4[2 * g8 + 1], ea = e4[2 * g8], eb = e4[2 * g8 + 1];
-        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        const float ee[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int k = g8 * 8 + i;
-          const float d = go[i] * tc_act_bwd<ACT_O>(fmaf(xh[i], gg[i], ee[i]));
-          const float gd = gg[i] * d;
-          dy[k] = d;
-          v[k] = xh[i];
-          s1 += gd;
-          s2 = fmaf(gd, xh[i], s2);
-        }
-      }
-      s_red[row * 8 + cs * 2] = s1;
-      s_red[row * 8 + cs * 2 + 1] = s2;
-      __syncthreads();
-      float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { t1 += s_red[row * 8 + 2 * i]; t2 += s_red[row * 8 + 2 * i + 1]; }
-      t1 *= (1.0f / L);
-      t2 *= (1.0f / L);
-      float tmp[32];
-      // d gamma2 += dy * xhat ; d beta2 += dy
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tmp[i] = dy[i] * v[i];
-      acc_dg2 += warp_colsum32(tmp, lane);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) tmp[i] = dy[i];
-      acc_dbe2 += warp_colsum32(tmp, lane);
-      // delta2 = rstd (gamma dy - mean(gamma dy) - xhat mean(gamma dy xhat))
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 g = g4[i];
-        dy[4 * i] = rstd2 * (g.x * dy[4 * i] - t1 - v[4 * i] * t2);
-        dy[4 * i + 1] = rstd2 * (g.y * dy[4 * i + 1] - t1 - v[4 * i + 1] * t2);
-        dy[4 * i + 2] = rstd2 * (g.z * dy[4 * i + 2] - t1 - v[4 * i + 2] * t2);
-        dy[4 * i + 3] = rstd2 * (g.w * dy[4 * i + 3] - t1 - v[4 * i + 3] * t2);
-      }
-#pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {  // each thread overwrites exactly the gout chunks it read above
-        const int c = c0 + g8 * 8;
-        *reinterpret_cast<uint4*>(sm + GS_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
-            make_uint4(pack_bf16(dy[g8 * 8], dy[g8 * 8 + 1]), pack_bf16(dy[g8 * 8 + 2], dy[g8 * 8 + 3]),
-                       pack_bf16(dy[g8 * 8 + 4], dy[g8 * 8 + 5]), pack_bf16(dy[g8 * 8 + 6], dy[g8 * 8 + 7]));
-      }
-      acc_db2 += warp_colsum32(dy, lane);
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-
-    MARK(2);
-    // ================= GEMM3: dG = delta2 W2 (two N = 128 halves) ; delta2 image -> HBM =================
-    if (tid == 0) {
-      bulk_s2g(A.d2_img + (size_t)tile * GS_BYTES, sm_u + GS_OFF, GS_BYTES);
-      bulk_commit();
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < NKBL; ++kb) {
-        const int slot = kb * 2;
-        full_wait(slot);
-        const uint32_t a_s = sm_u + GS_OFF + kb * A_BLK_BYTES, b_s = sm_u + slot * SEG_BLK;
-        umma_kblock(tmem + TM_DG, a_s, b_s, idesc_l, kb == 0);                       // hidden units [0, 128)
-        umma_kblock(tmem + TM_DG + L, a_s, b_s + L * ROW_BYTES, idesc_l, kb == 0);   // hidden units [128, 256)
-        umma_commit(BAR(B_FREE + slot));
-      }
-      umma_commit(BAR(ACC));
-    }
-    // stashed xhat1 of this thread's 64 hidden columns: 8 x 8 bf16, in flight under GEMM3
-    uint4 xq1[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xq1[j] = __ldg(A.xh1 + ((size_t)tile * (H / 8) + cs * 8 + j) * TILE_M + row);
-    if (tid == 32) {  // W1c^T pieces 2 / 3 replace W2^T K-block 0 as its MMAs retire
-      free_wait(0);
-      fill(0, piece_src(2), SEG_BLK);
-      fill(1, piece_src(3), SEG_BLK);
-    }
-    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
-    __syncthreads();
-    acc_par ^= 1;
-    tc_fence_after();
-
-    MARK(3);
-    // ================= EPI-C: d(y1) = dG * act'(y1), LayerNorm-1 adjoint -> delta1 image =================
-    {
-      const int c0 = cs * 64;
-      const uint32_t t_dg = t_lane + TM_DG + c0;
-      float u[32], tmp[32];
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_ld32(t_dg + ch * 32, u);
-        const int cb = c0 + ch * 32;
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float xh[8];
-          unpack8(xq1[ch * 4 + g8], xh);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float4 g = *reinterpret_cast<const float4*>(s_g1 + cb + g8 * 8 + 4 * h);
-            const float4 be = *reinterpret_cast<const float4*>(s_be1 + cb + g8 * 8 + 4 * h);
-            const float gg[4] = {g.x, g.y, g.z, g.w}, ee[4] = {be.x, be.y, be.z, be.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int i = g8 * 8 + 4 * h + k;
-              const float x = xh[4 * h + k];
-              const float d = u[i] * tc_act_bwd<ACT_H>(fmaf(x, gg[k], ee[k]));
-              const float gd = gg[k] * d;
-              u[i] = d;
-              tmp[i] = d * x;
-              s1 += gd;
-              s2 = fmaf(gd, x, s2);
-            }
-          }
-        }
-        tmem_st32(t_dg + ch * 32, u);  // park d(y1) where dG was
-        acc_dg1[ch] += warp_colsum32(tmp, lane);
-        acc_dbe1[ch] += warp_colsum32(u, lane);
-      }
-      __syncthreads();  // s_red free (EPI-B readers done)
-      s_red[row * 8 + cs * 2] = s1;
-      s_red[row * 8 + cs * 2 + 1] = s2;
-      __syncthreads();
-      float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { t1 += s_red[row * 8 + 2 * i]; t2 += s_red[row * 8 + 2 * i + 1]; }
-      t1 *= (1.0f / H);
-      t2 *= (1.0f / H);
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        tmem_ld32(t_dg + ch * 32, u);
-        const int cb = c0 + ch * 32;
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float xh[8];
-          unpack8(xq1[ch * 4 + g8], xh);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float4 g = *reinterpret_cast<const float4*>(s_g1 + cb + g8 * 8 + 4 * h);
-            const float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int i = g8 * 8 + 4 * h + k;
-              u[i] = rstd1 * (gg[k] * u[i] - t1 - xh[4 * h + k] * t2);
-            }
-          }
-          const int c = cb + g8 * 8;
-          *reinterpret_cast<uint4*>(sm + A2_OFF + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
-              make_uint4(pack_bf16(u[g8 * 8], u[g8 * 8 + 1]), pack_bf16(u[g8 * 8 + 2], u[g8 * 8 + 3]),
-                         pack_bf16(u[g8 * 8 + 4], u[g8 * 8 + 5]), pack_bf16(u[g8 * 8 + 6], u[g8 * 8 + 7]));
-        }
-        acc_db1[ch] += warp_colsum32(u, lane);
-      }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-
-    MARK(4);
-    // ================= GEMM4: d(e)_mlp = delta1 W1c, one N = 128 accumulator =================
-    if (tid == 0) {
-      bulk_s2g(A.d1_img + (size_t)tile * A2_BYTES, sm_u + A2_OFF, A2_BYTES);
-      bulk_commit();
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < NPIECE; ++kb) {
-        const int slot = (kb + 4) % NSLOT;
-        full_wait(slot);
-        umma_kblock(tmem + TM_DA0, sm_u + A2_OFF + kb * A_BLK_BYTES, sm_u + slot * SEG_BLK, idesc_l, kb == 0);
-        umma_commit(BAR(B_FREE + slot));
-      }
-      umma_commit(BAR(ACC));
-      bulk_wait_read0();  // delta1 / delta2 images have left shared memory before their regions are reused
-    }
-    float4 skipg[8];  // fp32 upstream gradient of this lane's 8 output chunks (skip path of d(e)), in flight under GEMM4
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int r = warp * 8 + k;
-      const bool live = (int64_t)tile * TILE_M + r < A.n_edges;
-      float4 go = live ? __ldg(reinterpret_cast<const float4*>(A.g_e + (size_t)s_eid[r] * L) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live && A.g_agg) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(A.g_agg + (size_t)s_dst[r] * L) + lane);
-        go.x += a.x; go.y += a.y; go.z += a.z; go.w += a.w;
-      }
-      skipg[k] = go;
-    }
-    if (warp == 0) mbar_wait(BAR(ACC), acc_par);  // one warp polls the mbarrier; the rest park on the hardware barrier
-    __syncthreads();  // also orders thread 0's bulk_wait_read0 before the staging writes below
-    acc_par ^= 1;
-    tc_fence_after();
-    // every MMA has retired: request the next tile's first weight blocks under EPI-D
-    if (tid == 32) {  // consume the remaining retirements: W2^T K-block 1 (slot 2), pieces 0 / 1 (slots 4 / 5), 2 / 3 (slots 0 / 1)
-      free_wait(2); free_wait(4); free_wait(5); free_wait(0); free_wait(1);
-      if (has_next) head_fill();
-    }
-
-    MARK(5);
-    // ================= EPI-D: rows of d(e) through a swizzled fp32 staging tile =================
-    {
-      float v[32];
-      tmem_ld32(t_lane + TM_DA0 + cs * 32, v);
-#pragma unroll
-      for (int g4 = 0; g4 < 8; ++g4) {
-        const int c4 = cs * 8 + g4;
-        *reinterpret_cast<float4*>(sm + A2_OFF + (size_t)row * (L * 4) + ((c4 ^ (row & 7)) << 4)) =
-            make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {  // 8 rows per warp, one float4 chunk per lane; skip connection: d(e) += gout (fp32)
-      const int r = warp * 8 + k, c4 = lane;
-      const int64_t j = (int64_t)tile * TILE_M + r;
-      if (j < A.n_edges) {
-        float4 y = *reinterpret_cast<const float4*>(sm + A2_OFF + (size_t)r * (L * 4) + ((c4 ^ (r & 7)) << 4));
-        y.x += skipg[k].x; y.y += skipg[k].y; y.z += skipg[k].z; y.w += skipg[k].w;
-        *reinterpret_cast<float4*>(A.d_e + (size_t)s_eid[r] * L + c4 * 4) = y;
-      }
-    }
-    fence_proxy_async();  // staging (generic proxy) precedes the next tile's bulk store from / writes into these bytes
-    tc_fence_before();
-    __syncthreads();
-    MARK(6);
-  }
-
-  // ---- ordered hand-off of the column sums: [cta][q][PAR_FLOATS], lane c owns its columns ----
-  {
-    float* o = A.colpart + ((size_t)blockIdx.x * 4 + q) * PAR_FLOATS;
-    // layout mirrors s_par: db1 | dgamma1 | dbeta1 | db2 | dgamma2 | dbeta2
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int c = cs * 64 + ch * 32 + lane;
-      o[c] = acc_db1[ch];
-      o[H + c] = acc_dg1[ch];
-      o[2 * H + c] = acc_dbe1[ch];
-    }
-    const int c = cs * 32 + lane;
-    o[3 * H + c] = acc_db2;
-    o[3 * H + L + c] = acc_dg2;
-    o[3 * H + 2 * L + c] = acc_dbe2;
-  }
-  if (tid == 0) bulk_wait0();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 #include "edge_bwd2_tc.cuh"
@@ -619,7 +230,7 @@ Layout make_layout(int64_t n_edges, int64_t n_nodes) {
   Layout Y{};
   Y.tiles = (int)((n_edges + TILE_M - 1) / TILE_M);
   Y.node_tiles = (int)((n_nodes + TILE_M - 1) / TILE_M);
-  Y.grid = std::max(1, std::min(Y.tiles, 2 * num_sms()));  // sized for the two-CTA kernel; the one-CTA kernel uses half
+  Y.grid = std::max(1, std::min(Y.tiles, 2 * num_sms()));  // two CTAs per SM
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = align_up(off, 1024); off = o + b; return o; };
   Y.d1 = take((size_t)Y.tiles * NKB2 * A_BLK_BYTES);
@@ -696,18 +307,11 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
     A.stagger_cycles = stagger;
   }
   HGNN_REQUIRE(p->act_hidden == HGNN_ACT_GELU && p->act_out == HGNN_ACT_TANH, "tc_edge_backward: only GELU / Tanh is built");
-  static int two_cta = -1;  // HGNN_BWD_V2=0 selects the one-CTA-per-SM kernel (A/B comparisons)
-  if (two_cta < 0) { const char* e = getenv("HGNN_BWD_V2"); two_cta = e ? atoi(e) : 1; }
-  int grid = Y.grid;
-  if (two_cta) {
+  const int grid = Y.grid;
+  {
     auto kern = v2::k_tc_edge_bwd2<HGNN_ACT_GELU, HGNN_ACT_TANH>;
     HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v2::SMEM_BYTES2));
     kern<<<grid, v2::NT2, v2::SMEM_BYTES2, st>>>(A);
-  } else {
-    grid = std::max(1, std::min(Y.tiles, num_sms()));
-    auto kern = k_tc_edge_bwd<HGNN_ACT_GELU, HGNN_ACT_TANH>;
-    HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    kern<<<grid, NT, SMEM_BYTES, st>>>(A);
   }
   int rc = check_launch("tc_edge_backward");
   if (rc) return rc;
@@ -741,7 +345,7 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   const ImgPlan ps{src_rows, src_rowptr}, pd{dst_rows, dst_rowptr};
   k_img_segment_reduce<<<dim3((unsigned)((n_nodes + 7) / 8), 2), 256, 0, st>>>(A.d1_img, ps, pd, n_nodes, R);
   k_img_segment_reduce_long<<<dim3((unsigned)((n_nodes + 255) / 256), 2), 256, 0, st>>>(A.d1_img, ps, pd, n_nodes, R);
-  if (two_cta) {  // d bias1 = column sums of R_dst (written after k_colpart_reduce left zeros there)
+  {  // d bias1 = column sums of R_dst (written after k_colpart_reduce left zeros there)
     k_rows_colsum_partial<<<Y.rsum_parts, H, 0, st>>>(R + (size_t)n_nodes * H, n_nodes, (float*)(w + Y.rsum));
     k_ordered_colsum<<<H / 32, 256, 0, st>>>((const float*)(w + Y.rsum), Y.rsum_parts, H, dvec1, H, nullptr);
   }

@@ -282,15 +282,12 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const uint16_t* __restrict__ xb16, const fl
             const float4 b = *reinterpret_cast<const float4*>(s_b2 + c);
             const float4 g = *reinterpret_cast<const float4*>(s_g2 + c);
             const float4 be = *reinterpret_cast<const float4*>(s_be2 + c);
-            xh[4 * h + 0] = fmaf(v[g8 * 8 + 4 * h + 0] + b.x, st.rstd, nmr);
-            xh[4 * h + 1] = fmaf(v[g8 * 8 + 4 * h + 1] + b.y, st.rstd, nmr);
-            xh[4 * h + 2] = fmaf(v[g8 * 8 + 4 * h + 2] + b.z, st.rstd, nmr);
-            xh[4 * h + 3] = fmaf(v[g8 * 8 + 4 * h + 3] + b.w, st.rstd, nmr);
-            float4 o;
-            o.x = tc_act<ACT_O>(fmaf(xh[4 * h + 0], g.x, be.x));
-            o.y = tc_act<ACT_O>(fmaf(xh[4 * h + 1], g.y, be.y));
-            o.z = tc_act<ACT_O>(fmaf(xh[4 * h + 2], g.z, be.z));
-            o.w = tc_act<ACT_O>(fmaf(xh[4 * h + 3], g.w, be.w));
+            const float2 x0 = fma2(add2(make_float2(v[g8 * 8 + 4 * h], v[g8 * 8 + 4 * h + 1]), make_float2(b.x, b.y)), splat2(st.rstd), splat2(nmr));
+            const float2 x1 = fma2(add2(make_float2(v[g8 * 8 + 4 * h + 2], v[g8 * 8 + 4 * h + 3]), make_float2(b.z, b.w)), splat2(st.rstd), splat2(nmr));
+            xh[4 * h + 0] = x0.x; xh[4 * h + 1] = x0.y; xh[4 * h + 2] = x1.x; xh[4 * h + 3] = x1.y;
+            const float2 o0 = tc_act2<ACT_O>(fma2(x0, make_float2(g.x, g.y), make_float2(be.x, be.y)));
+            const float2 o1 = tc_act2<ACT_O>(fma2(x1, make_float2(g.z, g.w), make_float2(be.z, be.w)));
+            const float4 o = make_float4(o0.x, o0.y, o1.x, o1.y);
             *reinterpret_cast<float4*>(region + (size_t)row * (L * 4) + (((c >> 2) ^ (row & 7)) << 4)) = o;
           }
           if (xh2_t)
@@ -370,6 +367,8 @@ k_tc_edge_fwd(hgnn_tc_edge_params P, const uint16_t* __restrict__ xb16, const fl
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, C::TMEM_COLS);
 }
+
+#include "edge_fwd_pp.cuh"
 
 // bf16 shadow copy of the node rows (each row is gathered ~2 E/N times per step: convert once, gather half the bytes)
 __global__ void __launch_bounds__(256) k_rows_to_bf16(const float* __restrict__ x, int64_t n8, uint4* __restrict__ out) {
@@ -512,6 +511,32 @@ extern "C" int hgnn_tc_debug_gemm(const float* A, const void* w_packed, int64_t 
   return check_launch("tc_debug_gemm");
 }
 
+static int fwd_pp_enabled() {  // HGNN_FWD_PP=1 selects the persistent warp-specialised ping-pong kernel (A/B comparisons;
+  static int v = -1;           // measured equal to the two-CTA kernel within 5 %, see profiles/r02_fwd_pingpong.md)
+  if (v < 0) { const char* e = getenv("HGNN_FWD_PP"); v = e ? atoi(e) : 0; }
+  return v;
+}
+#ifdef HGNN_DEBUG_MBAR
+// debug builds only: {timed out?, block, thread, barrier smem address, parity, dynamic smem bytes, -, -} of the first stuck wait
+extern "C" int hgnn_tc_debug_mbar_timeout(int* out8) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out8, g_mbar_dbg, sizeof(int) * 8);
+}
+#endif
+#ifdef HGNN_TRACE
+// trace builds only: copies the event records of CTA 0 (3 x uint64 each) and resets the counter; returns the record count
+extern "C" int hgnn_tc_debug_trace(unsigned long long* out, int max_records) {
+  cudaDeviceSynchronize();
+  unsigned int n = 0;
+  cudaMemcpyFromSymbol(&n, pp::g_trace_n, sizeof(n));
+  if ((int)n > max_records) n = (unsigned)max_records;
+  if (n > 8192) n = 8192;
+  cudaMemcpyFromSymbol(out, pp::g_trace, sizeof(unsigned long long) * 3 * n);
+  unsigned int z = 0;
+  cudaMemcpyToSymbol(pp::g_trace_n, &z, sizeof(z));
+  return (int)n;
+}
+#endif
 static void* g_fwd_phase_clk = nullptr;
 static int fwd_stagger() {
   static int v = -1;
@@ -540,13 +565,23 @@ static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const f
     const int64_t n8 = n_nodes * L / 8;
     k_rows_to_bf16<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(x, n8, reinterpret_cast<uint4*>(xb16));
   }
-  size_t smem = Cfg<L>::SMEM;
-  auto kern = k_tc_edge_fwd<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
-  HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t tiles = (n_edges + TILE_M - 1) / TILE_M;
-  unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
-  kern<<<grid, TC_THREADS, smem, st>>>(*p, xb16, e, src, dst, perm, n_edges, e_out, rowptr, agg, stash, edge_stash_layout(n_edges, L),
-                                        (unsigned long long*)g_fwd_phase_clk, fwd_stagger());
+  if (fwd_pp_enabled() && L == 128) {  // persistent ping-pong kernel: one CTA per SM, two tiles in flight
+    if constexpr (L == 128) {
+      size_t smem = pp::PpCfg<L>::SMEM;
+      auto kern = pp::k_tc_edge_fwd_pp<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
+      HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)num_sms());
+      kern<<<grid, pp::PP_THREADS, smem, st>>>(*p, xb16, e, src, dst, perm, n_edges, e_out, rowptr, agg, stash, edge_stash_layout(n_edges, L));
+    }
+  } else {
+    size_t smem = Cfg<L>::SMEM;
+    auto kern = k_tc_edge_fwd<L, HGNN_ACT_GELU, HGNN_ACT_TANH>;
+    HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
+    kern<<<grid, TC_THREADS, smem, st>>>(*p, xb16, e, src, dst, perm, n_edges, e_out, rowptr, agg, stash, edge_stash_layout(n_edges, L),
+                                          (unsigned long long*)g_fwd_phase_clk, fwd_stagger());
+  }
   if (agg) {
     int64_t threads = n_nodes * (L / 4);
     k_agg_fixup<L><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(e_out, perm, rowptr, n_nodes, agg);

@@ -187,10 +187,12 @@ __global__ void __launch_bounds__(RF_THREADS, 2) k_tc_row_fwd(RowFwdArgs A) {
             if constexpr (RAW) {
               o = make_float4(v[g4 * 4 + 0] + b.x, v[g4 * 4 + 1] + b.y, v[g4 * 4 + 2] + b.z, v[g4 * 4 + 3] + b.w);
             } else {
-              o.x = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 0] + b.x, rstd, nmr), g.x, be.x));
-              o.y = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 1] + b.y, rstd, nmr), g.y, be.y));
-              o.z = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 2] + b.z, rstd, nmr), g.z, be.z));
-              o.w = tc_act<ACT>(fmaf(fmaf(v[g4 * 4 + 3] + b.w, rstd, nmr), g.w, be.w));
+              const float2 rs2 = splat2(rstd), nmr2 = splat2(nmr);
+              const float2 o0 = tc_act2<ACT>(fma2(fma2(add2(make_float2(v[g4 * 4 + 0], v[g4 * 4 + 1]), make_float2(b.x, b.y)), rs2, nmr2),
+                                                  make_float2(g.x, g.y), make_float2(be.x, be.y)));
+              const float2 o1 = tc_act2<ACT>(fma2(fma2(add2(make_float2(v[g4 * 4 + 2], v[g4 * 4 + 3]), make_float2(b.z, b.w)), rs2, nmr2),
+                                                  make_float2(g.z, g.w), make_float2(be.z, be.w)));
+              o = make_float4(o0.x, o0.y, o1.x, o1.y);
             }
             *reinterpret_cast<float4*>(region + (size_t)row * (C::SW * 4) + (((sc4 + g4) ^ (row & 7)) << 4)) = o;
           }

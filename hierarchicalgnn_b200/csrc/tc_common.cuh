@@ -38,14 +38,53 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same, with a suspend-time hint (ns): the hardware parks the thread until the phase completes or the time is up, so a
+// waiting role costs (almost) no issue slots — plain try_wait returns after a few tens of cycles and the loop around it
+// competes with the warps that have work
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU
+#ifdef HGNN_DEBUG_MBAR
+// debug builds (-DHGNN_DEBUG_MBAR): the first wait that times out records who / where, every later wait falls through, the
+// kernel ends (with garbage) and the host reads the record (per translation unit: hgnn_tc_debug_mbar_timeout in edge_tc.cu)
+static __device__ int g_mbar_dbg[8];
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (*(volatile int*)&g_mbar_dbg[0] != 0) return;
+    if (clock64() - t0 > 200000000LL) {
+      if (atomicCAS(&g_mbar_dbg[0], 0, 1) == 0) {
+        g_mbar_dbg[1] = (int)blockIdx.x; g_mbar_dbg[2] = (int)threadIdx.x; g_mbar_dbg[3] = (int)bar; g_mbar_dbg[4] = (int)parity;
+        uint32_t dyn; asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn)); g_mbar_dbg[5] = (int)dyn;
+        __threadfence();
+      }
+      return;
+    }
   }
 }
+#else
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t n = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {   // parked up to 20 us per attempt
+    if ((++n & 255u) == 0) {                           // the clock is read once per 256 attempts
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 8000000000LL) __trap();  // seconds: a protocol bug becomes a CUDA error, not a hang
+    }
+  }
+}
+#endif
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -69,6 +108,25 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float4* ptr, uint64_t pol) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
   return v;
 }
+// non-blocking test of a phase (no suspend): for schedulers that have something else to do
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging; src_bytes < 16 zero-fills the rest
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (tensor core / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -171,28 +229,71 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }  // rcp(+inf) = +0
 
-// GELU(y) = y * Phi(y) with Phi(y) ~= sigmoid(y * (c0 + c1 y^2 + c2 y^4)), y^2 clamped to 64.
+// hardware tanh (MUFU.TANH, one special-function slot; max relative error 2^-11, far below the bf16 rounding of every
+// value that passes through it here)
+__device__ __forceinline__ float tanh_approx(float x) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// ---- packed fp32 pairs: FFMA2 / FADD2 / FMUL2 issue two lanes of arithmetic per slot on sm_100 (profiles/micro/ffma2.cu);
+// the LayerNorm / activation epilogues are issue-bound, so everything that can be paired is ----
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+
+// GELU(y) = y * Phi(y) with Phi(y) ~= sigmoid(z), z = y * (c0 + c1 y^2 + c2 y^4), y^2 clamped to 64.
 // Coefficients fitted against the exact erf form: max |error| of GELU = 2.8e-5 over the reals
-// (profiles/fit_gelu.py). 7 FP32 ops + ex2 + rcp; the erf/exp form cost ~3x as many issue slots.
+// (profiles/fit_gelu.py). The backward's derivative takes sigmoid(z) = 1/2 + 1/2 tanh(z/2) through the hardware tanh (one
+// special-function op instead of ex2 + rcp: its 2^-11 lands on gradients that are rounded to bf16 right after).
 constexpr float kG0 = 1.5949518066125585f, kG1 = 0.07406933810902123f, kG2 = -0.0007124377042967553f;
 constexpr float kLog2e = 1.4426950408889634f;
 struct GeluParts { float sig, y2; };
 __device__ __forceinline__ GeluParts gelu_sigmoid(float y) {
   GeluParts g;
   g.y2 = fminf(y * y, 64.0f);
-  const float zn = y * fmaf(fmaf(-kG2 * kLog2e, g.y2, -kG1 * kLog2e), g.y2, -kG0 * kLog2e);  // -z * log2(e)
-  g.sig = rcp_approx(1.0f + ex2_approx(zn));
+  const float zh = y * fmaf(fmaf(0.5f * kG2, g.y2, 0.5f * kG1), g.y2, 0.5f * kG0);  // z / 2
+  g.sig = fmaf(0.5f, tanh_approx(zh), 0.5f);
   return g;
 }
-__device__ __forceinline__ float fast_gelu(float y) { return y * gelu_sigmoid(y).sig; }
+// forward: ex2 + rcp (1e-6) — g feeds GEMM2 and the LayerNorm behind it amplifies what the hardware tanh would add
+__device__ __forceinline__ float fast_gelu(float y) {
+  const float y2 = fminf(y * y, 64.0f);
+  const float zn = y * fmaf(fmaf(-kG2 * kLog2e, y2, -kG1 * kLog2e), y2, -kG0 * kLog2e);  // -z * log2(e)
+  return y * rcp_approx(1.0f + ex2_approx(zn));
+}
+__device__ __forceinline__ float2 fast_gelu2(float2 y) {
+  float2 y2 = mul2(y, y);
+  y2.x = fminf(y2.x, 64.0f);
+  y2.y = fminf(y2.y, 64.0f);
+  const float2 p = fma2(fma2(splat2(-kG2 * kLog2e), y2, splat2(-kG1 * kLog2e)), y2, splat2(-kG0 * kLog2e));
+  const float2 zn = mul2(y, p);
+  const float2 d = add2(make_float2(ex2_approx(zn.x), ex2_approx(zn.y)), splat2(1.0f));
+  return mul2(y, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+}
 // exact derivative of fast_gelu: sig * (1 + y (1 - sig) z'(y)),  z' = c0 + 3 c1 y^2 + 5 c2 y^4
 __device__ __forceinline__ float fast_gelu_bwd(float y) {
   const GeluParts g = gelu_sigmoid(y);
   const float zp = fmaf(fmaf(5.0f * kG2, g.y2, 3.0f * kG1), g.y2, kG0);
-  return g.sig * fmaf(y * (1.0f - g.sig), zp, 1.0f);
+  return g.sig * fmaf(fmaf(-y, g.sig, y), zp, 1.0f);
 }
-// tanh(y) = 1 - 2 / (1 + e^{2y}); saturates correctly through ex2 -> inf / 0
+__device__ __forceinline__ float2 fast_gelu_bwd2(float2 y) {
+  float2 y2 = mul2(y, y);
+  y2.x = fminf(y2.x, 64.0f);
+  y2.y = fminf(y2.y, 64.0f);
+  const float2 p = fma2(fma2(splat2(0.5f * kG2), y2, splat2(0.5f * kG1)), y2, splat2(0.5f * kG0));
+  const float2 zh = mul2(y, p);
+  const float2 sig = fma2(splat2(0.5f), make_float2(tanh_approx(zh.x), tanh_approx(zh.y)), splat2(0.5f));
+  const float2 zp = fma2(fma2(splat2(5.0f * kG2), y2, splat2(3.0f * kG1)), y2, splat2(kG0));
+  const float2 w = fma2(make_float2(-y.x, -y.y), sig, y);  // y (1 - sig)
+  return mul2(sig, fma2(w, zp, splat2(1.0f)));
+}
+// tanh(y) = 1 - 2 / (1 + e^{2y}); saturates correctly through ex2 -> inf / 0. The OUTPUT activation of the edge / node
+// networks lands in fp32 latents, so it keeps the ex2 + rcp form (1e-6) instead of the hardware tanh (5e-4).
 __device__ __forceinline__ float fast_tanh(float y) { return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(y * (2.0f * kLog2e))), 1.0f); }
+__device__ __forceinline__ float2 fast_tanh2(float2 y) {
+  const float2 a = mul2(y, splat2(2.0f * kLog2e));
+  const float2 d = add2(make_float2(ex2_approx(a.x), ex2_approx(a.y)), splat2(1.0f));
+  return fma2(splat2(-2.0f), make_float2(rcp_approx(d.x), rcp_approx(d.y)), splat2(1.0f));
+}
 // A&S 7.1.26 erf (|err| <= 1.5e-7) kept for activations that need it
 __device__ __forceinline__ float fast_erf(float x) {
   float ax = fabsf(x);
@@ -231,29 +332,60 @@ __device__ __forceinline__ float tc_act_bwd(float y) {
   }
 }
 
+// pairs: the GELU / Tanh of the HGNN edge and node networks have packed forms, the rest go lane by lane
+template <int ACT>
+__device__ __forceinline__ float2 tc_act2(float2 y) {
+  if constexpr (ACT == HGNN_ACT_GELU) return fast_gelu2(y);
+  else if constexpr (ACT == HGNN_ACT_TANH) return fast_tanh2(y);
+  else return make_float2(tc_act<ACT>(y.x), tc_act<ACT>(y.y));
+}
+template <int ACT>
+__device__ __forceinline__ float2 tc_act_bwd2(float2 y) {
+  if constexpr (ACT == HGNN_ACT_GELU) {
+    return fast_gelu_bwd2(y);
+  } else if constexpr (ACT == HGNN_ACT_TANH) {
+    const float2 t = make_float2(tanh_approx(y.x), tanh_approx(y.y));
+    return fma2(make_float2(-t.x, -t.y), t, splat2(1.0f));
+  } else {
+    return make_float2(tc_act_bwd<ACT>(y.x), tc_act_bwd<ACT>(y.y));
+  }
+}
+// 8 bf16 (one 16-byte chunk of an image / x-hat stash) -> 4 fp32 pairs: a shift / a mask per value
+__device__ __forceinline__ void unpack8_2(const uint4& q, float2 (&f)[4]) {
+  f[0] = make_float2(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u));
+  f[1] = make_float2(__uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+  f[2] = make_float2(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u));
+  f[3] = make_float2(__uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float2 v) { return pack_bf16(v.x, v.y); }
+
 // ---- LayerNorm epilogue pieces over a TMEM row (lane = row, this thread owns NCH*32 consecutive columns) ----
 // partial statistics of (accumulator + bias): single pass around a pivot taken from the row itself
 // (no catastrophic cancellation: |pivot - mean| is of the order of the row's spread)
 template <int NCH>
 __device__ __forceinline__ void ln_partial(uint32_t taddr, const float* __restrict__ sbias, float& mean_loc, float& m2_loc) {
   float v[32];
-  float pv = 0.f, sum = 0.f, sq = 0.f;
+  float pv = 0.f;
+  float2 sum = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f), npv = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     tmem_ld32(taddr + ch * 32, v);
     const float4* b4 = reinterpret_cast<const float4*>(sbias + ch * 32);
-    if (ch == 0) pv = v[0] + sbias[0];
+    if (ch == 0) { pv = v[0] + sbias[0]; npv = splat2(-pv); }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 b = b4[i];
-      const float d0 = v[4 * i] + b.x - pv, d1 = v[4 * i + 1] + b.y - pv, d2 = v[4 * i + 2] + b.z - pv, d3 = v[4 * i + 3] + b.w - pv;
-      sum += (d0 + d1) + (d2 + d3);
-      sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+      const float2 d0 = add2(add2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(b.x, b.y)), npv);
+      const float2 d1 = add2(add2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w)), npv);
+      sum = add2(sum, add2(d0, d1));
+      sq = fma2(d0, d0, sq);
+      sq = fma2(d1, d1, sq);
     }
   }
   constexpr float inv = 1.0f / (NCH * 32);
-  mean_loc = fmaf(sum, inv, pv);
-  m2_loc = fmaxf(sq - sum * sum * inv, 0.f);
+  const float sm = sum.x + sum.y, sqs = sq.x + sq.y;
+  mean_loc = fmaf(sm, inv, pv);
+  m2_loc = fmaxf(sqs - sm * sm * inv, 0.f);
 }
 
 // act(LayerNorm(accumulator + bias)) -> bf16, written as the K-major swizzled A-operand image of the next GEMM.
@@ -265,7 +397,7 @@ __device__ __forceinline__ void ln_act_to_image(uint32_t taddr, const float* __r
                                                 const float* __restrict__ sbe, int c0, float mean, float rstd,
                                                 uint8_t* __restrict__ img, int row, uint4* __restrict__ xh_out = nullptr) {
   float v[32];
-  const float nmr = -mean * rstd;
+  const float2 rs2 = splat2(rstd), nmr2 = splat2(-mean * rstd);
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     tmem_ld32(taddr + ch * 32, v);
@@ -273,26 +405,21 @@ __device__ __forceinline__ void ln_act_to_image(uint32_t taddr, const float* __r
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
       const int c = cb + g8 * 8;
-      float o[8], xh[8];
+      float2 o[4], xh[4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 b = *reinterpret_cast<const float4*>(sb + c + 4 * h);
         const float4 g = *reinterpret_cast<const float4*>(sg + c + 4 * h);
         const float4 be = *reinterpret_cast<const float4*>(sbe + c + 4 * h);
-        xh[4 * h + 0] = fmaf(v[g8 * 8 + 4 * h + 0] + b.x, rstd, nmr);
-        xh[4 * h + 1] = fmaf(v[g8 * 8 + 4 * h + 1] + b.y, rstd, nmr);
-        xh[4 * h + 2] = fmaf(v[g8 * 8 + 4 * h + 2] + b.z, rstd, nmr);
-        xh[4 * h + 3] = fmaf(v[g8 * 8 + 4 * h + 3] + b.w, rstd, nmr);
-        o[4 * h + 0] = tc_act<ACT>(fmaf(xh[4 * h + 0], g.x, be.x));
-        o[4 * h + 1] = tc_act<ACT>(fmaf(xh[4 * h + 1], g.y, be.y));
-        o[4 * h + 2] = tc_act<ACT>(fmaf(xh[4 * h + 2], g.z, be.z));
-        o[4 * h + 3] = tc_act<ACT>(fmaf(xh[4 * h + 3], g.w, be.w));
+        xh[2 * h] = fma2(add2(make_float2(v[g8 * 8 + 4 * h], v[g8 * 8 + 4 * h + 1]), make_float2(b.x, b.y)), rs2, nmr2);
+        xh[2 * h + 1] = fma2(add2(make_float2(v[g8 * 8 + 4 * h + 2], v[g8 * 8 + 4 * h + 3]), make_float2(b.z, b.w)), rs2, nmr2);
+        o[2 * h] = tc_act2<ACT>(fma2(xh[2 * h], make_float2(g.x, g.y), make_float2(be.x, be.y)));
+        o[2 * h + 1] = tc_act2<ACT>(fma2(xh[2 * h + 1], make_float2(g.z, g.w), make_float2(be.z, be.w)));
       }
       *reinterpret_cast<uint4*>(img + (c / KBLK) * A_BLK_BYTES + sw128_off(row, (c % KBLK) >> 3)) =
-          make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          make_uint4(pack_bf16(o[0]), pack_bf16(o[1]), pack_bf16(o[2]), pack_bf16(o[3]));
       if (xh_out)
-        xh_out[(size_t)(c >> 3) * TILE_M + row] =
-            make_uint4(pack_bf16(xh[0], xh[1]), pack_bf16(xh[2], xh[3]), pack_bf16(xh[4], xh[5]), pack_bf16(xh[6], xh[7]));
+        xh_out[(size_t)(c >> 3) * TILE_M + row] = make_uint4(pack_bf16(xh[0]), pack_bf16(xh[1]), pack_bf16(xh[2]), pack_bf16(xh[3]));
     }
   }
 }
