@@ -95,6 +95,8 @@ SIGNATURES = {
                                          C.POINTER(vp * MAX_LAYERS), vp, sz, vp]),
     "hgnn_mlp_backward_weights": (C.c_int, [C.POINTER(MlpDesc), i64, C.POINTER(vp * MAX_LAYERS), vp, sz, vp]),
     "hgnn_knn_radius": (C.c_int, [vp, i64, vp, i64, i64, i64, f32, vp, vp]),
+    "hgnn_knn_radius_workspace_bytes": (sz, [i64, i64, i64]),
+    "hgnn_knn_radius_ws": (C.c_int, [vp, i64, vp, i64, i64, i64, f32, vp, vp, sz, vp]),
     "hgnn_knn_edges_workspace_bytes": (sz, [i64]),
     "hgnn_knn_edges": (C.c_int, [vp, i64, i64, vp, vp, vp, sz, vp]),
     "hgnn_symmetrize_workspace_bytes": (sz, [i64]),

@@ -153,18 +153,24 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < 16; ++u) fma_acc(acc, w[u], v[u]);
   }
-  for (; j + 4 <= end; j += 4) {
-    int i0 = perm ? perm[j] : j, i1 = perm ? perm[j + 1] : j + 1, i2 = perm ? perm[j + 2] : j + 2, i3 = perm ? perm[j + 3] : j + 3;
-    int64_t r0 = gather ? gather[i0] : i0, r1 = gather ? gather[i1] : i1, r2 = gather ? gather[i2] : i2, r3 = gather ? gather[i3] : i3;
-    float w0 = weight ? weight[i0] : 1.f, w1 = weight ? weight[i1] : 1.f, w2 = weight ? weight[i2] : 1.f, w3 = weight ? weight[i3] : 1.f;
-    V v0 = rows[r0 * chunks + c], v1 = rows[r1 * chunks + c], v2 = rows[r2 * chunks + c], v3 = rows[r3 * chunks + c];
-    fma_acc(acc, w0, v0); fma_acc(acc, w1, v1); fma_acc(acc, w2, v2); fma_acc(acc, w3, v3);
-  }
-  for (; j < end; ++j) {
-    int i0 = perm ? perm[j] : j;
-    int64_t r0 = gather ? gather[i0] : i0;
-    float w0 = weight ? weight[i0] : 1.f;
-    fma_acc(acc, w0, rows[r0 * chunks + c]);
+  // ordinary segments: predicated batches of 8 — every index load, then every row load of the batch is in flight before the
+  // first add (a serial tail of dependent perm -> row round trips cost more than the batch body); summed in row order
+  for (; j < end; j += 8) {
+    V v[8];
+    float w[8];
+    int64_t r[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool ok = j + u < end;
+      const int i = ok ? (perm ? perm[j + u] : j + u) : 0;
+      r[u] = ok ? (gather ? (int64_t)gather[i] : (int64_t)i) : -1;
+      w[u] = (ok && weight) ? weight[i] : 1.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = r[u] >= 0 ? rows[r[u] * chunks + c] : zero_v<V>();
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r[u] >= 0) fma_acc(acc, w[u], v[u]);
   }
   if (mean) scale_v(acc, 1.0f / (float)max(end - beg, 1));
   reinterpret_cast<V*>(out)[s * chunks + c] = acc;
@@ -236,18 +242,36 @@ __global__ void __launch_bounds__(LONG_THREADS) k_segment_reduce_long(const floa
   }
 }
 
+// four rows per thread: four independent index -> row load chains in flight (one row per thread left the kernel at 45 % of the
+// HBM roof: 16 bytes in flight per thread cannot cover the latency)
+constexpr int GATHER_ROWS_PER_THREAD = 4;
 template <int VEC>
 __global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ src, int chunks, const int32_t* __restrict__ idx,
                               const float* __restrict__ weight, int64_t n, float* __restrict__ out) {
   using V = typename VecT<VEC>::type;
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t i = t / chunks;
-  int c = (int)(t - i * chunks);
-  if (i >= n) return;
-  int64_t r = idx ? idx[i] : i;
-  V v = reinterpret_cast<const V*>(src)[r * chunks + c];
-  if (weight) scale_v(v, weight[i]);
-  reinterpret_cast<V*>(out)[i * chunks + c] = v;
+  constexpr int R = GATHER_ROWS_PER_THREAD;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t g = t / chunks;
+  const int c = (int)(t - g * chunks);
+  const int64_t i0 = g * R;
+  if (i0 >= n) return;
+  int64_t r[R];
+  float w[R];
+  V v[R];
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const int64_t i = i0 + u;
+    r[u] = i < n ? (idx ? (int64_t)idx[i] : i) : -1;
+    w[u] = (i < n && weight) ? weight[i] : 1.f;
+  }
+#pragma unroll
+  for (int u = 0; u < R; ++u) v[u] = r[u] >= 0 ? reinterpret_cast<const V*>(src)[r[u] * chunks + c] : zero_v<V>();
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    if (r[u] < 0) continue;
+    if (weight) scale_v(v[u], w[u]);
+    reinterpret_cast<V*>(out)[(i0 + u) * chunks + c] = v[u];
+  }
 }
 
 // LANES threads cooperate on one item (LANES = 1, 8 or 32)
@@ -316,7 +340,7 @@ extern "C" int hgnn_gather_rows(const float* src, int64_t width, const int32_t* 
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = (width % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
   int chunks = vec ? (int)(width / 4) : (int)width;
-  int64_t threads = n_items * chunks;
+  int64_t threads = (n_items + GATHER_ROWS_PER_THREAD - 1) / GATHER_ROWS_PER_THREAD * chunks;
   unsigned grid = (unsigned)((threads + 255) / 256);
   if (vec) k_gather_rows<4><<<grid, 256, 0, st>>>(src, chunks, idx, weight, n_items, out);
   else k_gather_rows<1><<<grid, 256, 0, st>>>(src, chunks, idx, weight, n_items, out);
@@ -345,10 +369,16 @@ constexpr int KNN_THREADS = 128;
 constexpr int KNN_TILE = 128;
 constexpr int KNN_KMAX = 32;
 
-template <int DIM>  // DIM > 0: compile-time dimension with the query in registers; 0: runtime dim (<= 32)
+// One thread per query, references tiled through shared memory, register top-k with strict-< insertion (an equal distance
+// never displaces an earlier = smaller index). KCAP = compile-time capacity of the register list (8 / 16 / 32 >= k): the
+// insertion chain and the register footprint follow k instead of the maximum. blockIdx.y = reference split: a CTA scans
+// the contiguous reference range [split * ref_per_split, ...) and, when there is more than one split, leaves its sorted
+// partial list (distance, index) in the workspace for k_knn_merge — small problems (1 200 x 1 200) otherwise occupy ten SMs.
+template <int DIM, int KCAP>  // DIM > 0: compile-time dimension with the query in registers; 0: runtime dim (<= 32)
 __global__ void __launch_bounds__(KNN_THREADS) k_knn_radius(const float* __restrict__ query, int64_t nq, const float* __restrict__ ref,
-                                                           int64_t nr, int dim_rt, int k, float r2, int64_t* __restrict__ idx) {
-  extern __shared__ float smem[];
+                                                           int64_t nr, int dim_rt, int k, float r2, int64_t ref_per_split,
+                                                           int64_t* __restrict__ idx, float* __restrict__ part_d, int32_t* __restrict__ part_i) {
+  extern __shared__ __align__(16) float smem[];
   const int dim = DIM > 0 ? DIM : dim_rt;
   float* s_ref = smem;                           // [KNN_TILE][dim]
   float* s_q = smem + KNN_TILE * dim;            // [KNN_THREADS][dim+1] (runtime-dim path only)
@@ -361,21 +391,28 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_radius(const float* __restr
   } else {
     for (int d = 0; d < dim; ++d) s_q[threadIdx.x * (dim + 1) + d] = live ? query[q * dim + d] : 0.f;
   }
-  float bd[KNN_KMAX];
-  int bi[KNN_KMAX];
+  float bd[KCAP];
+  int bi[KCAP];
 #pragma unroll
-  for (int j = 0; j < KNN_KMAX; ++j) { bd[j] = INFINITY; bi[j] = -1; }
+  for (int j = 0; j < KCAP; ++j) { bd[j] = INFINITY; bi[j] = -1; }
   float kth = INFINITY;  // current k-th best distance
 
-  for (int64_t base = 0; base < nr; base += KNN_TILE) {
-    int cnt = (int)min((int64_t)KNN_TILE, nr - base);
+  const int64_t ref_lo = (int64_t)blockIdx.y * ref_per_split;
+  const int64_t ref_hi = min(nr, ref_lo + ref_per_split);
+  for (int64_t base = ref_lo; base < ref_hi; base += KNN_TILE) {
+    int cnt = (int)min((int64_t)KNN_TILE, ref_hi - base);
     __syncthreads();
     for (int t = threadIdx.x; t < cnt * dim; t += KNN_THREADS) s_ref[t] = ref[base * dim + t];
     __syncthreads();
     if (!live) continue;
     for (int j = 0; j < cnt; ++j) {
       float d2 = 0.f;
-      if (DIM > 0) {
+      if (DIM == 8) {  // two 16-byte broadcast loads per reference instead of eight scalar ones; same fma order
+        const float4 a = *reinterpret_cast<const float4*>(s_ref + j * 8), b = *reinterpret_cast<const float4*>(s_ref + j * 8 + 4);
+        const float rv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { float df = qreg[d] - rv[d]; d2 = fmaf(df, df, d2); }
+      } else if (DIM > 0) {
 #pragma unroll
         for (int d = 0; d < (DIM > 0 ? DIM : 1); ++d) { float df = qreg[d] - s_ref[j * dim + d]; d2 = fmaf(df, df, d2); }
       } else {
@@ -384,22 +421,53 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_radius(const float* __restr
       if (d2 < r2 && d2 < kth) {
         float cd = d2;
         int ci = (int)(base + j);
+        bool placed = false;
 #pragma unroll
-        for (int m = 0; m < KNN_KMAX; ++m) {
+        for (int m = 0; m < KCAP; ++m) {
           if (m < k) {
-            // strict '<': an equal distance never displaces an earlier (smaller) index
-            if (cd < bd[m]) { float td = bd[m]; int ti = bi[m]; bd[m] = cd; bi[m] = ci; cd = td; ci = ti; }
+            // strict '<' for the new candidate: an equal distance never displaces an earlier (smaller) index. Once it is
+            // placed, everything below shifts down by one unconditionally — a displaced entry compared with '<' would
+            // jump over an equal-distance entry that was behind it and reverse their order
+            if (placed || cd < bd[m]) { float td = bd[m]; int ti = bi[m]; bd[m] = cd; bi[m] = ci; cd = td; ci = ti; placed = true; }
           }
         }
         // refresh the k-th best (bd[k-1]) without dynamic register indexing
 #pragma unroll
-        for (int m = 0; m < KNN_KMAX; ++m) if (m == k - 1) kth = bd[m];
+        for (int m = 0; m < KCAP; ++m) if (m == k - 1) kth = bd[m];
       }
     }
   }
   if (live) {
+    if (gridDim.y == 1) {
 #pragma unroll
-    for (int m = 0; m < KNN_KMAX; ++m) if (m < k) idx[q * k + m] = (int64_t)bi[m];
+      for (int m = 0; m < KCAP; ++m) if (m < k) idx[q * k + m] = (int64_t)bi[m];
+    } else {
+      const int64_t o = ((int64_t)blockIdx.y * nq + q) * k;
+#pragma unroll
+      for (int m = 0; m < KCAP; ++m) if (m < k) { part_d[o + m] = bd[m]; part_i[o + m] = bi[m]; }
+    }
+  }
+}
+
+// merges the per-split sorted lists of one query: k rounds of "smallest head", ties to the lower split = the smaller index
+// (splits are increasing reference ranges), i.e. exactly the list a single scan would have produced
+__global__ void k_knn_merge(const float* __restrict__ part_d, const int32_t* __restrict__ part_i, int n_split, int64_t nq, int k,
+                            int64_t* __restrict__ idx) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  unsigned char head[64];
+  for (int s = 0; s < n_split; ++s) head[s] = 0;
+  for (int m = 0; m < k; ++m) {
+    float best = INFINITY;
+    int bs = -1;
+    for (int s = 0; s < n_split; ++s) {
+      if (head[s] >= k) continue;
+      const float d = part_d[((int64_t)s * nq + q) * k + head[s]];
+      if (d < best) { best = d; bs = s; }
+    }
+    if (bs < 0) { idx[q * k + m] = -1; continue; }
+    idx[q * k + m] = (int64_t)part_i[((int64_t)bs * nq + q) * k + head[bs]];
+    ++head[bs];
   }
 }
 
@@ -425,20 +493,60 @@ __global__ void k_knn_fill(const int64_t* __restrict__ idx, int64_t nq, int k, c
 
 }  // namespace
 
-extern "C" int hgnn_knn_radius(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
-                               float radius, int64_t* idx, void* stream) {
+static int knn_splits(int64_t n_query, int64_t n_ref) {
+  const int64_t qblocks = (n_query + KNN_THREADS - 1) / KNN_THREADS;
+  const int64_t ref_tiles = (n_ref + KNN_TILE - 1) / KNN_TILE;
+  int64_t want = (2 * (int64_t)num_sms() + qblocks - 1) / qblocks;  // aim at two CTAs per SM
+  want = std::min<int64_t>(std::min<int64_t>(want, ref_tiles), 64);
+  return (int)std::max<int64_t>(want, 1);
+}
+
+extern "C" size_t hgnn_knn_radius_workspace_bytes(int64_t n_query, int64_t n_ref, int64_t k) {
+  const int sp = knn_splits(n_query, n_ref);
+  return sp <= 1 ? 0 : (size_t)sp * (size_t)n_query * (size_t)k * 8 + 256;
+}
+
+template <int DIM>
+static void launch_knn(int kcap, dim3 grid, size_t smem, cudaStream_t st, const float* query, int64_t nq, const float* ref, int64_t nr,
+                       int dim, int k, float r2, int64_t per, int64_t* idx, float* pd, int32_t* pi) {
+  if (kcap == 8) k_knn_radius<DIM, 8><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi);
+  else if (kcap == 16) k_knn_radius<DIM, 16><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi);
+  else k_knn_radius<DIM, 32><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi);
+}
+
+// ws may be NULL (or too small): the scan then runs unsplit, one CTA per 128 queries
+extern "C" int hgnn_knn_radius_ws(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                                  float radius, int64_t* idx, void* ws, size_t ws_bytes, void* stream) {
   if (n_query <= 0 || k <= 0) return HGNN_OK;
   HGNN_REQUIRE(query && idx, "knn_radius: NULL pointer");
   HGNN_REQUIRE(dim >= 1 && dim <= 32, "knn_radius: dim must be in [1,32], got %lld", (long long)dim);
   HGNN_REQUIRE(k <= KNN_KMAX, "knn_radius: k must be <= %d, got %lld", KNN_KMAX, (long long)k);
   HGNN_REQUIRE(n_ref >= 0 && n_ref < INT32_MAX, "knn_radius: n_ref out of range");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned grid = (unsigned)((n_query + KNN_THREADS - 1) / KNN_THREADS);
+  int sp = knn_splits(n_query, n_ref);
+  if (sp > 1 && (ws == nullptr || ws_bytes < hgnn_knn_radius_workspace_bytes(n_query, n_ref, k))) sp = 1;
+  const int64_t tiles = (n_ref + KNN_TILE - 1) / KNN_TILE;
+  const int64_t per = (tiles + sp - 1) / sp * KNN_TILE;  // references per split (whole tiles)
+  sp = (int)std::max<int64_t>(1, (n_ref + per - 1) / std::max<int64_t>(per, 1));
+  float* pd = nullptr;
+  int32_t* pi = nullptr;
+  if (sp > 1) {
+    pd = (float*)align_up((uintptr_t)ws, 256);
+    pi = (int32_t*)(pd + (size_t)sp * n_query * k);
+  }
+  dim3 grid((unsigned)((n_query + KNN_THREADS - 1) / KNN_THREADS), (unsigned)sp);
   float r2 = radius * radius;
   size_t smem = (size_t)(KNN_TILE * dim + KNN_THREADS * (dim + 1)) * sizeof(float);
-  if (dim == 8) k_knn_radius<8><<<grid, KNN_THREADS, smem, st>>>(query, n_query, ref, n_ref, 8, (int)k, r2, idx);
-  else k_knn_radius<0><<<grid, KNN_THREADS, smem, st>>>(query, n_query, ref, n_ref, (int)dim, (int)k, r2, idx);
+  const int kcap = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
+  if (dim == 8) launch_knn<8>(kcap, grid, smem, st, query, n_query, ref, n_ref, 8, (int)k, r2, per, idx, pd, pi);
+  else launch_knn<0>(kcap, grid, smem, st, query, n_query, ref, n_ref, (int)dim, (int)k, r2, per, idx, pd, pi);
+  if (sp > 1) k_knn_merge<<<(unsigned)((n_query + 127) / 128), 128, 0, st>>>(pd, pi, sp, n_query, (int)k, idx);
   return check_launch("knn_radius");
+}
+
+extern "C" int hgnn_knn_radius(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                               float radius, int64_t* idx, void* stream) {
+  return hgnn_knn_radius_ws(query, n_query, ref, n_ref, dim, k, radius, idx, nullptr, 0, stream);
 }
 
 extern "C" size_t hgnn_knn_edges_workspace_bytes(int64_t n_query) {

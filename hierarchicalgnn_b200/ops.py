@@ -1100,9 +1100,12 @@ def knn_radius(query: Tensor, ref: Tensor, k: int, radius: float) -> Tensor:
     q, r = _f32(query.detach()), _f32(ref.detach())
     idx = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
     if q.shape[0] and k:
-        check(_lib.lib().hgnn_knn_radius(_ptr(q), q.shape[0], _ptr(r), r.shape[0], q.shape[1], k, float(radius), _ptr(idx),
-                                         _stream()), "knn_radius")
-        _count()
+        L = _lib.lib()
+        nb = L.hgnn_knn_radius_workspace_bytes(q.shape[0], r.shape[0], k)  # > 0: small problem, split over reference ranges
+        ws = _workspace(nb, q.device) if nb else None
+        check(L.hgnn_knn_radius_ws(_ptr(q), q.shape[0], _ptr(r), r.shape[0], q.shape[1], k, float(radius), _ptr(idx),
+                                   _ptr(ws), ws.numel() if ws is not None else 0, _stream()), "knn_radius")
+        _count(2 if nb else 1)
     return idx
 
 

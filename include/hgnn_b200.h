@@ -151,6 +151,12 @@ int hgnn_mlp_backward_weights(const hgnn_mlp_desc* d, int64_t rows, float* const
  * ------------------------------------------------------------------------ */
 int hgnn_knn_radius(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
                     float radius, int64_t* idx, void* stream);
+/* Same result, bit for bit. With a workspace (hgnn_knn_radius_workspace_bytes; 0 bytes for large problems) a small
+ * problem is split over contiguous reference ranges (grid = query blocks x splits, two CTAs per SM) and the per-split
+ * sorted lists are merged (ties to the lower range = the smaller index); without one it runs as hgnn_knn_radius. */
+size_t hgnn_knn_radius_workspace_bytes(int64_t n_query, int64_t n_ref, int64_t k);
+int hgnn_knn_radius_ws(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                       float radius, int64_t* idx, void* ws, size_t ws_bytes, void* stream);
 
 /* Compacts idx (>= 0 entries, query-major, rank-minor: gnn_utils.py:195-202)
  * into graph[2, n_query*k] (row 0 = query id, row 1 = neighbour id; only the

@@ -7,6 +7,7 @@ from hierarchicalgnn_b200.synth import synth_event
 from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
 
 which = sys.argv[1] if len(sys.argv) > 1 else "bc"
+fresh = len(sys.argv) > 2 and sys.argv[2] == "fresh"   # a new edge-list tensor every step (as a data loader delivers): no cached plans
 ev = synth_event(1200, 10, 0.0, 4.0, seed=1000)
 x, g = ev.x.cuda(), ev.edge_index.cuda()
 torch.manual_seed(0)
@@ -15,14 +16,14 @@ if which == "bc":
     clusters = (ev.pid - 1).cuda()
     def step():
         m.zero_grad(set_to_none=True)
-        bg, sc, emb = m(x.clone(), g, clusters=clusters)
+        bg, sc, emb = m(x.clone(), g.clone() if fresh else g, clusters=clusters)
         (sc.sum() + emb.sum()).backward()
 else:
     m = model_selector("EC-IN"); kaiming_init(m); m.cuda()
     y = ev.y_pid.float().cuda()
     def step():
         m.zero_grad(set_to_none=True)
-        torch.nn.functional.binary_cross_entropy(m(x.clone(), g), y).backward()
+        torch.nn.functional.binary_cross_entropy(m(x.clone(), g.clone() if fresh else g), y).backward()
 for _ in range(3): step()
 torch.cuda.synchronize()
 t0 = time.perf_counter()

@@ -215,6 +215,36 @@ def test_knn_tie_rule_smaller_index_first(ops):
     assert got.tolist() == [[0, 2, 3]]
     got = ops.knn_radius(q.to(DEV), r.to(DEV), 3, 0.5).cpu()  # strict '<' radius
     assert got.tolist() == [[-1, -1, -1]]
+    # a closer point arriving AFTER a tied pair pushes both down without reversing them
+    r2 = torch.tensor([[0.0, 0.5], [0.0, -0.5], [0.0, 0.1], [0.5, 0.0]])
+    got = ops.knn_radius(q.to(DEV), r2.to(DEV), 4, 2.0).cpu()
+    assert got.tolist() == [[2, 0, 1, 3]]
+
+
+@pytest.mark.parametrize("nq,nr,dim,k", [(1200, 1200, 8, 10), (300, 1000, 8, 7), (77, 5000, 8, 5), (130, 300, 5, 12), (1, 129, 8, 3)])
+def test_knn_reference_split_path_is_bit_identical_to_the_single_scan(ops, nq, nr, dim, k):
+    """Small problems are split over contiguous reference ranges (grid = query blocks x splits) and the per-split sorted
+    lists merged; the result must equal the unsplit scan bit for bit, including ties (duplicated reference rows: the
+    smaller index first) and rows with fewer than k neighbours inside the radius."""
+    from hierarchicalgnn_b200 import _lib
+    g = torch.Generator().manual_seed(nq + nr)
+    q = torch.randn(nq, dim, generator=g)
+    r = torch.randn(nr, dim, generator=g)
+    r[nr // 2:nr // 2 + nr // 8] = r[:nr // 8]          # exact duplicates in different reference ranges: distance ties
+    radius = 1.9
+    L = _lib.lib()
+    assert L.hgnn_knn_radius_workspace_bytes(nq, nr, k) > 0, "shape does not take the split path"
+    qd, rd = q.to(DEV), r.to(DEV)
+    one = torch.empty((nq, k), dtype=torch.int64, device=DEV)
+    assert L.hgnn_knn_radius(qd.data_ptr(), nq, rd.data_ptr(), nr, dim, k, radius, one.data_ptr(), None) == 0
+    split = ops.knn_radius(qd, rd, k, radius)
+    torch.cuda.synchronize()
+    assert torch.equal(split, one)
+    if nq >= 50:
+        assert bool((split < 0).any()) and bool((split >= 0).any())  # padded rows and real neighbours both occur
+    want = O.knn_radius(q, r, k, radius)
+    agree = (split.cpu() == want).float().mean()
+    assert agree > 0.999  # fp64 oracle vs fp32 sums: only near-ties may swap
 
 
 def test_edge_max_dist(ops):
