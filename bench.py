@@ -616,7 +616,7 @@ def run_partition(args, dev=None, world=None, rank=None, barrier=None, emit=True
     import torch.distributed as dist
     from hierarchicalgnn_b200 import ops
     from hierarchicalgnn_b200.gnn_utils import InteractionGNNCell
-    from hierarchicalgnn_b200.parallel import (cuda_cell_callables, pad_rows, partition_by_destination,
+    from hierarchicalgnn_b200.parallel import (SymmetricRows, cuda_cell_callables, pad_rows, partition_by_destination,
                                                partitioned_interaction_cell)
     from hierarchicalgnn_b200.synth import synth_edge_problem
     from hierarchicalgnn_b200.training_utils import kaiming_init
@@ -637,20 +637,26 @@ def run_partition(args, dev=None, world=None, rank=None, barrier=None, emit=True
     steps = steps or args.steps
     L = args.latent
     E = args.edges if (own_pg and args.edges != 1_000_000) else 3_000_000
+    n_cells = max(1, int(os.environ.get("HGNN_PART_CELLS", "2")))
     torch.manual_seed(0)
-    cell = InteractionGNNCell(hparams(L))
-    kaiming_init(cell)
-    cell.to(dev)
+    cells = []
+    for _ in range(n_cells):
+        c = InteractionGNNCell(hparams(L))
+        kaiming_init(c)
+        cells.append(c.to(dev))
     nodes_h, edges_h, graph_h = synth_edge_problem(E, L, seed=2000, nodes_per_edge=0.04)
     N = nodes_h.shape[0]
     g = torch.Generator().manual_seed(11)
     cot_n, cot_e = torch.randn(N, L, generator=g), torch.randn(E, L, generator=g)
-    node_fn, edge_fn, seg = cuda_cell_callables(cell)
-    params = list(cell.parameters())
+    # every cell but the last leaves scatter_add(e', dst) behind for the next cell's node update (fused segmented reduce)
+    calls = [cuda_cell_callables(c, fuse_aggregate=(i + 1 < n_cells)) for i, c in enumerate(cells)]
+    params = [p for c in cells for p in c.parameters()]
     solo = None
     if world > 1:
         groups = [dist.new_group([r]) for r in range(world)]  # every rank creates every group (collective call)
         solo = groups[rank]
+    use_symm = world > 1 and os.environ.get("HGNN_PART_SYMM", "1") != "0"
+    coll = {"impl": "nccl"}
 
     def make_step(w, r, group):
         part = partition_by_destination(graph_h, N, w, r)
@@ -659,29 +665,45 @@ def run_partition(args, dev=None, world=None, rank=None, barrier=None, emit=True
         nodes = pad_rows(nodes_h, w * part.block).to(dev).requires_grad_(True)
         e_loc = edges_h[part.edge_ids].to(dev).requires_grad_(True)
         part.graph, part.dst_local, part.edge_ids = part.graph.to(dev), part.dst_local.to(dev), part.edge_ids.to(dev)
+        sr = None
+        if w > 1 and use_symm:
+            try:  # the repo's own peer-memory row collectives (csrc/p2p.cu) over symmetric tables; NCCL otherwise
+                sr = SymmetricRows(part.block, L, dev, group=group, slots=n_cells)
+                coll["impl"] = "peer-memory kernels, multimem (NVLS)" if sr.mc_base else "peer-memory kernels, peer pointers"
+            except Exception as ex:  # noqa: BLE001
+                coll["impl"] = f"nccl (symmetric memory unavailable: {type(ex).__name__})"
+                sr = None
 
         def step(_i=0):
-            n2, e2 = partitioned_interaction_cell(part, nodes, e_loc, node_fn, edge_fn, seg, group=group)
-            grads = torch.autograd.grad([n2[own], e2], [nodes, e_loc] + params, [cot_n_d, cot_e_d])
+            x, e, agg, xo = nodes, e_loc, None, None
+            for ci, (node_fn, edge_fn, seg) in enumerate(calls):
+                x, e, agg, xo = partitioned_interaction_cell(part, x, e, node_fn, edge_fn, seg, group=group, symmetric=sr,
+                                                             agg_owned=agg, return_agg=True, x_owned=xo, slot=ci,
+                                                             return_owned=True)
+            grads = torch.autograd.grad([x[own], e], [nodes, e_loc] + params, [cot_n_d, cot_e_d])
             if w > 1:
-                flat = torch.cat([x.reshape(-1) for x in grads[2:]])
+                flat = torch.cat([t.reshape(-1) for t in grads[2:]])
                 dist.all_reduce(flat, group=group)
                 # replicated input nodes: each rank holds the gradient of its own block only (the other rows are zero),
                 # so the sum over ranks is an all-gather of the owned blocks
-                gfull = torch.empty_like(grads[0])
-                dist.all_gather_into_tensor(gfull, grads[0][part.node_lo:part.node_lo + part.block].contiguous(), group=group)
-            return n2, e2
-        return step, part
+                blk = grads[0][part.node_lo:part.node_lo + part.block].contiguous()
+                if sr is not None:
+                    sr.all_gather(blk)
+                else:
+                    gfull = torch.empty_like(grads[0])
+                    dist.all_gather_into_tensor(gfull, blk, group=group)
+            return x, e
+        return step, part, sr
 
     one_gpu_ms = None
     if world > 1:  # the 1-GPU denominator, measured here and now with the same kernels
-        step1, _ = make_step(1, 0, solo)
+        step1, _, _ = make_step(1, 0, solo)
         for _ in range(3):
             step1()
         one_gpu_ms = _timed(step1, steps, barrier, world, dev)
         del step1
         torch.cuda.empty_cache()
-    step, part = make_step(world, rank, None)
+    step, part, sr = make_step(world, rank, None)
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(dev.index) if (rank == 0 and own_pg) else None
@@ -689,13 +711,26 @@ def run_partition(args, dev=None, world=None, rank=None, barrier=None, emit=True
     ms = _timed(step, steps, barrier, world, dev)
     launches = ops.LAUNCHES["count"] - l0
     clocks = sampler.stop() if sampler else None
-    res = {"workload": f"InteractionGNNCell fwd+bwd on one full-pile-up shaped event, L={L} E={E} N={N}, destination-partitioned "
-                       f"x{world} (BASELINE config 5)", "ms_per_step": ms, "steps": steps, "edge_steps_per_s": E / (ms * 1e-3),
+    # the two row collectives of a cell on their own (same tables, same barriers), for the record
+    if world > 1:
+        blk = torch.randn(part.block, L, device=dev)
+        full = torch.randn(world * part.block, L, device=dev)
+        if sr is not None:
+            coll["all_gather_ms"] = _timed(lambda i: sr.all_gather(blk), 10, barrier, world, dev)
+            coll["reduce_scatter_ms"] = _timed(lambda i: sr.reduce_scatter(full), 10, barrier, world, dev)
+        else:
+            o1, o2 = torch.empty_like(full), torch.empty_like(blk)
+            coll["all_gather_ms"] = _timed(lambda i: dist.all_gather_into_tensor(o1, blk), 10, barrier, world, dev)
+            coll["reduce_scatter_ms"] = _timed(lambda i: dist.reduce_scatter_tensor(o2, full), 10, barrier, world, dev)
+        coll["table_bytes"] = int(world * part.block * L * 4)
+    res = {"workload": f"{n_cells} InteractionGNNCell(s) fwd+bwd on one full-pile-up shaped event, L={L} E={E} N={N}, destination-"
+                       f"partitioned x{world} (BASELINE config 5)", "ms_per_step": ms, "steps": steps,
+           "cells": n_cells, "edge_steps_per_s": n_cells * E / (ms * 1e-3),
            "one_gpu_ms_per_step": one_gpu_ms, "speedup_vs_1gpu": (one_gpu_ms / ms) if one_gpu_ms else None,
-           "edges_rank0": int(part.edge_ids.numel()), "scaling": "strong"}
+           "edges_rank0": int(part.edge_ids.numel()), "scaling": "strong", "collectives": coll if world > 1 else None}
     if emit and rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "metric": METRIC, "value": n_cells * E / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": ops.compute_dtype(), "data": "synthetic",
             "config": {"workload": res["workload"], "latent": L, "edges_total": E,

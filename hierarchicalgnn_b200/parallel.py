@@ -26,6 +26,7 @@ segment sum) so the same bookkeeping is exercised on CPU/gloo in the tests
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Sequence
 
@@ -309,7 +310,94 @@ class _AllGatherRows(torch.autograd.Function):
         return out, None
 
 
-def all_gather_rows(local: Tensor, group=None) -> Tensor:
+class SymmetricRows:
+    """The two [world * block, width] fp32 tables of the destination-partitioned event (replicated node rows; node-gradient
+    partials) as SYMMETRIC memory: one allocation per rank, mapped into every peer (``torch.distributed._symmetric_memory``
+    does the handle exchange), so that the row collectives are this repo's own peer-memory kernels
+    (``csrc/p2p.cu``: ``multimem.st`` / ``multimem.ld_reduce`` through the NVSwitch, or plain peer stores / loads) instead of
+    NCCL calls between kernels. ``all_gather`` / ``reduce_scatter`` bracket the kernels with the symmetric-memory barrier:
+    before a table is overwritten (every peer has finished with its previous contents) and after it is written (before
+    anybody reads it)."""
+
+    def __init__(self, block: int, width: int, device, group=None, use_multicast: Optional[bool] = None, slots: int = 1):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.block, self.width, self.slots = int(block), int(width), max(1, int(slots))
+        gname = self.group.group_name
+        rows = self.world * self.block
+        # tables [0, slots): all-gather destinations (one per cell of a stack, so that a cell's gathered table can stay
+        # alive as an autograd saved tensor while the next cell gathers); table [slots]: reduce-scatter source
+        self.tables = symm.empty((self.slots + 1, rows, self.width), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.tables, gname)
+        self.table_bytes = rows * self.width * 4
+        mc = 0
+        if use_multicast is None:
+            use_multicast = os.environ.get("HGNN_P2P_MULTICAST", "1") != "0"
+        if use_multicast:  # 0 / None when the box has no NVLS multicast object for this allocation
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.mc_base = mc
+        self._peers = [(ctypes.c_uint64 * self.world)(*[int(b) + t * self.table_bytes for b in self.hdl.buffer_ptrs])
+                       for t in range(self.slots + 1)]
+        self.channel = 0
+        self._next = 0
+
+    def _barrier(self):
+        self.hdl.barrier(channel=self.channel)
+
+    def _mc(self, t: int):
+        return (self.mc_base + t * self.table_bytes) if self.mc_base else None
+
+    def all_gather(self, local: Tensor, slot: Optional[int] = None) -> Tensor:
+        """local [block, width] -> [world * block, width] holding every rank's block. With ``slot`` the result IS the
+        symmetric table of that slot (valid until the same slot is gathered into again: one slot per cell of a stack, and
+        the caller's step boundary — a collective every rank takes part in — separates the last reader from the next
+        writer); without it the shared slot 0 is used under a leading barrier and the result is a private copy."""
+        from . import ops, _lib
+        local = ops._f32(local)
+        assert tuple(local.shape) == (self.block, self.width), (tuple(local.shape), self.block, self.width)
+        t = 0 if slot is None else int(slot) % self.slots
+        if slot is None:
+            self._barrier()                   # every peer has copied the previous table out
+        ops.check(_lib.lib().hgnn_p2p_all_gather_rows(local.data_ptr(), self.block, self.width, self._mc(t), self._peers[t],
+                                                      self.world, self.rank, ops._stream()), "p2p_all_gather_rows")
+        ops._count()
+        self._barrier()                       # every block has landed everywhere
+        return self.tables[t].clone() if slot is None else self.tables[t]
+
+    def reduce_scatter(self, full: Tensor) -> Tensor:
+        """full [world * block, width] partials -> [block, width] = sum over ranks of this rank's block."""
+        from . import ops, _lib
+        full = ops._f32(full)
+        t = self.slots
+        self._barrier()                       # every peer has reduced the previous partials
+        self.tables[t].copy_(full)
+        self._barrier()                       # every rank's partials are in place
+        out = torch.empty((self.block, self.width), dtype=torch.float32, device=full.device)
+        ops.check(_lib.lib().hgnn_p2p_reduce_scatter_rows(out.data_ptr(), self.block, self.width, self._mc(t), self._peers[t],
+                                                          self.world, self.rank, ops._stream()), "p2p_reduce_scatter_rows")
+        ops._count()
+        return out
+
+
+class _SymmAllGatherRows(torch.autograd.Function):
+    """Row all-gather through the symmetric tables (peer-memory kernels); the adjoint is the sum reduce-scatter."""
+
+    @staticmethod
+    def forward(ctx, local: Tensor, sr: SymmetricRows, slot):
+        ctx.sr = sr
+        out = sr.all_gather(local, slot)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad: Tensor):
+        return ctx.sr.reduce_scatter(grad.contiguous()), None, None
+
+
+def all_gather_rows(local: Tensor, group=None, symmetric: Optional[SymmetricRows] = None, slot: Optional[int] = None) -> Tensor:
+    if symmetric is not None:
+        return _SymmAllGatherRows.apply(local, symmetric, slot)
     return _AllGatherRows.apply(local, group)
 
 
@@ -322,29 +410,174 @@ def pad_rows(t: Tensor, rows: int) -> Tensor:
 def partitioned_interaction_cell(part: EdgePartition, nodes_full: Tensor, edges_local: Tensor,
                                  node_fn: Callable[[Tensor, Tensor], Tensor],
                                  edge_fn: Callable[[Tensor, Tensor, Tensor], Tensor],
-                                 segment_sum: Callable[[Tensor, Tensor, int], Tensor], group=None):
+                                 segment_sum: Callable[[Tensor, Tensor, int], Tensor], group=None,
+                                 symmetric: Optional[SymmetricRows] = None, agg_owned: Optional[Tensor] = None,
+                                 return_agg: bool = False, x_owned: Optional[Tensor] = None, slot: Optional[int] = None,
+                                 return_owned: bool = False):
     """One InteractionGNNCell (gnn_utils.py:66-71) on a destination partition.
 
     nodes_full  [world*B, L]  replicated node latents (rows >= n_nodes are padding)
     edges_local [E_g, L]      latents of the owned edges
     node_fn(x_owned, agg_owned) -> x_owned'       (node MLP + skip on the owned block)
-    edge_fn(x_full, e_local, graph_local) -> e_local'
+    edge_fn(x_full, e_local, graph_local) -> e_local'  or  (e_local', agg_full') when it fuses the next cell's aggregate
     segment_sum(rows, seg_ids, n_seg) -> [n_seg, L]
-    Returns (nodes_full', edges_local')."""
+    agg_owned   [B, L]        incoming-edge sums of the owned block if a previous cell's edge step already produced them
+    x_owned     [B, L]        the owned block of nodes_full as its own tensor (the previous cell's block before it was
+                              gathered): its gradient then stays a [B, L] block instead of a zero-padded [world*B, L]
+                              table added to the gathered table's gradient
+    Returns (nodes_full', edges_local'), then — with ``return_agg`` — the owned block of scatter_add(edges_local') or
+    None, then — with ``return_owned`` — the owned block x_owned' that was gathered."""
     lo = part.node_lo
-    agg = segment_sum(edges_local, part.dst_local, part.block)         # complete for owned nodes: no exchange
-    x_owned = nodes_full[lo:lo + part.block]
-    x_new = node_fn(x_owned, agg)
+    if agg_owned is None:
+        agg_owned = segment_sum(edges_local, part.dst_local, part.block)  # complete for owned nodes: no exchange
+    if x_owned is None:
+        x_owned = nodes_full[lo:lo + part.block]
+    x_new = node_fn(x_owned, agg_owned)
     if part.n_owned < part.block:                                       # keep padding rows inert
         keep = (torch.arange(part.block, device=x_new.device) < part.n_owned).unsqueeze(1)
         x_new = torch.where(keep, x_new, torch.zeros_like(x_new))
-    nodes_new = all_gather_rows(x_new, group)                           # fwd: all-gather; bwd: reduce-scatter(sum)
-    edges_new = edge_fn(nodes_new, edges_local, part.graph)
-    return nodes_new, edges_new
+    nodes_new = all_gather_rows(x_new, group, symmetric, slot)          # fwd: all-gather; bwd: reduce-scatter(sum)
+    res = edge_fn(nodes_new, edges_local, part.graph)
+    edges_new, agg_next = (res if isinstance(res, tuple) else (res, None))
+    if agg_next is not None:
+        agg_next = agg_next[lo:lo + part.block]
+    out = [nodes_new, edges_new]
+    if return_agg:
+        out.append(agg_next)
+    if return_owned:
+        out.append(x_new)
+    return tuple(out)
 
 
-def cuda_cell_callables(cell):
-    """Binds a hierarchicalgnn_b200 InteractionGNNCell to the partition driver."""
+class _AllReduceSum(torch.autograd.Function):
+    """Sum over ranks of per-rank partials whose consumers are REPLICATED (every rank goes on to compute the same thing
+    from the sum): the gradient arriving at the sum is already identical on every rank and complete, so the adjoint is
+    the identity."""
+
+    @staticmethod
+    def forward(ctx, partial: Tensor, group):
+        out = partial.clone()
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(out, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad: Tensor):
+        return grad, None
+
+
+class _ReplicatedToLocal(torch.autograd.Function):
+    """Marks the point where a REPLICATED tensor (identical on every rank, computed redundantly) enters rank-local work:
+    forward is the identity; each rank's gradient is only its share, so the adjoint sums over ranks — every replica then
+    back-propagates the complete gradient and the replicas stay identical."""
+
+    @staticmethod
+    def forward(ctx, t: Tensor, group):
+        ctx.group = group
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, grad: Tensor):
+        g = grad.contiguous().clone()
+        if dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            dist.all_reduce(g, group=ctx.group)
+        return g, None
+
+
+@dataclass
+class BipartitePartition:
+    """The rows of the hit -> supernode assignment graph (HGNN_GMM.py:236-271) whose HIT lies in this rank's node block."""
+    ids: Tensor          # [E_b,g] positions in the global bipartite edge list
+    node_local: Tensor   # [E_b,g] hit id relative to node_lo
+    supernode: Tensor    # [E_b,g] supernode id (global: supernodes are replicated)
+
+
+def partition_bipartite(bipartite_graph: Tensor, part: EdgePartition) -> BipartitePartition:
+    node = bipartite_graph[0]
+    mine = ((node >= part.node_lo) & (node < part.node_hi)).nonzero().squeeze(1)
+    return BipartitePartition(mine, (node[mine] - part.node_lo).contiguous(), bipartite_graph[1][mine].contiguous())
+
+
+def partitioned_hierarchical_cell(part: EdgePartition, bpart: BipartitePartition, nodes_full: Tensor, edges_local: Tensor,
+                                  supernodes: Tensor, superedges: Tensor, bweights_local: Tensor, super_graph: Tensor,
+                                  super_edge_weights: Tensor, fns: dict, group=None, symmetric: Optional[SymmetricRows] = None,
+                                  agg_owned: Optional[Tensor] = None, x_owned: Optional[Tensor] = None,
+                                  slot: Optional[int] = None, skip_edge_updates: bool = False):
+    """One HierarchicalGNNCell (gnn_utils.py:119-169) on a destination partition. Hits and hit-hit edges are partitioned as
+    in ``partitioned_interaction_cell``; the supernode side (S << N rows: supernodes, superedges, the supernode graph and
+    its weights) is REPLICATED — every rank computes it redundantly from identical inputs — and the hit <-> supernode
+    messages cross between the two worlds:
+
+      up    hits -> supernodes   each rank sums its owned hits' weighted rows per supernode; the partials are all-reduced
+      down  supernodes -> hits   rank-local (every rank holds all supernodes); the adjoint all-reduces the supernode gradient
+
+    fns: supernode(supernodes, attention, up), node(x_owned, agg_owned, down_owned), superedge(supernodes, superedges,
+    super_graph), edge(x_full, e_local, graph_local) [-> e' or (e', agg_full)], segment_sum(rows, ids, n),
+    weighted_sum(rows, weights, gather_ids, seg_ids, n) = scatter_add(weights * rows[gather_ids], seg_ids, n).
+    Returns dict(nodes, edges, supernodes, superedges, agg_owned, x_owned). The weight gradients of fns["node"] / fns["edge"]
+    are per-rank partials (sum them over ranks); those of fns["supernode"] / fns["superedge"] are complete on every rank."""
+    lo, B, S = part.node_lo, part.block, supernodes.shape[0]
+    if x_owned is None:
+        x_owned = nodes_full[lo:lo + B]
+    # supernode update (gnn_utils.py:137-145)
+    up = _AllReduceSum.apply(fns["weighted_sum"](x_owned, bweights_local, bpart.node_local, bpart.supernode, S), group)
+    attention = fns["weighted_sum"](superedges, super_edge_weights, None, super_graph[1], S)
+    supernodes_new = fns["supernode"](supernodes, attention, up)
+    # node update (gnn_utils.py:119-127): incoming hit-hit edge sums (local), messages from the supernodes (local reads of
+    # the replicated table)
+    sn_local = _ReplicatedToLocal.apply(supernodes_new, group)
+    down = fns["weighted_sum"](sn_local, bweights_local, bpart.supernode, bpart.node_local, B)
+    if agg_owned is None:
+        agg_owned = fns["segment_sum"](edges_local, part.dst_local, B)
+    x_new = fns["node"](x_owned, agg_owned, down)
+    if part.n_owned < B:
+        keep = (torch.arange(B, device=x_new.device) < part.n_owned).unsqueeze(1)
+        x_new = torch.where(keep, x_new, torch.zeros_like(x_new))
+    nodes_new = all_gather_rows(x_new, group, symmetric, slot)
+    edges_new, superedges_new, agg_next = edges_local, superedges, None
+    if not skip_edge_updates:  # (the last cell of a block: HGNN_GMM.py skips the dead edge updates)
+        superedges_new = fns["superedge"](supernodes_new, superedges, super_graph)
+        res = fns["edge"](nodes_new, edges_local, part.graph)
+        edges_new, agg_next = (res if isinstance(res, tuple) else (res, None))
+        if agg_next is not None:
+            agg_next = agg_next[lo:lo + B]
+    return dict(nodes=nodes_new, edges=edges_new, supernodes=supernodes_new, superedges=superedges_new,
+                agg_owned=agg_next, x_owned=x_new)
+
+
+def cuda_hier_cell_callables(cell, fuse_aggregate: bool = False) -> dict:
+    """Binds a hierarchicalgnn_b200 HierarchicalGNNCell to ``partitioned_hierarchical_cell``."""
+    from . import ops
+    from .gnn_utils import GraphPlans
+
+    def weighted_sum(rows, weights, gather_ids, seg_ids, n):
+        seg_plan = ops.plan_for(seg_ids, n)
+        if gather_ids is None:
+            return ops._GatherScatter.apply(rows, weights, None, seg_plan, False)
+        return ops.gather_scatter(rows, weights, ops.plan_for(gather_ids, rows.shape[0]), seg_plan)
+
+    def edge(x_full, e_local, graph_local):
+        gp = GraphPlans(graph_local, x_full.shape[0], x_full.shape[0], dst_sorted=True)
+        if fuse_aggregate:
+            e_new, agg = cell.edge_network.edge_step(x_full, e_local, gp.by_src, gp.by_dst)
+            return (e_new, agg) if agg is not None else e_new
+        return cell.edge_network.fused([x_full, x_full, e_local], [gp.by_src, gp.by_dst, None], skip=2)
+
+    def superedge(supernodes, superedges, super_graph):
+        S = supernodes.shape[0]
+        gp = GraphPlans(super_graph, S, S)
+        return cell.superedge_network.fused([supernodes, supernodes, superedges], [gp.by_src, gp.by_dst, None], skip=2)
+
+    return dict(supernode=lambda sn, att, up: cell.supernode_network.fused([sn, att, up], skip=0),
+                node=lambda x, agg, down: cell.node_network.fused([x, agg, down], skip=0),
+                superedge=superedge, edge=edge, weighted_sum=weighted_sum,
+                segment_sum=lambda rows, seg, n: ops.scatter_add(rows, seg, dim_size=n))
+
+
+def cuda_cell_callables(cell, fuse_aggregate: bool = False):
+    """Binds a hierarchicalgnn_b200 InteractionGNNCell to the partition driver. With ``fuse_aggregate`` the edge step also
+    returns scatter_add(e', dst) over ALL node rows (its own fused segmented reduce: rows outside the owned block stay zero),
+    which the driver hands to the next cell instead of running a separate segment sum."""
     from . import ops
     from .gnn_utils import GraphPlans
 
@@ -353,6 +586,11 @@ def cuda_cell_callables(cell):
 
     def edge_fn(x_full, e_local, graph_local):
         gp = GraphPlans(graph_local, x_full.shape[0], x_full.shape[0], dst_sorted=True)  # partition_by_destination sorts
+        if fuse_aggregate:
+            e_new, agg = cell.edge_network.edge_step(x_full, e_local, gp.by_src, gp.by_dst)
+            if agg is not None:
+                return e_new, agg
+            return e_new
         return cell.edge_network.fused([x_full, x_full, e_local], [gp.by_src, gp.by_dst, None], skip=2)
 
     def segment_sum(rows, seg, n):

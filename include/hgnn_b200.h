@@ -363,6 +363,24 @@ void hgnn_tc_debug_set_phase_clock(void* dev_u64x16);
 /* Same for hgnn_tc_edge_forward: tile setup, GEMM1 (gather), EPI1, GEMM2, EPI2, store pass, fused aggregate. */
 void hgnn_tc_debug_set_fwd_phase_clock(void* dev_u64x16);
 
+/* ------------------------------------------------------------------------
+ * Row collectives of the destination-partitioned event over NVLink / NVSwitch
+ * peer memory (the reference has no distributed code).
+ * The [world * rows, width] fp32 tables are SYMMETRIC buffers: the same
+ * allocation on every rank, mapped into every peer. `mc_base` is the multicast
+ * (NVLS) address of the table — multimem.st / multimem.ld_reduce move each
+ * block once and add inside the switch — or NULL, in which case `peer_bases`
+ * (host array of `world` device addresses, one per rank's copy) is used with
+ * plain peer stores / loads summed in rank order. Neither call synchronises
+ * ranks: bracket them with a cross-rank barrier.
+ *   all_gather     local[rows, width] -> slot `rank` of every rank's table
+ *   reduce_scatter out[rows, width]   =  sum over ranks of slot `rank` of their tables
+ * ------------------------------------------------------------------------ */
+int hgnn_p2p_all_gather_rows(const float* local, int64_t rows, int64_t width, void* mc_base, const uint64_t* peer_bases,
+                             int world, int rank, void* stream);
+int hgnn_p2p_reduce_scatter_rows(float* out, int64_t rows, int64_t width, const void* mc_base, const uint64_t* peer_bases,
+                                 int world, int rank, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

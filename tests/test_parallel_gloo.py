@@ -123,7 +123,7 @@ def _dp_trainer_case(rank, world):
     tr.buckets.remove()
 
 
-def _partition_case(rank, world):
+def _partition_case(rank, world, carry=False):
     from hierarchicalgnn_b200.parallel import (allreduce_gradients, pad_rows, partition_by_destination,
                                                partitioned_interaction_cell)
     from hierarchicalgnn_b200.synth import synth_edge_problem
@@ -158,8 +158,25 @@ def _partition_case(rank, world):
     n_full = pad_rows(nodes, world * part.block).clone().requires_grad_(True)
     e_loc = edges[part.edge_ids].clone().requires_grad_(True)
     pn, pe = n_full, e_loc
-    for _ in range(2):
-        pn, pe = partitioned_interaction_cell(part, pn, pe, node_fn, edge_fn, O.scatter_add)
+    if carry:
+        # the edge step also returns scatter_add(e', dst) over all node rows (as the CUDA edge kernel's fused segmented
+        # reduce does); the driver hands its owned block to the next cell instead of running a segment sum there
+        n_seg_calls = []
+        def seg(rows, ids, n):
+            n_seg_calls.append(1)
+            return O.scatter_add(rows, ids, n)
+        def edge_fn_agg(x, e, g):
+            e2_ = edge_fn(x, e, g)
+            return e2_, O.scatter_add(e2_, g[1], x.shape[0])
+        agg = xo = None
+        for _ in range(2):  # the owned block is carried too (its gradient stays a [B, L] block)
+            pn, pe, agg, xo = partitioned_interaction_cell(part, pn, pe, node_fn, edge_fn_agg, seg, agg_owned=agg, return_agg=True,
+                                                           x_owned=xo, return_owned=True)
+        assert len(n_seg_calls) == 1 and agg is not None and agg.shape[0] == part.block
+        assert torch.equal(xo, pn[part.node_lo:part.node_lo + part.block])
+    else:
+        for _ in range(2):
+            pn, pe = partitioned_interaction_cell(part, pn, pe, node_fn, edge_fn, O.scatter_add)
     torch.testing.assert_close(pn[:N], n2.detach(), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(pe, e2.detach()[part.edge_ids], rtol=1e-5, atol=1e-6)
     # each rank back-propagates its share of the objective: owned nodes + owned edges
@@ -178,6 +195,94 @@ def _partition_case(rank, world):
             torch.testing.assert_close(v.grad, sd_ref[k].grad, rtol=1e-4, atol=1e-5, msg=lambda m: f"{k}: {m}")
 
 
+def _hier_partition_case(rank, world):
+    """Two stacked HierarchicalGNNCells, destination-partitioned (hits / hit edges partitioned, supernode side replicated)
+    against the single-process oracle: outputs, every input gradient, every weight gradient."""
+    from hierarchicalgnn_b200.parallel import (pad_rows, partition_by_destination, partition_bipartite,
+                                               partitioned_hierarchical_cell)
+    from hierarchicalgnn_b200.synth import synth_edge_problem
+    from oracle.reference_harness import kaiming_init
+    from hierarchicalgnn_b200.utils import make_mlp
+    L, E, S, ES = 16, 500, 9, 40
+    hp = dict(latent=L, hidden=2 * L, nb_edge_layer=2, nb_node_layer=3, layernorm=True, hidden_activation="GELU")
+    torch.manual_seed(0)
+    nets = torch.nn.ModuleDict({
+        "edge_network": make_mlp(3 * L, 2 * L, L, 2, layer_norm=True, output_activation="Tanh"),
+        "node_network": make_mlp(3 * L, 2 * L, L, 3, layer_norm=True),
+        "supernode_network": make_mlp(3 * L, 2 * L, L, 3, layer_norm=True),
+        "superedge_network": make_mlp(3 * L, 2 * L, L, 2, layer_norm=True, output_activation="Tanh")})
+    kaiming_init(nets)
+    nodes, edges, graph = synth_edge_problem(E, L, seed=3)
+    N = nodes.shape[0] - 1
+    nodes, graph = nodes[:N], graph.clamp(max=N - 1)
+    g = torch.Generator().manual_seed(7)
+    supernodes, superedges = torch.randn(S, L, generator=g), torch.randn(ES, L, generator=g)
+    sgraph = torch.randint(0, S, (2, ES), generator=g)
+    sweights = torch.rand(ES, 1, generator=g)
+    bgraph = torch.stack([torch.arange(N).repeat(2), torch.randint(0, S, (2 * N,), generator=g)])  # two supernodes per hit
+    bweights = torch.rand(2 * N, 1, generator=g)
+    cots = [torch.randn(*shape, generator=g) for shape in ((N, L), (E, L), (S, L), (ES, L))]
+
+    def leaves(*ts):
+        return [t.clone().requires_grad_(True) for t in ts]
+
+    # single-process oracle
+    sd_ref = O.leaf_state({"c." + k: v for k, v in nets.state_dict().items()})
+    r_n, r_e, r_s, r_se, r_bw, r_sw = leaves(nodes, edges, supernodes, superedges, bweights, sweights)
+    a, b, c, d = r_n, r_e, r_s, r_se
+    for _ in range(2):
+        a, b, c, d = O.hierarchical_cell(sd_ref, "c", hp, a, b, c, d, graph, bgraph, r_bw, sgraph, r_sw)
+    sum((o * ct).sum() for o, ct in zip((a, b, c, d), cots)).backward()
+
+    # partitioned run
+    part = partition_by_destination(graph, N, world, rank)
+    bpart = partition_bipartite(bgraph, part)
+    sd = O.leaf_state({"c." + k: v for k, v in nets.state_dict().items()})
+    mlp = lambda name, x, n: O.mlp_apply(sd, "c." + name, x, n, "GELU", "GELU", True)
+    wsum = lambda rows, w, gi, si, n: O.scatter_add(w * (rows if gi is None else rows[gi]), si, n)
+    fns = dict(supernode=lambda sn, att, up: mlp("supernode_network", torch.cat([sn, att, up], -1), 3) + sn,
+               node=lambda x, agg, down: mlp("node_network", torch.cat([x, agg, down], -1), 3) + x,
+               superedge=lambda sn, se, sg: O.edge_step(sd, "c.superedge_network", hp, sn, se, sg),
+               edge=lambda x, e, gr: O.edge_step(sd, "c.edge_network", hp, x, e, gr),
+               weighted_sum=wsum, segment_sum=O.scatter_add)
+    p_n, p_s, p_se, p_sw = leaves(pad_rows(nodes, world * part.block), supernodes, superedges, sweights)
+    p_e, p_bw = leaves(edges[part.edge_ids], bweights[bpart.ids])
+    st = dict(nodes=p_n, edges=p_e, supernodes=p_s, superedges=p_se, agg_owned=None, x_owned=None)
+    for _ in range(2):
+        st = partitioned_hierarchical_cell(part, bpart, st["nodes"], st["edges"], st["supernodes"], st["superedges"], p_bw,
+                                           sgraph, p_sw, fns, x_owned=st["x_owned"])
+    torch.testing.assert_close(st["nodes"][:N], a.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(st["edges"], b.detach()[part.edge_ids], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(st["supernodes"], c.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(st["superedges"], d.detach(), rtol=1e-5, atol=1e-6)
+    # objective: owned hits + owned edges on this rank; the replicated supernode side is counted once (rank 0)
+    own = slice(part.node_lo, part.node_hi)
+    loss = (st["nodes"][own] * cots[0][own]).sum() + (st["edges"] * cots[1][part.edge_ids]).sum()
+    rep = (st["supernodes"] * cots[2]).sum() + (st["superedges"] * cots[3]).sum()
+    # every replica must back-propagate the same replicated objective to stay identical: all ranks add it
+    (loss + rep).backward()
+    torch.testing.assert_close(p_e.grad, r_e.grad[part.edge_ids], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(p_bw.grad, r_bw.grad[bpart.ids], rtol=1e-4, atol=1e-5)
+    gn = p_n.grad.clone()
+    dist.all_reduce(gn)
+    torch.testing.assert_close(gn[:N], r_n.grad, rtol=1e-4, atol=1e-5)
+    # replicated inputs: complete and identical on every rank, no reduction
+    for got, want in ((p_s.grad, r_s.grad), (p_se.grad, r_se.grad), (p_sw.grad, r_sw.grad)):
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    for k, v in sd.items():
+        if not v.requires_grad:
+            continue
+        gk = v.grad.clone()
+        if ".node_network." in k or ".edge_network." in k:   # per-rank partials
+            dist.all_reduce(gk)
+        # (fp32 sums over the edges in a different order: 5e-5 absolute on O(1) weight gradients)
+        torch.testing.assert_close(gk, sd_ref[k].grad, rtol=1e-4, atol=5e-5, msg=lambda m: f"{k}: {m}")
+
+
+def test_destination_partitioned_hierarchical_cells_match_single_process_world2():
+    _run(_hier_partition_case)
+
+
 def test_data_parallel_gradient_allreduce_world2():
     _run(_dp_case)
 
@@ -188,6 +293,14 @@ def test_data_parallel_trainer_overlapped_buckets_world2():
 
 def test_destination_partitioned_cells_match_single_process_world2():
     _run(_partition_case)
+
+
+def _partition_case_carry(rank, world):
+    _partition_case(rank, world, carry=True)
+
+
+def test_destination_partitioned_cells_with_carried_aggregate_world2():
+    _run(_partition_case_carry)
 
 
 def test_partition_covers_every_edge_once():
