@@ -683,7 +683,10 @@ def run_partition(args, dev=None, world=None, rank=None, barrier=None, emit=True
             grads = torch.autograd.grad([x[own], e], [nodes, e_loc] + params, [cot_n_d, cot_e_d])
             if w > 1:
                 flat = torch.cat([t.reshape(-1) for t in grads[2:]])
-                dist.all_reduce(flat, group=group)
+                if sr is not None:
+                    sr.all_reduce_(flat)
+                else:
+                    dist.all_reduce(flat, group=group)
                 # replicated input nodes: each rank holds the gradient of its own block only (the other rows are zero),
                 # so the sum over ranks is an all-gather of the owned blocks
                 blk = grads[0][part.node_lo:part.node_lo + part.block].contiguous()

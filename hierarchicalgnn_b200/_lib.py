@@ -96,6 +96,7 @@ SIGNATURES = {
     "hgnn_mlp_backward_weights": (C.c_int, [C.POINTER(MlpDesc), i64, C.POINTER(vp * MAX_LAYERS), vp, sz, vp]),
     "hgnn_p2p_all_gather_rows": (C.c_int, [vp, i64, i64, vp, vp, C.c_int, C.c_int, vp]),
     "hgnn_p2p_reduce_scatter_rows": (C.c_int, [vp, i64, i64, vp, vp, C.c_int, C.c_int, vp]),
+    "hgnn_p2p_all_reduce": (C.c_int, [i64, vp, vp, C.c_int, C.c_int, vp]),
     "hgnn_knn_radius": (C.c_int, [vp, i64, vp, i64, i64, i64, f32, vp, vp]),
     "hgnn_knn_radius_workspace_bytes": (sz, [i64, i64, i64]),
     "hgnn_knn_radius_ws": (C.c_int, [vp, i64, vp, i64, i64, i64, f32, vp, vp, sz, vp]),

@@ -71,6 +71,28 @@ __global__ void __launch_bounds__(P2P_THREADS) k_reduce_scatter_rows(float4* __r
   }
 }
 
+// in-place sum over ranks of the first n4 chunks of the symmetric buffer, left in every rank's copy: rank r reduces the
+// r-th slice (inside the switch with multimem.ld_reduce, or peer by peer in rank order) and stores the result to all
+__global__ void __launch_bounds__(P2P_THREADS) k_all_reduce(int64_t n4, float* mc_base, PeerPtrs peers, int world, int rank) {
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t lo = (int64_t)rank * per, hi = min(n4, lo + per);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+    if (mc_base) {
+      multimem_st4(mc_base + i * 4, multimem_ld_add4(mc_base + i * 4));
+    } else {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int w = 0; w < world; ++w) {
+        const float4 v = reinterpret_cast<const float4*>(peers.p[w])[i];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+#pragma unroll 1
+      for (int w = 0; w < world; ++w) reinterpret_cast<float4*>(peers.p[w])[i] = acc;
+    }
+  }
+}
+
 int fill_peers(PeerPtrs& P, const uint64_t* peer_bases, int world) {
   for (int w = 0; w < MAX_WORLD; ++w) P.p[w] = nullptr;
   if (peer_bases)
@@ -109,4 +131,16 @@ extern "C" int hgnn_p2p_reduce_scatter_rows(float* out, int64_t rows, int64_t wi
   const int64_t n4 = rows * width / 4;
   k_reduce_scatter_rows<<<p2p_grid(n4), P2P_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(out), n4, (const float*)mc_base, P, world, rank);
   return check_launch("p2p_reduce_scatter_rows");
+}
+
+extern "C" int hgnn_p2p_all_reduce(int64_t n_floats, void* mc_base, const uint64_t* peer_bases, int world, int rank, void* stream) {
+  HGNN_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, "p2p_all_reduce: bad world / rank");
+  HGNN_REQUIRE(mc_base || peer_bases, "p2p_all_reduce: need a multicast base or the peer bases");
+  HGNN_REQUIRE(n_floats % 4 == 0, "p2p_all_reduce: the buffer must be whole 16-byte chunks");
+  if (n_floats <= 0) return HGNN_OK;
+  PeerPtrs P;
+  fill_peers(P, peer_bases, world);
+  const int64_t n4 = n_floats / 4;
+  k_all_reduce<<<p2p_grid((n4 + world - 1) / world), P2P_THREADS, 0, (cudaStream_t)stream>>>(n4, (float*)mc_base, P, world, rank);
+  return check_launch("p2p_all_reduce");
 }

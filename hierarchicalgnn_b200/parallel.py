@@ -341,7 +341,10 @@ class SymmetricRows:
         self._peers = [(ctypes.c_uint64 * self.world)(*[int(b) + t * self.table_bytes for b in self.hdl.buffer_ptrs])
                        for t in range(self.slots + 1)]
         self.channel = 0
-        self._next = 0
+        # one independent tensor per table over the same memory (own TensorImpl, own version counter — NOT views of
+        # self.tables): a gathered table is an autograd saved tensor while the reduce-scatter table is copied into in place
+        n_el = rows * self.width
+        self._alias = [self.hdl.get_buffer(self.rank, (rows, self.width), torch.float32, t * n_el) for t in range(self.slots + 1)]
 
     def _barrier(self):
         self.hdl.barrier(channel=self.channel)
@@ -364,7 +367,7 @@ class SymmetricRows:
                                                       self.world, self.rank, ops._stream()), "p2p_all_gather_rows")
         ops._count()
         self._barrier()                       # every block has landed everywhere
-        return self.tables[t].clone() if slot is None else self.tables[t]
+        return self._alias[t].clone() if slot is None else self._alias[t]
 
     def reduce_scatter(self, full: Tensor) -> Tensor:
         """full [world * block, width] partials -> [block, width] = sum over ranks of this rank's block."""
@@ -372,13 +375,37 @@ class SymmetricRows:
         full = ops._f32(full)
         t = self.slots
         self._barrier()                       # every peer has reduced the previous partials
-        self.tables[t].copy_(full)
+        self._alias[t].copy_(full)
         self._barrier()                       # every rank's partials are in place
         out = torch.empty((self.block, self.width), dtype=torch.float32, device=full.device)
         ops.check(_lib.lib().hgnn_p2p_reduce_scatter_rows(out.data_ptr(), self.block, self.width, self._mc(t), self._peers[t],
                                                           self.world, self.rank, ops._stream()), "p2p_reduce_scatter_rows")
         ops._count()
         return out
+
+
+    def all_reduce_(self, flat: Tensor) -> Tensor:
+        """In-place sum over ranks of a flat fp32 tensor (the weight gradients of a step) through the reduce-scatter table:
+        one kernel, each rank reduces 1/world of it inside the switch and stores the result to every rank."""
+        from . import ops, _lib
+        n = flat.numel()
+        t = self.slots
+        buf = self._alias[t].view(-1)
+        n_pad = (n + 3) // 4 * 4
+        if flat.dtype != torch.float32 or n_pad > buf.numel():
+            dist.all_reduce(flat, group=self.group)
+            return flat
+        self._barrier()                       # the table is free (previous partials reduced everywhere)
+        buf[:n].copy_(flat.reshape(-1))
+        if n_pad > n:
+            buf[n:n_pad].zero_()
+        self._barrier()                       # every rank's addend is in place
+        ops.check(_lib.lib().hgnn_p2p_all_reduce(n_pad, self._mc(t), self._peers[t], self.world, self.rank, ops._stream()),
+                  "p2p_all_reduce")
+        ops._count()
+        self._barrier()                       # every slice has been stored everywhere
+        flat.reshape(-1).copy_(buf[:n])
+        return flat
 
 
 class _SymmAllGatherRows(torch.autograd.Function):

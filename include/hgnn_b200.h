@@ -380,6 +380,9 @@ int hgnn_p2p_all_gather_rows(const float* local, int64_t rows, int64_t width, vo
                              int world, int rank, void* stream);
 int hgnn_p2p_reduce_scatter_rows(float* out, int64_t rows, int64_t width, const void* mc_base, const uint64_t* peer_bases,
                                  int world, int rank, void* stream);
+/* In-place sum over ranks of the first n_floats (multiple of 4) of the symmetric buffer, left in every rank's copy
+ * (weight-gradient all-reduce): rank r reduces the r-th slice and stores the result to all ranks. */
+int hgnn_p2p_all_reduce(int64_t n_floats, void* mc_base, const uint64_t* peer_bases, int world, int rank, void* stream);
 
 #ifdef __cplusplus
 }

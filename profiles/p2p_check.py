@@ -46,10 +46,15 @@ for mc in (True, False):
     torch.cuda.synchronize()
     ok_ag = torch.equal(got_ag, want_ag)
     err_rs = float((got_rs - want_rs).abs().max())
+    flat = torch.randn(350_001, device=dev)
+    want_ar = flat.clone(); dist.all_reduce(want_ar)
+    got_ar = sr.all_reduce_(flat.clone())
+    err_ar = float((got_ar - want_ar).abs().max())
+    t_ar = timeit(lambda: sr.all_reduce_(flat))
     t_ag, t_rs = timeit(lambda: sr.all_gather(x)), timeit(lambda: sr.reduce_scatter(full))
     if rank == 0:
         print(f"multicast requested {mc}, used {bool(sr.mc_base)}: all-gather equal {ok_ag}, reduce-scatter max |diff| vs NCCL {err_rs:.2e}; "
-              f"all-gather {t_ag * 1e3:.0f} us, reduce-scatter {t_rs * 1e3:.0f} us  (table {world * block * width * 4 / 1e6:.1f} MB)")
+              f"all-reduce (1.4 MB) max |diff| {err_ar:.2e}, {t_ar * 1e3:.0f} us; all-gather {t_ag * 1e3:.0f} us, reduce-scatter {t_rs * 1e3:.0f} us  (table {world * block * width * 4 / 1e6:.1f} MB)")
     del sr
 out = torch.empty_like(want_ag)
 t_ag = timeit(lambda: dist.all_gather_into_tensor(out, x))
