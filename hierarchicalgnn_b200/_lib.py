@@ -57,6 +57,7 @@ class TcEdgeParams(C.Structure):
         ("b2", C.c_void_p),
         ("gamma2", C.c_void_p),
         ("beta2", C.c_void_p),
+        ("debug_phase_clock", C.c_void_p),
     ]
 
 
@@ -121,8 +122,6 @@ SIGNATURES = {
     #  dW1, dW2, dv1, dv2, ws, ws_bytes, stream, aux_stream)
     "hgnn_tc_edge_backward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp,
                                         vp, vp, vp, vp, vp, sz, vp, vp]),
-    "hgnn_tc_debug_set_phase_clock": (None, [vp]),
-    "hgnn_tc_debug_set_fwd_phase_clock": (None, [vp]),
     "hgnn_narrow_in_supported": (C.c_int, [C.POINTER(MlpDesc)]),
     "hgnn_narrow_in_forward": (C.c_int, [C.POINTER(MlpDesc), i64, vp, vp]),
     "hgnn_narrow_in_backward_workspace_bytes": (sz, [i64]),

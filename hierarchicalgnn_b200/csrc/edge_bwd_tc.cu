@@ -252,9 +252,6 @@ Layout make_layout(int64_t n_edges, int64_t n_nodes) {
 
 }  // namespace
 
-static void* g_phase_clk = nullptr;
-// debug hook (not part of the stable ABI): device buffer of 16 uint64 that CTA 0 fills with per-phase cycle counts
-extern "C" void hgnn_tc_debug_set_phase_clock(void* dev_u64x16) { g_phase_clk = dev_u64x16; }
 
 extern "C" size_t hgnn_tc_edge_backward_workspace_bytes(int64_t n_edges, int64_t n_nodes) {
   return make_layout(n_edges > 0 ? n_edges : 1, n_nodes > 0 ? n_nodes : 1).total + 1024;
@@ -300,7 +297,7 @@ extern "C" int hgnn_tc_edge_backward(const hgnn_tc_edge_params* p, const void* w
   A.d1_img = w + Y.d1; A.d2_img = w + Y.d2;
   A.colpart = (float*)(w + Y.colpart);
   A.n_edges = n_edges;
-  A.phase_clk = (unsigned long long*)g_phase_clk;
+  A.phase_clk = (unsigned long long*)p->debug_phase_clock;
   {
     static int stagger = -1;
     if (stagger < 0) { const char* e = getenv("HGNN_BWD_STAGGER"); stagger = e ? atoi(e) : 0; }

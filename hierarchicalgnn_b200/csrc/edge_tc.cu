@@ -537,14 +537,11 @@ extern "C" int hgnn_tc_debug_trace(unsigned long long* out, int max_records) {
   return (int)n;
 }
 #endif
-static void* g_fwd_phase_clk = nullptr;
 static int fwd_stagger() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("HGNN_FWD_STAGGER"); v = e ? atoi(e) : 0; }
   return v;
 }
-// debug hook (not part of the stable ABI): device buffer of 16 uint64 that CTA 0 of the forward kernel fills with per-phase cycles
-extern "C" void hgnn_tc_debug_set_fwd_phase_clock(void* dev_u64x16) { g_fwd_phase_clk = dev_u64x16; }
 
 extern "C" size_t hgnn_tc_edge_forward_workspace_bytes(int64_t n_edges, int64_t n_nodes, int64_t latent) {
   (void)n_edges;
@@ -580,7 +577,7 @@ static int launch_edge_fwd(const hgnn_tc_edge_params* p, const float* x, const f
     HGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)std::min<int64_t>(tiles, 2 * (int64_t)num_sms());
     kern<<<grid, TC_THREADS, smem, st>>>(*p, xb16, e, src, dst, perm, n_edges, e_out, rowptr, agg, stash, edge_stash_layout(n_edges, L),
-                                          (unsigned long long*)g_fwd_phase_clk, fwd_stagger());
+                                          (unsigned long long*)p->debug_phase_clock, fwd_stagger());
   }
   if (agg) {
     int64_t threads = n_nodes * (L / 4);

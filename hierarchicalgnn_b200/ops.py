@@ -566,6 +566,9 @@ def tc_debug_wgrad(A: Tensor, B: Tensor) -> Tensor:
     return out
 
 
+DEBUG_PHASE_CLOCK = {"ptr": None}  # host-side switch of the per-call profiling pointer in hgnn_tc_edge_params
+
+
 def _tc_params(meta: MlpMeta, layers, w1p, w2p):
     (W1, b1, g1, be1), (W2, b2, g2, be2) = layers
     p = _lib.TcEdgeParams()
@@ -575,6 +578,7 @@ def _tc_params(meta: MlpMeta, layers, w1p, w2p):
     p.w1_packed, p.w2_packed = w1p.data_ptr(), w2p.data_ptr()
     p.b1, p.gamma1, p.beta1 = b1.data_ptr(), g1.data_ptr(), be1.data_ptr()
     p.b2, p.gamma2, p.beta2 = b2.data_ptr(), g2.data_ptr(), be2.data_ptr()
+    p.debug_phase_clock = DEBUG_PHASE_CLOCK["ptr"]  # None in production; profiles/bwd_phase_clock.py sets it per call
     return p
 
 

@@ -212,6 +212,10 @@ typedef struct {
   const float* b2;
   const float* gamma2;
   const float* beta2;
+  /* Profiling, per call (NULL in production): device buffer of 16 uint64 in which CTA 0 of the forward / backward kernel
+   * accumulates the cycles of each phase of its tile loop (forward: setup, GEMM1 + gather, EPI1, GEMM2, EPI2, store pass,
+   * fused aggregate; backward: setup, LOAD, EPI-B, GEMM3, EPI-C, GEMM4, EPI-D). The library keeps no global state. */
+  void* debug_phase_clock;
 } hgnn_tc_edge_params;
 
 int hgnn_tc_supported(int64_t latent, int64_t hidden, int64_t n_layers, int layer_norm, int act_hidden, int act_out);
@@ -356,12 +360,6 @@ int hgnn_tc_wgrad_supported(int64_t n_out, int64_t fan_in);
 size_t hgnn_tc_wgrad_workspace_bytes(int64_t rows, int64_t n_out, int64_t fan_in);
 int hgnn_tc_wgrad(const void* delta_img, int64_t n_out, const void* a_img, int64_t fan_in, int64_t rows, float* dW, void* ws,
                   size_t ws_bytes, void* stream);
-
-/* Profiling hook: when set (device buffer of 16 uint64), CTA 0 of hgnn_tc_edge_backward accumulates the cycles it
- * spends in each phase of the tile loop (GEMM1, EPI-A, GEMM2, EPI-B, GEMM3, EPI-C, GEMM4, EPI-D). NULL disables. */
-void hgnn_tc_debug_set_phase_clock(void* dev_u64x16);
-/* Same for hgnn_tc_edge_forward: tile setup, GEMM1 (gather), EPI1, GEMM2, EPI2, store pass, fused aggregate. */
-void hgnn_tc_debug_set_fwd_phase_clock(void* dev_u64x16);
 
 /* ------------------------------------------------------------------------
  * Row collectives of the destination-partitioned event over NVLink / NVSwitch

@@ -1,4 +1,4 @@
-"""Per-phase cycle breakdown of the tensor-core backward kernel (CTA 0), via the hgnn_tc_debug_set_phase_clock hook."""
+"""Per-phase cycle breakdown of the tensor-core backward kernel (CTA 0), via the per-call hgnn_tc_edge_params.debug_phase_clock pointer."""
 import sys, torch
 sys.path.insert(0, '.')
 from hierarchicalgnn_b200 import ops, _lib
@@ -18,9 +18,9 @@ def step():
     torch.autograd.grad([e2, agg], [n, e] + list(cell.edge_network.parameters()), [cot_e, cot_a])
 for _ in range(3): step()
 clk = torch.zeros(16, dtype=torch.int64, device="cuda")
-_lib.lib().hgnn_tc_debug_set_phase_clock(clk.data_ptr())
+ops.DEBUG_PHASE_CLOCK["ptr"] = clk.data_ptr()
 step(); torch.cuda.synchronize()
-_lib.lib().hgnn_tc_debug_set_phase_clock(None)
+ops.DEBUG_PHASE_CLOCK["ptr"] = None
 c = clk.cpu().tolist()
 names = ["setup", "LOAD(gout)", "EPI-B", "GEMM3", "EPI-C", "GEMM4", "EPI-D"]
 tiles = (E + 127) // 128 // 148 + 1
@@ -30,9 +30,9 @@ for nm, v in zip(names, c[:7]):
 print(f"total {tot / tiles:.0f} cycles/tile over ~{tiles} tiles")
 # forward kernel
 clk.zero_()
-_lib.lib().hgnn_tc_debug_set_fwd_phase_clock(clk.data_ptr())
+ops.DEBUG_PHASE_CLOCK["ptr"] = clk.data_ptr()
 step(); torch.cuda.synchronize()
-_lib.lib().hgnn_tc_debug_set_fwd_phase_clock(None)
+ops.DEBUG_PHASE_CLOCK["ptr"] = None
 c = clk.cpu().tolist()
 names = ["setup", "GEMM1(gather)", "EPI1", "GEMM2", "EPI2", "store pass", "aggregate"]
 tiles_f = (E + 127) // 128 // 296 + 1
