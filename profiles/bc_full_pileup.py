@@ -22,3 +22,7 @@ ops.PROFILE = None
 print("sum %.2f" % sum(t for _, t in prof.values()))
 for k, (n, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]:
     print(f"   {k:24s} calls {n:4d}  total {t:8.2f} ms")
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as p:
+    fb(); torch.cuda.synchronize()
+print(p.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
