@@ -78,6 +78,7 @@ extern "C" int hgnn_csr_build(const int64_t* keys, int64_t n_items, int64_t n_se
     return HGNN_OK;
   }
   HGNN_REQUIRE(keys && perm, "csr_build: NULL keys/perm");
+  HGNN_REQUIRE(n_segments > 0, "csr_build: %lld items but no segments", (long long)n_items);
   Workspace w(ws, ws_bytes);
   int32_t* k_in = w.take<int32_t>(n_items);
   int32_t* k_out = w.take<int32_t>(n_items);

@@ -176,6 +176,13 @@ class SegmentPlan:
         n = keys.numel()
         self.n_items = n
         self.n_segments = int(n_segments)
+        if n and self.n_segments <= 0:
+            raise _lib.HgnnError(f"SegmentPlan: {n} keys but n_segments = {n_segments}")
+        if n and os.environ.get("HGNN_CHECK_INDICES", "0") != "0":  # one host sync per plan: off by default (the kernel clamps)
+            lo, hi = int(keys.min()), int(keys.max())
+            if lo < 0 or hi >= self.n_segments:
+                raise _lib.HgnnError(f"SegmentPlan: index out of range: keys span [{lo}, {hi}], n_segments = {self.n_segments} "
+                                     "(torch_scatter would raise here; without HGNN_CHECK_INDICES the index is clamped)")
         dev = keys.device
         self.perm = torch.empty(n, dtype=torch.int32, device=dev)
         self.rowptr = torch.empty(self.n_segments + 1, dtype=torch.int32, device=dev)

@@ -247,6 +247,22 @@ def test_knn_reference_split_path_is_bit_identical_to_the_single_scan(ops, nq, n
     assert agree > 0.999  # fp64 oracle vs fp32 sums: only near-ties may swap
 
 
+def test_out_of_range_segment_ids_raise_when_checking_is_on(ops, monkeypatch):
+    """torch_scatter raises on an out-of-range index; the CSR build clamps it (no host sync by default).
+    HGNN_CHECK_INDICES=1 restores the check at one sync per plan; zero segments with items is always an error."""
+    from hierarchicalgnn_b200 import _lib
+    idx = torch.tensor([0, 3, 7, 2], device=DEV)
+    monkeypatch.setenv("HGNN_CHECK_INDICES", "1")
+    with pytest.raises(_lib.HgnnError):
+        ops.SegmentPlan(idx, 5)
+    with pytest.raises(_lib.HgnnError):
+        ops.SegmentPlan(torch.tensor([0, -1], device=DEV), 5)
+    ops.SegmentPlan(idx, 8)
+    monkeypatch.setenv("HGNN_CHECK_INDICES", "0")
+    with pytest.raises(_lib.HgnnError):
+        ops.SegmentPlan(idx, 0)
+
+
 def test_edge_max_dist(ops):
     g = torch.Generator().manual_seed(9)
     a, b = torch.randn(40, 8, generator=g), torch.randn(30, 8, generator=g)
