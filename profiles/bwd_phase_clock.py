@@ -26,7 +26,7 @@ torch.autograd.grad([e2, agg], [n, e] + list(cell.edge_network.parameters()), [c
 ops.DEBUG_PHASE_CLOCK["ptr"] = None
 c = clk.cpu().tolist()
 names = ["setup", "LOAD(gout)", "EPI-B", "GEMM3", "EPI-C", "GEMM4", "EPI-D"]
-tiles = (E + 127) // 128 // 148 + 1
+tiles = (E + 127) // 128 // 296 + 1  # two CTAs per SM
 tot = sum(c[:7])
 for nm, v in zip(names, c[:7]):
     print(f"{nm:14s} {v / tiles:9.0f} cyc/tile  {100 * v / tot:5.1f}%")

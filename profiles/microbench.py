@@ -23,7 +23,7 @@ def timeit(fn, n=10, warm=3):
     return a.elapsed_time(b) / n
 
 
-print("# Round-1 microbenchmarks (one B200; `python profiles/microbench.py`)\n")
+print("# Microbenchmarks (one B200; `python profiles/microbench.py`)\n")
 print(f"HBM peak used for fractions: {PEAK:.0f} GB/s (MEASURED_PEAKS.json)\n")
 print("## HBM-bound kernels (algorithmic bytes / time)\n")
 print("| kernel | shape | ms | GB/s | of peak |\n|---|---|---:|---:|---:|")
@@ -65,8 +65,12 @@ print(f"| `hgnn_connected_components` | {E:,} edges, 120,000 vertices | {t:.3f} 
 
 print("\n## Fused edge step, forward + backward (edge-steps/s; destination-sorted edges, N = E/10)\n")
 print("| latent | E | graph | path | ms/step | M edge-steps/s |\n|---:|---:|---|---|---:|---:|")
-for L, E, pl in [(128, 100_000, False), (128, 1_000_000, False), (128, 4_000_000, False), (128, 1_000_000, True),
-                 (64, 1_000_000, False), (32, 1_000_000, False), (256, 250_000, False)]:
+# BASELINE config 2: latent 32-256 x 1e5-1e7 edges (the largest sizes are capped by what the layer-wise paths keep alive)
+for L, E, pl in [(128, 100_000, False), (128, 1_000_000, False), (128, 4_000_000, False), (128, 10_000_000, False),
+                 (128, 1_000_000, True),
+                 (64, 100_000, False), (64, 1_000_000, False), (64, 10_000_000, False),
+                 (32, 100_000, False), (32, 1_000_000, False), (32, 10_000_000, False),
+                 (256, 100_000, False), (256, 1_000_000, False), (256, 4_000_000, False)]:
     hp = dict(latent=L, hidden=2 * L, nb_edge_layer=2, nb_node_layer=3, layernorm=True, hidden_activation="GELU")
     torch.manual_seed(0)
     cell = InteractionGNNCell(hp); kaiming_init(cell); cell.to(DEV)
