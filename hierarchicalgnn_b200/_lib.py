@@ -88,6 +88,7 @@ SIGNATURES = {
     "hgnn_csr_build": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, sz, vp]),
     "hgnn_index_to_i32": (C.c_int, [vp, i64, i64, vp, vp, vp]),
     "hgnn_segment_reduce": (C.c_int, [vp, i64, vp, vp, vp, vp, i64, C.c_int, vp, vp]),
+    "hgnn_segment_reduce_ld": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i64, C.c_int, vp, vp]),
     "hgnn_gather_rows": (C.c_int, [vp, i64, vp, vp, i64, vp, vp]),
     "hgnn_edge_dot": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp]),
     "hgnn_mlp_forward": (C.c_int, [C.POINTER(MlpDesc), i64, vp, vp]),

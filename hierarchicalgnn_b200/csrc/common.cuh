@@ -53,7 +53,7 @@ inline int num_sms() {
 // graph_ops.cu: ordered segmented row sums; skip_short = only the hub segments (> 512 rows; one CTA each), for callers
 // whose own kernel already produced the short ones
 int launch_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight, const int32_t* perm,
-                          const int32_t* rowptr, int64_t n_segments, int mean, float* out, bool skip_short, cudaStream_t st);
+                          const int32_t* rowptr, int64_t n_segments, int mean, float* out, bool skip_short, cudaStream_t st, int64_t src_ld = 0);
 
 // simple bump allocator over the caller-provided workspace
 struct Workspace {

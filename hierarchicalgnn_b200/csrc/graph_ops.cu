@@ -129,7 +129,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict__ src, int chunks, const int32_t* __restrict__ gather,
                                  const float* __restrict__ weight, const int32_t* __restrict__ perm,
                                  const int32_t* __restrict__ rowptr, int64_t n_seg, int mean, float* __restrict__ out,
-                                 int long_threshold) {
+                                 int long_threshold, int64_t ldv) {  // ldv: source row stride in vector units (chunks when dense)
   using V = typename VecT<VEC>::type;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t s = t / chunks;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict_
       const int i = perm ? perm[j + u] : j + u;
       const int64_t r = gather ? gather[i] : i;
       w[u] = weight ? weight[i] : 1.f;
-      v[u] = rows[r * chunks + c];
+      v[u] = rows[r * ldv + c];
     }
 #pragma unroll
     for (int u = 0; u < 16; ++u) fma_acc(acc, w[u], v[u]);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const float* __restrict_
       w[u] = (ok && weight) ? weight[i] : 1.f;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = r[u] >= 0 ? rows[r[u] * chunks + c] : zero_v<V>();
+    for (int u = 0; u < 8; ++u) v[u] = r[u] >= 0 ? rows[r[u] * ldv + c] : zero_v<V>();
 #pragma unroll
     for (int u = 0; u < 8; ++u)
       if (r[u] >= 0) fma_acc(acc, w[u], v[u]);
@@ -185,7 +185,8 @@ template <int VEC>
 __global__ void __launch_bounds__(LONG_THREADS) k_segment_reduce_long(const float* __restrict__ src, int chunks,
                                                                       const int32_t* __restrict__ gather, const float* __restrict__ weight,
                                                                       const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr,
-                                                                      int64_t n_seg, int mean, float* __restrict__ out, int long_threshold) {
+                                                                      int64_t n_seg, int mean, float* __restrict__ out, int long_threshold,
+                                                                      int64_t ldv) {
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   V* part_sum = reinterpret_cast<V*>(sm_raw);
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(LONG_THREADS) k_segment_reduce_long(const floa
           const int i = perm ? perm[j + u] : j + u;
           const int64_t r = gather ? gather[i] : i;
           w[u] = weight ? weight[i] : 1.f;
-          v[u] = rows[r * chunks + c];
+          v[u] = rows[r * ldv + c];
         }
 #pragma unroll
         for (int u = 0; u < 16; ++u) fma_acc(acc, w[u], v[u]);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(LONG_THREADS) k_segment_reduce_long(const floa
       for (; j < b1; ++j) {
         const int i = perm ? perm[j] : j;
         const int64_t r = gather ? gather[i] : i;
-        fma_acc(acc, weight ? weight[i] : 1.f, rows[r * chunks + c]);
+        fma_acc(acc, weight ? weight[i] : 1.f, rows[r * ldv + c]);
       }
       part_sum[part * chunks + c] = acc;
     }
@@ -305,21 +306,24 @@ __global__ void __launch_bounds__(256) k_edge_dot(const float* __restrict__ a, c
 namespace hgnn {
 // launches the per-thread kernel for ordinary segments and the per-CTA kernel for hub segments (> 512 rows)
 int launch_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight, const int32_t* perm,
-                          const int32_t* rowptr, int64_t n_segments, int mean, float* out, bool skip_short, cudaStream_t st) {
-  bool vec = (width % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
+                          const int32_t* rowptr, int64_t n_segments, int mean, float* out, bool skip_short, cudaStream_t st,
+                          int64_t src_ld) {
+  if (src_ld <= 0) src_ld = width;  // dense rows
+  bool vec = (width % 4 == 0) && (src_ld % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
   int chunks = vec ? (int)(width / 4) : (int)width;
+  const int64_t ldv = vec ? src_ld / 4 : src_ld;
   const int long_threshold = chunks <= 256 ? 512 : 0;  // hub path needs >= 4 row parts per 1024-thread CTA
   if (!skip_short) {
     int64_t threads = n_segments * chunks;
     unsigned grid = (unsigned)((threads + 255) / 256);
-    if (vec) k_segment_reduce<4><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
-    else k_segment_reduce<1><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
+    if (vec) k_segment_reduce<4><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold, ldv);
+    else k_segment_reduce<1><<<grid, 256, 0, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold, ldv);
   }
   if (long_threshold > 0) {
     unsigned grid = (unsigned)((n_segments + LONG_THREADS - 1) / LONG_THREADS);  // one segment id per thread to inspect
     size_t smem = (size_t)LONG_THREADS * (vec ? 16 : 4);
-    if (vec) k_segment_reduce_long<4><<<grid, LONG_THREADS, smem, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
-    else k_segment_reduce_long<1><<<grid, LONG_THREADS, smem, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold);
+    if (vec) k_segment_reduce_long<4><<<grid, LONG_THREADS, smem, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold, ldv);
+    else k_segment_reduce_long<1><<<grid, LONG_THREADS, smem, st>>>(src, chunks, gather, weight, perm, rowptr, n_segments, mean, out, long_threshold, ldv);
   }
   return check_launch("segment_reduce");
 }
@@ -332,6 +336,15 @@ extern "C" int hgnn_segment_reduce(const float* src, int64_t width, const int32_
   HGNN_REQUIRE(src && rowptr && out, "segment_reduce: NULL pointer");
   HGNN_REQUIRE(width <= 65536, "segment_reduce: width too large");
   return hgnn::launch_segment_reduce(src, width, gather, weight, perm, rowptr, n_segments, mean, out, false, (cudaStream_t)stream);
+}
+
+extern "C" int hgnn_segment_reduce_ld(const float* src, int64_t width, int64_t src_ld, const int32_t* gather, const float* weight,
+                                      const int32_t* perm, const int32_t* rowptr, int64_t n_segments, int mean, float* out,
+                                      void* stream) {
+  if (n_segments <= 0 || width <= 0) return HGNN_OK;
+  HGNN_REQUIRE(src && rowptr && out, "segment_reduce: NULL pointer");
+  HGNN_REQUIRE(width <= 65536 && src_ld >= width, "segment_reduce: bad width / row stride");
+  return hgnn::launch_segment_reduce(src, width, gather, weight, perm, rowptr, n_segments, mean, out, false, (cudaStream_t)stream, src_ld);
 }
 
 extern "C" int hgnn_gather_rows(const float* src, int64_t width, const int32_t* idx, const float* weight, int64_t n_items,

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 using namespace hgnn;
 
@@ -461,6 +462,270 @@ __global__ void __launch_bounds__(SK_THREADS) k_ln_act_bwd(const float* __restri
   for (int i = threadIdx.x; i < 3 * N; i += SK_THREADS) o[i] = s_acc[i];
 }
 
+// ---- vectorised variants for widths that are multiples of 128 (the layer shapes of latent 128 / 256): lane l owns the float4
+// at columns 4 l + 128 j, so a warp moves 512 contiguous bytes per load / store; the activations are the tensor-core path's
+// fast forms (these kernels only run beside tcgen05 GEMMs: bf16 operands, fp32 LayerNorm) selected at compile time.
+template <int ACT>
+__device__ __forceinline__ float ln_act_f(int act, float y) {
+  if constexpr (ACT >= 0) return hgnn::tc::tc_act<ACT>(y);
+  else return act_fwd(act, y);
+}
+template <int ACT>
+__device__ __forceinline__ float ln_act_b(int act, float y) {
+  if constexpr (ACT >= 0) return hgnn::tc::tc_act_bwd<ACT>(y);
+  else return act_bwd(act, y);
+}
+
+template <int NV, int ACT>
+__global__ void __launch_bounds__(SK_THREADS, 3) k_ln_act_fwd_v(const float* __restrict__ h, int64_t rows, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int act,
+                                                             const float* __restrict__ skip, float* __restrict__ out) {
+  constexpr int N = 128 * NV;
+  constexpr int RU = 4 / NV;  // rows per warp iteration: every load of RU rows is in flight before the first reduction
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 g[NV], b[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    g[j] = *reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * j);
+    b[j] = *reinterpret_cast<const float4*>(beta + 4 * lane + 128 * j);
+  }
+  const float invN = 1.0f / N;
+  for (int64_t r0 = ((int64_t)blockIdx.x * SK_WARPS + warp) * RU; r0 < rows; r0 += (int64_t)gridDim.x * SK_WARPS * RU) {
+    float4 v[RU][NV], sk[RU][NV];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int64_t r = min(r0 + u, rows - 1);  // a tail row is recomputed, not stored twice (guard below)
+      const float4* hr = reinterpret_cast<const float4*>(h + (size_t)r * N) + lane;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[u][j] = __ldg(hr + 32 * j);
+      if (skip) {
+        const float4* sr = reinterpret_cast<const float4*>(skip + (size_t)r * N) + lane;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) sk[u][j] = __ldg(sr + 32 * j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) sum += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+      const float mean = warp_sum(sum) * invN;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float d0 = v[u][j].x - mean, d1 = v[u][j].y - mean, d2 = v[u][j].z - mean, d3 = v[u][j].w - mean;
+        sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+      }
+      const float rstd = rsqrtf(warp_sum(sq) * invN + eps);
+      if (r0 + u >= rows) continue;
+      float4* orow = reinterpret_cast<float4*>(out + (size_t)(r0 + u) * N) + lane;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float4 y;
+        y.x = ln_act_f<ACT>(act, fmaf((v[u][j].x - mean) * rstd, g[j].x, b[j].x));
+        y.y = ln_act_f<ACT>(act, fmaf((v[u][j].y - mean) * rstd, g[j].y, b[j].y));
+        y.z = ln_act_f<ACT>(act, fmaf((v[u][j].z - mean) * rstd, g[j].z, b[j].z));
+        y.w = ln_act_f<ACT>(act, fmaf((v[u][j].w - mean) * rstd, g[j].w, b[j].w));
+        if (skip) { y.x += sk[u][j].x; y.y += sk[u][j].y; y.z += sk[u][j].z; y.w += sk[u][j].w; }
+        orow[32 * j] = y;
+      }
+    }
+  }
+}
+
+template <int NV, int ACT>
+__global__ void __launch_bounds__(SK_THREADS, 2) k_ln_act_bwd_v(const float* __restrict__ h, const float* __restrict__ gout, int64_t rows,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                             int act, float* __restrict__ delta, float* __restrict__ partial) {
+  constexpr int N = 128 * NV;
+  constexpr int RU = NV == 1 ? 2 : 1;  // rows per warp iteration (loads of both rows in flight together)
+  extern __shared__ float s_acc[];  // [3][N]
+  for (int i = threadIdx.x; i < 3 * N; i += SK_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g[NV][4], b[NV][4], ab[NV][4], ag[NV][4], abe[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 gg = *reinterpret_cast<const float4*>(gamma + 4 * lane + 128 * j), bb = *reinterpret_cast<const float4*>(beta + 4 * lane + 128 * j);
+    g[j][0] = gg.x; g[j][1] = gg.y; g[j][2] = gg.z; g[j][3] = gg.w;
+    b[j][0] = bb.x; b[j][1] = bb.y; b[j][2] = bb.z; b[j][3] = bb.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ab[j][k] = ag[j][k] = abe[j][k] = 0.f;
+  }
+  const float invN = 1.0f / N;
+  for (int64_t r0 = ((int64_t)blockIdx.x * SK_WARPS + warp) * RU; r0 < rows; r0 += (int64_t)gridDim.x * SK_WARPS * RU) {
+    float v[RU][NV][4], go[RU][NV][4];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const bool live = r0 + u < rows;
+      const int64_t r = live ? r0 + u : rows - 1;
+      const float4* hr = reinterpret_cast<const float4*>(h + (size_t)r * N) + lane;
+      const float4* gr = reinterpret_cast<const float4*>(gout + (size_t)r * N) + lane;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 a = __ldg(hr + 32 * j);
+        float4 c = __ldg(gr + 32 * j);
+        if (!live) c = make_float4(0.f, 0.f, 0.f, 0.f);  // a tail row past the end contributes nothing
+        v[u][j][0] = a.x; v[u][j][1] = a.y; v[u][j][2] = a.z; v[u][j][3] = a.w;
+        go[u][j][0] = c.x; go[u][j][1] = c.y; go[u][j][2] = c.z; go[u][j][3] = c.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) sum += (v[u][j][0] + v[u][j][1]) + (v[u][j][2] + v[u][j][3]);
+      const float mean = warp_sum(sum) * invN;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float d = v[u][j][k] - mean; sq = fmaf(d, d, sq); }
+      const float rstd = rsqrtf(warp_sum(sq) * invN + eps);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float xh = (v[u][j][k] - mean) * rstd;
+          const float d = go[u][j][k] * ln_act_b<ACT>(act, fmaf(xh, g[j][k], b[j][k]));
+          ag[j][k] = fmaf(d, xh, ag[j][k]);
+          abe[j][k] += d;
+          const float gd = g[j][k] * d;
+          v[u][j][k] = xh;
+          go[u][j][k] = gd;
+          s1 += gd;
+          s2 = fmaf(gd, xh, s2);
+        }
+      s1 = warp_sum(s1) * invN;
+      s2 = warp_sum(s2) * invN;
+      if (r0 + u >= rows) continue;  // (its addends above were zeros)
+      float4* drow = reinterpret_cast<float4*>(delta + (size_t)(r0 + u) * N) + lane;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float dl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { dl[k] = rstd * (go[u][j][k] - s1 - v[u][j][k] * s2); ab[j][k] += dl[k]; }
+        drow[32 * j] = make_float4(dl[0], dl[1], dl[2], dl[3]);
+      }
+    }
+  }
+  for (int w = 0; w < SK_WARPS; ++w) {  // ordered accumulation over the warps
+    if (warp == w) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * lane + 128 * j + k;
+          s_acc[c] += ab[j][k];
+          s_acc[N + c] += ag[j][k];
+          s_acc[2 * N + c] += abe[j][k];
+        }
+    }
+    __syncthreads();
+  }
+  float* o = partial + (size_t)blockIdx.x * 3 * N;
+  for (int i = threadIdx.x; i < 3 * N; i += SK_THREADS) o[i] = s_acc[i];
+}
+
+// width 64 (the hidden width of latent 32, the latent of latent 64): 16 lanes x float4 per row, two rows per warp
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(SK_THREADS) k_ln_act_fwd_64(const float* __restrict__ h, int64_t rows, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, int act,
+                                                              const float* __restrict__ skip, float* __restrict__ out) {
+  constexpr int N = 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 4, c4 = lane & 15;
+  const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c4), b = *reinterpret_cast<const float4*>(beta + 4 * c4);
+  for (int64_t r0 = ((int64_t)blockIdx.x * SK_WARPS + warp) * 2; r0 < rows; r0 += (int64_t)gridDim.x * SK_WARPS * 2) {
+    const int64_t r = r0 + sub;
+    const bool live = r < rows;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), sk = v;
+    if (live) {
+      v = __ldg(reinterpret_cast<const float4*>(h + (size_t)r * N) + c4);
+      if (skip) sk = __ldg(reinterpret_cast<const float4*>(skip + (size_t)r * N) + c4);
+    }
+    const float mean = half_warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / N);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    const float rstd = rsqrtf(half_warp_sum(fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)))) * (1.0f / N) + eps);
+    if (live) {
+      float4 y;
+      y.x = ln_act_f<ACT>(act, fmaf(d0 * rstd, g.x, b.x)) + sk.x;
+      y.y = ln_act_f<ACT>(act, fmaf(d1 * rstd, g.y, b.y)) + sk.y;
+      y.z = ln_act_f<ACT>(act, fmaf(d2 * rstd, g.z, b.z)) + sk.z;
+      y.w = ln_act_f<ACT>(act, fmaf(d3 * rstd, g.w, b.w)) + sk.w;
+      reinterpret_cast<float4*>(out + (size_t)r * N)[c4] = y;
+    }
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(SK_THREADS) k_ln_act_bwd_64(const float* __restrict__ h, const float* __restrict__ gout, int64_t rows,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                              int act, float* __restrict__ delta, float* __restrict__ partial) {
+  constexpr int N = 64;
+  extern __shared__ float s_acc[];  // [3][N]
+  for (int i = threadIdx.x; i < 3 * N; i += SK_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane >> 4, c4 = lane & 15;
+  const float4 g4 = *reinterpret_cast<const float4*>(gamma + 4 * c4), b4 = *reinterpret_cast<const float4*>(beta + 4 * c4);
+  const float g[4] = {g4.x, g4.y, g4.z, g4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+  float ab[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f}, abe[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t r0 = ((int64_t)blockIdx.x * SK_WARPS + warp) * 2; r0 < rows; r0 += (int64_t)gridDim.x * SK_WARPS * 2) {
+    const int64_t r = r0 + sub;
+    const bool live = r < rows;
+    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), gv = hv;
+    if (live) {
+      hv = __ldg(reinterpret_cast<const float4*>(h + (size_t)r * N) + c4);
+      gv = __ldg(reinterpret_cast<const float4*>(gout + (size_t)r * N) + c4);
+    }
+    float v[4] = {hv.x, hv.y, hv.z, hv.w}, go[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float mean = half_warp_sum((v[0] + v[1]) + (v[2] + v[3])) * (1.0f / N);
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] -= mean; sq = fmaf(v[k], v[k], sq); }
+    const float rstd = rsqrtf(half_warp_sum(sq) * (1.0f / N) + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = v[k] * rstd;
+      const float d = go[k] * ln_act_b<ACT>(act, fmaf(xh, g[k], b[k]));  // padding rows: gout = 0 -> d = 0
+      ag[k] = fmaf(d, xh, ag[k]);
+      abe[k] += d;
+      const float gd = g[k] * d;
+      v[k] = xh;
+      go[k] = gd;
+      s1 += gd;
+      s2 = fmaf(gd, xh, s2);
+    }
+    s1 = half_warp_sum(s1) * (1.0f / N);
+    s2 = half_warp_sum(s2) * (1.0f / N);
+    float dl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { dl[k] = live ? rstd * (go[k] - s1 - v[k] * s2) : 0.f; ab[k] += dl[k]; }
+    if (live) reinterpret_cast<float4*>(delta + (size_t)r * N)[c4] = make_float4(dl[0], dl[1], dl[2], dl[3]);
+  }
+  for (int w = 0; w < 2 * SK_WARPS; ++w) {  // ordered accumulation over the (warp, row half) pairs
+    if (2 * warp + sub == w) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = 4 * c4 + k;
+        s_acc[c] += ab[k];
+        s_acc[N + c] += ag[k];
+        s_acc[2 * N + c] += abe[k];
+      }
+    }
+    __syncthreads();
+  }
+  float* o = partial + (size_t)blockIdx.x * 3 * N;
+  for (int i = threadIdx.x; i < 3 * N; i += SK_THREADS) o[i] = s_acc[i];
+}
+
 __global__ void k_partial_reduce(const float* __restrict__ partial, int n_part, int width, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= width) return;
@@ -628,8 +893,33 @@ extern "C" int hgnn_ln_act_forward(const float* h, int64_t rows, int64_t n, cons
   if (rows <= 0) return HGNN_OK;
   HGNN_REQUIRE(h && gamma && beta && out, "ln_act_forward: NULL pointer");
   HGNN_REQUIRE(act >= HGNN_ACT_NONE && act <= HGNN_ACT_SIGMOID, "ln_act_forward: unknown activation %d", act);
-  const int grid = skinny_grid(rows, SK_WARPS * 4);
+  // grid-stride kernels without cross-CTA state: three CTAs per SM resident (the vectorised kernels are bounded to 80 registers)
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + SK_WARPS * 4 - 1) / (SK_WARPS * 4), 6 * (int64_t)num_sms()));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool al16 = (((uintptr_t)h | (uintptr_t)out | (uintptr_t)skip | (uintptr_t)gamma | (uintptr_t)beta) % 16) == 0;
+  if (n == 64 && al16) {
+    if (act == HGNN_ACT_GELU) k_ln_act_fwd_64<HGNN_ACT_GELU><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out);
+    else if (act == HGNN_ACT_TANH) k_ln_act_fwd_64<HGNN_ACT_TANH><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out);
+    else k_ln_act_fwd_64<-1><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out);
+    return check_launch("ln_act_forward");
+  }
+  const bool vec = n % 128 == 0 && al16;
+  if (vec) {
+#define HGNN_LN_FWD(NV, ACT) k_ln_act_fwd_v<NV, ACT><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out)
+#define HGNN_LN_FWD_ACT(NV)                                       \
+    do {                                                          \
+      if (act == HGNN_ACT_GELU) HGNN_LN_FWD(NV, HGNN_ACT_GELU);   \
+      else if (act == HGNN_ACT_TANH) HGNN_LN_FWD(NV, HGNN_ACT_TANH); \
+      else if (act == HGNN_ACT_NONE) HGNN_LN_FWD(NV, HGNN_ACT_NONE); \
+      else HGNN_LN_FWD(NV, -1);                                   \
+    } while (0)
+    if (n == 128) HGNN_LN_FWD_ACT(1);
+    else if (n == 256) HGNN_LN_FWD_ACT(2);
+    else HGNN_LN_FWD_ACT(4);
+#undef HGNN_LN_FWD_ACT
+#undef HGNN_LN_FWD
+    return check_launch("ln_act_forward");
+  }
   switch (n / 32) {
     case 2: k_ln_act_fwd<2><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out); break;
     case 4: k_ln_act_fwd<4><<<grid, SK_THREADS, 0, st>>>(h, rows, gamma, beta, eps, act, skip, out); break;
@@ -657,6 +947,28 @@ extern "C" int hgnn_ln_act_backward(const float* h, const float* grad_out, int64
   HGNN_REQUIRE(ws_bytes >= (size_t)grid * 3 * n * 4, "ln_act_backward: workspace too small");
   float* partial = (float*)ws;
   const size_t smem = (size_t)3 * n * 4;
+  const bool al16 = (((uintptr_t)h | (uintptr_t)grad_out | (uintptr_t)delta | (uintptr_t)gamma | (uintptr_t)beta) % 16) == 0;
+  const bool vec = n % 128 == 0 && al16;
+  if (n == 64 && al16) {
+    if (act == HGNN_ACT_GELU) k_ln_act_bwd_64<HGNN_ACT_GELU><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial);
+    else if (act == HGNN_ACT_TANH) k_ln_act_bwd_64<HGNN_ACT_TANH><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial);
+    else k_ln_act_bwd_64<-1><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial);
+  } else
+  if (vec) {
+#define HGNN_LN_BWD(NV, ACT) k_ln_act_bwd_v<NV, ACT><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial)
+#define HGNN_LN_BWD_ACT(NV)                                       \
+    do {                                                          \
+      if (act == HGNN_ACT_GELU) HGNN_LN_BWD(NV, HGNN_ACT_GELU);   \
+      else if (act == HGNN_ACT_TANH) HGNN_LN_BWD(NV, HGNN_ACT_TANH); \
+      else if (act == HGNN_ACT_NONE) HGNN_LN_BWD(NV, HGNN_ACT_NONE); \
+      else HGNN_LN_BWD(NV, -1);                                   \
+    } while (0)
+    if (n == 128) HGNN_LN_BWD_ACT(1);
+    else if (n == 256) HGNN_LN_BWD_ACT(2);
+    else HGNN_LN_BWD_ACT(4);
+#undef HGNN_LN_BWD_ACT
+#undef HGNN_LN_BWD
+  } else
   switch (n / 32) {
     case 2: k_ln_act_bwd<2><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial); break;
     case 4: k_ln_act_bwd<4><<<grid, SK_THREADS, smem, st>>>(h, grad_out, rows, gamma, beta, eps, act, delta, partial); break;

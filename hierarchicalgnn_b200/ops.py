@@ -237,17 +237,28 @@ def clear_plan_cache():
 # ---------------------------------------------------------------------------
 # raw launches
 # ---------------------------------------------------------------------------
+def _rows_view(src: Tensor):
+    """(tensor, row stride in floats) for the kernels that take a source row stride: a column slice of a wider fp32 matrix
+    (unit column stride) is used in place, anything else is made dense."""
+    if src.dtype != torch.float32:
+        raise _lib.HgnnError(f"expected float32 features, got {src.dtype}")
+    if src.dim() == 2 and src.stride(1) == 1 and src.stride(0) >= src.shape[1] and src.shape[0] > 0:
+        return src, src.stride(0)
+    src = src.contiguous()
+    return src, src.shape[1]
+
+
 def segment_reduce_raw(src: Tensor, plan: SegmentPlan, gather32: Optional[Tensor] = None,
                        weight: Optional[Tensor] = None, mean: bool = False) -> Tensor:
-    src = _f32(src)
+    src, ld = _rows_view(src)
     width = src.shape[1]
     if plan.n_items == 0:
         return torch.zeros((plan.n_segments, width), dtype=torch.float32, device=src.device)
     out = torch.empty((plan.n_segments, width), dtype=torch.float32, device=src.device)
     if plan.n_segments and width:
         with _timed("segment_reduce"):
-            check(_lib.lib().hgnn_segment_reduce(_ptr(src), width, _ptr(gather32), _ptr(weight), _ptr(plan.perm),
-                                                 _ptr(plan.rowptr), plan.n_segments, int(mean), _ptr(out), _stream()),
+            check(_lib.lib().hgnn_segment_reduce_ld(_ptr(src), width, ld, _ptr(gather32), _ptr(weight), _ptr(plan.perm),
+                                                    _ptr(plan.rowptr), plan.n_segments, int(mean), _ptr(out), _stream()),
                   "segment_reduce")
         _count(2)  # per-thread kernel for ordinary segments + per-CTA kernel for hub segments
     return out
@@ -774,7 +785,7 @@ class _NarrowIn(torch.autograd.Function):
                 if plan is not None:
                     if plan.n_segments != segs[s].shape[0]:
                         raise _lib.HgnnError("narrow-in layer: gather plan does not cover the gathered tensor")
-                    gs = segment_reduce_raw(gs.contiguous(), plan)
+                    gs = segment_reduce_raw(gs, plan)  # column slice of d_in, reduced in place (row stride)
             grads.append(gs)
             off += w
         grads += [dW, dvec[0]]
@@ -946,7 +957,7 @@ class _TcRowLayer(torch.autograd.Function):
                 if plan is not None:
                     if plan.n_segments != ctx.seg_rows[s]:
                         raise _lib.HgnnError("row layer: gather plan does not cover the gathered tensor")
-                    gs = segment_reduce_raw(gs.contiguous(), plan)
+                    gs = segment_reduce_raw(gs, plan)  # column slice of d_in, reduced in place (row stride)
             grads.append(gs)
             off += w
         if meta.has_skip:
@@ -1080,7 +1091,7 @@ class _TcSplitLayer(torch.autograd.Function):
                 if plan is not None:
                     if plan.n_segments != ctx.seg_rows[s]:
                         raise _lib.HgnnError("generic layer: gather plan does not cover the gathered tensor")
-                    gs = segment_reduce_raw(gs.contiguous(), plan)
+                    gs = segment_reduce_raw(gs, plan)  # column slice of d_in, reduced in place (row stride)
             grads.append(gs)
             off += w
         if meta.has_skip:

@@ -78,6 +78,11 @@ int hgnn_index_to_i32(const int64_t* in, int64_t n, int64_t limit, int32_t* out,
 int hgnn_segment_reduce(const float* src, int64_t width, const int32_t* gather, const float* weight,
                         const int32_t* perm, const int32_t* rowptr, int64_t n_segments, int mean, float* out,
                         void* stream);
+/* Same with an explicit source row stride (floats): rows of a column slice of a wider matrix are reduced in place
+ * (the column blocks of a layer's input gradient, one per gathered segment) instead of being copied out first. */
+int hgnn_segment_reduce_ld(const float* src, int64_t width, int64_t src_ld, const int32_t* gather, const float* weight,
+                           const int32_t* perm, const int32_t* rowptr, int64_t n_segments, int mean, float* out,
+                           void* stream);
 
 /* out[i, :] = w[i] * src[idx[i], :]  (idx NULL = identity). Adjoint of an
  * ungathered segment reduce; also the row gather used by the encoders. */
