@@ -24,7 +24,12 @@ class BipartiteClassificationBase(LightningModule):
         self.save_hyperparameters(hparams)
 
     def configure_optimizers(self):
-        opt = torch.optim.AdamW(self.parameters(), lr=self.hparams["lr"], betas=(0.9, 0.999), eps=1e-08, amsgrad=True)
+        params = list(self.parameters())
+        # same optimiser and hyper-parameters as the reference; on CUDA parameters the fused multi-tensor implementation
+        # (one launch per step instead of a dozen per parameter group chunk)
+        fused = bool(params) and all(p.is_cuda for p in params)
+        opt = torch.optim.AdamW(params, lr=self.hparams["lr"], betas=(0.9, 0.999), eps=1e-08, amsgrad=True,
+                                **({"fused": True} if fused else {}))
         sched = torch.optim.lr_scheduler.StepLR(opt, step_size=self.hparams["patience"], gamma=self.hparams["factor"])
         return [opt], [{"scheduler": sched, "interval": "epoch", "frequency": 1}]
 
@@ -40,7 +45,6 @@ class BipartiteClassificationBase(LightningModule):
 
     # ---- assignment term: bipartite_classification_base.py:152-191 ----
     def assignment_loss(self, batch, bipartite_graph, bipartite_scores):
-        from scipy.sparse import csr_matrix
         from scipy.sparse.csgraph import min_weight_full_bipartite_matching
         dev = bipartite_scores.device
         original_pid, pid = torch.unique(batch.pid, return_inverse=True)
@@ -52,7 +56,7 @@ class BipartiteClassificationBase(LightningModule):
             rows = torch.cat([pid[bipartite_graph[0]], torch.arange(n_p, device=dev)])
             cols = torch.cat([bipartite_graph[1], torch.arange(n_s, n_s + n_p, device=dev)])
             vals = torch.cat([bipartite_scores.detach(), torch.full((n_p,), 1e-12, device=dev)])
-            table = csr_matrix((vals.cpu().numpy(), (rows.cpu().numpy(), cols.cpu().numpy())), shape=(n_p, n_s + n_p))
+            table = self._score_table(rows, cols, vals, n_p, n_s + n_p)
             rm, cm = min_weight_full_bipartite_matching(table, maximize=True)
             rm, cm = torch.as_tensor(rm, device=dev).long(), torch.as_tensor(cm, device=dev).long()
             real = (original_pid[rm] != 0) & (cm < n_s)
@@ -68,6 +72,29 @@ class BipartiteClassificationBase(LightningModule):
             ts, fs = (w * truth).sum().clamp(min=1e-30), (w * ~truth).sum().clamp(min=1e-30)
             w = torch.where(truth, w / ts * torch.sigmoid(ratio), w / fs * torch.sigmoid(-ratio)).float()
         return torch.dot(F.binary_cross_entropy(bipartite_scores, truth.float(), reduction="none"), w)
+
+    @staticmethod
+    def _score_table(rows, cols, vals, n_rows, n_cols):
+        """The particle x (supernode + virtual supernode) score table of the matching as a canonical scipy CSR matrix.
+        The reference hands scipy the COO triplets and lets it sort them and sum the duplicates on the host
+        (bipartite_classification_base.py:163-173: 3 ms of the 7 ms the matching stage takes on a 1 GeV event); on CUDA
+        tensors the same table is assembled on the device — sorted unique (row, column) keys, duplicate scores summed per key
+        in a fixed order (segment reduce, no float atomics), row pointers from a histogram — and scipy receives
+        (data, indices, indptr) as they are."""
+        from scipy.sparse import csr_matrix
+        if not vals.is_cuda:
+            return csr_matrix((vals.numpy(), (rows.numpy(), cols.numpy())), shape=(n_rows, n_cols))
+        from .. import ops
+        keys = rows * n_cols + cols
+        uniq, inverse = torch.unique(keys, return_inverse=True)
+        data = ops.scatter_add(vals.float().unsqueeze(1).contiguous(), inverse, dim_size=uniq.numel()).squeeze(1)
+        r = torch.div(uniq, n_cols, rounding_mode="floor")
+        indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=vals.device)
+        indptr[1:] = torch.bincount(r, minlength=n_rows).cumsum(0)
+        idx = torch.cat([(uniq - r * n_cols), indptr]).to(torch.int32).cpu().numpy()  # one transfer for both index arrays
+        m = csr_matrix((data.cpu().numpy(), idx[:uniq.numel()], idx[uniq.numel():]), shape=(n_rows, n_cols))
+        m.has_sorted_indices = True
+        return m
 
     def loss_schedule(self):
         if self.hparams.get("loss_schedule") is not None:

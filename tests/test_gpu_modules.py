@@ -1,6 +1,7 @@
 """GPU parity of the drop-in modules against fixtures recorded from the
 UNMODIFIED reference (tests/golden, oracle/make_golden.py): same state dict in,
 same outputs / gradients / buffer updates out, at fp32 tolerance."""
+import numpy as np
 import pytest
 import torch
 
@@ -249,3 +250,25 @@ def test_ec_full_config_tensor_core_path_scores_and_auc_vs_fp64_oracle():
         ops.set_precision(old)
     assert float((got - want).abs().max()) < 1e-2
     assert abs(O.roc_auc(got, ev.y_pid) - O.roc_auc(want, ev.y_pid)) <= 1e-3
+
+
+def test_matching_score_table_device_assembly_matches_scipy_coo_path():
+    """The assignment loss hands scipy a CSR table assembled on the device (BipartiteClassificationBase._score_table); it has
+    to be the table scipy builds itself from the COO triplets (reference bipartite_classification_base.py:163-173):
+    same pattern, sorted column indices, duplicates summed (fp32 sum order may differ: 1e-6 relative)."""
+    from scipy.sparse import csr_matrix
+    from hierarchicalgnn_b200.BipartiteClassification.bipartite_classification_base import BipartiteClassificationBase
+    g = torch.Generator().manual_seed(5)
+    n_p, n_s, nnz = 700, 300, 40000  # many duplicate (particle, supernode) pairs, as hits of one particle share supernodes
+    rows = torch.cat([torch.randint(0, n_p, (nnz,), generator=g), torch.arange(n_p)])
+    cols = torch.cat([torch.randint(0, n_s, (nnz,), generator=g), torch.arange(n_s, n_s + n_p)])
+    vals = torch.cat([torch.rand(nnz, generator=g), torch.full((n_p,), 1e-12)])
+    want = csr_matrix((vals.numpy(), (rows.numpy(), cols.numpy())), shape=(n_p, n_s + n_p))
+    want.sum_duplicates()
+    got = BipartiteClassificationBase._score_table(rows.cuda(), cols.cuda(), vals.cuda(), n_p, n_s + n_p)
+    assert got.shape == want.shape and got.nnz == want.nnz
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    np.testing.assert_allclose(got.data, want.data, rtol=2e-6, atol=0)
+    # an empty row set and a single entry
+    one = BipartiteClassificationBase._score_table(torch.tensor([0]).cuda(), torch.tensor([1]).cuda(), torch.tensor([0.5]).cuda(), 2, 3)
+    assert one.toarray().tolist() == [[0.0, 0.5, 0.0], [0.0, 0.0, 0.0]]
