@@ -145,6 +145,7 @@ SIGNATURES = {
     "hgnn_tc_row_forward": (C.c_int, [C.POINTER(TcRowLayer), i64, vp, vp, vp]),
     "hgnn_tc_row_backward_workspace_bytes": (sz, [i64, i64, i64]),
     "hgnn_tc_row_backward": (C.c_int, [C.POINTER(TcRowLayer), vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]),
+    "hgnn_tc_row_backward_split": (C.c_int, [C.POINTER(TcRowLayer), vp, vp, i64, vp, C.POINTER(vp), vp, vp, vp, sz, vp]),
     "hgnn_tc_edge_stash_bytes": (sz, [i64, i64]),
     "hgnn_tc_edge_forward": (C.c_int, [C.POINTER(TcEdgeParams), vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz, vp]),
 }

@@ -254,7 +254,8 @@ struct RowBwdArgs {
   float eps;
   const uint8_t* a_img;
   const float* gout;         // [rows, N]
-  float* d_in;               // [rows, K]
+  float* d_piece[3];         // d(input) columns [128 p, 128 p + 128): base pointer of the piece (NULL = not wanted) ...
+  int d_ld[3];               // ... and its row stride in floats (one [rows, K] matrix, or one dense matrix per gathered segment)
   uint8_t* d_img;            // [tiles][N/64][16 KB] delta image (operand of the weight-gradient GEMM)
   float* colpart;            // [grid][4][3 N]
   int64_t rows;
@@ -526,9 +527,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_tc_row_bwd(RowBwdArgs A) {
       for (int k = 0; k < 8; ++k) {  // 8 rows per warp, one float4 chunk per lane
         const int r = warp * 8 + k, c4 = lane;
         const int64_t j = (int64_t)tile * TILE_M + r;
-        if (j < A.rows) {
+        if (j < A.rows && A.d_piece[sg] != nullptr) {
           float4 y = *reinterpret_cast<const float4*>(sm + (size_t)r * 512 + ((c4 ^ (r & 7)) << 4));
-          *reinterpret_cast<float4*>(A.d_in + (size_t)j * A.K + sg * 128 + c4 * 4) = y;
+          *reinterpret_cast<float4*>(A.d_piece[sg] + (size_t)j * A.d_ld[sg] + c4 * 4) = y;
         }
       }
       __syncthreads();
@@ -552,14 +553,6 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_tc_row_bwd(RowBwdArgs A) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
-}
-
-__global__ void k_row_colpart_reduce(const float* __restrict__ part, int n_part, int width, float* __restrict__ dvec) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= width) return;
-  float s = 0.f;
-  for (int p = 0; p < n_part; ++p) s += part[(size_t)p * width + i];
-  dvec[i] = s;
 }
 
 bool act_built(int act) { return act == HGNN_ACT_GELU || act == HGNN_ACT_TANH || act == HGNN_ACT_RELU || act == HGNN_ACT_SILU; }
@@ -711,10 +704,13 @@ extern "C" size_t hgnn_tc_row_backward_workspace_bytes(int64_t rows, int64_t k, 
   return bwd_layout(rows > 0 ? rows : 1, (int)k, (int)n_out).total + 1024;
 }
 
-extern "C" int hgnn_tc_row_backward(const hgnn_tc_row_layer* d, const void* wt_packed, const void* a_img, int64_t rows,
-                                    const float* grad_out, float* d_in, float* dW, float* dvec, void* ws, size_t ws_bytes,
-                                    void* stream) {
-  int rc = validate(d, "tc_row_backward");
+namespace {
+
+// d_seg == nullptr: d(input) goes to d_in as one [rows, K] matrix; else segment s goes to d_seg[s] as a dense
+// [rows, seg_width[s]] matrix (NULL entry = that segment's gradient is not wanted: its columns are never stored)
+int row_backward(const hgnn_tc_row_layer* d, const void* wt_packed, const void* a_img, int64_t rows, const float* grad_out,
+                 float* d_in, float* const* d_seg, float* dW, float* dvec, void* ws, size_t ws_bytes, void* stream, const char* who) {
+  int rc = validate(d, who);
   if (rc) return rc;
   const int K = layer_k(d), N = d->n_out;
   cudaStream_t st = (cudaStream_t)stream;
@@ -723,25 +719,56 @@ extern "C" int hgnn_tc_row_backward(const hgnn_tc_row_layer* d, const void* wt_p
     if (dvec) HGNN_CUDA_TRY(cudaMemsetAsync(dvec, 0, (size_t)3 * N * 4, st));
     return HGNN_OK;
   }
-  HGNN_REQUIRE(wt_packed && a_img && grad_out && d_in && dW && dvec && ws && d->w_packed && d->bias && d->gamma && d->beta,
-               "tc_row_backward: NULL pointer");
-  HGNN_REQUIRE(rows < INT32_MAX, "tc_row_backward: too many rows");
+  HGNN_REQUIRE(wt_packed && a_img && grad_out && (d_in || d_seg) && dW && dvec && ws && d->w_packed && d->bias && d->gamma && d->beta,
+               "%s: NULL pointer", who);
+  HGNN_REQUIRE(rows < INT32_MAX, "%s: too many rows", who);
   BwdLayout Y = bwd_layout(rows, K, N);
   uintptr_t base = align_up((uintptr_t)ws, 1024);
-  if (ws_bytes < (base - (uintptr_t)ws) + Y.total) return fail(HGNN_ERR_WORKSPACE, "tc_row_backward: workspace too small");
+  if (ws_bytes < (base - (uintptr_t)ws) + Y.total) return fail(HGNN_ERR_WORKSPACE, "%s: workspace too small", who);
   uint8_t* w = (uint8_t*)base;
   RowBwdArgs a{};
   a.nkb = K / KBLK; a.K = K;
   a.w_packed = (const uint8_t*)d->w_packed; a.wt_packed = (const uint8_t*)wt_packed;
   a.bias = d->bias; a.gamma = d->gamma; a.beta = d->beta; a.eps = d->ln_eps;
   a.a_img = (const uint8_t*)a_img; a.gout = grad_out;
-  a.d_in = d_in; a.d_img = w + Y.d_img; a.colpart = (float*)(w + Y.colpart); a.rows = rows;
+  if (d_seg == nullptr) {
+    for (int p = 0; p < K / 128; ++p) { a.d_piece[p] = d_in + p * 128; a.d_ld[p] = K; }
+  } else {
+    int col = 0;
+    for (int s = 0; s < d->n_seg; ++s) {
+      const int wdt = d->seg_width[s];
+      HGNN_REQUIRE(wdt % 128 == 0, "%s: per-segment gradients need segment widths that are multiples of 128 (segment %d is %d wide)", who, s, wdt);
+      HGNN_REQUIRE(d_seg[s] == nullptr || ((uintptr_t)d_seg[s] % 16) == 0, "%s: segment gradient %d is not 16-byte aligned", who, s);
+      for (int c = 0; c < wdt; c += 128) {
+        a.d_piece[(col + c) / 128] = d_seg[s] ? d_seg[s] + c : nullptr;
+        a.d_ld[(col + c) / 128] = wdt;
+      }
+      col += wdt;
+    }
+  }
+  a.d_img = w + Y.d_img; a.colpart = (float*)(w + Y.colpart); a.rows = rows;
   rc = ROW_DISPATCH(launch_bwd, N, d->act, a, Y.grid, st);
   if (rc) return rc;
-  k_row_colpart_reduce<<<(3 * N + 255) / 256, 256, 0, st>>>(a.colpart, Y.grid * 4, 3 * N, dvec);
-  // dW[:, 128 p .. 128 p + 128) = delta^T A[:, same columns]
+  // dW[:, 128 p .. 128 p + 128) = delta^T A[:, same columns]; the launch that sums the split-K partials in order also sums
+  // the per-CTA column-sum partials (d bias | d gamma | d beta)
   WgradProblem pr[3];
   for (int p = 0; p < Y.n_prob; ++p)
     pr[p] = WgradProblem{a.d_img, N, 0, N, a.a_img, K, p * 128, 128, dW, K, 0, p * 128, 0};
-  return launch_wgrad(pr, Y.n_prob, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, st);
+  ColumnSums cs{a.colpart, Y.grid * 4, 3 * N, dvec};
+  return launch_wgrad(pr, Y.n_prob, Y.tiles, w + Y.wgrad, Y.wgrad_bytes, st, &cs);
+}
+
+}  // namespace
+
+extern "C" int hgnn_tc_row_backward(const hgnn_tc_row_layer* d, const void* wt_packed, const void* a_img, int64_t rows,
+                                    const float* grad_out, float* d_in, float* dW, float* dvec, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  return row_backward(d, wt_packed, a_img, rows, grad_out, d_in, nullptr, dW, dvec, ws, ws_bytes, stream, "tc_row_backward");
+}
+
+extern "C" int hgnn_tc_row_backward_split(const hgnn_tc_row_layer* d, const void* wt_packed, const void* a_img, int64_t rows,
+                                          const float* grad_out, float* const* d_seg, float* dW, float* dvec, void* ws,
+                                          size_t ws_bytes, void* stream) {
+  HGNN_REQUIRE(d_seg != nullptr, "tc_row_backward_split: d_seg is NULL");
+  return row_backward(d, wt_packed, a_img, rows, grad_out, nullptr, d_seg, dW, dvec, ws, ws_bytes, stream, "tc_row_backward_split");
 }

@@ -594,7 +594,10 @@ struct WgradProblem {
 };
 size_t wgrad_workspace_bytes(const WgradProblem* probs, int n, int splits);
 int wgrad_splits(int n_roles, int n_tiles);
-int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st);
+// optional passenger of the ordered reduce launch: out[i] = sum_p part[p][i] over n_part partial rows of `width` floats, in order
+struct ColumnSums { const float* part; int n_part, width; float* out; };
+int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st,
+                 const ColumnSums* colsums = nullptr);
 // fp32 [rows, cols] (cols % 64 == 0) -> bf16 tile image, padding rows of the last tile zeroed
 int launch_make_image(const float* src, int64_t rows, int cols, uint8_t* img, cudaStream_t st);
 

@@ -124,16 +124,57 @@ struct WgReduceArgs {
   const float* partial[WG_MAX_ROLES];
   float* out[WG_MAX_ROLES];
   int M[WG_MAX_ROLES], N[WG_MAX_ROLES], ld[WG_MAX_ROLES], row_off[WG_MAX_ROLES], col_off[WG_MAX_ROLES], transpose[WG_MAX_ROLES];
-  int splits;
+  int splits, n_prob;
+  ColumnSums cs;  // blockIdx.y == n_prob: the column-sum passenger
 };
 __global__ void k_wgrad_reduce(WgReduceArgs a) {
   const int p = blockIdx.y;
-  const int M = a.M[p], N = a.N[p];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == a.n_prob) {
+    // column-sum passenger: a block owns 32 columns; its 8 warps sum 8 consecutive ranges of the partial rows (a fixed
+    // split for a given n_part), combined in range order through shared memory: bit-reproducible, 8x shorter chains
+    __shared__ float s_part[8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    if (blockIdx.x * 32 >= a.cs.width) return;
+    const int per = (a.cs.n_part + 7) / 8;
+    const int k0 = min(a.cs.n_part, grp * per), k1 = min(a.cs.n_part, k0 + per);
+    float s = 0.f;
+    if (col < a.cs.width) {
+      const float* part = a.cs.part + col;
+      int k = k0;
+      for (; k + 8 <= k1; k += 8) {  // eight loads in flight, summed in partial order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = part[(size_t)(k + u) * a.cs.width];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
+      for (; k < k1; ++k) s += part[(size_t)k * a.cs.width];
+    }
+    s_part[grp][lane] = s;
+    __syncthreads();
+    if (grp == 0 && col < a.cs.width) {
+      float t = s_part[0][lane];
+#pragma unroll
+      for (int g = 1; g < 8; ++g) t += s_part[g][lane];
+      a.cs.out[col] = t;
+    }
+    return;
+  }
+  const int M = a.M[p], N = a.N[p];
   if (i >= M * N) return;
   const float* partial = a.partial[p];
   float s = 0.f;
-  for (int k = 0; k < a.splits; ++k) s += partial[(size_t)k * M * N + i];
+  int k = 0;
+  for (; k + 4 <= a.splits; k += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = partial[(size_t)(k + u) * M * N + i];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s += v[u];
+  }
+  for (; k < a.splits; ++k) s += partial[(size_t)k * M * N + i];
   int m = i / N, n = i % N;
   if (a.transpose[p]) a.out[p][(size_t)(a.row_off[p] + n) * a.ld[p] + a.col_off[p] + m] = s;
   else a.out[p][(size_t)(a.row_off[p] + m) * a.ld[p] + a.col_off[p] + n] = s;
@@ -174,12 +215,16 @@ int launch_make_image(const float* src, int64_t rows, int cols, uint8_t* img, cu
   return check_launch("make_image");
 }
 
+// split-K over the row tiles: at most one CTA per SM over all problems of the launch, and at least WG_MIN_TILES tiles per CTA
+// (every split costs an [M, N] fp32 partial written and read back: with one tile per split a 12 000-row layer moved
+// 24 MB of partials for a 0.4 MB gradient)
+constexpr int WG_MIN_TILES = 4;
 int wgrad_splits(int n_roles, int n_tiles) {
   int s = std::max(1, num_sms() / std::max(1, n_roles));
-  return std::max(1, std::min(s, n_tiles));
+  return std::max(1, std::min(s, (n_tiles + WG_MIN_TILES - 1) / WG_MIN_TILES));
 }
 
-int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st) {
+int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t ws_bytes, cudaStream_t st, const ColumnSums* colsums) {
   HGNN_REQUIRE(n >= 1 && n <= WG_MAX_ROLES, "wgrad: 1..%d problems per launch", WG_MAX_ROLES);
   WgArgs a{};
   a.n_roles = n;
@@ -205,14 +250,16 @@ int launch_wgrad(const WgradProblem* probs, int n, int n_tiles, void* ws, size_t
   k_tc_wgrad<<<n * a.splits, WG_THREADS, smem, st>>>(a);
   WgReduceArgs ra{};
   ra.splits = a.splits;
+  ra.n_prob = n;
   int max_total = 0;
+  if (colsums) { ra.cs = *colsums; max_total = colsums->width * 8; }  // 32 columns per 256-thread block
   for (int i = 0; i < n; ++i) {
     const WgradProblem& p = probs[i];
     ra.partial[i] = a.role[i].partial; ra.out[i] = p.out;
     ra.M[i] = p.ca; ra.N[i] = p.cb; ra.ld[i] = p.ld; ra.row_off[i] = p.row_off; ra.col_off[i] = p.col_off; ra.transpose[i] = p.transpose;
     max_total = std::max(max_total, p.ca * p.cb);
   }
-  k_wgrad_reduce<<<dim3((max_total + 255) / 256, n), 256, 0, st>>>(ra);
+  k_wgrad_reduce<<<dim3((max_total + 255) / 256, n + (colsums ? 1 : 0)), 256, 0, st>>>(ra);
   return check_launch("tc_wgrad");
 }
 

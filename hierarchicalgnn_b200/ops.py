@@ -908,15 +908,20 @@ class _TcRowLayer(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad[2:])
         a_img = None
         if need_bwd and rows:
-            a_img = torch.empty(_lib.lib().hgnn_tc_row_image_bytes(rows, K), dtype=torch.uint8, device=W.device)
+            # = hgnn_tc_row_image_bytes(rows, K): one 16 KB block per 128-row tile and 64 input columns
+            a_img = torch.empty(((rows + 127) // 128) * (K // 64) * 16384, dtype=torch.uint8, device=W.device)
         if rows:
-            with _timed("tc_row_forward"):
+            if PROFILE is None:
                 check(_lib.lib().hgnn_tc_row_forward(C.byref(d), rows, _ptr(out), _ptr(a_img), _stream()), "tc_row_forward")
+            else:
+                with _timed("tc_row_forward"):
+                    check(_lib.lib().hgnn_tc_row_forward(C.byref(d), rows, _ptr(out), _ptr(a_img), _stream()), "tc_row_forward")
             _count()
             TC_ROW_CALLS["count"] += 1
         ctx.meta, ctx.n_seg, ctx.rows = meta, n_seg, rows
         ctx.widths = [t.shape[1] for t in segs]
         ctx.seg_rows = [t.shape[0] for t in segs]
+        ctx.desc = d  # the backward reuses the descriptor (weights / LayerNorm pointers: saved tensors, same storage)
         _save_with_scratch(ctx, [W, b, g, be], a_img)
         return out
 
@@ -928,36 +933,51 @@ class _TcRowLayer(torch.autograd.Function):
         dev = W.device
         N, K = W.shape
         w_packed, wt_packed = meta.pack()
-        d, _ = _row_desc(meta, [None] * n_seg, W, b, g, be, w_packed)
-        for s in range(n_seg):
-            d.seg_width[s] = ctx.widths[s]
-        d_in = torch.empty((rows, K), dtype=torch.float32, device=dev)
+        d = ctx.desc
+        d.w_packed = _ptr(w_packed)
+        widths = ctx.widths
+        need = ctx.needs_input_grad[2:]
+        # one dense gradient matrix per segment (what the consumers upstream want: no strided views of a [rows, K] matrix,
+        # nothing stored for segments without a gradient) whenever the kernel's 128-column pieces line up with the segments
+        split = n_seg > 1 and all(w % 128 == 0 for w in widths)
         dW = torch.empty_like(W)
         dvec = torch.empty((3, N), dtype=torch.float32, device=dev)
         L_ = _lib.lib()
+        d_in = None
+        d_segs: List[Optional[Tensor]] = [None] * n_seg
+        if split:
+            for s in range(n_seg):
+                if need[s]:
+                    d_segs[s] = torch.empty((rows, widths[s]), dtype=torch.float32, device=dev)
+        else:
+            d_in = torch.empty((rows, K), dtype=torch.float32, device=dev)
         if rows:
             ws = _workspace(L_.hgnn_tc_row_backward_workspace_bytes(rows, K, N), dev)
             with _timed("tc_row_backward"):
-                check(L_.hgnn_tc_row_backward(C.byref(d), _ptr(wt_packed), _ptr(a_img), rows, _ptr(gout), _ptr(d_in), _ptr(dW),
-                                              _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "tc_row_backward")
-            _count(4)  # data-gradient kernel, column-sum reduce, weight-gradient GEMM, its ordered reduce
+                if split:
+                    ptrs = (C.c_void_p * MAX_SEGS)(*[_ptr(t) for t in d_segs])
+                    check(L_.hgnn_tc_row_backward_split(C.byref(d), _ptr(wt_packed), _ptr(a_img), rows, _ptr(gout), ptrs, _ptr(dW),
+                                                        _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "tc_row_backward_split")
+                else:
+                    check(L_.hgnn_tc_row_backward(C.byref(d), _ptr(wt_packed), _ptr(a_img), rows, _ptr(gout), _ptr(d_in), _ptr(dW),
+                                                  _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "tc_row_backward")
+            _count(3)  # data-gradient kernel, weight-gradient GEMM, ordered reduce of its partials and of the column sums
             TC_ROW_CALLS["count"] += 1
         else:
             dW.zero_()
             dvec.zero_()
         grads: List[Optional[Tensor]] = [None, None]
-        need = ctx.needs_input_grad[2:]
         off = 0
         for s in range(n_seg):
-            w = ctx.widths[s]
+            w = widths[s]
             gs = None
             if need[s]:
-                gs = d_in if n_seg == 1 else d_in[:, off:off + w]
+                gs = d_segs[s] if split else (d_in if n_seg == 1 else d_in[:, off:off + w])
                 plan = meta.seg_plans[s]
                 if plan is not None:
                     if plan.n_segments != ctx.seg_rows[s]:
                         raise _lib.HgnnError("row layer: gather plan does not cover the gathered tensor")
-                    gs = segment_reduce_raw(gs, plan)  # column slice of d_in, reduced in place (row stride)
+                    gs = segment_reduce_raw(gs, plan)  # (a column slice of d_in is reduced in place: row stride)
             grads.append(gs)
             off += w
         if meta.has_skip:

@@ -317,6 +317,13 @@ size_t hgnn_tc_row_backward_workspace_bytes(int64_t rows, int64_t fan_in, int64_
 int hgnn_tc_row_backward(const hgnn_tc_row_layer* d, const void* wt_packed, const void* a_img, int64_t rows,
                          const float* grad_out, float* d_in, float* dW, float* dvec, void* ws, size_t ws_bytes,
                          void* stream);
+/* Same backward with d(input) delivered per gathered segment instead of as one [rows, fan_in] matrix: d_seg[s] is a dense
+ * [rows, seg_width[s]] matrix, or NULL when that segment needs no gradient (its columns are then never stored). Segment widths
+ * must be multiples of 128. What the autograd of torch.cat([a, b, c], dim=-1) feeding a Linear hands back to a, b and c
+ * (reference gnn_utils.py:101,124-127,139-142) without the strided views of one wide matrix. */
+int hgnn_tc_row_backward_split(const hgnn_tc_row_layer* d, const void* wt_packed, const void* a_img, int64_t rows,
+                               const float* grad_out, float* const* d_seg, float* dW, float* dvec, void* ws, size_t ws_bytes,
+                               void* stream);
 
 /* ------------------------------------------------------------------------
  * Skinny layers (fp32, one warp per row) — the make_mlp layers that are pure bandwidth:

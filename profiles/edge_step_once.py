@@ -1,6 +1,6 @@
 """Runs the fused edge step (forward in training mode = with stash, then backward) a few times on a mid-size problem:
 the command line profiled under ncu for the per-kernel counters / source-level stall reasons of the edge kernels.
-Usage: python profiles/edge_step_once.py [E] [iters] [fwd|infer]"""
+Usage: python profiles/edge_step_once.py [E] [iters] [fwd|infer|full] [nodes_per_edge]"""
 import sys, torch
 sys.path.insert(0, '.')
 from hierarchicalgnn_b200 import ops
@@ -15,7 +15,8 @@ L = 128
 hp = dict(latent=L, hidden=2 * L, nb_edge_layer=2, nb_node_layer=3, layernorm=True, hidden_activation="GELU")
 torch.manual_seed(0)
 cell = InteractionGNNCell(hp); kaiming_init(cell); cell.cuda()
-n, e, g = synth_edge_problem(E, L)
+npe = float(sys.argv[4]) if len(sys.argv) > 4 else 0.1
+n, e, g = synth_edge_problem(E, L, nodes_per_edge=npe)
 order = torch.argsort(g[1], stable=True)
 g, e = g[:, order].contiguous(), e[order].contiguous()
 n, e, g = n.cuda().requires_grad_(True), e.cuda().requires_grad_(True), g.cuda()
@@ -36,4 +37,4 @@ torch.cuda.synchronize(); a.record()
 for i in range(iters):  # back to back: the queue stays full, host launch time is hidden
     step()
 b.record(); torch.cuda.synchronize()
-print(f"E={E} {a.elapsed_time(b) / iters:.3f} ms per iteration ({iters} iterations)")
+print(f"E={E} nodes/edge={npe} {a.elapsed_time(b) / iters:.3f} ms per iteration ({iters} iterations)")

@@ -106,6 +106,40 @@ def test_tc_row_layer_forward_and_backward(widths, n_out, rows, n_src, gathered,
         assert torch.equal(res_d.grad.cpu(), cot)  # residual gradient is the cotangent itself
 
 
+def test_tc_row_layer_per_segment_gradients_skip_segments_without_grad():
+    """hgnn_tc_row_backward_split: 128-wide segments get one dense gradient matrix each; a segment that needs no gradient is
+    never stored (NULL piece) and the others are bit-identical to the run where every segment needs one. A 256-wide segment
+    spans two of the kernel's 128-column pieces."""
+    from hierarchicalgnn_b200 import ops
+    for widths, n_out, rows in (([128, 128, 128], 256, 1300), ([256, 128], 128, 700)):
+        W, b, gamma, beta, segs, idx = _layer_case(widths, n_out, rows, 0, seed=11, gathered=[False] * len(widths))
+        cot = torch.randn(rows, n_out, generator=torch.Generator().manual_seed(2)).to(DEV)
+        grads = []
+        for frozen in (None, 0, len(widths) - 1):
+            Wd, bd, gd, bed = [t.to(DEV).requires_grad_(True) for t in (W, b, gamma, beta)]
+            segs_d = [t.to(DEV).requires_grad_(s != frozen) for s, t in enumerate(segs)]
+            packed = (ops.tc_pack_weight(Wd), ops.tc_pack_weight_t(Wd))
+            meta = ops.RowLayerMeta([None] * len(widths), "GELU", 1e-5, False, lambda: packed)
+            y = ops.tc_row_layer(meta, segs_d, None, Wd, bd, gd, bed)
+            (y * cot).sum().backward()
+            for t in segs_d:
+                assert t.grad is None or (t.grad.is_contiguous() and t.grad.shape == t.shape)
+            grads.append([t.grad for t in segs_d] + [Wd.grad, bd.grad, gd.grad, bed.grad])
+        full = grads[0]
+        # fp64 reference of the input gradients (relative Frobenius, bf16 operands)
+        leaves = [t.clone().double().requires_grad_(True) for t in segs]
+        want = _reference(W.double(), b.double(), gamma.double(), beta.double(), leaves, idx, "GELU", None, emulate=False)
+        (want * cot.cpu().double()).sum().backward()
+        for got, ref in zip(full, leaves):
+            assert float((got.cpu().double() - ref.grad).norm() / ref.grad.norm()) < 1.5e-2
+        for part, frozen in ((grads[1], 0), (grads[2], len(widths) - 1)):
+            for s, (a, b_) in enumerate(zip(part, full)):
+                if s == frozen:
+                    assert a is None
+                else:
+                    assert torch.equal(a, b_)
+
+
 def test_tc_row_layer_is_deterministic():
     from hierarchicalgnn_b200 import ops
     widths, n_out, rows = [128, 128], 256, 5000
