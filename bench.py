@@ -16,8 +16,9 @@ Besides `value` (device-timed, inputs resident) the line carries
                  6 + 6 cells) forward + backward on synthetic 1 GeV events, x[N,3] / edge_index / cluster labels uploaded
                  from pinned memory every step, the loss read back; same metric (edge-steps/s = E_d * 12 cells / time)
   models         device-timed and end-to-end times of BASELINE configs 1 (EC-IN forward) and 3 (BC fwd+bwd) on 1 GeV events
-  dp_training    (N > 1) BASELINE config 4: BC training steps (loss, backward with the bucketed all-reduce overlapped,
-                 clip 0.5, AdamW) on per-rank 1 GeV events
+  dp_training    BASELINE config 4: BC training steps (loss, backward with the bucketed all-reduce overlapped,
+                 clip 0.5, AdamW) on per-rank batches of 1 GeV events (HGNN_BENCH_EVENTS_PER_STEP, default 8, collated into
+                 one disjoint graph; models.config3_bc_fwd_bwd_1gev_batched is the forward + backward of such a batch)
   partition      (N > 1) BASELINE config 5: one full-pile-up shaped event, destination-partitioned (strong scaling)
   roofline, cpu_baseline   as the contract asks.
 
@@ -280,6 +281,24 @@ def _event_pool(n_events, seed0, n_particles=1200):
     return pool
 
 
+def _batch_pool(n_batches, events_per_batch, seed0, n_particles=1200):
+    """Pinned host copies of `n_batches` collated batches of synthetic 1 GeV events (torch_geometric Batch layout:
+    hierarchicalgnn_b200.synth.collate_events): x, edge_index, event id per hit, cluster labels (= particle), pid, pt."""
+    from hierarchicalgnn_b200.synth import collate_events, synth_event
+    pool = []
+    for i in range(n_batches):
+        evs = [synth_event(n_particles, 10, 0.0, 4.0, seed=seed0 + i * events_per_batch + j) for j in range(events_per_batch)]
+        b = collate_events(evs)
+        pool.append(dict(x=b.x.pin_memory(), graph=b.edge_index.pin_memory(), clusters=b.clusters.pin_memory(),
+                         batch=b.batch.pin_memory(), pid=b.pid.pin_memory(), pt=b.pt.pin_memory(),
+                         e_directed=2 * b.edge_index.shape[1], n_events=events_per_batch))
+    return pool
+
+
+def _events_per_step():
+    return max(1, int(os.environ.get("HGNN_BENCH_EVENTS_PER_STEP", "8")))
+
+
 def _timed(fn, k, barrier, world, dev):
     """k calls of fn(i) between two CUDA events on the current stream, barrier + synchronize on both sides; max over ranks."""
     import torch.distributed as dist
@@ -349,7 +368,45 @@ def model_benchmarks(args, dev, world, rank, barrier):
         "device_ms_per_step": dms, "e2e_ms_per_step": ems, "steps": k, "edge_steps_per_event": es,
         "device_edge_steps_per_s": world * es / (dms * 1e-3), "e2e_edge_steps_per_s": world * es / (ems * 1e-3),
         "events_per_s_e2e": world / (ems * 1e-3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
-    del bc, bc_params, resident
+    # ---- the same step on a collated batch of events (one disjoint graph per step: BASELINE config 4's "batches of events") ----
+    B = _events_per_step()
+    bpool = _batch_pool(2, B, 5000 + 64 * rank)
+    keys = ("x", "graph", "clusters", "batch")
+
+    def bc_batch_step(x, graph, clusters, batch):
+        for p in bc_params:
+            p.grad = None
+        bg, scores, emb = bc(x, graph, clusters=clusters, batch=batch, n_events=B)
+        loss = scores.mean() + emb.square().mean()
+        loss.backward()
+        return loss.detach()
+
+    bres = [tuple(b[k_].to(dev) for k_ in keys) for b in bpool]
+
+    def bcb_device(i):
+        x, g, c, bt = bres[i % len(bres)]
+        bc_batch_step(x.clone(), g, c, bt)
+
+    def bcb_e2e(i):
+        b = bpool[i % len(bpool)]
+        x, g, c, bt = (b[k_].to(dev, non_blocking=True) for k_ in keys)
+        loss_host.copy_(bc_batch_step(x, g, c, bt).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(3):
+        bcb_device(i)
+        bcb_e2e(i)
+    dms = _timed(bcb_device, k, barrier, world, dev)
+    ems = _timed(bcb_e2e, k, barrier, world, dev)
+    es = sum(bpool[i % len(bpool)]["e_directed"] for i in range(k)) / k * n_cells
+    h2d = sum(sum(bpool[i % len(bpool)][k_].numel() * bpool[i % len(bpool)][k_].element_size() for k_ in keys) for i in range(k)) // k
+    out["config3_bc_fwd_bwd_1gev_batched"] = {
+        "workload": f"BC_HierarchicalGNN_GMM latent 128, {n_cells} cells, forward + backward, {B} synthetic 1 GeV events collated "
+                    f"into one disjoint graph per step (supernodes = particles; kNN graphs searched per event), {world} GPU(s)",
+        "events_per_step_per_gpu": B, "device_ms_per_step": dms, "e2e_ms_per_step": ems, "steps": k, "edge_steps_per_step": es,
+        "device_edge_steps_per_s": world * es / (dms * 1e-3), "e2e_edge_steps_per_s": world * es / (ems * 1e-3),
+        "events_per_s_e2e": world * B / (ems * 1e-3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
+    del bc, bc_params, resident, bres
 
     # ---- config 1: EC_InteractionGNN forward (inference), latent 128, 14 cells ----
     if not args.no_models:
@@ -400,11 +457,12 @@ def dp_training_benchmark(args, dev, world, rank, barrier):
     model.to(dev).train()
     opt = model.configure_optimizers()[0][0]
     trainer = DataParallelTrainer(model, opt, clip=0.5, bucket_bytes=4 << 20)
-    pool = _event_pool(4, 3000 + 16 * rank)
+    B = _events_per_step()
+    pool = _batch_pool(3, B, 3000 + 64 * rank)
     dev_pool = []
-    for ev in pool:
-        dev_pool.append(SimpleNamespace(x=ev["x"].to(dev), edge_index=ev["graph"].to(dev), pid=ev["pid"].to(dev),
-                                        pt=ev["pt"].to(dev), clusters=ev["clusters"].to(dev)))
+    for b in pool:
+        dev_pool.append(SimpleNamespace(x=b["x"].to(dev), edge_index=b["graph"].to(dev), pid=b["pid"].to(dev), pt=b["pt"].to(dev),
+                                        clusters=b["clusters"].to(dev), batch=b["batch"].to(dev), num_graphs=B))
     cur = {}
     model.hgnn_block.clustering = lambda x, emb, graph: cur["clusters"]  # supernodes = particles
 
@@ -422,8 +480,9 @@ def dp_training_benchmark(args, dev, world, rank, barrier):
     es = sum(pool[i % len(pool)]["e_directed"] for i in range(k)) / k * n_cells
     grad_bytes = sum(b["flat"].numel() for b in trainer.buckets.buckets) * 4
     res = {"workload": f"BC_HierarchicalGNN_GMM latent 128 training step (loss + backward + overlapped all-reduce + clip 0.5 + AdamW), "
-                       f"1 synthetic 1 GeV event per GPU per step, {world} GPUs",
-           "ms_per_step": ms, "steps": k, "events_per_s": world / (ms * 1e-3), "edge_steps_per_s": world * es / (ms * 1e-3),
+                       f"{B} synthetic 1 GeV events per GPU per step (collated into one disjoint graph), {world} GPU(s)",
+           "events_per_step_per_gpu": B,
+           "ms_per_step": ms, "steps": k, "events_per_s": world * B / (ms * 1e-3), "edge_steps_per_s": world * es / (ms * 1e-3),
            "gradient_bytes": grad_bytes, "buckets": len(trainer.buckets.buckets),
            "timing": "wall of the training loop on the device clock (CUDA events, max over ranks); includes the host-side scipy matching"}
     trainer.buckets.remove()
@@ -574,8 +633,9 @@ def run_gpu(args):
                "pipeline": "per step: x[N,3] f32 + edge_index[2,E] i64 + cluster labels[N] i64 copied from pinned host memory on the "
                            "compute stream, model forward + backward, 4 B loss read back (host sync)"}
     extra = {}
-    if world > 1 and not args.no_models:
+    if not args.no_models:
         extra["dp_training"] = dp_training_benchmark(args, dev, world, rank, barrier)
+    if world > 1 and not args.no_models:
         extra["partition"] = partition_benchmark(args, dev, world, rank, barrier)
 
     cpu = None

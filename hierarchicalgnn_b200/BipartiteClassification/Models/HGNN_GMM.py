@@ -14,6 +14,7 @@ state-dict keys. What changed underneath:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -21,7 +22,7 @@ import torch.nn as nn
 from ... import ops
 from ...gnn_utils import (DynamicGraphConstruction, GraphPlans, HierarchicalGNNCell, InteractionGNNCell,
                           sort_edges_by_destination)
-from ...utils import make_mlp
+from ...utils import event_offsets, make_mlp
 from ..bipartite_classification_base import BipartiteClassificationBase
 
 
@@ -146,7 +147,11 @@ class HierarchicalGNNBlock(nn.Module):
                 clusters = self.get_cluster_labels(ops.connected_components(g, x.shape[0], None), x.shape[0])
             return clusters
 
-    def forward(self, x, embeddings, nodes, edges, graph, clusters=None):
+    def forward(self, x, embeddings, nodes, edges, graph, clusters=None, batch=None, n_events=None):
+        """``batch`` (ascending int64 event id of every hit) + ``n_events``: several events as one disjoint graph. Supernodes
+        never mix events (the clustering follows the edges), the two kNN graphs are searched event by event and the edge
+        weights normalised per event, so every hit and supernode sees what a call on its own event would have shown it.
+        Injected ``clusters`` must number the supernodes event by event (ascending)."""
         N = x.shape[0]
         gp = graph if isinstance(graph, GraphPlans) else GraphPlans(graph, N, N)
         if clusters is None:
@@ -157,10 +162,22 @@ class HierarchicalGNNBlock(nn.Module):
         means = nn.functional.normalize(means)
 
         hp = self.hparams
+        sup_kw, bip_kw = {}, {}
+        if batch is not None:
+            if n_events is None:
+                n_events = int(batch[-1]) + 1
+            with torch.no_grad():
+                hit_ptr = event_offsets(batch, n_events)
+                sn_event = torch.zeros(S, dtype=batch.dtype, device=batch.device).scatter_(0, clusters[member], batch[member])
+                if os.environ.get("HGNN_CHECK_INDICES", "0") != "0" and S > 1 and not bool((sn_event[1:] >= sn_event[:-1]).all()):
+                    raise ValueError("batched events: supernode (cluster) ids must ascend with the event id")
+                sn_ptr = event_offsets(sn_event, n_events)
+            sup_kw = dict(src_ptr=sn_ptr, dst_ptr=sn_ptr, src_event=sn_event)
+            bip_kw = dict(src_ptr=hit_ptr, dst_ptr=sn_ptr, src_event=batch)
         super_graph, super_edge_weights = self.super_graph_construction(
-            means, means, sym=True, norm=True, k=hp["supergraph_sparsity"])
+            means, means, sym=True, norm=True, k=hp["supergraph_sparsity"], **sup_kw)
         bipartite_graph, bipartite_edge_weights, _logits = self.bipartite_graph_construction(
-            embeddings, means, sym=False, norm=True, k=hp["bipartitegraph_sparsity"], logits=True)
+            embeddings, means, sym=False, norm=True, k=hp["bipartitegraph_sparsity"], logits=True, **bip_kw)
         self.log("clusters", len(means))
         bp = GraphPlans(bipartite_graph, N, S)
         sp = GraphPlans(super_graph, S, S)
@@ -185,12 +202,15 @@ class BC_HierarchicalGNN_GMM(BipartiteClassificationBase):
                                                layer_norm=hparams["layernorm"], output_activation=None,
                                                hidden_activation=hparams["hidden_output_activation"])
 
-    def forward(self, x, graph, clusters=None):
+    def forward(self, x, graph, clusters=None, batch=None, n_events=None):
+        """``batch`` / ``n_events``: a torch_geometric-style batch of events (x rows event by event, ``graph`` already offset,
+        ``batch`` = event id per hit) processed as one disjoint graph — see HierarchicalGNNBlock.forward."""
         N = x.shape[0]
         # destination-sorted once per event; nothing downstream depends on the edge order (HGNN_GMM.py:328-346)
         directed = GraphPlans(sort_edges_by_destination(torch.cat([graph, graph.flip(0)], dim=1))[0], N, N, dst_sorted=True)
         embeddings, nodes, edges = self.ignn_block(x, directed)
-        nodes, supernodes, bipartite_graph = self.hgnn_block(x, embeddings, nodes, edges, directed, clusters=clusters)
+        nodes, supernodes, bipartite_graph = self.hgnn_block(x, embeddings, nodes, edges, directed, clusters=clusters,
+                                                             batch=batch, n_events=n_events)
         bp = GraphPlans(bipartite_graph, N, supernodes.shape[0])
         scores = self.bipartite_output_layer.fused([nodes, supernodes], [bp.by_src, bp.by_dst]).squeeze()
         return bipartite_graph, torch.sigmoid(scores), embeddings

@@ -102,6 +102,8 @@ SIGNATURES = {
     "hgnn_knn_radius": (C.c_int, [vp, i64, vp, i64, i64, i64, f32, vp, vp]),
     "hgnn_knn_radius_workspace_bytes": (sz, [i64, i64, i64]),
     "hgnn_knn_radius_ws": (C.c_int, [vp, i64, vp, i64, i64, i64, f32, vp, vp, sz, vp]),
+    "hgnn_match_blocks_max": (C.c_int, [vp, vp, vp, i64, vp, i64, vp, C.c_int]),
+    "hgnn_knn_radius_batched": (C.c_int, [vp, i64, vp, i64, i64, i64, f32, vp, vp, i64, vp, vp, sz, vp]),
     "hgnn_knn_edges_workspace_bytes": (sz, [i64]),
     "hgnn_knn_edges": (C.c_int, [vp, i64, i64, vp, vp, vp, sz, vp]),
     "hgnn_symmetrize_workspace_bytes": (sz, [i64]),

@@ -391,13 +391,24 @@ constexpr int KNN_KMAX = 32;
 template <int DIM, int KCAP>  // DIM > 0: compile-time dimension with the query in registers; 0: runtime dim (<= 32)
 __global__ void __launch_bounds__(KNN_THREADS) k_knn_radius(const float* __restrict__ query, int64_t nq, const float* __restrict__ ref,
                                                            int64_t nr, int dim_rt, int k, float r2, int64_t ref_per_split,
-                                                           int64_t* __restrict__ idx, float* __restrict__ part_d, int32_t* __restrict__ part_i) {
+                                                           int64_t* __restrict__ idx, float* __restrict__ part_d, int32_t* __restrict__ part_i,
+                                                           const int32_t* __restrict__ qptr, const int32_t* __restrict__ rptr) {
   extern __shared__ __align__(16) float smem[];
   const int dim = DIM > 0 ? DIM : dim_rt;
   float* s_ref = smem;                           // [KNN_TILE][dim]
   float* s_q = smem + KNN_TILE * dim;            // [KNN_THREADS][dim+1] (runtime-dim path only)
-  int64_t q = (int64_t)blockIdx.x * KNN_THREADS + threadIdx.x;
-  bool live = q < nq;
+  // batched events (qptr / rptr = row offsets of the events, blockIdx.z = event): a query only ever meets the references of
+  // its own event — the block-diagonal search a per-event loop would run, in one launch. Indices stay global row numbers.
+  int64_t q_lo = 0, q_hi = nq, r_lo = 0, r_hi = nr;
+  if (qptr != nullptr) {
+    q_lo = qptr[blockIdx.z]; q_hi = qptr[blockIdx.z + 1];
+    r_lo = rptr[blockIdx.z]; r_hi = rptr[blockIdx.z + 1];
+    if (q_lo + (int64_t)blockIdx.x * KNN_THREADS >= q_hi) return;  // this event has fewer query blocks (whole CTA, before any barrier)
+    const int64_t tiles = (r_hi - r_lo + KNN_TILE - 1) / KNN_TILE;
+    ref_per_split = (tiles + gridDim.y - 1) / gridDim.y * KNN_TILE;
+  }
+  int64_t q = q_lo + (int64_t)blockIdx.x * KNN_THREADS + threadIdx.x;
+  bool live = q < q_hi;
   float qreg[DIM > 0 ? DIM : 1];
   if (DIM > 0) {
 #pragma unroll
@@ -411,8 +422,8 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_radius(const float* __restr
   for (int j = 0; j < KCAP; ++j) { bd[j] = INFINITY; bi[j] = -1; }
   float kth = INFINITY;  // current k-th best distance
 
-  const int64_t ref_lo = (int64_t)blockIdx.y * ref_per_split;
-  const int64_t ref_hi = min(nr, ref_lo + ref_per_split);
+  const int64_t ref_lo = r_lo + (int64_t)blockIdx.y * ref_per_split;
+  const int64_t ref_hi = min(r_hi, ref_lo + ref_per_split);
   for (int64_t base = ref_lo; base < ref_hi; base += KNN_TILE) {
     int cnt = (int)min((int64_t)KNN_TILE, ref_hi - base);
     __syncthreads();
@@ -522,45 +533,69 @@ extern "C" size_t hgnn_knn_radius_workspace_bytes(int64_t n_query, int64_t n_ref
 
 template <int DIM>
 static void launch_knn(int kcap, dim3 grid, size_t smem, cudaStream_t st, const float* query, int64_t nq, const float* ref, int64_t nr,
-                       int dim, int k, float r2, int64_t per, int64_t* idx, float* pd, int32_t* pi) {
-  if (kcap == 8) k_knn_radius<DIM, 8><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi);
-  else if (kcap == 16) k_knn_radius<DIM, 16><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi);
-  else k_knn_radius<DIM, 32><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi);
+                       int dim, int k, float r2, int64_t per, int64_t* idx, float* pd, int32_t* pi, const int32_t* qptr,
+                       const int32_t* rptr) {
+  if (kcap == 8) k_knn_radius<DIM, 8><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi, qptr, rptr);
+  else if (kcap == 16) k_knn_radius<DIM, 16><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi, qptr, rptr);
+  else k_knn_radius<DIM, 32><<<grid, KNN_THREADS, smem, st>>>(query, nq, ref, nr, dim, k, r2, per, idx, pd, pi, qptr, rptr);
 }
 
-// ws may be NULL (or too small): the scan then runs unsplit, one CTA per 128 queries
-extern "C" int hgnn_knn_radius_ws(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
-                                  float radius, int64_t* idx, void* ws, size_t ws_bytes, void* stream) {
+// ws may be NULL (or too small): the scan then runs unsplit, one CTA per 128 queries. n_events > 0: block-diagonal search,
+// event b = queries [query_ptr[b], query_ptr[b+1]) against references [ref_ptr[b], ref_ptr[b+1]) (device arrays of n_events + 1
+// int32 offsets; the host never reads them: every event gets the grid of the whole problem and idle CTAs leave at once)
+static int knn_radius_impl(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k, float radius,
+                           int64_t* idx, const int32_t* query_ptr, const int32_t* ref_ptr, int64_t n_events, void* ws,
+                           size_t ws_bytes, void* stream) {
   if (n_query <= 0 || k <= 0) return HGNN_OK;
   HGNN_REQUIRE(query && idx, "knn_radius: NULL pointer");
   HGNN_REQUIRE(dim >= 1 && dim <= 32, "knn_radius: dim must be in [1,32], got %lld", (long long)dim);
   HGNN_REQUIRE(k <= KNN_KMAX, "knn_radius: k must be <= %d, got %lld", KNN_KMAX, (long long)k);
-  HGNN_REQUIRE(n_ref >= 0 && n_ref < INT32_MAX, "knn_radius: n_ref out of range");
+  HGNN_REQUIRE(n_ref >= 0 && n_ref < INT32_MAX && n_query < INT32_MAX, "knn_radius: n_query / n_ref out of range");
+  HGNN_REQUIRE(n_events == 0 || (query_ptr && ref_ptr && n_events > 0 && n_events <= 65535),
+               "knn_radius: batched search needs query_ptr, ref_ptr and 1..65535 events");
   cudaStream_t st = (cudaStream_t)stream;
-  int sp = knn_splits(n_query, n_ref);
-  if (sp > 1 && (ws == nullptr || ws_bytes < hgnn_knn_radius_workspace_bytes(n_query, n_ref, k))) sp = 1;
+  // per-event problem size for the split heuristic: the average event (the offsets live on the device)
+  const int64_t ev = n_events > 0 ? n_events : 1;
+  const int64_t nr_ev = (n_ref + ev - 1) / ev;
+  int sp = n_events > 0 ? (int)std::max<int64_t>(1, std::min<int64_t>(knn_splits(n_query, nr_ev), (nr_ev + KNN_TILE - 1) / KNN_TILE))
+                        : knn_splits(n_query, n_ref);
+  if (sp > 1 && (ws == nullptr || ws_bytes < (size_t)sp * (size_t)n_query * (size_t)k * 8 + 256)) sp = 1;
   const int64_t tiles = (n_ref + KNN_TILE - 1) / KNN_TILE;
-  const int64_t per = (tiles + sp - 1) / sp * KNN_TILE;  // references per split (whole tiles)
-  sp = (int)std::max<int64_t>(1, (n_ref + per - 1) / std::max<int64_t>(per, 1));
+  int64_t per = (tiles + sp - 1) / sp * KNN_TILE;  // references per split (whole tiles); recomputed per event in the batched kernel
+  if (n_events == 0) sp = (int)std::max<int64_t>(1, (n_ref + per - 1) / std::max<int64_t>(per, 1));
   float* pd = nullptr;
   int32_t* pi = nullptr;
   if (sp > 1) {
     pd = (float*)align_up((uintptr_t)ws, 256);
     pi = (int32_t*)(pd + (size_t)sp * n_query * k);
   }
-  dim3 grid((unsigned)((n_query + KNN_THREADS - 1) / KNN_THREADS), (unsigned)sp);
+  dim3 grid((unsigned)((n_query + KNN_THREADS - 1) / KNN_THREADS), (unsigned)sp, (unsigned)ev);
   float r2 = radius * radius;
   size_t smem = (size_t)(KNN_TILE * dim + KNN_THREADS * (dim + 1)) * sizeof(float);
   const int kcap = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
-  if (dim == 8) launch_knn<8>(kcap, grid, smem, st, query, n_query, ref, n_ref, 8, (int)k, r2, per, idx, pd, pi);
-  else launch_knn<0>(kcap, grid, smem, st, query, n_query, ref, n_ref, (int)dim, (int)k, r2, per, idx, pd, pi);
+  const int32_t* qp = n_events > 0 ? query_ptr : nullptr;
+  const int32_t* rp = n_events > 0 ? ref_ptr : nullptr;
+  if (dim == 8) launch_knn<8>(kcap, grid, smem, st, query, n_query, ref, n_ref, 8, (int)k, r2, per, idx, pd, pi, qp, rp);
+  else launch_knn<0>(kcap, grid, smem, st, query, n_query, ref, n_ref, (int)dim, (int)k, r2, per, idx, pd, pi, qp, rp);
   if (sp > 1) k_knn_merge<<<(unsigned)((n_query + 127) / 128), 128, 0, st>>>(pd, pi, sp, n_query, (int)k, idx);
   return check_launch("knn_radius");
 }
 
+extern "C" int hgnn_knn_radius_ws(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                                  float radius, int64_t* idx, void* ws, size_t ws_bytes, void* stream) {
+  return knn_radius_impl(query, n_query, ref, n_ref, dim, k, radius, idx, nullptr, nullptr, 0, ws, ws_bytes, stream);
+}
+
 extern "C" int hgnn_knn_radius(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
                                float radius, int64_t* idx, void* stream) {
-  return hgnn_knn_radius_ws(query, n_query, ref, n_ref, dim, k, radius, idx, nullptr, 0, stream);
+  return knn_radius_impl(query, n_query, ref, n_ref, dim, k, radius, idx, nullptr, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int hgnn_knn_radius_batched(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                                       float radius, const int32_t* query_ptr, const int32_t* ref_ptr, int64_t n_events,
+                                       int64_t* idx, void* ws, size_t ws_bytes, void* stream) {
+  HGNN_REQUIRE(n_events >= 1, "knn_radius_batched: n_events must be >= 1");
+  return knn_radius_impl(query, n_query, ref, n_ref, dim, k, radius, idx, query_ptr, ref_ptr, n_events, ws, ws_bytes, stream);
 }
 
 extern "C" size_t hgnn_knn_edges_workspace_bytes(int64_t n_query) {

@@ -166,11 +166,12 @@ class DynamicGraphConstruction(nn.Module):
         self.weighting_function = getattr(torch, weighting_function)
         self.register_buffer("knn_radius", torch.ones(1), persistent=True)
 
-    def build_graph(self, src_embeddings, dst_embeddings, sym, k):
+    def build_graph(self, src_embeddings, dst_embeddings, sym, k, src_ptr=None, dst_ptr=None):
         """The no-grad half (gnn_utils.py:193-205): radius-kNN, optional symmetrize,
-        radius tracking. Returns graph[2, E'] int64."""
+        radius tracking. Returns graph[2, E'] int64. ``src_ptr`` / ``dst_ptr``: event offsets of a batch of events
+        (neighbours are only sought inside the row's own event)."""
         with torch.no_grad():
-            idx = find_neighbors(src_embeddings, dst_embeddings, r_max=self.knn_radius, k_max=k)
+            idx = find_neighbors(src_embeddings, dst_embeddings, r_max=self.knn_radius, k_max=k, ptr1=src_ptr, ptr2=dst_ptr)
             graph = ops.knn_edges(idx)
             if sym:
                 graph = ops.symmetrize(graph, max(src_embeddings.shape[0], dst_embeddings.shape[0]))
@@ -179,14 +180,22 @@ class DynamicGraphConstruction(nn.Module):
                 self.knn_radius = 0.9 * self.knn_radius + 0.11 * dmax
         return graph
 
-    def forward(self, src_embeddings, dst_embeddings, sym=False, norm=False, k=10, logits=False, graph=None):
+    def forward(self, src_embeddings, dst_embeddings, sym=False, norm=False, k=10, logits=False, graph=None,
+                src_ptr=None, dst_ptr=None, src_event=None):
+        """``src_ptr`` / ``dst_ptr`` / ``src_event`` (event offsets of the source and destination rows, event id of every
+        source row) describe a batch of events: the graph is built event by event and ``norm`` divides by the mean weight
+        of the edge's own event, as a loop over single events would (the reference sees one event per call)."""
         if graph is None:
-            graph = self.build_graph(src_embeddings, dst_embeddings, sym, k)
+            graph = self.build_graph(src_embeddings, dst_embeddings, sym, k, src_ptr, dst_ptr)
         gp = GraphPlans(graph, src_embeddings.shape[0], dst_embeddings.shape[0])
         likelihood = ops.edge_dot(src_embeddings, dst_embeddings, gp.by_src, gp.by_dst)
         edge_weights_logits = self.weight_normalization(likelihood.unsqueeze(1)).squeeze()
         edge_weights = self.weighting_function(edge_weights_logits)
-        if norm:
+        if norm and src_event is not None and graph.shape[1] > 0:
+            edge_event = src_event[graph[0]]
+            per_event = ops.scatter_mean(edge_weights.reshape(-1, 1), edge_event, dim_size=src_ptr.numel() - 1)
+            edge_weights = edge_weights.reshape(-1) / per_event[edge_event, 0]
+        elif norm:
             edge_weights = edge_weights / edge_weights.mean()
         edge_weights = edge_weights.unsqueeze(1)
         if logits:

@@ -1135,18 +1135,31 @@ def fused_mlp(meta: MlpMeta, segs: Sequence[Tensor], params: Sequence[Tensor]) -
 # ---------------------------------------------------------------------------
 # graph construction
 # ---------------------------------------------------------------------------
-def knn_radius(query: Tensor, ref: Tensor, k: int, radius: float) -> Tensor:
+def knn_radius(query: Tensor, ref: Tensor, k: int, radius: float, query_ptr: Optional[Tensor] = None,
+               ref_ptr: Optional[Tensor] = None) -> Tensor:
     """[n_query, k] int64 neighbour ids, ascending distance, d < radius, -1 padded
-    (frnn.frnn_grid_points as used by find_neighbors, utils.py:228-239)."""
-    _need_cuda(query, ref)
+    (frnn.frnn_grid_points as used by find_neighbors, utils.py:228-239).
+    ``query_ptr`` / ``ref_ptr`` (int32 CUDA tensors of n_events + 1 row offsets): a batch of events searched in one launch,
+    every query against the references of its own event only; ids are rows of ``ref``."""
+    _need_cuda(query, ref, query_ptr, ref_ptr)
     q, r = _f32(query.detach()), _f32(ref.detach())
     idx = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+    if (query_ptr is None) != (ref_ptr is None):
+        raise _lib.HgnnError("knn_radius: query_ptr and ref_ptr come together")
     if q.shape[0] and k:
         L = _lib.lib()
         nb = L.hgnn_knn_radius_workspace_bytes(q.shape[0], r.shape[0], k)  # > 0: small problem, split over reference ranges
         ws = _workspace(nb, q.device) if nb else None
-        check(L.hgnn_knn_radius_ws(_ptr(q), q.shape[0], _ptr(r), r.shape[0], q.shape[1], k, float(radius), _ptr(idx),
-                                   _ptr(ws), ws.numel() if ws is not None else 0, _stream()), "knn_radius")
+        if query_ptr is None:
+            check(L.hgnn_knn_radius_ws(_ptr(q), q.shape[0], _ptr(r), r.shape[0], q.shape[1], k, float(radius), _ptr(idx),
+                                       _ptr(ws), ws.numel() if ws is not None else 0, _stream()), "knn_radius")
+        else:
+            if (query_ptr.dtype != torch.int32 or ref_ptr.dtype != torch.int32 or query_ptr.dim() != 1
+                    or query_ptr.shape != ref_ptr.shape or query_ptr.numel() < 2):
+                raise _lib.HgnnError("knn_radius: query_ptr / ref_ptr must be int32 vectors of n_events + 1 offsets")
+            check(L.hgnn_knn_radius_batched(_ptr(q), q.shape[0], _ptr(r), r.shape[0], q.shape[1], k, float(radius),
+                                            _ptr(query_ptr.contiguous()), _ptr(ref_ptr.contiguous()), query_ptr.numel() - 1,
+                                            _ptr(idx), _ptr(ws), ws.numel() if ws is not None else 0, _stream()), "knn_radius_batched")
         _count(2 if nb else 1)
     return idx
 

@@ -81,3 +81,29 @@ def direction_embeddings(event, dim=8, noise=0.02, seed=0):
     centres = torch.randn(event.n_particles + 1, dim, generator=g)
     emb = centres[event.pid] + noise * torch.randn(event.x.shape[0], dim, generator=g)
     return torch.nn.functional.normalize(emb).float()
+
+
+def collate_events(events):
+    """Several events as one disjoint graph, laid out like a torch_geometric ``Batch``: rows event by event, ``edge_index``
+    offset by the hits before it, ``batch`` = event id per hit, ``ptr`` = hit offsets, ``num_graphs``. ``pid`` stays the
+    per-event particle id (as torch_geometric leaves it); ``clusters`` (supernode = particle, pid - 1, offset by the
+    particles of the earlier events; -1 for noise) is what the benchmarks inject in place of the learned clustering."""
+    xs, gs, pids, pts, ys, bs, cl = [], [], [], [], [], [], []
+    n_hits = n_part = 0
+    ptr = [0]
+    for b, ev in enumerate(events):
+        xs.append(ev.x)
+        gs.append(ev.edge_index + n_hits)
+        pids.append(ev.pid)
+        pts.append(ev.pt)
+        ys.append(ev.y_pid)
+        bs.append(torch.full((ev.x.shape[0],), b, dtype=torch.long))
+        c = ev.pid - 1
+        cl.append(torch.where(c >= 0, c + n_part, c))
+        n_hits += ev.x.shape[0]
+        n_part += ev.n_particles
+        ptr.append(n_hits)
+    y = torch.cat(ys)
+    return SimpleNamespace(x=torch.cat(xs).contiguous(), edge_index=torch.cat(gs, 1).contiguous(), pid=torch.cat(pids),
+                           pt=torch.cat(pts), y_pid=y, y=y.clone(), batch=torch.cat(bs), ptr=torch.tensor(ptr),
+                           num_graphs=len(events), clusters=torch.cat(cl), n_particles=n_part)

@@ -268,8 +268,16 @@ def make_mlp(input_size, hidden_size, output_size, hidden_layers, hidden_activat
     return FusedMLP(*mods)
 
 
-def find_neighbors(embedding1, embedding2, r_max=1.0, k_max=10):
+def find_neighbors(embedding1, embedding2, r_max=1.0, k_max=10, ptr1=None, ptr2=None):
     """[P1, k_max] int64 neighbour table, -1 padded (brute-force tiled CUDA kernel
-    in place of frnn.frnn_grid_points)."""
+    in place of frnn.frnn_grid_points). ``ptr1`` / ``ptr2``: int32 row offsets of the events of a batch — rows of
+    ``embedding1`` then only find neighbours of their own event (ops.knn_radius)."""
     r = float(r_max.reshape(-1)[0]) if torch.is_tensor(r_max) else float(r_max)
-    return ops.knn_radius(embedding1, embedding2, int(k_max), r)
+    return ops.knn_radius(embedding1, embedding2, int(k_max), r, ptr1, ptr2)
+
+
+def event_offsets(event_of_row, n_events):
+    """int32 [n_events + 1] row offsets of the events of a batch from the ascending event id of every row (the ``batch``
+    vector of a torch_geometric Batch); stays on the device."""
+    edges = torch.arange(n_events + 1, device=event_of_row.device, dtype=event_of_row.dtype)
+    return torch.searchsorted(event_of_row.contiguous(), edges).to(torch.int32)

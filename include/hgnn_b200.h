@@ -162,6 +162,14 @@ int hgnn_knn_radius(const float* query, int64_t n_query, const float* ref, int64
 size_t hgnn_knn_radius_workspace_bytes(int64_t n_query, int64_t n_ref, int64_t k);
 int hgnn_knn_radius_ws(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
                        float radius, int64_t* idx, void* ws, size_t ws_bytes, void* stream);
+/* A batch of events in one launch: query rows [query_ptr[b], query_ptr[b+1]) only meet reference rows
+ * [ref_ptr[b], ref_ptr[b+1]) — the result of calling hgnn_knn_radius once per event (the reference's loaders hand the
+ * model one event at a time, bipartite_classification_base.py:42, so its find_neighbors never sees two), with the
+ * neighbour ids kept as row numbers of the whole `ref` matrix. query_ptr / ref_ptr: DEVICE arrays of n_events + 1
+ * ascending int32 offsets (first 0, last n_query / n_ref); they are never read on the host. Workspace as above (optional). */
+int hgnn_knn_radius_batched(const float* query, int64_t n_query, const float* ref, int64_t n_ref, int64_t dim, int64_t k,
+                            float radius, const int32_t* query_ptr, const int32_t* ref_ptr, int64_t n_events, int64_t* idx,
+                            void* ws, size_t ws_bytes, void* stream);
 
 /* Compacts idx (>= 0 entries, query-major, rank-minor: gnn_utils.py:195-202)
  * into graph[2, n_query*k] (row 0 = query id, row 1 = neighbour id; only the
@@ -393,6 +401,18 @@ int hgnn_p2p_reduce_scatter_rows(float* out, int64_t rows, int64_t width, const 
 /* In-place sum over ranks of the first n_floats (multiple of 4) of the symmetric buffer, left in every rank's copy
  * (weight-gradient all-reduce): rank r reduces the r-th slice and stores the result to all ranks. */
 int hgnn_p2p_all_reduce(int64_t n_floats, void* mc_base, const uint64_t* peer_bases, int world, int rank, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Loss side, HOST function (no device work, plain host pointers): maximum-weight matching that covers every row of a
+ * block-diagonal sparse score table, the blocks solved side by side on host threads. Replaces
+ * scipy.sparse.csgraph.min_weight_full_bipartite_matching(table, maximize=True) (reference
+ * bipartite_classification_base.py:173, one event per call) for a collated batch of events: block b = rows
+ * [row_ptr[b], row_ptr[b+1]) of the CSR table (indptr / indices / data, n_rows rows; a block only meets the columns
+ * its rows list). col_of_row[n_rows] out = the matched column of every row. n_threads <= 0: one per hardware thread.
+ * Error (HGNN_ERR_BAD_ARG) when a block has no matching that covers its rows.
+ * ------------------------------------------------------------------------ */
+int hgnn_match_blocks_max(const int32_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                          const int64_t* row_ptr, int64_t n_blocks, int64_t* col_of_row, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -264,3 +264,77 @@ def test_kaiming_init_moves_the_version_counter_and_drops_packed_images():
     net.__dict__["_split_cache"] = {0: "stale"}
     invalidate_packed_weights(net)
     assert "_split_cache" not in net.__dict__
+
+
+def test_assignment_loss_on_collated_events_treats_particles_per_event():
+    """A torch_geometric-style batch keeps the per-event particle ids, so the same id names different particles in different
+    events. With the ``batch`` vector the assignment loss (reference bipartite_classification_base.py:152-191, which only
+    ever sees one event) matches particles per event: the loss equals the one computed after relabelling the particles with
+    globally unique ids, and a single event gives the same loss with and without the vector. CPU tensors: scipy matching."""
+    from types import SimpleNamespace
+    from hierarchicalgnn_b200.training_utils import model_selector
+    model = model_selector("BC-HGNN-GMM", dict(latent=128))
+    g = torch.Generator().manual_seed(4)
+    hits, parts, sn = [60, 45], [7, 5], [6, 4]
+    pid, pt, ev, graph, h0, s0 = [], [], [], [], 0, 0
+    for b in range(2):
+        p = torch.randint(0, parts[b] + 1, (hits[b],), generator=g)  # 0 = noise, ids collide between the events
+        pid.append(p)
+        ppt = 0.5 + 2.0 * torch.rand(parts[b] + 1, generator=g)
+        pt.append(torch.where(p > 0, ppt[p], torch.zeros(())))
+        ev.append(torch.full((hits[b],), b))
+        src = torch.arange(hits[b]).repeat_interleave(3)
+        dst = torch.randint(0, sn[b], (src.numel(),), generator=g)
+        graph.append(torch.stack([src + h0, dst + s0]))
+        h0 += hits[b]
+        s0 += sn[b]
+    pid, pt, ev, graph = torch.cat(pid), torch.cat(pt), torch.cat(ev), torch.unique(torch.cat(graph, 1), dim=1)
+    scores = torch.rand(graph.shape[1], generator=g).clamp(0.05, 0.95)
+    collated = SimpleNamespace(pid=pid, pt=pt, batch=ev)
+    unique_ids = SimpleNamespace(pid=torch.where(pid > 0, pid + 100 * ev, pid), pt=pt)
+    a = model.assignment_loss(collated, graph, scores)
+    b = model.assignment_loss(unique_ids, graph, scores)
+    assert torch.isfinite(a) and abs(float(a) - float(b)) < 1e-6 * max(1.0, abs(float(b)))
+    # colliding ids WITHOUT the vector merge particles of different events: a different (wrong) loss
+    c = model.assignment_loss(SimpleNamespace(pid=pid, pt=pt), graph, scores)
+    assert abs(float(c) - float(b)) > 1e-4
+    one = slice(0, hits[0])
+    e0 = graph[0] < hits[0]
+    x = model.assignment_loss(SimpleNamespace(pid=pid[one], pt=pt[one]), graph[:, e0], scores[e0])
+    y = model.assignment_loss(SimpleNamespace(pid=pid[one], pt=pt[one], batch=ev[one]), graph[:, e0], scores[e0])
+    assert float(x) == float(y)
+
+
+def test_native_block_matching_equals_scipy_per_block():
+    """hgnn_match_blocks_max (host threads, csrc/matching.cu) against scipy.sparse.csgraph.min_weight_full_bipartite_matching
+    (what the reference calls, bipartite_classification_base.py:173): same matched columns block by block on random
+    particle x (supernode + virtual supernode) score tables, an empty block in the middle, and an error for a block
+    that has no matching covering its rows."""
+    import numpy as np
+    from scipy.sparse import block_diag, csr_matrix
+    from scipy.sparse.csgraph import min_weight_full_bipartite_matching
+    from hierarchicalgnn_b200 import _lib
+    from hierarchicalgnn_b200.BipartiteClassification.bipartite_classification_base import BipartiteClassificationBase as Base
+    rng = np.random.default_rng(5)
+
+    def table(n_p, n_s, nnz):
+        rows = np.concatenate([rng.integers(0, n_p, nnz), np.arange(n_p)])
+        cols = np.concatenate([rng.integers(0, n_s, nnz), np.arange(n_s, n_s + n_p)])
+        vals = np.concatenate([rng.random(nnz), np.full(n_p, 1e-12)]).astype(np.float32)
+        m = csr_matrix((vals, (rows, cols)), shape=(n_p, n_s + n_p))
+        m.sum_duplicates()
+        return m
+    blocks = [table(40, 25, 300), table(1, 1, 1), table(300, 280, 6000), table(90, 5, 400)]
+    big = block_diag(blocks, format="csr")
+    ptr = [0, 40, 40, 41, 341, 431]  # an empty block between the first two
+    rows, cols = Base._match_blocks(big, ptr)
+    assert rows.tolist() == list(range(431)) and len(set(cols.tolist())) == 431
+    r0 = c0 = 0
+    for b in blocks:
+        r, c = min_weight_full_bipartite_matching(b, maximize=True)
+        assert np.array_equal(cols[r0:r0 + b.shape[0]] - c0, c[np.argsort(r)])
+        r0, c0 = r0 + b.shape[0], c0 + b.shape[1]
+    # two rows that can only take the same column: no covering matching -> error, not a wrong answer
+    bad = csr_matrix((np.ones(2, dtype=np.float32), (np.array([0, 1]), np.array([0, 0]))), shape=(2, 3))
+    with pytest.raises(_lib.HgnnError):
+        Base._match_blocks(bad, [0, 2])

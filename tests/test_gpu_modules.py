@@ -272,3 +272,82 @@ def test_matching_score_table_device_assembly_matches_scipy_coo_path():
     # an empty row set and a single entry
     one = BipartiteClassificationBase._score_table(torch.tensor([0]).cuda(), torch.tensor([1]).cuda(), torch.tensor([0.5]).cuda(), 2, 3)
     assert one.toarray().tolist() == [[0.0, 0.5, 0.0], [0.0, 0.0, 0.0]]
+
+
+def test_batched_knn_equals_per_event_knn_bit_exact():
+    """hgnn_knn_radius_batched: every query meets the references of its own event only; the table is the per-event tables
+    (hgnn_knn_radius) with the neighbour ids offset — bit for bit, ties included, for ragged and empty events."""
+    from hierarchicalgnn_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for dim, k, r in ((8, 5, 0.9), (8, 10, 0.7), (3, 16, 0.5)):
+        nq = [300, 0, 1, 777, 130]
+        nr = [200, 50, 0, 300, 129]
+        qs = [torch.nn.functional.normalize(torch.randn(n, dim, generator=g)) for n in nq]
+        rs = [torch.nn.functional.normalize(torch.randn(n, dim, generator=g)) for n in nr]
+        rs[3][5] = rs[3][7]  # an exact tie
+        qptr = torch.tensor([0] + list(torch.tensor(nq).cumsum(0)), dtype=torch.int32).cuda()
+        rptr = torch.tensor([0] + list(torch.tensor(nr).cumsum(0)), dtype=torch.int32).cuda()
+        got = ops.knn_radius(torch.cat(qs).cuda(), torch.cat(rs).cuda(), k, r, qptr, rptr).cpu()
+        want = []
+        for b in range(len(nq)):
+            if nq[b] == 0:
+                continue
+            t = ops.knn_radius(qs[b].cuda(), rs[b].cuda(), k, r).cpu() if nr[b] else torch.full((nq[b], k), -1, dtype=torch.long)
+            want.append(torch.where(t >= 0, t + int(rptr[b]), t))
+        assert torch.equal(got, torch.cat(want))
+        assert bool((got >= 0).any())
+
+
+def test_bc_model_batched_events_equal_single_event_calls():
+    """Three events collated into one disjoint graph (torch_geometric Batch layout) through BC_HierarchicalGNN_GMM in eval
+    mode, supernodes = particles: per-hit embeddings, the bipartite graph and its scores equal what three single-event calls
+    return (same kernels row by row; the kNN graphs are searched per event and the edge weights normalised per event)."""
+    from hierarchicalgnn_b200.synth import collate_events, synth_event
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    torch.manual_seed(0)
+    model = model_selector("BC-HGNN-GMM", dict(latent=128))
+    kaiming_init(model)
+    model.cuda().eval()
+    evs = [synth_event(150, 8, 0.05, 3.0, seed=7), synth_event(90, 10, 0.0, 4.0, seed=8), synth_event(200, 6, 0.1, 2.0, seed=9)]
+    big = collate_events(evs)
+    with torch.no_grad():
+        singles = [model(ev.x.cuda(), ev.edge_index.cuda(), clusters=(ev.pid - 1).cuda()) for ev in evs]
+        bg, sc, emb = model(big.x.cuda(), big.edge_index.cuda(), clusters=big.clusters.cuda(), batch=big.batch.cuda(),
+                            n_events=big.num_graphs)
+    assert torch.equal(emb, torch.cat([s[2] for s in singles]))
+    hit0 = sn0 = 0
+    want_g, want_s = [], []
+    for ev, (g1, s1, _e) in zip(evs, singles):
+        want_g.append(g1 + torch.tensor([[hit0], [sn0]], device=g1.device))
+        want_s.append(s1.reshape(-1))
+        hit0 += ev.x.shape[0]
+        sn0 += ev.n_particles
+    want_g, want_s = torch.cat(want_g, 1), torch.cat(want_s)
+    assert torch.equal(bg, want_g)  # same edges in the same (query-major) order
+    assert float((sc.reshape(-1) - want_s).abs().max()) < 1e-5
+
+
+def test_clustering_of_batched_events_equals_per_event_clustering():
+    """HierarchicalGNNBlock.clustering on collated events (HGNN_GMM.py:183-232): connected components never cross events, so
+    with the score cut fixed the cluster labels are the per-event labels, numbered event by event."""
+    from hierarchicalgnn_b200.gnn_utils import GraphPlans
+    from hierarchicalgnn_b200.synth import collate_events, direction_embeddings, synth_event
+    from hierarchicalgnn_b200.training_utils import model_selector
+    model = model_selector("BC-HGNN-GMM", dict(latent=128)).cuda().eval()
+    blk = model.hgnn_block
+    blk.score_cut.fill_(1.5)
+    evs = [synth_event(150, 8, 0.05, 3.0, seed=7), synth_event(90, 10, 0.0, 4.0, seed=8), synth_event(200, 6, 0.1, 2.0, seed=9)]
+    embs = [direction_embeddings(ev, seed=i) for i, ev in enumerate(evs)]
+    big = collate_events(evs)
+
+    def run(x, emb, graph):
+        g = torch.cat([graph, graph.flip(0)], 1).cuda()
+        return blk.clustering(x.cuda(), emb.cuda(), GraphPlans(g, x.shape[0], x.shape[0]))
+    got = run(big.x, torch.cat(embs), big.edge_index)
+    want, off = [], 0
+    for ev, emb in zip(evs, embs):
+        c = run(ev.x, emb, ev.edge_index)
+        assert int(c.max()) > 10
+        want.append(torch.where(c >= 0, c + off, c))
+        off += int(c.max()) + 1
+    assert torch.equal(got, torch.cat(want))
