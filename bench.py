@@ -13,8 +13,10 @@ gradients are all-reduced over NCCL, the only exchange the DP path has).
 
 Besides `value` (device-timed, inputs resident) the line carries
   e2e            BASELINE config 3 through the public model API from HOST buffers: BC_HierarchicalGNN_GMM (latent 128,
-                 6 + 6 cells) forward + backward on synthetic 1 GeV events, x[N,3] / edge_index / cluster labels uploaded
-                 from pinned memory every step, the loss read back; same metric (edge-steps/s = E_d * 12 cells / time)
+                 6 + 6 cells) forward + backward on synthetic 1 GeV events, HGNN_BENCH_EVENTS_PER_STEP (default 8) events
+                 collated into one disjoint graph per step (torch_geometric Batch layout), x[N,3] / edge_index / cluster
+                 labels / event ids uploaded from pinned memory every step, the loss read back; same metric (edge-steps/s
+                 = E_d * 12 cells / time). e2e.single_event = the same with ONE event per step (host-bound)
   models         device-timed and end-to-end times of BASELINE configs 1 (EC-IN forward) and 3 (BC fwd+bwd) on 1 GeV events
   dp_training    BASELINE config 4: BC training steps (loss, backward with the bucketed all-reduce overlapped,
                  clip 0.5, AdamW) on per-rank batches of 1 GeV events (HGNN_BENCH_EVENTS_PER_STEP, default 8, collated into
@@ -625,13 +627,17 @@ def run_gpu(args):
     e2e, models = None, None
     if not args.no_e2e:
         models = model_benchmarks(args, dev, world, rank, barrier)
-        m3 = models["config3_bc_fwd_bwd_1gev"]
+        m3, m1 = models["config3_bc_fwd_bwd_1gev_batched"], models["config3_bc_fwd_bwd_1gev"]
         e2e = {"value": m3["e2e_edge_steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": m3["h2d_bytes_per_step"],
                "d2h_bytes_per_step": m3["d2h_bytes_per_step"], "ms_per_step": m3["e2e_ms_per_step"], "steps": m3["steps"],
-               "device_ms_per_step": m3["device_ms_per_step"],
+               "device_ms_per_step": m3["device_ms_per_step"], "events_per_step_per_gpu": m3["events_per_step_per_gpu"],
                "workload": m3["workload"],
-               "pipeline": "per step: x[N,3] f32 + edge_index[2,E] i64 + cluster labels[N] i64 copied from pinned host memory on the "
-                           "compute stream, model forward + backward, 4 B loss read back (host sync)"}
+               "pipeline": "per step: x[N,3] f32 + edge_index[2,E] i64 + cluster labels[N] i64 + event id per hit[N] i64 of the collated "
+                           "events copied from pinned host memory on the compute stream, model forward + backward (model(x, edge_index, "
+                           "clusters=, batch=)), 4 B loss read back (host sync)",
+               "single_event": {"value": m1["e2e_edge_steps_per_s"], "ms_per_step": m1["e2e_ms_per_step"],
+                                "device_ms_per_step": m1["device_ms_per_step"], "h2d_bytes_per_step": m1["h2d_bytes_per_step"],
+                                "workload": m1["workload"]}}
     extra = {}
     if not args.no_models:
         extra["dp_training"] = dp_training_benchmark(args, dev, world, rank, barrier)
