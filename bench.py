@@ -442,6 +442,32 @@ def model_benchmarks(args, dev, world, rank, barrier):
             "workload": f"EC_InteractionGNN latent 128, {n_cells} cells, forward only, synthetic 1 GeV events",
             "device_ms_per_step": dms, "e2e_ms_per_step": ems, "steps": k, "edge_steps_per_event": es,
             "device_edge_steps_per_s": world * es / (dms * 1e-3), "e2e_edge_steps_per_s": world * es / (ems * 1e-3)}
+        # the same forward on a collated batch (a flat interaction network needs no event vector: the graph is disjoint)
+        bres = [(b["x"].to(dev), b["graph"].to(dev)) for b in bpool]
+
+        def ecb_device(i):
+            x, g = bres[i % len(bres)]
+            with torch.no_grad():
+                ec(x, g)
+
+        def ecb_e2e(i):
+            b = bpool[i % len(bpool)]
+            x, g = b["x"].to(dev, non_blocking=True), b["graph"].to(dev, non_blocking=True)
+            with torch.no_grad():
+                score_host.copy_(ec(x, g).mean().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for i in range(3):
+            ecb_device(i)
+            ecb_e2e(i)
+        dms = _timed(ecb_device, k, barrier, world, dev)
+        ems = _timed(ecb_e2e, k, barrier, world, dev)
+        es = sum(bpool[i % len(bpool)]["e_directed"] for i in range(k)) / k * n_cells
+        out["config1_ec_forward_1gev_batched"] = {
+            "workload": f"EC_InteractionGNN latent 128, {n_cells} cells, forward only, {B} synthetic 1 GeV events collated per step",
+            "events_per_step_per_gpu": B, "device_ms_per_step": dms, "e2e_ms_per_step": ems, "steps": k, "edge_steps_per_step": es,
+            "device_edge_steps_per_s": world * es / (dms * 1e-3), "e2e_edge_steps_per_s": world * es / (ems * 1e-3),
+            "events_per_s_e2e": world * B / (ems * 1e-3)}
     return out
 
 

@@ -192,9 +192,7 @@ class DynamicGraphConstruction(nn.Module):
         edge_weights_logits = self.weight_normalization(likelihood.unsqueeze(1)).squeeze()
         edge_weights = self.weighting_function(edge_weights_logits)
         if norm and src_event is not None and graph.shape[1] > 0:
-            edge_event = src_event[graph[0]]
-            per_event = ops.scatter_mean(edge_weights.reshape(-1, 1), edge_event, dim_size=src_ptr.numel() - 1)
-            edge_weights = edge_weights.reshape(-1) / per_event[edge_event, 0]
+            edge_weights = ops.segment_mean_normalize(edge_weights.reshape(-1), src_event[graph[0]], src_ptr.numel() - 1)
         elif norm:
             edge_weights = edge_weights / edge_weights.mean()
         edge_weights = edge_weights.unsqueeze(1)

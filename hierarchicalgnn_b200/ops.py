@@ -360,6 +360,38 @@ def gather_scatter(src: Tensor, weight: Optional[Tensor], gather_plan: SegmentPl
 
 
 # ---------------------------------------------------------------------------
+# autograd: value / mean of its segment
+# ---------------------------------------------------------------------------
+class _SegmentMeanNormalize(torch.autograd.Function):
+    """out[i] = w[i] / mean(w over the segment of i). The per-event form of ``edge_weights / edge_weights.mean()``
+    (gnn_utils.py:213-214) for a batch of events; the adjoint is two ordered segment sums (autograd through
+    ``mean[segment]`` would scatter-add hundreds of thousands of gradients into a handful of rows)."""
+
+    @staticmethod
+    def forward(ctx, w, plan: SegmentPlan):
+        w = _f32(w).reshape(-1)
+        seg = plan.keys32.long()
+        inv_n = plan.inv_counts()
+        mean = segment_reduce_raw(w.unsqueeze(1), plan)[:, 0] * inv_n
+        inv_mean = 1.0 / mean
+        ctx.save_for_backward(w, inv_mean, inv_n, seg)
+        ctx.plan = plan
+        return w * inv_mean[seg]
+
+    @staticmethod
+    def backward(ctx, g):
+        w, inv_mean, inv_n, seg = ctx.saved_tensors
+        g = _f32(g).reshape(-1)
+        t = segment_reduce_raw((g * w).unsqueeze(1), ctx.plan)[:, 0]  # sum_i g_i w_i per segment
+        return g * inv_mean[seg] - (t * inv_n * inv_mean * inv_mean)[seg], None
+
+
+def segment_mean_normalize(w: Tensor, segment: Tensor, n_segments: int) -> Tensor:
+    """w / (mean of w over its segment); ``segment``: int64 segment id per element."""
+    return _SegmentMeanNormalize.apply(w, plan_for(segment, n_segments))
+
+
+# ---------------------------------------------------------------------------
 # autograd: gathered row dot
 # ---------------------------------------------------------------------------
 class _EdgeDot(torch.autograd.Function):

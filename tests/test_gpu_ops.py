@@ -338,3 +338,24 @@ def test_scatter_add_hub_segments(ops, width):
     out = ops.gather_scatter(td, w.to(DEV), ops.plan_for(gi.to(DEV), 500), ops.plan_for(idx.to(DEV), n_seg))
     want2 = torch.zeros(n_seg, width, dtype=torch.float64).index_add_(0, idx, (w.double() * table.double()[gi]))
     assert float((out.detach().cpu().double() - want2).abs().max()) < 2e-5 * float(deg.max()) ** 0.5
+
+
+def test_segment_mean_normalize_forward_and_adjoint_vs_torch():
+    """w / mean(w over its segment) — the per-event form of edge_weights / edge_weights.mean() (gnn_utils.py:213-214) —
+    against plain torch autograd in fp64, including an empty segment and a one-element segment."""
+    from hierarchicalgnn_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    seg = torch.cat([torch.zeros(700), torch.full((1,), 2.0), torch.full((1300,), 3.0), torch.full((40,), 5.0)]).long()
+    seg = seg[torch.randperm(seg.numel(), generator=g)]
+    w = (0.2 + torch.rand(seg.numel(), generator=g))
+    cot = torch.randn(seg.numel(), generator=g)
+    wr = w.double().requires_grad_(True)
+    sums = torch.zeros(6, dtype=torch.float64).index_add(0, seg, wr)
+    cnt = torch.bincount(seg, minlength=6).clamp(min=1)
+    want = wr / (sums / cnt)[seg]
+    (want * cot.double()).sum().backward()
+    wd = w.cuda().requires_grad_(True)
+    got = ops.segment_mean_normalize(wd, seg.cuda(), 6)
+    (got * cot.cuda()).sum().backward()
+    assert float((got.detach().cpu().double() - want.detach()).abs().max()) < 1e-5
+    assert float((wd.grad.cpu().double() - wr.grad).abs().max()) < 1e-5 * float(wr.grad.abs().max())
