@@ -30,6 +30,7 @@ struct NarrowInArgs {
 };
 
 // lane k < K fetches input column k of row r (through the segment gathers); everyone gets all K values by shuffle
+template <int KMAX = NI_MAX_K>
 __device__ __forceinline__ void load_row(const NarrowInArgs& A, int64_t r, int lane, int my_seg, int my_col, float (&a)[NI_MAX_K]) {
   float mine = 0.f;
   if (lane < A.K) {
@@ -37,7 +38,7 @@ __device__ __forceinline__ void load_row(const NarrowInArgs& A, int64_t r, int l
     mine = __ldg(A.seg_ptr[my_seg] + sr * A.seg_width[my_seg] + my_col);
   }
 #pragma unroll
-  for (int k = 0; k < NI_MAX_K; ++k) a[k] = __shfl_sync(0xffffffffu, mine, k);
+  for (int k = 0; k < NI_MAX_K; ++k) a[k] = k < KMAX ? __shfl_sync(0xffffffffu, mine, k) : 0.f;
 }
 
 __device__ __forceinline__ void lane_source(const NarrowInArgs& A, int lane, int& seg, int& col) {
@@ -88,8 +89,11 @@ __device__ __forceinline__ void stage_params(const NarrowInArgs& A, float* sm) {
   }
 }
 
-template <int NJ>
+// KT > 0: compile-time fan-in (3 = hit coordinates, 6 = the two end points of an edge: the encoders' first layers), the
+// FMA chains and shuffles follow it instead of the maximum of 8
+template <int NJ, int KT>
 __global__ void __launch_bounds__(SK_THREADS) k_narrow_in_fwd(NarrowInArgs A, float* __restrict__ out) {
+  constexpr int KMAX = KT > 0 ? KT : NI_MAX_K;
   extern __shared__ float sm[];
   const int N = A.N;
   stage_params<NJ>(A, sm);
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_narrow_in_fwd(NarrowInArgs A, fl
   const float invN = 1.0f / N;
   for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < A.rows; r += (int64_t)gridDim.x * SK_WARPS) {
     float a[NI_MAX_K];
-    load_row(A, r, lane, my_seg, my_col, a);
+    load_row<KMAX>(A, r, lane, my_seg, my_col, a);
     float h[NJ];
     float sum = 0.f;
 #pragma unroll
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(SK_THREADS) k_narrow_in_fwd(NarrowInArgs A, fl
       const int c = lane + 32 * j;
       float v = sb[c];
 #pragma unroll
-      for (int k = 0; k < NI_MAX_K; ++k)
-        if (k < A.K) v = fmaf(sm[k * N + c], a[k], v);
+      for (int k = 0; k < KMAX; ++k)
+        if (KT > 0 || k < A.K) v = fmaf(sm[k * N + c], a[k], v);
       h[j] = v;
       sum += v;
     }
@@ -129,9 +133,11 @@ __global__ void __launch_bounds__(SK_THREADS) k_narrow_in_fwd(NarrowInArgs A, fl
 }
 
 // partial layout per CTA: [K + 3][N] = dW^T rows (k-major) | d bias | d gamma | d beta
-template <int NJ>
+// DIN: the input gradient is wanted (false for the encoders: hit coordinates carry no gradient — its 2 K FMAs per column go)
+template <int NJ, int KT, bool DIN>
 __global__ void __launch_bounds__(SK_THREADS, 2) k_narrow_in_bwd(NarrowInArgs A, const float* __restrict__ gout, float* __restrict__ d_in,
                                                               float* __restrict__ partial) {
+  constexpr int KMAX = KT > 0 ? KT : NI_MAX_K;
   extern __shared__ float sm[];
   const int N = A.N;
   stage_params<NJ>(A, sm);
@@ -143,16 +149,16 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_narrow_in_bwd(NarrowInArgs A,
   int my_seg, my_col;
   lane_source(A, lane, my_seg, my_col);
   const float invN = 1.0f / N;
-  float aW[NJ][NI_MAX_K], ab[NJ], ag[NJ], abe[NJ];
+  float aW[NJ][KMAX], ab[NJ], ag[NJ], abe[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     ab[j] = ag[j] = abe[j] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NI_MAX_K; ++k) aW[j][k] = 0.f;
+    for (int k = 0; k < KMAX; ++k) aW[j][k] = 0.f;
   }
   for (int64_t r = (int64_t)blockIdx.x * SK_WARPS + warp; r < A.rows; r += (int64_t)gridDim.x * SK_WARPS) {
     float a[NI_MAX_K];
-    load_row(A, r, lane, my_seg, my_col, a);
+    load_row<KMAX>(A, r, lane, my_seg, my_col, a);
     float h[NJ], go[NJ];
     float sum = 0.f;
 #pragma unroll
@@ -161,8 +167,8 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_narrow_in_bwd(NarrowInArgs A,
       go[j] = __ldg(gout + (size_t)r * N + c);
       float v = sb[c];
 #pragma unroll
-      for (int k = 0; k < NI_MAX_K; ++k)
-        if (k < A.K) v = fmaf(sm[k * N + c], a[k], v);
+      for (int k = 0; k < KMAX; ++k)
+        if (KT > 0 || k < A.K) v = fmaf(sm[k * N + c], a[k], v);
       h[j] = v;
       sum += v;
     }
@@ -203,14 +209,14 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_narrow_in_bwd(NarrowInArgs A,
       const int c = lane + 32 * j;
       ab[j] += delta[j];
 #pragma unroll
-      for (int k = 0; k < NI_MAX_K; ++k) {
-        if (k < A.K) {
+      for (int k = 0; k < KMAX; ++k) {
+        if (KT > 0 || k < A.K) {
           aW[j][k] = fmaf(delta[j], a[k], aW[j][k]);
-          da[k] = fmaf(delta[j], sm[k * N + c], da[k]);
+          if (DIN) da[k] = fmaf(delta[j], sm[k * N + c], da[k]);
         }
       }
     }
-    if (d_in) {
+    if (DIN) {
       // after the transpose-reduce lane l holds column ((l & 4) | (l & 2) | (l & 1)) bit-reversed pairing: value index
       // = 4 * bit2(l) + 2 * bit1(l) + bit0(l) = l & 7
       const float mine = warp_sum8(da, lane);
@@ -224,8 +230,8 @@ __global__ void __launch_bounds__(SK_THREADS, 2) k_narrow_in_bwd(NarrowInArgs A,
       for (int j = 0; j < NJ; ++j) {
         const int c = lane + 32 * j;
 #pragma unroll
-        for (int k = 0; k < NI_MAX_K; ++k)
-          if (k < A.K) s_acc[k * N + c] += aW[j][k];
+        for (int k = 0; k < KMAX; ++k)
+          if (KT > 0 || k < A.K) s_acc[k * N + c] += aW[j][k];
         s_acc[(NI_MAX_K + 0) * N + c] += ab[j];
         s_acc[(NI_MAX_K + 1) * N + c] += ag[j];
         s_acc[(NI_MAX_K + 2) * N + c] += abe[j];
@@ -782,10 +788,14 @@ extern "C" int hgnn_narrow_in_forward(const hgnn_mlp_desc* d, int64_t rows, floa
   const int grid = skinny_grid(rows, SK_WARPS * 4);
   cudaStream_t st = (cudaStream_t)stream;
   switch (a.N / 32) {
-    case 1: k_narrow_in_fwd<1><<<grid, SK_THREADS, smem, st>>>(a, out); break;
-    case 2: k_narrow_in_fwd<2><<<grid, SK_THREADS, smem, st>>>(a, out); break;
-    case 4: k_narrow_in_fwd<4><<<grid, SK_THREADS, smem, st>>>(a, out); break;
-    default: k_narrow_in_fwd<8><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+    case 1: k_narrow_in_fwd<1, 0><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+    case 2: k_narrow_in_fwd<2, 0><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+    case 4: k_narrow_in_fwd<4, 0><<<grid, SK_THREADS, smem, st>>>(a, out); break;
+    default:
+      if (a.K == 3) k_narrow_in_fwd<8, 3><<<grid, SK_THREADS, smem, st>>>(a, out);
+      else if (a.K == 6) k_narrow_in_fwd<8, 6><<<grid, SK_THREADS, smem, st>>>(a, out);
+      else k_narrow_in_fwd<8, 0><<<grid, SK_THREADS, smem, st>>>(a, out);
+      break;
   }
   return check_launch("narrow_in_forward");
 }
@@ -812,10 +822,17 @@ extern "C" int hgnn_narrow_in_backward(const hgnn_mlp_desc* d, int64_t rows, con
   float* partial = (float*)ws;
   const size_t smem = (size_t)2 * (NI_MAX_K + 3) * a.N * 4;
   switch (a.N / 32) {
-    case 1: k_narrow_in_bwd<1><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
-    case 2: k_narrow_in_bwd<2><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
-    case 4: k_narrow_in_bwd<4><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
-    default: k_narrow_in_bwd<8><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    case 1: k_narrow_in_bwd<1, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    case 2: k_narrow_in_bwd<2, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    case 4: k_narrow_in_bwd<4, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    default:
+      if (d_in != nullptr && a.K == 3) k_narrow_in_bwd<8, 3, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (d_in != nullptr && a.K == 6) k_narrow_in_bwd<8, 6, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (d_in != nullptr) k_narrow_in_bwd<8, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (a.K == 3) k_narrow_in_bwd<8, 3, false><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (a.K == 6) k_narrow_in_bwd<8, 6, false><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else k_narrow_in_bwd<8, 0, false><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      break;
   }
   rc = check_launch("narrow_in_backward");
   if (rc) return rc;
