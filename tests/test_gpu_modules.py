@@ -351,3 +351,43 @@ def test_clustering_of_batched_events_equals_per_event_clustering():
         want.append(torch.where(c >= 0, c + off, c))
         off += int(c.max()) + 1
     assert torch.equal(got, torch.cat(want))
+
+
+def test_training_step_on_collated_events():
+    """BipartiteClassificationBase.training_step on a torch_geometric-style batch: a batch of ONE event carrying the event
+    vector gives exactly the loss of the plain single-event step (same graphs, same matching); a batch of three events gives a
+    finite loss and a gradient for every parameter that gets one on a single event."""
+    from types import SimpleNamespace
+    from hierarchicalgnn_b200.synth import collate_events, synth_event
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    evs = [synth_event(150, 8, 0.05, 3.0, seed=17), synth_event(90, 10, 0.0, 4.0, seed=18), synth_event(200, 6, 0.1, 2.0, seed=19)]
+
+    def fresh():
+        torch.manual_seed(0)
+        m = model_selector("BC-HGNN-GMM", dict(latent=128, loss_schedule=0.5))
+        kaiming_init(m)
+        return m.cuda().train()
+
+    def batch_of(events, with_vector):
+        b = collate_events(events)
+        ns = SimpleNamespace(x=b.x.cuda(), edge_index=b.edge_index.cuda(), pid=b.pid.cuda(), pt=b.pt.cuda())
+        if with_vector:
+            ns.batch, ns.num_graphs = b.batch.cuda(), b.num_graphs
+        return ns, b.clusters.cuda()
+
+    losses, grads = [], []
+    for events, vec in (([evs[0]], False), ([evs[0]], True), (evs, True)):
+        m = fresh()
+        b, clusters = batch_of(events, vec)
+        m.hgnn_block.clustering = lambda x, emb, graph: clusters  # supernodes = particles
+        loss = m.training_step(b, 0)
+        loss.backward()
+        assert torch.isfinite(loss)
+        losses.append(float(loss.detach()))
+        grads.append({k: p.grad for k, p in m.named_parameters()})
+    # the per-event mean of the edge weights is an ordered segment sum, torch.mean a tree: 1e-7 relative on the weights
+    assert abs(losses[0] - losses[1]) < 1e-5 * abs(losses[0])
+    for k, g in grads[0].items():
+        if g is not None and float(g.abs().max()) > 0:
+            assert float((g - grads[1][k]).norm()) < 1e-3 * float(g.norm()) + 1e-6, k  # (biases in front of a LayerNorm: analytically 0)
+            assert grads[2][k] is not None and bool(torch.isfinite(grads[2][k]).all()), k
