@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_narrow_in_fwd(NarrowInArgs A, fl
 // partial layout per CTA: [K + 3][N] = dW^T rows (k-major) | d bias | d gamma | d beta
 // DIN: the input gradient is wanted (false for the encoders: hit coordinates carry no gradient — its 2 K FMAs per column go)
 template <int NJ, int KT, bool DIN>
-__global__ void __launch_bounds__(SK_THREADS, 2) k_narrow_in_bwd(NarrowInArgs A, const float* __restrict__ gout, float* __restrict__ d_in,
+__global__ void __launch_bounds__(SK_THREADS, NJ > 8 ? 1 : 2) k_narrow_in_bwd(NarrowInArgs A, const float* __restrict__ gout, float* __restrict__ d_in,
                                                               float* __restrict__ partial) {
   constexpr int KMAX = KT > 0 ? KT : NI_MAX_K;
   extern __shared__ float sm[];
@@ -743,7 +743,7 @@ __global__ void k_partial_reduce(const float* __restrict__ partial, int n_part, 
 int narrow_in_args(const hgnn_mlp_desc* d, int64_t rows, NarrowInArgs& a, const char* who) {
   HGNN_REQUIRE(d != nullptr, "%s: desc is NULL", who);
   if (!hgnn_narrow_in_supported(d))
-    return fail(HGNN_ERR_UNSUPPORTED, "%s: needs one layer, fan-in <= %d, fan-out in {32, 64, 128, 256}", who, NI_MAX_K);
+    return fail(HGNN_ERR_UNSUPPORTED, "%s: needs one layer, fan-in <= %d, fan-out in {32, 64, 128, 256, 512}", who, NI_MAX_K);
   HGNN_REQUIRE(rows >= 0 && rows < INT32_MAX, "%s: rows out of range", who);
   a = NarrowInArgs{};
   a.n_seg = d->n_seg;
@@ -775,7 +775,7 @@ extern "C" int hgnn_narrow_in_supported(const hgnn_mlp_desc* d) {
     k += d->seg_width[s];
   }
   const int n = d->out_width[0];
-  return k <= NI_MAX_K && (n == 32 || n == 64 || n == 128 || n == 256);
+  return k <= NI_MAX_K && (n == 32 || n == 64 || n == 128 || n == 256 || n == 512);
 }
 
 extern "C" int hgnn_narrow_in_forward(const hgnn_mlp_desc* d, int64_t rows, float* out, void* stream) {
@@ -791,10 +791,15 @@ extern "C" int hgnn_narrow_in_forward(const hgnn_mlp_desc* d, int64_t rows, floa
     case 1: k_narrow_in_fwd<1, 0><<<grid, SK_THREADS, smem, st>>>(a, out); break;
     case 2: k_narrow_in_fwd<2, 0><<<grid, SK_THREADS, smem, st>>>(a, out); break;
     case 4: k_narrow_in_fwd<4, 0><<<grid, SK_THREADS, smem, st>>>(a, out); break;
-    default:
+    case 8:
       if (a.K == 3) k_narrow_in_fwd<8, 3><<<grid, SK_THREADS, smem, st>>>(a, out);
       else if (a.K == 6) k_narrow_in_fwd<8, 6><<<grid, SK_THREADS, smem, st>>>(a, out);
       else k_narrow_in_fwd<8, 0><<<grid, SK_THREADS, smem, st>>>(a, out);
+      break;
+    default:  // fan-out 512: the encoders of the latent-256 configs (hidden = 512)
+      if (a.K == 3) k_narrow_in_fwd<16, 3><<<grid, SK_THREADS, smem, st>>>(a, out);
+      else if (a.K == 6) k_narrow_in_fwd<16, 6><<<grid, SK_THREADS, smem, st>>>(a, out);
+      else k_narrow_in_fwd<16, 0><<<grid, SK_THREADS, smem, st>>>(a, out);
       break;
   }
   return check_launch("narrow_in_forward");
@@ -825,6 +830,14 @@ extern "C" int hgnn_narrow_in_backward(const hgnn_mlp_desc* d, int64_t rows, con
     case 1: k_narrow_in_bwd<1, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
     case 2: k_narrow_in_bwd<2, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
     case 4: k_narrow_in_bwd<4, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial); break;
+    case 16:
+      if (d_in != nullptr && a.K == 3) k_narrow_in_bwd<16, 3, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (d_in != nullptr && a.K == 6) k_narrow_in_bwd<16, 6, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (d_in != nullptr) k_narrow_in_bwd<16, 0, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (a.K == 3) k_narrow_in_bwd<16, 3, false><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else if (a.K == 6) k_narrow_in_bwd<16, 6, false><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      else k_narrow_in_bwd<16, 0, false><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
+      break;
     default:
       if (d_in != nullptr && a.K == 3) k_narrow_in_bwd<8, 3, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);
       else if (d_in != nullptr && a.K == 6) k_narrow_in_bwd<8, 6, true><<<grid, SK_THREADS, smem, st>>>(a, grad_out, d_in, partial);

@@ -760,7 +760,7 @@ def tc_edge_step_with_agg(meta: MlpMeta, x: Tensor, e: Tensor, params: Sequence[
 # ---------------------------------------------------------------------------
 @functools.lru_cache(maxsize=256)
 def narrow_in_supported(seg_widths, n_out: int) -> bool:
-    return 1 <= len(seg_widths) <= MAX_SEGS and sum(seg_widths) <= 8 and n_out in (32, 64, 128, 256)
+    return 1 <= len(seg_widths) <= MAX_SEGS and sum(seg_widths) <= 8 and n_out in (32, 64, 128, 256, 512)
 
 
 @functools.lru_cache(maxsize=256)

@@ -335,7 +335,7 @@ int hgnn_tc_row_backward_split(const hgnn_tc_row_layer* d, const void* wt_packed
 
 /* ------------------------------------------------------------------------
  * Skinny layers (fp32, one warp per row) — the make_mlp layers that are pure bandwidth:
- *  narrow-in : a one-layer hgnn_mlp_desc with fan-in <= 8 and fan-out in {32, 64, 128, 256} (the encoders' first
+ *  narrow-in : a one-layer hgnn_mlp_desc with fan-in <= 8 and fan-out in {32, 64, 128, 256, 512} (the encoders' first
  *              Linear on x[N,3] / [x[src] | x[dst]]: EC/Models/IN.py:29-33,84-85; BC/Models/HGNN_GMM.py:37-41),
  *              optional LayerNorm + activation; backward gives d_in[rows, fan_in] (optional), dW[fan_out, fan_in],
  *              dvec[3, fan_out] = (d bias, d gamma, d beta).

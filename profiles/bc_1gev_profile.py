@@ -11,7 +11,9 @@ ev = collate_events([synth_event(1200, 10, 0.0, 4.0, seed=1000 + i) for i in ran
 x, g = ev.x.cuda(), ev.edge_index.cuda()
 bt = ev.batch.cuda() if B > 1 else None
 torch.manual_seed(0)
-bc = model_selector("BC-HGNN-GMM", dict(latent=128)); kaiming_init(bc); bc.cuda().train()
+import os
+LAT = int(os.environ.get("HGNN_LATENT", "128"))  # 256 = the reference's BC default (layer-wise tensor-core path)
+bc = model_selector("BC-HGNN-GMM", dict(latent=LAT)); kaiming_init(bc); bc.cuda().train()
 clusters = ev.clusters.cuda()
 def fb(split=False):
     bc.zero_grad(set_to_none=True)
@@ -22,7 +24,7 @@ def fb(split=False):
 for _ in range(5): fb()
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(10): fb()
-torch.cuda.synchronize(); print(f"{B} event(s) per step"); print("BC 1 GeV fwd+bwd %.2f ms/step (back to back)" % ((time.perf_counter() - t0) / 10 * 1e3))
+torch.cuda.synchronize(); print(f"{B} event(s) per step, latent {LAT}"); print("BC 1 GeV fwd+bwd %.2f ms/step (back to back)" % ((time.perf_counter() - t0) / 10 * 1e3))
 tf = tb = 0.0
 for _ in range(5):
     torch.cuda.synchronize(); t0 = time.perf_counter(); t1 = fb(True); torch.cuda.synchronize(); t2 = time.perf_counter()

@@ -19,6 +19,9 @@ def rel(x, y):
     ([6], [False], 128, 77, 0, False, "Tanh"),
     ([8], [False], 32, 1, 0, True, None),
     ([2, 1], [True, False], 64, 300, 10, True, "ReLU"),
+    ([3], [False], 512, 3000, 0, True, "GELU"),          # node encoder layer 1 of the latent-256 configs (hidden 512)
+    ([3, 3], [True, True], 512, 9000, 500, True, "GELU"),  # edge encoder layer 1, hidden 512
+    ([5], [False], 512, 130, 0, True, "Tanh"),           # fan-out 512, generic fan-in
 ])
 def test_narrow_in_layer(widths, gathered, n_out, rows, n_src, ln, act):
     from hierarchicalgnn_b200 import ops
