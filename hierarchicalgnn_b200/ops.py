@@ -1113,18 +1113,50 @@ class _TcSplitLayer(torch.autograd.Function):
         L_ = _lib.lib()
         dW = torch.empty_like(W)
         dvec = torch.empty((3, N), dtype=torch.float32, device=dev)
-        d_in = torch.empty((rows, K), dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[2:]
+        widths = ctx.widths
+        offs = [sum(widths[:s]) for s in range(n_seg)]
+        _, bwd_chunks = meta.pack()
+
+        def seg_of(c0, n):  # the segment that holds input columns [c0, c0 + n) entirely, or None
+            for s in range(n_seg):
+                if offs[s] <= c0 and c0 + n <= offs[s] + widths[s]:
+                    return s
+            return None
+        # one dense gradient matrix per segment when every W^T chunk lies inside one segment (latent 256: 256-wide segments and
+        # chunks): no strided slices for the consumers to copy, no GEMM for a segment that needs no gradient
+        split = n_seg > 1 and all(seg_of(c0, n) is not None for c0, n, _ in bwd_chunks)
+        d_in = None
+        d_segs: List[Optional[Tensor]] = [None] * n_seg
+        if split:
+            for s in range(n_seg):
+                if need[s]:
+                    d_segs[s] = torch.empty((rows, widths[s]), dtype=torch.float32, device=dev)
+        else:
+            d_in = torch.empty((rows, K), dtype=torch.float32, device=dev)
         if rows:
-            _, bwd_chunks = meta.pack()
             delta = torch.empty((rows, N), dtype=torch.float32, device=dev)
             d_img = torch.empty(L_.hgnn_tc_row_image_bytes(rows, N), dtype=torch.uint8, device=dev)
             ws = _workspace(max(L_.hgnn_ln_act_backward_workspace_bytes(N), L_.hgnn_tc_wgrad_workspace_bytes(rows, N, K)), dev)
             with _timed("tc_split_backward"):
                 check(L_.hgnn_ln_act_backward(_ptr(h), _ptr(gout), rows, N, _ptr(g), _ptr(be), meta.eps, meta.act, _ptr(delta),
                                               _ptr(dvec), _ptr(ws), ws.numel(), _stream()), "ln_act_backward")
-                for i, (c0, n, img) in enumerate(bwd_chunks):  # d_in[:, c0 : c0 + n] = delta . W[:, c0 : c0 + n]
+                image_done = False  # the first GEMM that runs also leaves the bf16 image of delta (weight-gradient operand)
+                for c0, n, img in bwd_chunks:  # d_in[:, c0 : c0 + n] = delta . W[:, c0 : c0 + n]
+                    out, ld, col = d_in, K, c0
+                    if split:
+                        sg = seg_of(c0, n)
+                        if d_segs[sg] is None:
+                            continue
+                        out, ld, col = d_segs[sg], widths[sg], c0 - offs[sg]
                     d = _gemm_desc([delta], [None], n, img, None)
-                    check(L_.hgnn_tc_gemm(C.byref(d), rows, _ptr(d_in), K, c0, _ptr(d_img) if i == 0 else None, _stream()), "tc_gemm")
+                    check(L_.hgnn_tc_gemm(C.byref(d), rows, _ptr(out), ld, col, None if image_done else _ptr(d_img), _stream()), "tc_gemm")
+                    image_done = True
+                if not image_done:  # no input gradient wanted at all: one GEMM into scratch for the image
+                    c0, n, img = bwd_chunks[0]
+                    d = _gemm_desc([delta], [None], n, img, None)
+                    scratch = torch.empty((rows, n), dtype=torch.float32, device=dev)
+                    check(L_.hgnn_tc_gemm(C.byref(d), rows, _ptr(scratch), n, 0, _ptr(d_img), _stream()), "tc_gemm")
                 check(L_.hgnn_tc_wgrad(_ptr(d_img), N, _ptr(a_img), K, rows, _ptr(dW), _ptr(ws), ws.numel(), _stream()), "tc_wgrad")
             _count(2 + len(bwd_chunks) + 2 * ((N // 128 or 1) * (K // 128 or 1) // 4 + 1))
             TC_ROW_CALLS["count"] += 1
@@ -1132,18 +1164,17 @@ class _TcSplitLayer(torch.autograd.Function):
             dW.zero_()
             dvec.zero_()
         grads: List[Optional[Tensor]] = [None, None]
-        need = ctx.needs_input_grad[2:]
         off = 0
         for s in range(n_seg):
-            w = ctx.widths[s]
+            w = widths[s]
             gs = None
             if need[s]:
-                gs = d_in if n_seg == 1 else d_in[:, off:off + w]
+                gs = d_segs[s] if split else (d_in if n_seg == 1 else d_in[:, off:off + w])
                 plan = meta.seg_plans[s]
                 if plan is not None:
                     if plan.n_segments != ctx.seg_rows[s]:
                         raise _lib.HgnnError("generic layer: gather plan does not cover the gathered tensor")
-                    gs = segment_reduce_raw(gs, plan)  # column slice of d_in, reduced in place (row stride)
+                    gs = segment_reduce_raw(gs, plan)  # (a column slice of d_in is reduced in place: row stride)
             grads.append(gs)
             off += w
         if meta.has_skip:
