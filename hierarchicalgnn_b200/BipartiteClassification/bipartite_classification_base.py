@@ -157,6 +157,36 @@ class BipartiteClassificationBase(LightningModule):
         self.log_dict({"training_loss": loss, "embedding_loss": emb_loss, "assignment_loss": asgmt_loss})
         return loss
 
+    def shared_evaluation(self, batch, batch_idx=0, log=False):
+        """Validation / test step body (bipartite_classification_base.py:226-287): both loss terms (the schedule counts only
+        while training, else the assignment term alone), then the hit -> supernode assignments scoring >= ``score_cut`` as
+        track candidates for ``eval_metrics``. Returns (bipartite_graph, loss)."""
+        from ..EdgeClassifier.edge_classifier_base import _evaluation_event, _original_hits
+        from ..tracking_utils import default_response, eval_metrics
+        with torch.no_grad():
+            bipartite_graph, bipartite_scores, embeddings = self._forward_batch(batch)
+            emb_loss = self.embedding_loss(batch, embeddings)
+            asgmt_loss = self.assignment_loss(batch, bipartite_graph, bipartite_scores)
+            s = self.loss_schedule() if (self.training and hasattr(self.trainer, "current_epoch")) else 0
+            loss = s * emb_loss + (1 - s) * asgmt_loss
+            self.log_dict({"val_loss": loss, "val_embedding_loss": emb_loss, "val_assignment_loss": asgmt_loss})
+            bipartite_graph = bipartite_graph[:, bipartite_scores >= self.hparams["score_cut"]]
+            try:
+                metrics = eval_metrics(_original_hits(bipartite_graph, batch), _evaluation_event(batch, self.device),
+                                       pt_cut=self.hparams["ptcut"], nhits_cut=self.hparams["n_hits"],
+                                       majority_cut=self.hparams["majority_cut"], primary=False)
+            except (RuntimeError, IndexError, ValueError):  # the reference falls back to zeros on any failure here
+                metrics = dict(default_response)
+        if log:
+            self.log_dict(metrics)
+        return bipartite_graph, loss
+
+    def validation_step(self, batch, batch_idx=0):
+        return self.shared_evaluation(batch, batch_idx, log=True)[1]
+
+    def test_step(self, batch, batch_idx=0):
+        return self.shared_evaluation(batch, batch_idx, log=True)[1]
+
     def optimizer_step(self, epoch=None, batch_idx=None, optimizer=None, optimizer_idx=None, optimizer_closure=None,
                        on_tpu=False, using_native_amp=False, using_lbfgs=False):
         warm = self.hparams.get("warmup")

@@ -417,3 +417,43 @@ def roc_auc(scores: Tensor, labels: Tensor) -> float:
     if n1 == 0 or n0 == 0:
         return float("nan")
     return float((mean_rank[pos].sum() - n1 * (n1 + 1) / 2) / (n1 * n0))
+
+
+def eval_metrics_dense(bipartite_graph: Tensor, pid_all: Tensor, pt_all: Tensor, pt_cut=1.0, nhits_cut=5, majority_cut=0.5):
+    """Tracking metrics, restated line by line from the reference (Modules/tracking_utils.py:18-83, primary=False as both
+    shared_evaluation callers pass) with a DENSE numpy particle x candidate matrix in place of the cupy sparse one —
+    including its ``cluster_hashing`` tie-break (a factor rising from 1 to 1 + 1e-12 over the candidates). Small cases only."""
+    import numpy as np
+    bg = bipartite_graph.clone().long()
+    _, clusters, counts = bg[1].unique(return_inverse=True, return_counts=True)
+    bg = bg[:, counts[clusters] >= (nhits_cut * majority_cut)]
+    zero = {"track_eff": 0, "track_pur": 0, "hit_eff": 0, "hit_pur": 0}
+    if bg.shape[1] == 0:
+        return zero
+    bg[1] = bg[1].unique(return_inverse=True)[1]
+    original_pid, pid, nhits = torch.unique(pid_all, return_inverse=True, return_counts=True)
+    n_p, n_c = int(pid.max()) + 1, int(bg[1].max()) + 1
+    pt = np.full(n_p, np.inf)
+    for h in range(pid.numel()):
+        pt[int(pid[h])] = min(pt[int(pid[h])], float(pt_all[h]))
+    M = np.zeros((n_p, n_c))
+    for h, c in zip(pid[bg[0]].tolist(), bg[1].tolist()):
+        M[h, c] += 1.0
+    original_pid, nhits_np = original_pid.numpy(), nhits.numpy().astype(np.float64)
+    hashing = np.linspace(1, 1 + 1e-12, n_c).reshape(1, -1)
+    Mh = M * hashing
+    matching = (M >= majority_cut * M.sum(0, keepdims=True)) & (M >= majority_cut * nhits_np.reshape(-1, 1)) & (Mh == Mh.max(1, keepdims=True))
+    row, col = np.where(matching)
+    if row.shape[0] == 0:
+        return zero
+    matching_mask = (M[row, col] > majority_cut * nhits_cut) & (original_pid[row] != 0)
+    row, col = row[matching_mask], col[matching_mask]
+    if row.shape[0] == 0:
+        return zero
+    mask = (pt[row] > pt_cut) & (nhits_np[row] >= nhits_cut)
+    truth_mask = (pt > pt_cut) & (nhits_np >= nhits_cut)
+    track_eff = mask.sum() / truth_mask.sum()
+    hit_pur = (M[row, col] / M[:, col].sum(0)).mean()
+    track_pur = mask.sum() / (M.shape[1] - (~matching_mask).sum() - (~mask).sum())
+    hit_eff = (M[row, col][mask] / nhits_np[row][mask]).mean()
+    return {"track_eff": float(track_eff), "track_pur": float(track_pur), "hit_eff": float(hit_eff), "hit_pur": float(hit_pur)}

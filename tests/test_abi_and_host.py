@@ -338,3 +338,41 @@ def test_native_block_matching_equals_scipy_per_block():
     bad = csr_matrix((np.ones(2, dtype=np.float32), (np.array([0, 1]), np.array([0, 0]))), shape=(2, 3))
     with pytest.raises(_lib.HgnnError):
         Base._match_blocks(bad, [0, 2])
+
+
+def test_tracking_metrics_equal_the_dense_restatement_of_the_reference():
+    """hierarchicalgnn_b200.tracking_utils.eval_metrics (sorted list of the non-zero particle x candidate cells, torch ops)
+    against oracle.eval_metrics_dense (the reference's tracking_utils.py:18-83 with a dense matrix): noisy track candidates
+    built from the truth — merged tracks, split tracks, stolen hits, noise hits, tiny candidates — over several seeds and cuts."""
+    from types import SimpleNamespace
+    from hierarchicalgnn_b200.tracking_utils import eval_metrics
+    from oracle import hgnn_oracle as O
+    checked = 0
+    for seed in range(8):
+        g = torch.Generator().manual_seed(100 + seed)
+        n_part, hpp = 40, int(torch.randint(4, 10, (1,), generator=g))
+        pid = torch.arange(1, n_part + 1).repeat_interleave(hpp)
+        pid = torch.cat([pid, torch.zeros(30, dtype=torch.long)])  # noise hits
+        pt_p = 0.3 + 2.0 * torch.rand(n_part + 1, generator=g)
+        pt = torch.where(pid > 0, pt_p[pid], torch.zeros(()))
+        n = pid.numel()
+        cand = pid.clone() * 3  # candidate = particle, then damage
+        cand[pid == 0] = torch.randint(0, 3 * n_part, (30,), generator=g)
+        steal = torch.rand(n, generator=g) < 0.15
+        cand[steal] = torch.randint(0, 3 * n_part, (int(steal.sum()),), generator=g)
+        cand[(pid == 5) | (pid == 6)] = 15                   # two particles merged into one candidate
+        half = (pid == 9) & (torch.arange(n) % 2 == 0)
+        cand[half] = 1000                                     # a particle split over two candidates
+        hit_ids = torch.arange(n)
+        drop = torch.rand(n, generator=g) < 0.1              # unassigned hits
+        bg = torch.stack([hit_ids[~drop], cand[~drop]])
+        event = SimpleNamespace(pid=pid, pt=pt)
+        for pt_cut, nhits_cut, maj in ((1.0, 5, 0.5), (0.5, 3, 0.5), (1.0, 4, 0.7)):
+            want = O.eval_metrics_dense(bg, pid, pt, pt_cut, nhits_cut, maj)
+            got = eval_metrics(bg.clone(), event, pt_cut=pt_cut, nhits_cut=nhits_cut, majority_cut=maj, primary=False)
+            for k in want:
+                assert abs(float(got[k]) - float(want[k])) < 1e-9, (seed, pt_cut, k, got, want)
+            checked += want["track_eff"] > 0
+    assert checked >= 12
+    assert eval_metrics(torch.zeros(2, 0, dtype=torch.long), SimpleNamespace(pid=torch.ones(3, dtype=torch.long), pt=torch.ones(3))) == \
+        {"track_eff": 0, "track_pur": 0, "hit_eff": 0, "hit_pur": 0}

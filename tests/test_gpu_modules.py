@@ -391,3 +391,4 @@ def test_training_step_on_collated_events():
         if g is not None and float(g.abs().max()) > 0:
             assert float((g - grads[1][k]).norm()) < 1e-3 * float(g.norm()) + 1e-6, k  # (biases in front of a LayerNorm: analytically 0)
             assert grads[2][k] is not None and bool(torch.isfinite(grads[2][k]).all()), k
+
