@@ -392,3 +392,43 @@ def test_training_step_on_collated_events():
             assert float((g - grads[1][k]).norm()) < 1e-3 * float(g.norm()) + 1e-6, k  # (biases in front of a LayerNorm: analytically 0)
             assert grads[2][k] is not None and bool(torch.isfinite(grads[2][k]).all()), k
 
+
+
+def test_validation_steps_report_tracking_metrics():
+    """shared_evaluation / validation_step of both task bases (edge_classifier_base.py:135-197,
+    bipartite_classification_base.py:226-301): the EC step with a perfect scorer (score = truth) reconstructs every track of
+    a clean synthetic event — efficiency and purity 1 — and its loss equals the training loss of the same scores; the BC
+    step returns a finite loss, logs the four metrics, and with the event vector accepts a collated batch."""
+    from types import SimpleNamespace
+    from hierarchicalgnn_b200.synth import collate_events, synth_event
+    from hierarchicalgnn_b200.training_utils import kaiming_init, model_selector
+    ev = synth_event(120, 8, 0.0, 3.0, seed=31)
+    b = SimpleNamespace(x=ev.x.cuda(), edge_index=ev.edge_index.cuda(), pid=ev.pid.cuda(), pt=(ev.pt + 1.0).cuda(),
+                        y=ev.y.cuda(), y_pid=ev.y_pid.cuda())
+    ec = model_selector("EC-IN", dict(latent=128, n_interaction_graph_iters=1)).cuda().eval()
+    logged = {}
+    ec.log_dict = lambda d, *a, **k: logged.update({k_: (float(v) if torch.is_tensor(v) else v) for k_, v in d.items()})
+    ec.forward = lambda x, graph: b.y_pid.float().clamp(1e-4, 1 - 1e-4)  # a perfect scorer
+    graph, loss = ec.shared_evaluation(b, 0, log=True)
+    assert graph.shape[0] == 2 and torch.isfinite(loss)
+    assert logged["track_eff"] == 1.0 and logged["track_pur"] == 1.0 and logged["hit_eff"] == 1.0 and logged["hit_pur"] == 1.0
+    assert abs(float(ec.validation_step(b)) - float(ec.training_step(b))) < 1e-6
+
+    torch.manual_seed(0)
+    bc = model_selector("BC-HGNN-GMM", dict(latent=128, loss_schedule=0.5))
+    kaiming_init(bc)
+    bc.cuda().eval()
+    seen = {}
+    bc.log_dict = lambda d, *a, **k: seen.update(d)
+    evs = [synth_event(150, 8, 0.05, 3.0, seed=41), synth_event(90, 10, 0.0, 4.0, seed=42)]
+    for events in ([evs[0]], evs):
+        big = collate_events(events)
+        nb = SimpleNamespace(x=big.x.cuda(), edge_index=big.edge_index.cuda(), pid=big.pid.cuda(), pt=big.pt.cuda())
+        if len(events) > 1:
+            nb.batch, nb.num_graphs = big.batch.cuda(), big.num_graphs
+        clusters = big.clusters.cuda()
+        bc.hgnn_block.clustering = lambda x, emb, graph: clusters
+        seen.clear()
+        loss = bc.validation_step(nb)
+        assert torch.isfinite(loss) and not loss.requires_grad
+        assert {"val_loss", "val_embedding_loss", "val_assignment_loss", "track_eff", "track_pur", "hit_eff", "hit_pur"} <= set(seen)
