@@ -21,7 +21,8 @@ Besides `value` (device-timed, inputs resident) the line carries
   dp_training    BASELINE config 4: BC training steps (loss, backward with the bucketed all-reduce overlapped,
                  clip 0.5, AdamW) on per-rank batches of 1 GeV events (HGNN_BENCH_EVENTS_PER_STEP, default 8, collated into
                  one disjoint graph; models.config3_bc_fwd_bwd_1gev_batched is the forward + backward of such a batch)
-  partition      (N > 1) BASELINE config 5: one full-pile-up shaped event, destination-partitioned (strong scaling)
+  partition      (N > 1) BASELINE config 5: one full-pile-up shaped event, destination-partitioned (strong scaling): a stack
+                 of two InteractionGNNCells, and (partition.hierarchical) two HierarchicalGNNCells
   roofline, cpu_baseline   as the contract asks.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--latent L] [--edges E]
@@ -522,7 +523,92 @@ def partition_benchmark(args, dev, world, rank, barrier):
     interaction cell forward + backward, destination-partitioned over the ranks; the one-GPU time of the same event is
     measured in the same run (every rank runs it redundantly) so that the speed-up is self-contained."""
     res = run_partition(args, dev=dev, world=world, rank=rank, barrier=barrier, emit=False, steps=max(3, min(args.steps, 10)))
+    if os.environ.get("HGNN_PART_HIER", "1") != "0":
+        hier = hier_partition_benchmark(dev, world, rank, barrier, steps=max(3, min(args.steps, 6)))
+        if res is not None:
+            res["hierarchical"] = hier
     return res
+
+
+def hier_partition_benchmark(dev, world, rank, barrier, steps=5, E=3_000_000, L=128):
+    """The same strong-scaling measurement for the WHOLE hierarchical cell (gnn_utils.py:112-157): two HierarchicalGNNCells
+    forward + backward on the full-pile-up shaped event (hits and hit edges destination-partitioned, the supernode side —
+    S = N / 10 supernodes, N superedges, 3 hit -> supernode assignments per hit — replicated, its messages all-reduced),
+    against the un-partitioned cells on one GPU in the same run. Parity of the two is `profiles/hier_partition_check.py`."""
+    import torch.distributed as dist
+    from hierarchicalgnn_b200.gnn_utils import GraphPlans, HierarchicalGNNCell
+    from hierarchicalgnn_b200.parallel import (SymmetricRows, cuda_hier_cell_callables, pad_rows, partition_bipartite,
+                                               partition_by_destination, partitioned_hierarchical_cell)
+    from hierarchicalgnn_b200.synth import synth_edge_problem
+    from hierarchicalgnn_b200.training_utils import kaiming_init
+    torch.manual_seed(0)
+    cells = [HierarchicalGNNCell(hparams(L)) for _ in range(2)]
+    for c in cells:
+        kaiming_init(c)
+        c.to(dev)
+    nodes_h, edges_h, graph_h = synth_edge_problem(E, L, seed=2000, nodes_per_edge=0.04)
+    N = nodes_h.shape[0]
+    g = torch.Generator().manual_seed(5)
+    S, ES = max(N // 10, 8), max(N, 64)
+    sn_h, se_h = torch.randn(S, L, generator=g), torch.randn(ES, L, generator=g)
+    sg_h, sw_h = torch.randint(0, S, (2, ES), generator=g), torch.rand(ES, 1, generator=g)
+    bg_h = torch.stack([torch.arange(N).repeat(3), torch.randint(0, S, (3 * N,), generator=g)])
+    bw_h = torch.rand(3 * N, 1, generator=g) / 3
+    cots = [torch.randn(*sh, generator=g) for sh in ((N, L), (E, L), (S, L), (ES, L))]
+    order = torch.argsort(graph_h[1], stable=True)
+    graph_h, edges_h, cots[1] = graph_h[:, order].contiguous(), edges_h[order].contiguous(), cots[1][order].contiguous()
+
+    def leaf(t):
+        return t.to(dev).clone().requires_grad_(True)
+    params = [p for c in cells for p in c.parameters()]
+    sg, cd = sg_h.to(dev), [c.to(dev) for c in cots]
+
+    # ---- un-partitioned, every rank redundantly ----
+    r = dict(n=leaf(nodes_h), e=leaf(edges_h), s=leaf(sn_h), se=leaf(se_h), bw=leaf(bw_h), sw=leaf(sw_h))
+    graph, bg = graph_h.to(dev), bg_h.to(dev)
+    gp, bp, sp = GraphPlans(graph, N, N, dst_sorted=True), GraphPlans(bg, N, S), GraphPlans(sg, S, S)
+
+    def solo(_i=0):
+        a, b, c, d = r["n"], r["e"], r["s"], r["se"]
+        for i, cell in enumerate(cells):
+            a, b, c, d = cell(a, b, c, d, gp, bp, r["bw"], sp, r["sw"], skip_edge_updates=(i == 1))
+        torch.autograd.grad(sum((o * ct).sum() for o, ct in zip((a, b, c, d), cd)), list(r.values()) + params, allow_unused=True)
+    for i in range(2):
+        solo()
+    t1 = _timed(solo, steps, barrier, world, dev)
+    del r, graph, bg, gp, bp, sp
+
+    # ---- partitioned ----
+    part = partition_by_destination(graph_h, N, world, rank)
+    bpart = partition_bipartite(bg_h, part)
+    own = slice(part.node_lo, part.node_hi)
+    p = dict(n=leaf(pad_rows(nodes_h, world * part.block)), e=leaf(edges_h[part.edge_ids]), s=leaf(sn_h), se=leaf(se_h),
+             bw=leaf(bw_h[bpart.ids]), sw=leaf(sw_h))
+    cn, ce = cd[0][own], cd[1][part.edge_ids.to(dev)]
+    for k_ in ("graph", "dst_local", "edge_ids"):
+        setattr(part, k_, getattr(part, k_).to(dev))
+    bpart.ids, bpart.node_local, bpart.supernode = bpart.ids.to(dev), bpart.node_local.to(dev), bpart.supernode.to(dev)
+    fns = [cuda_hier_cell_callables(c, fuse_aggregate=(i == 0)) for i, c in enumerate(cells)]
+    sr = SymmetricRows(part.block, L, dev, slots=2) if world > 1 else None
+
+    def parted(_i=0):
+        st = dict(nodes=p["n"], edges=p["e"], supernodes=p["s"], superedges=p["se"], agg_owned=None, x_owned=None)
+        for i, f in enumerate(fns):
+            st = partitioned_hierarchical_cell(part, bpart, st["nodes"], st["edges"], st["supernodes"], st["superedges"], p["bw"],
+                                               sg, p["sw"], f, symmetric=sr, agg_owned=st["agg_owned"], x_owned=st["x_owned"],
+                                               slot=i, skip_edge_updates=(i == 1))
+        loss = ((st["nodes"][own] * cn).sum() + (st["edges"] * ce).sum() + (st["supernodes"] * cd[2]).sum()
+                + (st["superedges"] * cd[3]).sum())
+        grads = torch.autograd.grad(loss, list(p.values()) + params, allow_unused=True)
+        flat = torch.cat([x.reshape(-1) for x in grads[6:] if x is not None])
+        if world > 1:
+            dist.all_reduce(flat)  # the step-end weight-gradient all-reduce
+    for i in range(2):
+        parted()
+    tp = _timed(parted, steps, barrier, world, dev)
+    return {"workload": f"2 HierarchicalGNNCells fwd+bwd, L={L} E={E} N={N} S={S} supernodes, {ES} superedges, {3 * N} hit-supernode "
+                        f"assignments; hits and hit edges destination-partitioned x{world}, supernode side replicated",
+            "one_gpu_ms_per_step": t1, "ms_per_step": tp, "speedup_vs_1gpu": t1 / tp, "steps": steps}
 
 
 def run_gpu(args):
