@@ -785,7 +785,9 @@ extern "C" int hgnn_narrow_in_forward(const hgnn_mlp_desc* d, int64_t rows, floa
   if (rows == 0) return HGNN_OK;
   HGNN_REQUIRE(out != nullptr, "narrow_in_forward: out is NULL");
   const size_t smem = (size_t)(NI_MAX_K + 3) * a.N * 4;
-  const int grid = skinny_grid(rows, SK_WARPS * 4);
+  // 40 registers and 11 KB of shared memory per CTA: up to eight CTAs per SM hide the gather -> shuffle -> LayerNorm chain
+  // of a row (ncu: two CTAs per SM left the warp slots 25 % occupied)
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + SK_WARPS * 4 - 1) / (SK_WARPS * 4), 8 * (int64_t)num_sms()));
   cudaStream_t st = (cudaStream_t)stream;
   switch (a.N / 32) {
     case 1: k_narrow_in_fwd<1, 0><<<grid, SK_THREADS, smem, st>>>(a, out); break;
