@@ -13,13 +13,13 @@ gradients are all-reduced over NCCL, the only exchange the DP path has).
 
 Besides `value` (device-timed, inputs resident) the line carries
   e2e            BASELINE config 3 through the public model API from HOST buffers: BC_HierarchicalGNN_GMM (latent 128,
-                 6 + 6 cells) forward + backward on synthetic 1 GeV events, HGNN_BENCH_EVENTS_PER_STEP (default 8) events
+                 6 + 6 cells) forward + backward on synthetic 1 GeV events, HGNN_BENCH_EVENTS_PER_STEP (default 16) events
                  collated into one disjoint graph per step (torch_geometric Batch layout), x[N,3] / edge_index / cluster
                  labels / event ids uploaded from pinned memory every step, the loss read back; same metric (edge-steps/s
                  = E_d * 12 cells / time). e2e.single_event = the same with ONE event per step (host-bound)
   models         device-timed and end-to-end times of BASELINE configs 1 (EC-IN forward) and 3 (BC fwd+bwd) on 1 GeV events
   dp_training    BASELINE config 4: BC training steps (loss, backward with the bucketed all-reduce overlapped,
-                 clip 0.5, AdamW) on per-rank batches of 1 GeV events (HGNN_BENCH_EVENTS_PER_STEP, default 8, collated into
+                 clip 0.5, AdamW) on per-rank batches of 1 GeV events (HGNN_BENCH_EVENTS_PER_STEP, default 16, collated into
                  one disjoint graph; models.config3_bc_fwd_bwd_1gev_batched is the forward + backward of such a batch)
   partition      (N > 1) BASELINE config 5: one full-pile-up shaped event, destination-partitioned (strong scaling): a stack
                  of two InteractionGNNCells, and (partition.hierarchical) two HierarchicalGNNCells
@@ -299,7 +299,7 @@ def _batch_pool(n_batches, events_per_batch, seed0, n_particles=1200):
 
 
 def _events_per_step():
-    return max(1, int(os.environ.get("HGNN_BENCH_EVENTS_PER_STEP", "8")))
+    return max(1, int(os.environ.get("HGNN_BENCH_EVENTS_PER_STEP", "16")))
 
 
 def _timed(fn, k, barrier, world, dev):
