@@ -77,7 +77,13 @@ class FusedMLP(nn.Sequential):
                 any(t.requires_grad for t in segs) or any(p.requires_grad for p in ps)):
             packer = None  # the fused edge kernel has a tensor-core backward at latent 128 only: train layer by layer
         if packer is None:
-            groups = self._row_groups(segs, plans, skip)
+            # the split into kernel groups depends on shapes / gather pattern / precision only: decided once per pattern
+            key = (ops.get_precision(), tuple(t.shape[1] for t in segs), tuple(p is None for p in plans), skip,
+                   all(t.is_cuda for t in segs))
+            cache = self.__dict__.setdefault("_groups_cache", {})
+            if key not in cache:
+                cache[key] = self._row_groups(segs, plans, skip)
+            groups = cache[key]
             if groups is not None:
                 return self._run_groups(groups, list(segs), list(plans), skip)
             packer = self._tc_packer(segs, plans, skip, lns)
