@@ -376,3 +376,31 @@ def test_tracking_metrics_equal_the_dense_restatement_of_the_reference():
     assert checked >= 12
     assert eval_metrics(torch.zeros(2, 0, dtype=torch.long), SimpleNamespace(pid=torch.ones(3, dtype=torch.long), pt=torch.ones(3))) == \
         {"track_eff": 0, "track_pur": 0, "hit_eff": 0, "hit_pur": 0}
+
+
+def test_collate_events_and_event_offsets():
+    """synth.collate_events lays several events out like a torch_geometric Batch (rows event by event, edge_index offset,
+    batch vector, ptr, per-event particle ids kept, cluster labels offset event by event); utils.event_offsets recovers the
+    row offsets from the batch vector, empty events included."""
+    from hierarchicalgnn_b200.synth import collate_events, synth_event
+    from hierarchicalgnn_b200.utils import event_offsets
+    evs = [synth_event(20, 5, 0.1, 2.0, seed=1), synth_event(7, 4, 0.0, 3.0, seed=2), synth_event(11, 6, 0.2, 1.0, seed=3)]
+    b = collate_events(evs)
+    sizes = [e.x.shape[0] for e in evs]
+    assert b.num_graphs == 3 and b.ptr.tolist() == [0, sizes[0], sizes[0] + sizes[1], sum(sizes)]
+    assert torch.equal(torch.bincount(b.batch), torch.tensor(sizes))
+    off = 0
+    lo = 0
+    for i, e in enumerate(evs):
+        n, m = e.x.shape[0], e.edge_index.shape[1]
+        assert torch.equal(b.x[off:off + n], e.x) and torch.equal(b.pid[off:off + n], e.pid)
+        assert torch.equal(b.edge_index[:, lo:lo + m] - off, e.edge_index)
+        assert bool((b.batch[b.edge_index[0, lo:lo + m]] == i).all()) and bool((b.batch[b.edge_index[1, lo:lo + m]] == i).all())
+        off, lo = off + n, lo + m
+    real = b.clusters >= 0
+    assert torch.equal(b.clusters[~real], torch.full((int((~real).sum()),), -1))
+    assert int(b.clusters.max()) + 1 == sum(e.n_particles for e in evs)
+    ev_of_cluster = torch.zeros(int(b.clusters.max()) + 1, dtype=torch.long).scatter_(0, b.clusters[real], b.batch[real])
+    assert bool((ev_of_cluster[1:] >= ev_of_cluster[:-1]).all())  # supernode ids ascend with the event id
+    assert event_offsets(b.batch, 3).tolist() == b.ptr.tolist()
+    assert event_offsets(torch.tensor([0, 0, 2, 2, 2]), 4).tolist() == [0, 2, 2, 5, 5]  # events 1 and 3 are empty
