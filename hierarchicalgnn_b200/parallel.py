@@ -137,6 +137,7 @@ class GradientBuckets:
         self._fired = [0.0] * len(self.params)
         self._index = {id(p): i for i, p in enumerate(self.params)}
         self._dead = None  # indices of parameters that get a gradient on no rank (structural: decided on the first step)
+        self._next = 0
 
     def _close(self, plist):
         n = sum(p.numel() for p in plist)
@@ -153,10 +154,12 @@ class GradientBuckets:
         when its last parameter has arrived. (Pointing .grad at zeroed bucket views instead made autograd run one small
         in-place add per parameter: ~400 launches per BC-HGNN step.)"""
         self._fired = [0.0] * len(self.params)
+        self._next = 0  # buckets are reduced strictly in index order: every rank issues the same sequence of collectives
         for b in self.buckets:
             b["pending"] = len(b["params"])
             b["work"] = None
             b["packed"] = False
+            b["ready"] = False
             for p in b["params"]:
                 p.grad = None
 
@@ -184,17 +187,26 @@ class GradientBuckets:
         self._fired[self._index[id(p)]] = 1.0
         b["pending"] -= 1
         if b["pending"] == 0 and self.world > 1:
+            b["ready"] = True
+            self._launch(only_ready=True)
+
+    def _launch(self, only_ready: bool):
+        """Issue the all-reduce of the next buckets IN INDEX ORDER (a bucket that completed early waits for its predecessors:
+        ranks whose backward completes buckets in different orders — a branch taken on one rank only — would otherwise pair
+        different buckets in the same collective)."""
+        while self._next < len(self.buckets):
+            b = self.buckets[self._next]
+            if only_ready and not b["ready"]:
+                return
             self._pack(b)
             b["work"] = dist.all_reduce(b["flat"], group=self.group, async_op=True)
+            self._next += 1
 
     def finish(self):
         """After the backward: reduce the incomplete buckets, wait for all, average; un-set dead gradients. On one rank
         nothing is packed or copied: the gradients stay where autograd left them."""
         if self.world > 1:
-            for b in self.buckets:
-                if b["work"] is None:
-                    self._pack(b)
-                    b["work"] = dist.all_reduce(b["flat"], group=self.group, async_op=True)
+            self._launch(only_ready=False)
             fired = None
             if self._dead is None:  # one small MAX all-reduce + host read, first step only
                 fired = torch.tensor(self._fired, device=self.buckets[0]["flat"].device)

@@ -283,6 +283,52 @@ def test_destination_partitioned_hierarchical_cells_match_single_process_world2(
     _run(_hier_partition_case)
 
 
+class _BranchyTask(torch.nn.Module):
+    """``side`` only enters the loss on rank 0 (a branch taken per rank): its gradient exists on one rank only."""
+
+    def __init__(self):
+        super().__init__()
+        self.main = torch.nn.Linear(4, 1)
+        self.side = torch.nn.Linear(4, 1)
+        self.use_side = False
+
+    def training_step(self, batch, batch_idx=0):
+        y = self.main(batch)
+        if self.use_side:
+            y = y + self.side(batch)
+        return y.square().mean()
+
+
+def _one_sided_gradient_case(rank, world):
+    """GradientBuckets with a parameter whose gradient arrives on ONE rank only: the other rank contributes zeros to its bucket,
+    and after finish() every rank holds the same averaged gradient for it (not None, not stale)."""
+    from hierarchicalgnn_b200.parallel import GradientBuckets
+    torch.manual_seed(0)
+    m = _BranchyTask()
+    m.use_side = rank == 0
+    gb = GradientBuckets(list(m.parameters()), bucket_bytes=8)  # one parameter per bucket
+    data = torch.randn(world, 5, 4, generator=torch.Generator().manual_seed(2))
+    for _ in range(2):  # the second pass starts from the first one's views
+        gb.prepare()
+        assert all(p.grad is None for p in m.parameters())
+        m.training_step(data[rank]).backward()
+        gb.finish()
+        ref = _BranchyTask()
+        ref.load_state_dict(m.state_dict())
+        ref.use_side = True
+        g0 = torch.autograd.grad(ref.training_step(data[0]), list(ref.parameters()))
+        ref.use_side = False
+        g1 = torch.autograd.grad(ref.training_step(data[1]), list(ref.main.parameters()))
+        want = [(g0[0] + g1[0]) / 2, (g0[1] + g1[1]) / 2, g0[2] / 2, g0[3] / 2]
+        for p, w in zip(m.parameters(), want):
+            torch.testing.assert_close(p.grad, w, rtol=1e-5, atol=1e-7)
+    gb.remove()
+
+
+def test_gradient_buckets_one_sided_gradient_world2():
+    _run(_one_sided_gradient_case)
+
+
 def test_data_parallel_gradient_allreduce_world2():
     _run(_dp_case)
 
